@@ -1,0 +1,713 @@
+/*
+ * bias_oracle.c — CPU oracle (TEST INFRASTRUCTURE ONLY; see bias_oracle.h).
+ *
+ * A from-scratch C restatement of the serial Julia arithmetic on BIAS.jl's
+ * component-assignment hot path.  Citations are file:line under /root/reference.
+ * The product library (libbias_cuda) never links or loads this file.
+ */
+#include "bias_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ======================================================================
+ * src/common.jl
+ * ====================================================================== */
+
+/* Julia 0.4 Base.sum over a dense Float64 array: mapreduce_impl with blksize
+ * 1024 — a left-to-right loop below the block size, pairwise halves above it
+ * (Julia base/reduce.jl; third-party, unpinned beyond `REQUIRE: julia 0.4`).
+ * Used wherever the reference calls sum(::Vector{Float64}) (src/common.jl:48,
+ * src/conjugates.jl:193-195, src/distributions.jl:62). */
+static double jsum_rec(const double *a, int64_t lo, int64_t hi) /* inclusive */
+{
+    if (lo == hi) return a[lo];
+    if (lo + 1024 > hi) {
+        double v = a[lo] + a[lo + 1];
+        for (int64_t i = lo + 2; i <= hi; ++i) v += a[i];
+        return v;
+    }
+    int64_t mid = (int64_t)(((uint64_t)lo + (uint64_t)hi) >> 1);
+    double v1 = jsum_rec(a, lo, mid);
+    double v2 = jsum_rec(a, mid + 1, hi);
+    return v1 + v2;
+}
+
+double orc_julia_sum(const double *a, int64_t n)
+{
+    if (n <= 0) return 0.0;
+    return jsum_rec(a, 0, n - 1);
+}
+
+/* src/common.jl:42-52 — max-shift, exp, sum, divide (four passes). */
+void orc_lognormalize(double *pp, int64_t n)
+{
+    double pp_max = pp[0];
+    for (int64_t k = 1; k < n; ++k) if (pp[k] > pp_max) pp_max = pp[k];
+    for (int64_t k = 0; k < n; ++k) pp[k] = exp(pp[k] - pp_max);
+    double pp_sum = orc_julia_sum(pp, n);
+    for (int64_t k = 0; k < n; ++k) pp[k] /= pp_sum;
+}
+
+/* src/common.jl:69-79 — linear CDF walk with the strict test `cw < r`,
+ * clamped at the last entry.  r is supplied (the reference calls rand()). */
+int64_t orc_sample(const double *w, int64_t n, double r)
+{
+    int64_t i = 0;
+    double cw = w[0];
+    while (cw < r && i < n - 1) {
+        i += 1;
+        cw += w[i];
+    }
+    return i;
+}
+
+/* src/common.jl:157-175 — bar topics on a sqrt(V) x sqrt(V) grid, column-major
+ * flatten (Julia `b[:]`).  First half of the bars are grid rows, second half
+ * grid columns. */
+void orc_gen_bars(int64_t n_bars, int64_t n_vocab, double noise, double *bars)
+{
+    int64_t S = (int64_t)llround(sqrt((double)n_vocab));
+    int64_t half = (int64_t)llround((double)n_bars / 2.0);
+    /* Julia round(): half away from zero, same as llround */
+    double *b = (double *)malloc((size_t)(S * S) * sizeof(double));
+    for (int64_t i = 0; i < n_bars * n_vocab; ++i) bars[i] = 0.0;
+    for (int64_t kk = 0; kk < n_bars; ++kk) {
+        for (int64_t i = 0; i < S * S; ++i) b[i] = 0.0 + noise;
+        if (kk < half) {
+            for (int64_t c = 0; c < S; ++c) b[kk + c * S] = 1.0;          /* b[kk, :] */
+        } else {
+            int64_t col = kk - half;
+            for (int64_t r = 0; r < S; ++r) b[r + col * S] = 1.0;         /* b[:, kk-half] */
+        }
+        double s = orc_julia_sum(b, S * S);
+        for (int64_t i = 0; i < S * S && i < n_vocab; ++i) bars[kk * n_vocab + i] = b[i] / s;
+    }
+    free(b);
+}
+
+/* ======================================================================
+ * src/distributions.jl
+ * ====================================================================== */
+double orc_gaussian1d_pdf(double mu, double vv, double x)
+{
+    return exp(-(x - mu) * (x - mu) / (2 * vv)) / (sqrt(2 * M_PI * vv));   /* :36 */
+}
+double orc_gaussian1d_logpdf(double mu, double vv, double x)
+{
+    return log(orc_gaussian1d_pdf(mu, vv, x));                             /* :37 */
+}
+
+/* ======================================================================
+ * src/conjugates.jl
+ * ====================================================================== */
+void orc_comps_reset(orc_comps *c, int64_t k)
+{
+    c->nn[k] = 0;
+    if (c->kind == ORC_MD) {
+        c->mm[k] = 0;
+        memset(c->mi + k * c->dd, 0, (size_t)c->dd * sizeof(int64_t));
+    } else {
+        c->mu[k] = c->m0;                     /* ctor sets mu = m0, src/conjugates.jl:42-47 */
+    }
+}
+
+void orc_comps_move(orc_comps *c, int64_t dst, int64_t src)
+{
+    c->nn[dst] = c->nn[src];
+    if (c->kind == ORC_MD) {
+        c->mm[dst] = c->mm[src];
+        memmove(c->mi + dst * c->dd, c->mi + src * c->dd, (size_t)c->dd * sizeof(int64_t));
+    } else {
+        c->mu[dst] = c->mu[src];
+    }
+}
+
+void orc_additem(orc_comps *c, int64_t k, const orc_data *d, int64_t i)
+{
+    if (c->kind == ORC_G1G1) {                      /* src/conjugates.jl:60-63 */
+        double x = d->x[i];
+        c->nn[k] += 1;
+        double n = (double)c->nn[k];
+        c->mu[k] = ((n - 1) / n) * c->mu[k] + x / n;
+        return;
+    }
+    int64_t *mi = c->mi + k * c->dd;
+    if (d->kind == ORC_INT) {                       /* :153-157 */
+        mi[d->w[i]] += 1;
+        c->mm[k] += 1;
+        c->nn[k] += 1;
+    } else {                                        /* :163-170 */
+        for (int64_t t = d->sptr[i]; t < d->sptr[i + 1]; ++t) {
+            mi[d->sw[t]] += d->sc[t];
+            c->mm[k] += d->sc[t];
+        }
+        c->nn[k] += 1;
+    }
+}
+
+int orc_delitem(orc_comps *c, int64_t k, const orc_data *d, int64_t i)
+{
+    if (c->kind == ORC_G1G1) {                      /* src/conjugates.jl:64-74 */
+        double x = d->x[i];
+        if (c->nn[k] < 1) return -1;                /* the reference throws a String here (:66) */
+        if (c->nn[k] == 1) {
+            c->mu[k] = c->m0;
+            c->nn[k] = 0;
+        } else {
+            double n = (double)c->nn[k];
+            c->mu[k] = c->mu[k] * (n / (n - 1)) - x / (n - 1);
+            c->nn[k] -= 1;
+        }
+        return 0;
+    }
+    int64_t *mi = c->mi + k * c->dd;
+    if (d->kind == ORC_INT) {                       /* :158-162 */
+        mi[d->w[i]] -= 1;
+        c->mm[k] -= 1;
+        c->nn[k] -= 1;
+    } else {                                        /* :171-178 */
+        for (int64_t t = d->sptr[i]; t < d->sptr[i + 1]; ++t) {
+            mi[d->sw[t]] -= d->sc[t];
+            c->mm[k] -= d->sc[t];
+        }
+        c->nn[k] -= 1;
+    }
+    return 0;
+}
+
+void orc_g1g1_posterior(const orc_comps *c, int64_t k, double *mu, double *vv)
+{                                                   /* src/conjugates.jl:77-89 */
+    if (c->nn[k] > 0) {
+        double n = (double)c->nn[k];
+        double denom = c->vv + n * c->v0;
+        *mu = (n * c->v0 * c->mu[k] + c->vv * c->m0) / denom;
+        *vv = c->v0 * c->vv / denom;
+    } else {
+        *mu = c->m0;
+        *vv = c->v0;
+    }
+}
+
+/* logpredictive of a Sent under MultinomialDirichlet, src/conjugates.jl:181-198.
+ * The reference materialises lll = aa + mi over the whole vocabulary and sums
+ * lgamma(lll) - lgamma(aa + mi) over all V entries; entries of untouched words are
+ * exactly 0.0, so the dense vector is built here too and summed with Julia's sum. */
+static double md_logpred_sent(const orc_comps *c, int64_t k, const orc_data *d, int64_t i)
+{
+    const int64_t *mi = c->mi + k * c->dd;
+    int64_t V = c->dd;
+    double *lll = (double *)malloc((size_t)V * sizeof(double));
+    double *term = (double *)malloc((size_t)V * sizeof(double));
+    for (int64_t v = 0; v < V; ++v) lll[v] = c->aa + (double)mi[v];
+    int64_t mm = 0;
+    int64_t len = d->sptr[i + 1] - d->sptr[i];
+    double *lg = (double *)malloc((size_t)(len > 0 ? len : 1) * sizeof(double));
+    for (int64_t t = 0; t < len; ++t) {
+        int64_t w = d->sw[d->sptr[i] + t], cnt = d->sc[d->sptr[i] + t];
+        lll[w] += (double)cnt;
+        mm += cnt;
+        lg[t] = lgamma((double)cnt + 1.0);
+    }
+    for (int64_t v = 0; v < V; ++v) term[v] = lgamma(lll[v]) - lgamma(c->aa + (double)mi[v]);
+    double ll = lgamma((double)mm + 1.0) - orc_julia_sum(lg, len)
+              + lgamma(c->aa * (double)c->dd + (double)c->mm[k])
+              - lgamma(c->aa * (double)c->dd + (double)c->mm[k] + (double)mm)
+              + orc_julia_sum(term, V);
+    free(lll); free(term); free(lg);
+    return ll;
+}
+
+double orc_logpredictive(const orc_comps *c, int64_t k, const orc_data *d, int64_t i)
+{
+    if (c->kind == ORC_G1G1) {                      /* src/conjugates.jl:92-103 */
+        double mu, vv;
+        orc_g1g1_posterior(c, k, &mu, &vv);
+        double x = d->x[i];
+        double dummy = vv + c->vv;
+        return -((x - mu) * (x - mu)) / (2 * dummy) - 0.5 * log(2 * M_PI * dummy);
+    }
+    if (d->kind == ORC_INT) {                       /* :180 */
+        const int64_t *mi = c->mi + k * c->dd;
+        return log((c->aa + (double)mi[d->w[i]]) / (c->aa * (double)c->dd + (double)c->mm[k]));
+    }
+    return md_logpred_sent(c, k, d, i);
+}
+
+/* The per-item "likelihood" diagnostic.  For MultinomialDirichlet this is the
+ * posterior-MEAN probability, not a log (src/conjugates.jl:205-213 via :200-203 and
+ * src/distributions.jl:62): alpha = mi + aa over the vocabulary, divided by sum(alpha). */
+double orc_loglikelihood(const orc_comps *c, int64_t k, const orc_data *d, int64_t i)
+{
+    if (c->kind == ORC_G1G1) {                      /* :105 */
+        double mu, vv;
+        orc_g1g1_posterior(c, k, &mu, &vv);
+        return orc_gaussian1d_logpdf(mu, vv, d->x[i]);
+    }
+    const int64_t *mi = c->mi + k * c->dd;
+    int64_t V = c->dd;
+    double *alpha = (double *)malloc((size_t)V * sizeof(double));
+    for (int64_t v = 0; v < V; ++v) alpha[v] = (double)mi[v] + c->aa;
+    double s = orc_julia_sum(alpha, V);
+    double ll;
+    if (d->kind == ORC_INT) {
+        ll = alpha[d->w[i]] / s;
+    } else {
+        ll = 0.0;
+        for (int64_t t = d->sptr[i]; t < d->sptr[i + 1]; ++t)
+            ll += (double)d->sc[t] * (alpha[d->sw[t]] / s);
+    }
+    free(alpha);
+    return ll;
+}
+
+/* O(1) closed form of the MD x Int diagnostic (same value up to the rounding of sum(alpha)). */
+static double md_int_diag_fast(const orc_comps *c, int64_t k, int64_t w)
+{
+    return ((double)c->mi[k * c->dd + w] + c->aa) / ((double)c->mm[k] + c->aa * (double)c->dd);
+}
+
+/* ======================================================================
+ * src/LDA.jl
+ * ====================================================================== */
+double orc_lda_init(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
+                    const int64_t *z, int64_t *nn)
+{                                                   /* src/LDA.jl:91-98 */
+    int64_t K = c->K;
+    double ll = 0.0;
+    for (int64_t j = 0; j < D; ++j)
+        for (int64_t i = ptr[j]; i < ptr[j + 1]; ++i) {
+            int64_t k = z[i];
+            orc_additem(c, k, d, i);
+            nn[j * K + k] += 1;
+            ll += orc_loglikelihood(c, k, d, i);
+        }
+    return ll;
+}
+
+/* LDA_sample_zz scores, src/LDA.jl:35-37. */
+static void lda_scores(const orc_comps *c, const orc_data *d, int64_t i, const int64_t *nn_j,
+                       double alpha, double *pp)
+{
+    for (int64_t k = 0; k < c->K; ++k)
+        pp[k] = log((double)nn_j[k] + alpha) + orc_logpredictive(c, k, d, i);
+}
+
+double orc_lda_sweep(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
+                     int64_t *z, int64_t *nn, double alpha,
+                     const int64_t *doc_order, const int64_t *tok_order,
+                     const double *uniforms, int diag_mode)
+{                                                   /* src/LDA.jl:113-133 */
+    int64_t K = c->K;
+    double *pp = (double *)malloc((size_t)K * sizeof(double));
+    double ll = 0.0;
+    int64_t pos = 0;       /* cursor into tok_order, which is grouped by visiting order */
+    for (int64_t jo = 0; jo < D; ++jo) {
+        int64_t j = doc_order ? doc_order[jo] : jo;
+        int64_t len = ptr[j + 1] - ptr[j];
+        for (int64_t io = 0; io < len; ++io) {
+            int64_t i = tok_order ? tok_order[pos + io] : ptr[j] + io;
+            int64_t k = z[i];
+            orc_delitem(c, k, d, i);                /* :118-120 */
+            nn[j * K + k] -= 1;
+            lda_scores(c, d, i, nn + j * K, alpha, pp);    /* :124 -> :26-42 */
+            orc_lognormalize(pp, K);
+            k = orc_sample(pp, K, uniforms[i]);
+            z[i] = k;                               /* :128-131 */
+            orc_additem(c, k, d, i);
+            nn[j * K + k] += 1;
+            if (diag_mode == 2) ll += orc_loglikelihood(c, k, d, i);
+            else if (diag_mode == 1) {
+                if (c->kind == ORC_MD && d->kind == ORC_INT) ll += md_int_diag_fast(c, k, d->w[i]);
+                else ll += orc_loglikelihood(c, k, d, i);
+            }
+        }
+        pos += len;
+    }
+    free(pp);
+    return ll;
+}
+
+int64_t orc_lda_conditional(orc_comps *c, const orc_data *d, int64_t j, int64_t i,
+                            int64_t zi, int64_t *nn, double alpha, double r,
+                            double *raw, double *prob)
+{
+    int64_t K = c->K;
+    double mu_saved = (c->kind == ORC_G1G1) ? c->mu[zi] : 0.0;
+    orc_delitem(c, zi, d, i);
+    nn[j * K + zi] -= 1;
+    lda_scores(c, d, i, nn + j * K, alpha, raw);
+    memcpy(prob, raw, (size_t)K * sizeof(double));
+    orc_lognormalize(prob, K);
+    int64_t k = orc_sample(prob, K, r);
+    orc_additem(c, zi, d, i);
+    nn[j * K + zi] += 1;
+    if (c->kind == ORC_G1G1) c->mu[zi] = mu_saved;  /* undo running-mean drift: state is restored exactly */
+    return k;
+}
+
+/* ======================================================================
+ * src/BMM.jl
+ * ====================================================================== */
+double orc_bmm_init(orc_comps *c, const orc_data *d, int64_t N, const int64_t *z, int64_t *nn)
+{                                                   /* src/BMM.jl:70-75 */
+    double ll = 0.0;
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t k = z[i];
+        orc_additem(c, k, d, i);
+        nn[k] += 1;
+        ll += orc_loglikelihood(c, k, d, i);
+    }
+    return ll;
+}
+
+static void bmm_scores(const orc_comps *c, const orc_data *d, int64_t i, const int64_t *nn,
+                       double alpha, double *pp)
+{                                                   /* src/BMM.jl:102-105 */
+    for (int64_t k = 0; k < c->K; ++k)
+        pp[k] = log((double)nn[k] + alpha) + orc_logpredictive(c, k, d, i);
+}
+
+double orc_bmm_sweep(orc_comps *c, const orc_data *d, int64_t N, int64_t *z, int64_t *nn,
+                     double alpha, const int64_t *order, const double *uniforms)
+{                                                   /* src/BMM.jl:92-115 */
+    int64_t K = c->K;
+    double *pp = (double *)malloc((size_t)K * sizeof(double));
+    double ll = 0.0;
+    for (int64_t io = 0; io < N; ++io) {
+        int64_t i = order ? order[io] : io;
+        int64_t k = z[i];
+        nn[k] -= 1;
+        orc_delitem(c, k, d, i);
+        bmm_scores(c, d, i, nn, alpha, pp);
+        orc_lognormalize(pp, K);
+        k = orc_sample(pp, K, uniforms[i]);
+        z[i] = k;
+        nn[k] += 1;
+        orc_additem(c, k, d, i);
+        ll += orc_loglikelihood(c, k, d, i);
+    }
+    free(pp);
+    return ll;
+}
+
+int64_t orc_bmm_conditional(orc_comps *c, const orc_data *d, int64_t i, int64_t zi, int64_t *nn,
+                            double alpha, double r, double *raw, double *prob)
+{
+    int64_t K = c->K;
+    double mu_saved = (c->kind == ORC_G1G1) ? c->mu[zi] : 0.0;
+    nn[zi] -= 1;
+    orc_delitem(c, zi, d, i);
+    bmm_scores(c, d, i, nn, alpha, raw);
+    memcpy(prob, raw, (size_t)K * sizeof(double));
+    orc_lognormalize(prob, K);
+    int64_t k = orc_sample(prob, K, r);
+    nn[zi] += 1;
+    orc_additem(c, zi, d, i);
+    if (c->kind == ORC_G1G1) c->mu[zi] = mu_saved;
+    return k;
+}
+
+/* ======================================================================
+ * RNG (the reference uses Julia's global MersenneTwister and Distributions.jl,
+ * neither reproducible here: draws are "parity unpinned").
+ * ====================================================================== */
+static uint64_t splitmix64(uint64_t *x)
+{
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void orc_rng_seed(orc_rng *g, uint64_t seed)
+{
+    for (int i = 0; i < 4; ++i) g->s[i] = splitmix64(&seed);
+}
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static uint64_t rng_next(orc_rng *g)
+{   /* xoshiro256** */
+    uint64_t *s = g->s;
+    uint64_t result = rotl64(s[1] * 5, 7) * 9;
+    uint64_t t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+    s[2] ^= t; s[3] = rotl64(s[3], 45);
+    return result;
+}
+double orc_rand(orc_rng *g) { return (double)(rng_next(g) >> 11) * (1.0 / 9007199254740992.0); }
+double orc_randn(orc_rng *g)
+{
+    double u1, u2;
+    do { u1 = orc_rand(g); } while (u1 <= 0.0);
+    u2 = orc_rand(g);
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2);
+}
+double orc_rand_gamma(orc_rng *g, double shape)
+{
+    if (shape < 1.0) {
+        double u;
+        do { u = orc_rand(g); } while (u <= 0.0);
+        return orc_rand_gamma(g, shape + 1.0) * pow(u, 1.0 / shape);
+    }
+    double dd = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * dd);
+    for (;;) {
+        double x, v;
+        do { x = orc_randn(g); v = 1.0 + cc * x; } while (v <= 0.0);
+        v = v * v * v;
+        double u = orc_rand(g);
+        if (u < 1.0 - 0.0331 * x * x * x * x) return dd * v;
+        if (u > 0.0 && log(u) < 0.5 * x * x + dd * (1.0 - v + log(v))) return dd * v;
+    }
+}
+double orc_rand_beta(orc_rng *g, double a, double b)
+{
+    double x = orc_rand_gamma(g, a), y = orc_rand_gamma(g, b);
+    return x / (x + y);
+}
+void orc_randperm(orc_rng *g, int64_t n, int64_t *out)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = i;
+    for (int64_t i = n - 1; i > 0; --i) {
+        int64_t j = (int64_t)(orc_rand(g) * (double)(i + 1));
+        if (j > i) j = i;
+        int64_t t = out[i]; out[i] = out[j]; out[j] = t;
+    }
+}
+
+/* ======================================================================
+ * src/HDP.jl — direct-assignment sampler
+ * ====================================================================== */
+double orc_hdp_init(orc_hdp *h, orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
+                    const int64_t *z, int64_t *nn)
+{                                                   /* src/HDP.jl:217-228 */
+    int64_t S = h->Kmax;
+    double ll = 0.0;
+    for (int64_t j = 0; j < D; ++j)
+        for (int64_t i = ptr[j]; i < ptr[j + 1]; ++i) {
+            int64_t k = z[i];
+            orc_additem(c, k, d, i);
+            nn[j * S + k] += 1;
+            ll += orc_loglikelihood(c, k, d, i);
+        }
+    for (int64_t k = 0; k <= h->KK; ++k) h->beta[k] = 1.0 / (double)(h->KK + 1);   /* :228 */
+    return ll;
+}
+
+static int64_t hdp_colsum(const int64_t *nn, int64_t D, int64_t S, int64_t k)
+{
+    int64_t s = 0;
+    for (int64_t j = 0; j < D; ++j) s += nn[j * S + k];
+    return s;
+}
+
+/* Remove component kk: del_column + splice!(components) + shift every zz > kk down +
+ * fold its stick into the unrepresented mass (src/HDP.jl:251-262 and :293-306). */
+static void hdp_delete_component(orc_hdp *h, orc_comps *c, int64_t D, const int64_t *ptr,
+                                 int64_t *z, int64_t *nn, int64_t kk)
+{
+    int64_t S = h->Kmax, KK = h->KK;
+    for (int64_t j = 0; j < D; ++j)
+        for (int64_t k = kk; k < KK - 1; ++k) nn[j * S + k] = nn[j * S + k + 1];
+    for (int64_t j = 0; j < D; ++j) nn[j * S + KK - 1] = 0;
+    for (int64_t k = kk; k < KK - 1; ++k) orc_comps_move(c, k, k + 1);
+    orc_comps_reset(c, KK - 1);
+    int64_t N = ptr[D];
+    for (int64_t i = 0; i < N; ++i) if (z[i] > kk) z[i] -= 1;
+    h->beta[KK] += h->beta[kk];
+    for (int64_t k = kk; k < KK; ++k) h->beta[k] = h->beta[k + 1];
+    h->KK -= 1;
+}
+
+static void hdp_scores(const orc_hdp *h, orc_comps *c, const orc_data *d, int64_t i,
+                       const int64_t *nn_j, double *pp)
+{                                                   /* src/HDP.jl:312-315 */
+    int64_t KK = h->KK;
+    for (int64_t l = 0; l < KK; ++l)
+        pp[l] = log((double)nn_j[l] + h->aa * h->beta[l]) + orc_logpredictive(c, l, d, i);
+    /* the new-component term uses the empty prototype hdp.component: slot Kmax-1 is
+     * reserved by the callers as an always-empty scratch component when KK < Kmax */
+    pp[KK] = log(h->aa * h->beta[KK]) + orc_logpredictive(c, c->K - 1, d, i);
+}
+
+double orc_hdp_sweep(orc_hdp *h, orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
+                     int64_t *z, int64_t *nn, orc_rng *g, const double *uniforms, int shuffle)
+{
+    int64_t S = h->Kmax;
+    double *pp = (double *)malloc((size_t)(S + 1) * sizeof(double));
+    double ll = 0.0;
+
+    /* :248-264 — `for kk = 1:hdp.KK` evaluates its range once while the body shrinks
+     * hdp.KK; after a deletion the column that slid into kk is skipped.  Where the
+     * reference would index past the shrunken matrix (BoundsError) we stop. */
+    int64_t KK0 = h->KK;
+    for (int64_t kk = 0; kk < KK0; ++kk) {
+        if (kk >= h->KK) break;
+        if (hdp_colsum(nn, D, S, kk) == 0) hdp_delete_component(h, c, D, ptr, z, nn, kk);
+    }
+
+    int64_t *dorder = (int64_t *)malloc((size_t)(D > 0 ? D : 1) * sizeof(int64_t));
+    if (shuffle) orc_randperm(g, D, dorder); else for (int64_t j = 0; j < D; ++j) dorder[j] = j;
+    for (int64_t jo = 0; jo < D; ++jo) {
+        int64_t j = dorder[jo];
+        int64_t len = ptr[j + 1] - ptr[j];
+        int64_t *torder = (int64_t *)malloc((size_t)(len > 0 ? len : 1) * sizeof(int64_t));
+        if (shuffle) orc_randperm(g, len, torder); else for (int64_t t = 0; t < len; ++t) torder[t] = t;
+        for (int64_t io = 0; io < len; ++io) {
+            int64_t i = ptr[j] + torder[io];
+            int64_t kk = z[i];
+            orc_delitem(c, kk, d, i);               /* :285-287 */
+            nn[j * S + kk] -= 1;
+            if (hdp_colsum(nn, D, S, kk) == 0)      /* :291-307 */
+                hdp_delete_component(h, c, D, ptr, z, nn, kk);
+
+            hdp_scores(h, c, d, i, nn + j * S, pp); /* :312-315 */
+            orc_lognormalize(pp, h->KK + 1);        /* :316 */
+            double r = uniforms ? uniforms[i] : orc_rand(g);
+            kk = orc_sample(pp, h->KK + 1, r);      /* :317 */
+
+            if (kk == h->KK) {                      /* :320-331 */
+                if (h->KK + 1 >= S) {               /* capacity (last slot is the empty prototype) */
+                    free(torder); free(dorder); free(pp);
+                    return NAN;
+                }
+                orc_comps_reset(c, h->KK);
+                double b = orc_rand_beta(g, 1.0, h->gg);
+                double b_new = h->beta[h->KK];
+                h->beta[h->KK] = b * b_new;
+                h->beta[h->KK + 1] = (1 - b) * b_new;
+                h->KK += 1;
+            }
+            z[i] = kk;                              /* :335-338 */
+            orc_additem(c, kk, d, i);
+            nn[j * S + kk] += 1;
+            ll += orc_loglikelihood(c, kk, d, i);
+        }
+        free(torder);
+    }
+    free(dorder); free(pp);
+    return ll;
+}
+
+int64_t orc_hdp_conditional(const orc_hdp *h, orc_comps *c, const orc_data *d, int64_t j, int64_t i,
+                            int64_t zi, int64_t *nn, double r, double *raw, double *prob)
+{
+    int64_t S = h->Kmax, n = h->KK + 1;
+    double mu_saved = (c->kind == ORC_G1G1) ? c->mu[zi] : 0.0;
+    orc_delitem(c, zi, d, i);
+    nn[j * S + zi] -= 1;
+    hdp_scores(h, c, d, i, nn + j * S, raw);
+    memcpy(prob, raw, (size_t)n * sizeof(double));
+    orc_lognormalize(prob, n);
+    int64_t k = orc_sample(prob, n, r);
+    orc_additem(c, zi, d, i);
+    nn[j * S + zi] += 1;
+    if (c->kind == ORC_G1G1) c->mu[zi] = mu_saved;
+    return k;
+}
+
+/* Normalised log unsigned Stirling numbers of the first kind via
+ * s(n+1, m) = n s(n, m) + s(n, m-1) in log space; each row shifted so max = 0.
+ * Any per-row scaling cancels in lognormalize! (src/HDP.jl:353-358). */
+void orc_stirling_table(int64_t nmax, double *out)
+{
+    if (nmax < 1) return;
+    double *prev = (double *)malloc((size_t)(nmax + 2) * sizeof(double));
+    double *cur = (double *)malloc((size_t)(nmax + 2) * sizeof(double));
+    prev[1] = 0.0;                                  /* s(1,1) = 1 */
+    out[0] = 0.0;
+    for (int64_t n = 1; n < nmax; ++n) {            /* build row n+1 from row n (unnormalised logs kept in prev) */
+        double logn = log((double)n);
+        double mx = -INFINITY;
+        for (int64_t m = 1; m <= n + 1; ++m) {
+            double a = (m <= n) ? logn + prev[m] : -INFINITY;    /* n * s(n, m) */
+            double b = (m >= 2) ? prev[m - 1] : -INFINITY;       /* s(n, m-1) */
+            double hi = a > b ? a : b, lo = a > b ? b : a;
+            double v = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
+            cur[m] = v;
+            if (v > mx) mx = v;
+        }
+        double *row = out + (n + 1) * n / 2;
+        for (int64_t m = 1; m <= n + 1; ++m) {
+            cur[m] -= mx;                           /* keep the running row normalised too: avoids growth */
+            row[m - 1] = cur[m];
+        }
+        double *t = prev; prev = cur; cur = t;
+    }
+    free(prev); free(cur);
+}
+
+int64_t orc_hdp_table_conditional(const double *lstir, int64_t n, double a, double r, double *prob)
+{                                                   /* src/HDP.jl:353-358 */
+    const double *row = lstir + n * (n - 1) / 2;
+    double la = log(a);
+    for (int64_t m = 1; m <= n; ++m) prob[m - 1] = row[m - 1] + (double)m * la;
+    orc_lognormalize(prob, n);
+    return orc_sample(prob, n, r) + 1;
+}
+
+void orc_hdp_sample_hyperparam(orc_hdp *h, int64_t D, const int64_t *ptr, int64_t m, orc_rng *g)
+{                                                   /* src/HDP.jl:124-159 */
+    double sum_logw = 0.0;
+    int64_t sum_s = 0;
+    double *logw = (double *)malloc((size_t)(D > 0 ? D : 1) * sizeof(double));
+    for (int64_t j = 0; j < D; ++j) {
+        double nj = (double)(ptr[j + 1] - ptr[j]);
+        double w = orc_rand_beta(g, h->aa + 1.0, nj);          /* :136 */
+        logw[j] = log(w);
+    }
+    for (int64_t j = 0; j < D; ++j) {
+        double nj = (double)(ptr[j + 1] - ptr[j]);
+        double p = nj / h->aa;                                  /* :138-139 */
+        p = p / (p + 1.0);
+        sum_s += (orc_rand(g) < p) ? 1 : 0;                     /* Binomial(1, p), :143 */
+    }
+    sum_logw = orc_julia_sum(logw, D);
+    free(logw);
+    double aa_shape = h->a1 + (double)m - (double)sum_s;        /* :146 */
+    double aa_rate = h->a2 - sum_logw;                          /* :147 */
+    h->aa = orc_rand_gamma(g, aa_shape) / aa_rate;              /* :148 */
+
+    double eta = orc_rand_beta(g, h->gg + 1.0, (double)m);      /* :151 */
+    double pi_eta = 1.0 / (1.0 + ((double)m * (h->g2 - log(eta))) / (h->g1 + (double)h->KK - 1.0));  /* :152 */
+    if (orc_rand(g) < pi_eta)
+        h->gg = orc_rand_gamma(g, h->g1 + (double)h->KK) / (h->g2 - log(eta));        /* :155 */
+    else
+        h->gg = orc_rand_gamma(g, h->g1 + (double)h->KK - 1.0) / (h->g2 - log(eta));  /* :157 */
+}
+
+int orc_hdp_resample_beta(orc_hdp *h, int64_t D, const int64_t *ptr, const int64_t *nn,
+                          const double *lstir, int64_t nmax, int n_internals, int sample_hyper,
+                          orc_rng *g, int64_t *M_out)
+{                                                   /* src/HDP.jl:343-373 */
+    int64_t S = h->Kmax, KK = h->KK;
+    int64_t maxn = 1;
+    for (int64_t j = 0; j < D; ++j)
+        for (int64_t k = 0; k < KK; ++k) {
+            if (nn[j * S + k] > nmax) return -1;    /* the reference hits a BoundsError on the 10k table */
+            if (nn[j * S + k] > maxn) maxn = nn[j * S + k];
+        }
+    double *rr = (double *)malloc((size_t)maxn * sizeof(double));
+    double *MM = (double *)malloc((size_t)(KK + 1) * sizeof(double));
+    memset(M_out, 0, (size_t)(D * S) * sizeof(int64_t));
+    for (int hh = 0; hh < n_internals; ++hh) {
+        for (int64_t j = 0; j < D; ++j)
+            for (int64_t k = 0; k < KK; ++k) {
+                int64_t n = nn[j * S + k];
+                if (n == 0) M_out[j * S + k] = 0;
+                else M_out[j * S + k] = orc_hdp_table_conditional(lstir, n, h->aa * h->beta[k], orc_rand(g), rr);
+            }
+        int64_t m = 0;
+        for (int64_t k = 0; k < KK; ++k) {
+            int64_t s = 0;
+            for (int64_t j = 0; j < D; ++j) s += M_out[j * S + k];
+            MM[k] = (double)s;
+            m += s;
+        }
+        MM[KK] = h->gg;                              /* :363 */
+        double tot = 0.0;                            /* beta ~ Dirichlet(MM), :364 */
+        for (int64_t k = 0; k <= KK; ++k) { h->beta[k] = orc_rand_gamma(g, MM[k]); tot += h->beta[k]; }
+        for (int64_t k = 0; k <= KK; ++k) h->beta[k] /= tot;
+        if (sample_hyper) orc_hdp_sample_hyperparam(h, D, ptr, m, g);     /* :369-372 */
+    }
+    free(rr); free(MM);
+    return 0;
+}
