@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — LDA collapsed-Gibbs token-samples/sec at K=1024 (BASELINE.json headline metric).
+
+Workload (BASELINE config 3): LDA, K=1024, V=50,000, 100M-token synthetic corpus (500,000
+documents x 200 tokens; phi_k ~ Dirichlet(0.01), theta_d ~ Dirichlet(0.1); beta=0.1 per word,
+alpha=0.1), documents sharded contiguously over the ranks, one all-reduce of the count deltas
+per sweep.  A "step" is one full sweep over the corpus (every token: remove -> K scores -> draw
+-> add, reference src/LDA.jl:113-133).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (one rank per GPU)
+  python bench.py --impl reference ...                         the reference's serial CPU sampler
+                                                               (oracle port), bounded sample
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, V, D_TOTAL, L_DOC = 1024, 50_000, 500_000, 200
+ALPHA, BETA = 0.1, 0.1          # aa_total = BETA * V
+PHI_CONC, THETA_CONC = 0.01, 0.1
+B_ALG = 4 * K + 12              # algorithmic bytes per token-sample
+SEED = 123
+CHUNK_DOCS = 10_000             # corpus is generated chunk by chunk, seeded by chunk index
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ synthetic corpus
+def topic_cdf_torch(device):
+    """phi_k ~ Dirichlet(PHI_CONC * 1_V), returned as a flat float64 CDF with topic offsets."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED)
+    conc = torch.full((K, V), PHI_CONC, device=device, dtype=torch.float64)
+    phi = torch._standard_gamma(conc, generator=g) if hasattr(torch, "_standard_gamma") else torch.distributions.Gamma(conc, 1.0).sample()
+    phi = phi + 1e-300
+    phi /= phi.sum(1, keepdim=True)
+    cdf = torch.cumsum(phi, 1)
+    cdf[:, -1] = 1.0
+    return (cdf + torch.arange(K, device=device, dtype=torch.float64)[:, None]).reshape(-1)
+
+
+def gen_docs_torch(cdf_flat, d0, d1, device):
+    """Words of documents [d0, d1): theta_d ~ Dirichlet(THETA_CONC), topic ~ theta_d, word ~ phi_topic."""
+    import torch
+    out = []
+    c0 = d0 // CHUNK_DOCS
+    c1 = (d1 + CHUNK_DOCS - 1) // CHUNK_DOCS
+    for c in range(c0, c1):
+        lo, hi = c * CHUNK_DOCS, min((c + 1) * CHUNK_DOCS, D_TOTAL)
+        g = torch.Generator(device=device)
+        g.manual_seed(SEED * 1_000_003 + c)
+        conc = torch.full((hi - lo, K), THETA_CONC, device=device, dtype=torch.float32)
+        theta = torch._standard_gamma(conc, generator=g) + 1e-30
+        topics = torch.multinomial(theta, L_DOC, replacement=True, generator=g)           # [docs, L]
+        u = torch.rand(topics.shape, device=device, dtype=torch.float64, generator=g)
+        flat = torch.searchsorted(cdf_flat, topics.to(torch.float64) + u)
+        words = (flat - topics * V).clamp_(0, V - 1).to(torch.int32)
+        a, b_ = max(d0, lo) - lo, min(d1, hi) - lo
+        out.append(words[a:b_].reshape(-1))
+    return torch.cat(out) if out else torch.zeros(0, dtype=torch.int32, device=device)
+
+
+def gen_docs_numpy(d0, d1):
+    """CPU generator of the same model (used by the reference arm on a bounded sample)."""
+    rng = np.random.default_rng(SEED)
+    phi = rng.gamma(PHI_CONC, size=(K, V)) + 1e-300
+    phi /= phi.sum(1, keepdims=True)
+    cdf = np.cumsum(phi, axis=1)
+    rng = np.random.default_rng(SEED + 1 + d0)
+    n = d1 - d0
+    theta = rng.gamma(THETA_CONC, size=(n, K)) + 1e-300
+    tc = np.cumsum(theta, axis=1)
+    words = np.empty((n, L_DOC), dtype=np.int64)
+    for r in range(n):
+        z = np.minimum(np.searchsorted(tc[r], rng.random(L_DOC) * tc[r, -1]), K - 1)
+        uw = rng.random(L_DOC)
+        for t in range(L_DOC):
+            words[r, t] = min(np.searchsorted(cdf[z[t]], uw[t] * cdf[z[t], -1]), V - 1)
+    return words.reshape(-1)
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline_run(n_docs: int, n_sweeps: int, warm: int = 0):
+    """The reference's serial sampler (oracle/bias_oracle.c, a port of src/LDA.jl:113-133) on the
+    first n_docs documents of the workload at full K and V, sampling-only (the O(V) monitoring
+    diagnostic of src/conjugates.jl:205 is skipped, which favours the reference)."""
+    from oracle import oracle as orc
+    words = gen_docs_numpy(0, n_docs)
+    ptr = np.arange(n_docs + 1, dtype=np.int64) * L_DOC
+    rng = np.random.default_rng(7)
+    z0 = rng.integers(0, K, len(words))
+    state = orc.LDAState(orc.Comps.md(K, V, BETA * V), orc.Data.words(words), ptr, z0, ALPHA)
+    times = []
+    for s in range(warm + n_sweeps):
+        u = rng.random(len(words))
+        t0 = time.perf_counter()
+        state.sweep(u, diag_mode=0)
+        if s >= warm:
+            times.append(time.perf_counter() - t0)
+    return len(words), times
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_docs = min(args.ref_docs, 400)          # ~5 s of serial CPU work per step
+    n_tok, times = cpu_baseline_run(n_docs, args.steps, args.warmup)
+    total = float(sum(times))
+    v = n_tok * len(times) / total
+    sample = (f"first {n_docs} documents ({n_tok} tokens) of the K={K}, V={V} workload per step, "
+              f"serial Float64 sampler, sampling only")
+    line = {
+        "impl": "reference", "metric": "lda_gibbs_token_samples_per_sec_K1024", "value": v, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LDA collapsed Gibbs K=1024 V=50000 (BASELINE config 3), bounded sample",
+                   "tokens_per_step": n_tok, "K": K, "V": V},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    import bias_jl_b200 as b
+    from bias_jl_b200.sharding import GpuShard, ShardedSampler, shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_docs_total = args.docs
+    d0, d1 = shard_bounds(n_docs_total, rank, world)
+    t_gen = time.perf_counter()
+    cdf = topic_cdf_torch(dev)
+    words_dev = gen_docs_torch(cdf, d0, d1, dev)
+    del cdf
+    n_local = int(words_dev.numel())
+    gz = torch.Generator(device=dev)
+    gz.manual_seed(SEED + 17 + rank)
+    z_dev = torch.randint(0, K, (n_local,), device=dev, dtype=torch.int32, generator=gz)
+    # host copies in pinned memory: the C ABI takes host buffers (the Julia arrays)
+    words_h = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    z_h = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    words_h.copy_(words_dev)
+    z_h.copy_(z_dev)
+    torch.cuda.synchronize()
+    del words_dev, z_dev
+    torch.cuda.empty_cache()
+    ptr = np.arange(d1 - d0 + 1, dtype=np.int64) * L_DOC
+    gen_s = time.perf_counter() - t_gen
+
+    stream = torch.cuda.current_stream()
+    ctx = b.Context(local, seed=SEED + rank, stream=stream.cuda_stream)
+    lda = b.LDA(b.MultinomialDirichlet(V, BETA * V), K, ALPHA)
+    data = b.FlatData.from_csr(b._lib.INT, n_local, group_ptr=ptr, word=words_h.numpy())
+
+    def make_sampler():
+        rs = b.ResidentSampler(ctx, lda, data, z_h.numpy())
+        return rs, ShardedSampler(GpuShard(rs, dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm: inputs already in HBM when the timed region starts ----
+    rs, sh = make_sampler()
+    for _ in range(args.warmup):
+        sh.sweep(1)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    launches0 = ctx.launches
+    kernel_ms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sh.sweep(1)
+        if args.kernel_timing:
+            kernel_ms.append(rs.last_sweep_ms()[0])      # waits for this step's kernel: off by default
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = ctx.launches - launches0
+    clock_rec = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    stats = rs.stats()
+
+    # dominant-kernel duration: the sweep kernel alone, CUDA events on the launching stream
+    barrier()
+    k_ms = []
+    for _ in range(min(3, args.steps)):
+        rs.sweep(1)
+        k_ms.append(rs.last_sweep_ms()[0])
+    kern_ms = max_over_ranks(float(np.mean(k_ms)))
+    rs.close()
+
+    # ---- end-to-end arm: host buffers in, host assignments out, every step ----
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rs2, sh2 = make_sampler()              # H2D: words, zz, doc offsets; initialisation pass
+        sh2.sweep(1)
+        out = rs2.get_zz()                     # D2H: zz
+        rs2.close()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d = n_local * 4 * 2 + ptr.nbytes
+    d2h = n_local * 4
+    del out
+
+    n_total = n_docs_total * L_DOC
+    value = n_total * args.steps / (ms_total * 1e-3)
+    e2e_value = n_total * e2e_steps / e2e_s
+    peak, peak_src = peaks()
+    tokens_per_launch = n_local
+    achieved = B_ALG * tokens_per_launch / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "lda_sweep_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_tok, times = cpu_baseline_run(args.ref_docs, 1, 0)
+        cpu = {"value": n_tok / times[0], "unit": "tokens/s", "cores": 1, "kind": "port",
+               "sample": f"first {args.ref_docs} documents ({n_tok} tokens) of the same workload, one sweep of the "
+                         f"serial Float64 sampler (oracle port of src/LDA.jl:113-133), sampling only"}
+    if rank == 0:
+        line = {
+            "metric": "lda_gibbs_token_samples_per_sec_K1024", "value": value, "unit": "tokens/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"LDA collapsed Gibbs K={K} V={V} {n_total} tokens ({n_docs_total} docs x {L_DOC}), "
+                                   f"BASELINE config 3", "K": K, "V": V, "tokens": n_total, "docs": n_docs_total,
+                       "parallelism": f"documents sharded over {world} GPU(s), 1 all-reduce of count deltas per sweep",
+                       "l2": "inputs larger than L2 (n_wk 205 MB + tokens 800 MB per sweep vs 126 MB L2)",
+                       "corpus_gen_s": round(gen_s, 2)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "lda_md_int_sweep_kernel<8>",
+                         "kernel_ms": kern_ms, "alg_bytes_per_token": B_ALG, "tokens_per_launch": tokens_per_launch},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clock_rec,
+            "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=D_TOTAL, help="documents in the corpus (default: the full 100M-token workload)")
+    ap.add_argument("--ref-docs", type=int, default=1000, help="documents in the CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--kernel-timing", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 3) if os.environ.get("BIAS_BENCH_STRICT", "1") == "1" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

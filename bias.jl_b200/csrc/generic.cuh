@@ -1,0 +1,344 @@
+// generic.cuh — one warp per item, Float64, log domain: the assignment step for every
+// (model, conjugate, datum) combination of the reference, and the verification mode.
+//
+//   LDA  src/LDA.jl:26-42,116-131      score_k = log(n_jk + aa)          + logpredictive_k(x)
+//   BMM  src/BMM.jl:95-113             score_k = log(n_k  + aa)          + logpredictive_k(x)
+//   HDP  src/HDP.jl:285-338            score_k = log(n_jk + aa*beta_k)   + logpredictive_k(x), k < KK
+//                                      score_KK = log(aa*beta_u) + logpredictive(prototype, x)
+//   logpredictive: src/conjugates.jl:92-103 (Gaussian1DGaussian1D), :180 (MD x Int), :181-198 (MD x Sent)
+//   lognormalize!: src/common.jl:42-52     sample: src/common.jl:69-79
+//
+// The item's own contribution is removed arithmetically from the counts it reads
+// (delitem!, src/conjugates.jl:64-74,158-178) and the tables are touched with atomics only
+// when the assignment changes.
+//
+// faithful = 1 (verification): after the K scores are in shared memory, lane 0 alone performs
+// the max-shifted exp, the left-to-right sum, the division and the strict `cw < r` walk in the
+// reference's operation order, so draws for supplied uniforms are reproducible bit for bit up
+// to the last-ulp differences between CUDA's and glibc's log/exp/lgamma.
+// faithful = 0 (production): the exp and the CDF scan are spread over the warp.
+#pragma once
+#include "common.cuh"
+
+namespace bias {
+
+struct GenericParams {
+    int32_t model;              // BIAS_MODEL_*
+    int32_t kind, datum;        // conjugate kind / datum kind
+    int32_t K, Kpad, n_out;     // n_out = K, or K+1 for HDP
+    int64_t n_work;
+    const int64_t *item_idx;    // nullable: work index -> item (verification / pending lists)
+    const int32_t *work_idx32;  // nullable: same, 32-bit list (HDP pending list)
+    const int32_t *row_of;      // item -> row of prior_rows (group id); nullable => row 0
+    int32_t row_by_work;        // 1: row_of is indexed by work index instead of item
+    int32_t *prior_rows;        // [rows][Kpad] n_jk (LDA/HDP) or n_items (BMM)
+    int32_t prior_is_items;     // BMM: prior_rows aliases n_items
+    // observations
+    const int32_t *word;
+    const double *x;
+    const int64_t *sent_ptr;
+    const int32_t *sent_word;
+    const int32_t *sent_count;
+    int32_t *z;
+    // component statistics
+    int32_t *n_wk;              // MD   [V][Kpad]
+    int32_t *n_k;               // MD   [Kpad] token totals (mm)
+    int32_t *n_items;           // both [Kpad] items per component (nn)
+    double *sumx;               // G1G1 [Kpad] sum of assigned x
+    int64_t V;
+    double beta;                // MD per-dimension concentration (aa/dd)
+    double m0, v0, vv;
+    double alpha;               // LDA/BMM aa; HDP aa (alpha0)
+    const double *hdp_beta;     // HDP my_beta[KK+1]
+    // RNG
+    uint64_t seed;
+    uint32_t sweep;
+    uint32_t rng_stream;
+    const double *ext_uniforms; // nullable, indexed by work index when item_idx != NULL else by item
+    // modes / outputs
+    int32_t frozen, faithful;
+    double *raw_out, *prob_out; // [n_work][n_out], nullable
+    int32_t *draw_out;          // [n_work], frozen mode
+    double *diag_sum;
+    unsigned long long *moved;
+    // HDP deferred births
+    int32_t *pending_list;
+    unsigned int *pending_count;
+};
+
+constexpr int kGenWarps = 4;
+constexpr int kGenThreads = kGenWarps * 32;
+__host__ __device__ inline size_t generic_smem_bytes(int n_out) {
+    return (size_t)kGenWarps * (size_t)((n_out + 3) & ~3) * sizeof(double);
+}
+
+#ifdef __CUDACC__
+
+// Julia 0.4 Base.sum association (left-to-right below 1024 elements, pairwise halves above).
+__device__ inline double jsum_dev(const double *a, int lo, int hi) {
+    if (lo == hi) return a[lo];
+    if (lo + 1024 > hi) {
+        double v = a[lo] + a[lo + 1];
+        for (int i = lo + 2; i <= hi; ++i) v += a[i];
+        return v;
+    }
+    const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+    return jsum_dev(a, lo, mid) + jsum_dev(a, mid + 1, hi);
+}
+
+__device__ __forceinline__ double g1g1_logpred(double n, double sx, double x, double m0, double v0, double vv) {
+    double mu, vp;
+    if (n > 0.0) {                       // posterior, src/conjugates.jl:77-89 with n*v0*mean == v0*sum(x)
+        const double denom = vv + n * v0;
+        mu = (v0 * sx + vv * m0) / denom;
+        vp = v0 * vv / denom;
+    } else {
+        mu = m0;
+        vp = v0;
+    }
+    const double dummy = vp + vv;        // src/conjugates.jl:98-99
+    return -((x - mu) * (x - mu)) / (2.0 * dummy) - 0.5 * log(2.0 * 3.141592653589793 * dummy);
+}
+
+__device__ __forceinline__ double g1g1_loglik(double n, double sx, double x, double m0, double v0, double vv) {
+    double mu, vp;                       // logpdf(posterior(me), x), src/conjugates.jl:105, src/distributions.jl:36-37
+    if (n > 0.0) {
+        const double denom = vv + n * v0;
+        mu = (v0 * sx + vv * m0) / denom;
+        vp = v0 * vv / denom;
+    } else {
+        mu = m0;
+        vp = v0;
+    }
+    return log(exp(-(x - mu) * (x - mu) / (2.0 * vp)) / sqrt(2.0 * 3.141592653589793 * vp));
+}
+
+__global__ void __launch_bounds__(kGenThreads)
+generic_sweep_kernel(const GenericParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_out = p.n_out;
+    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * ((n_out + 3) & ~3);
+    const Philox philox(p.seed);
+    const int64_t n_warps = (int64_t)gridDim.x * kGenWarps;
+    const bool is_hdp = p.model == BIAS_MODEL_HDP;
+    const int K = p.K, Kpad = p.Kpad;
+    double diag_acc = 0.0;
+    unsigned long long moved_acc = 0;
+
+    for (int64_t q = (int64_t)blockIdx.x * kGenWarps + warp; q < p.n_work; q += n_warps) {
+        const int64_t i = p.item_idx ? p.item_idx[q] : (p.work_idx32 ? (int64_t)p.work_idx32[q] : q);
+        const int zold = p.z[i];                      // -1: the item is currently unassigned (HDP pending)
+        int32_t *prow = p.prior_rows + (p.row_of ? (size_t)p.row_of[p.row_by_work ? q : i] * Kpad : 0);
+
+        // ---- the datum ----
+        int w = 0;
+        double xv = 0.0;
+        int64_t s0 = 0, s1 = 0;
+        double m_tot = 0.0, coef = 0.0;
+        if (p.datum == BIAS_INT) {
+            w = p.word[i];
+        } else if (p.datum == BIAS_F64) {
+            xv = p.x[i];
+        } else {
+            s0 = p.sent_ptr[i];
+            s1 = p.sent_ptr[i + 1];
+            double mloc = 0.0, lg = 0.0;
+            for (int64_t t = s0 + lane; t < s1; t += 32) {
+                const double c = (double)p.sent_count[t];
+                mloc += c;
+                lg += lgamma(c + 1.0);
+            }
+            m_tot = warp_sum(mloc);
+            coef = lgamma(m_tot + 1.0) - warp_sum(lg);   // k-independent, src/conjugates.jl:193
+        }
+
+        // ---- K (+1) scores ----
+        double lmax = -INFINITY;
+        for (int k = lane; k < n_out; k += 32) {
+            const bool own = (k == zold);
+            const bool fresh = (k >= K);                  // HDP new-component slot: the empty prototype
+            double prior;
+            if (is_hdp) {
+                prior = fresh ? log(p.alpha * p.hdp_beta[K])
+                              : log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + p.alpha * p.hdp_beta[k]);
+            } else {
+                prior = log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + p.alpha);
+            }
+            double lp;
+            if (p.kind == BIAS_G1G1) {
+                double n = 0.0, sx = 0.0;
+                if (!fresh) {
+                    n = (double)(__ldcg(p.n_items + k) - (own ? 1 : 0));
+                    sx = __ldcg(p.sumx + k) - (own ? xv : 0.0);
+                }
+                lp = g1g1_logpred(n, sx, xv, p.m0, p.v0, p.vv);
+            } else if (p.datum == BIAS_INT) {
+                double nw = 0.0, nk = 0.0;
+                if (!fresh) {
+                    nw = (double)(__ldcg(p.n_wk + (size_t)w * Kpad + k) - (own ? 1 : 0));
+                    nk = (double)(__ldcg(p.n_k + k) - (own ? 1 : 0));
+                }
+                lp = log((p.beta + nw) / (p.beta * (double)p.V + nk));       // src/conjugates.jl:180
+            } else {
+                double nk = 0.0;
+                if (!fresh) nk = (double)__ldcg(p.n_k + k) - (own ? m_tot : 0.0);
+                double acc = 0.0;
+                for (int64_t t = s0; t < s1; ++t) {
+                    const int wt = p.sent_word[t];
+                    const double ct = (double)p.sent_count[t];
+                    double nw = 0.0;
+                    if (!fresh) nw = (double)__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0.0);
+                    acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
+                }
+                const double bv = p.beta * (double)p.V;
+                lp = coef + lgamma(bv + nk) - lgamma(bv + nk + m_tot) + acc; // src/conjugates.jl:193-195
+            }
+            const double s = prior + lp;
+            sc[k] = s;
+            lmax = fmax(lmax, s);
+        }
+        lmax = warp_max(lmax);
+        __syncwarp();
+
+        const int64_t uidx = (p.item_idx || p.work_idx32) ? q : i;
+        double u;
+        if (p.ext_uniforms) {
+            u = p.ext_uniforms[uidx];
+        } else {
+            uint32_t o[4];
+            philox((uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep, p.rng_stream, o);
+            u = u01_double(o[0], o[1]);
+        }
+
+        int knew = 0;
+        if (p.faithful) {
+            if (p.raw_out)
+                for (int k = lane; k < n_out; k += 32) p.raw_out[(size_t)q * n_out + k] = sc[k];
+            __syncwarp();
+            if (lane == 0) {
+                for (int k = 0; k < n_out; ++k) sc[k] = exp(sc[k] - lmax);
+                const double tot = jsum_dev(sc, 0, n_out - 1);
+                for (int k = 0; k < n_out; ++k) sc[k] /= tot;
+                int idx = 0;
+                double cw = sc[0];
+                while (cw < u && idx < n_out - 1) {
+                    idx += 1;
+                    cw += sc[idx];
+                }
+                knew = idx;
+            }
+            knew = __shfl_sync(kFull, knew, 0);
+            __syncwarp();
+            if (p.prob_out)
+                for (int k = lane; k < n_out; k += 32) p.prob_out[(size_t)q * n_out + k] = sc[k];
+        } else {
+            // production: exp in parallel, CDF by 32-wide chunk scans in k order
+            double carry = 0.0;
+            for (int b = 0; b < n_out; b += 32) {
+                const int k = b + lane;
+                double e = 0.0;
+                if (k < n_out) {
+                    e = exp(sc[k] - lmax);
+                    sc[k] = e;
+                }
+                carry += warp_sum(e);
+            }
+            __syncwarp();
+            const double target = u * carry;
+            double base = 0.0;
+            knew = n_out - 1;
+            for (int b = 0; b < n_out; b += 32) {
+                const int k = b + lane;
+                const double e = (k < n_out) ? sc[k] : 0.0;
+                const double incl = base + warp_incl_scan(e, lane);
+                const unsigned bal = __ballot_sync(kFull, (k < n_out) && (incl >= target));
+                if (bal) {
+                    knew = b + __ffs(bal) - 1;
+                    break;
+                }
+                base = __shfl_sync(kFull, incl, 31);
+            }
+        }
+        __syncwarp();
+
+        if (p.frozen) {
+            if (lane == 0 && p.draw_out) p.draw_out[q] = knew;
+            continue;
+        }
+
+        // ---- HDP: a draw of the new-component slot is deferred to the serial birth pass ----
+        const bool born = is_hdp && knew >= K;
+        const int kdst = born ? -1 : knew;
+        if (kdst != zold) {
+            // remove from zold (if assigned), add to kdst (if not deferred)
+            if (p.kind == BIAS_MD) {
+                if (p.datum == BIAS_INT) {
+                    if (lane == 0) {
+                        if (zold >= 0) { atomicAdd(p.n_wk + (size_t)w * Kpad + zold, -1); atomicAdd(p.n_k + zold, -1); }
+                        if (kdst >= 0) { atomicAdd(p.n_wk + (size_t)w * Kpad + kdst, 1); atomicAdd(p.n_k + kdst, 1); }
+                    }
+                } else {
+                    for (int64_t t = s0 + lane; t < s1; t += 32) {
+                        const int wt = p.sent_word[t], ct = p.sent_count[t];
+                        if (zold >= 0) atomicAdd(p.n_wk + (size_t)wt * Kpad + zold, -ct);
+                        if (kdst >= 0) atomicAdd(p.n_wk + (size_t)wt * Kpad + kdst, ct);
+                    }
+                    if (lane == 0) {
+                        if (zold >= 0) atomicAdd(p.n_k + zold, -(int)m_tot);
+                        if (kdst >= 0) atomicAdd(p.n_k + kdst, (int)m_tot);
+                    }
+                }
+            } else if (lane == 0) {
+                if (zold >= 0) atomicAdd(p.sumx + zold, -xv);
+                if (kdst >= 0) atomicAdd(p.sumx + kdst, xv);
+            }
+            if (lane == 0) {
+                if (zold >= 0) atomicAdd(p.n_items + zold, -1);
+                if (kdst >= 0) atomicAdd(p.n_items + kdst, 1);
+                if (!p.prior_is_items) {
+                    if (zold >= 0) atomicAdd(prow + zold, -1);
+                    if (kdst >= 0) atomicAdd(prow + kdst, 1);
+                }
+                p.z[i] = kdst;
+                if (born) {
+                    const unsigned slot = atomicAdd(p.pending_count, 1u);
+                    p.pending_list[slot] = (int32_t)i;
+                } else {
+                    moved_acc += 1;
+                }
+            }
+        }
+
+        // ---- the reference's per-item diagnostic, evaluated after the add (src/LDA.jl:131) ----
+        if (!born && p.diag_sum) {
+            if (p.kind == BIAS_G1G1) {
+                if (lane == 0) {
+                    const double n = (double)__ldcg(p.n_items + knew);
+                    diag_acc += g1g1_loglik(n, __ldcg(p.sumx + knew), xv, p.m0, p.v0, p.vv);
+                }
+            } else if (p.datum == BIAS_INT) {
+                if (lane == 0)
+                    diag_acc += ((double)__ldcg(p.n_wk + (size_t)w * Kpad + knew) + p.beta) /
+                                ((double)__ldcg(p.n_k + knew) + p.beta * (double)p.V);
+            } else {
+                double part = 0.0;
+                const double den = (double)__ldcg(p.n_k + knew) + p.beta * (double)p.V;
+                for (int64_t t = s0 + lane; t < s1; t += 32)
+                    part += (double)p.sent_count[t] *
+                            (((double)__ldcg(p.n_wk + (size_t)p.sent_word[t] * Kpad + knew) + p.beta) / den);
+                part = warp_sum(part);
+                if (lane == 0) diag_acc += part;
+            }
+        }
+    }
+
+    if (!p.frozen && lane == 0) {
+        if (p.diag_sum) atomicAdd(p.diag_sum, diag_acc);
+        if (p.moved && moved_acc) atomicAdd(p.moved, moved_acc);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bias

@@ -1,0 +1,781 @@
+// model.cu — C ABI of libbias_cuda: context, resident sampler state, LDA / BMM sweeps,
+// verification entry points and the multi-GPU delta exchange.  HDP lives in hdp.cu.
+#include <cstring>
+#include <cstdlib>
+#include <algorithm>
+#include <new>
+#include "model.hpp"
+#include "lda_fast.cuh"
+#include "generic.cuh"
+#include "util_kernels.cuh"
+
+namespace bias {
+
+static thread_local std::string g_err;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    BIAS_CUDA_TRY(cudaMalloc((void **)p, n * sizeof(T)));
+    return BIAS_OK;
+}
+
+static int grid_for(bias_ctx *ctx, int64_t n, int threads, int per_sm = 8) {
+    int64_t blocks = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)ctx->num_sms * per_sm;
+    return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+// ---------------------------------------------------------------------------------------
+// fast LDA kernel launch
+// ---------------------------------------------------------------------------------------
+template <int NCH>
+static int launch_lda_fast_t(bias_model *m, const LdaFastParams &p) {
+    static int ctas_per_sm = 0;
+    const size_t smem = lda_fast_smem_bytes(NCH);
+    const int threads = lda_fast_warps(NCH) * 32;
+    if (ctas_per_sm == 0) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_kernel<NCH>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_kernel<NCH>, threads, smem));
+        if (occ < 1) return fail(BIAS_ECUDA, "LDA sweep kernel does not fit on an SM (K padded to %d)", NCH * 128);
+        ctas_per_sm = occ;
+    }
+    int64_t want = (p.D + lda_fast_warps(NCH) - 1) / lda_fast_warps(NCH);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms * ctas_per_sm));
+    lda_md_int_sweep_kernel<NCH><<<grid, threads, smem, m->ctx->stream>>>(p);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    return BIAS_OK;
+}
+
+static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen, int32_t *draws_out) {
+    LdaFastParams p{};
+    p.doc_ptr = m->group_ptr;
+    p.word = m->word;
+    p.z = m->z;
+    p.n_wk = m->n_wk;
+    p.n_k = m->n_k;
+    p.D = m->G;
+    p.K = m->K;
+    p.Kpad = m->Kpad;
+    p.V = (int32_t)m->V;
+    p.alpha = (float)m->alpha;
+    p.beta = (float)m->conj.aa;
+    p.vbeta = (float)(m->conj.aa * (double)m->V);
+    p.doc_counter = m->scratch + 2;
+    p.seed = m->ctx->seed;
+    p.sweep = m->sweep_index;
+    p.ext_uniforms = ext_uniforms;
+    p.draws_out = draws_out;
+    p.frozen = frozen;
+    p.diag_sum = reinterpret_cast<double *>(m->scratch);
+    p.moved = m->scratch + 1;
+    switch (m->Kpad / 128) {
+        case 1: return launch_lda_fast_t<1>(m, p);
+        case 2: return launch_lda_fast_t<2>(m, p);
+        case 4: return launch_lda_fast_t<4>(m, p);
+        case 8: return launch_lda_fast_t<8>(m, p);
+        case 16: return launch_lda_fast_t<16>(m, p);
+        case 32: return launch_lda_fast_t<32>(m, p);
+    }
+    return fail(BIAS_EINVAL, "unsupported padded K %d for the fast LDA kernel", m->Kpad);
+}
+
+// ---------------------------------------------------------------------------------------
+// generic kernel launch
+// ---------------------------------------------------------------------------------------
+int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const int32_t *work_idx32,
+                   const int32_t *row_of, int32_t *prior_rows, const double *ext_uniforms, int frozen,
+                   int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,
+                   int row_by_work) {
+    if (n_work <= 0) return BIAS_OK;
+    GenericParams p{};
+    p.model = m->model;
+    p.kind = m->conj.kind;
+    p.datum = m->conj.datum;
+    p.K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    p.Kpad = m->Kpad;
+    p.n_out = (m->model == BIAS_MODEL_HDP) ? p.K + 1 : p.K;
+    p.n_work = n_work;
+    p.item_idx = item_idx;
+    p.work_idx32 = work_idx32;
+    p.row_of = row_of;
+    p.row_by_work = row_by_work;
+    p.prior_rows = prior_rows;
+    p.prior_is_items = (prior_rows == m->n_items) ? 1 : 0;
+    p.word = m->word;
+    p.x = m->x;
+    p.sent_ptr = m->sent_ptr;
+    p.sent_word = m->sent_word;
+    p.sent_count = m->sent_count;
+    p.z = m->z;
+    p.n_wk = m->n_wk;
+    p.n_k = m->n_k;
+    p.n_items = m->n_items;
+    p.sumx = m->sumx;
+    p.V = m->V;
+    p.beta = m->conj.aa;
+    p.m0 = m->conj.m0;
+    p.v0 = m->conj.v0;
+    p.vv = m->conj.vv;
+    p.alpha = (m->model == BIAS_MODEL_HDP) ? m->hdp.aa : m->alpha;
+    p.hdp_beta = m->d_beta;
+    p.seed = m->ctx->seed;
+    p.sweep = m->sweep_index;
+    p.rng_stream = rng_stream;
+    p.ext_uniforms = ext_uniforms;
+    p.frozen = frozen;
+    p.faithful = faithful;
+    p.raw_out = raw_out;
+    p.prob_out = prob_out;
+    p.draw_out = draw_out;
+    p.diag_sum = frozen ? nullptr : reinterpret_cast<double *>(m->scratch);
+    p.moved = m->scratch + 1;
+    p.pending_list = m->pending;
+    p.pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
+
+    const size_t smem = generic_smem_bytes(p.n_out);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    int64_t blocks = (n_work + kGenWarps - 1) / kGenWarps;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)m->ctx->num_sms * 12));
+    generic_sweep_kernel<<<grid, kGenThreads, smem, m->ctx->stream>>>(p);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    return BIAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// initialisation pass: additem! for every item
+// ---------------------------------------------------------------------------------------
+int rebuild_counts(bias_model *m) {
+    cudaStream_t st = m->ctx->stream;
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->i32_block, 0, (size_t)m->n_i32 * sizeof(int32_t), st));
+    if (m->n_f64) BIAS_CUDA_TRY(cudaMemsetAsync(m->f64_block, 0, (size_t)m->n_f64 * sizeof(double), st));
+    const int threads = 256;
+    if (m->N > 0) {
+        if (m->conj.kind == BIAS_MD && m->conj.datum == BIAS_INT) {
+            build_md_int_kernel<<<grid_for(m->ctx, m->N, threads), threads, (size_t)m->Kpad * sizeof(int32_t), st>>>(
+                m->word, m->z, m->N, m->Kpad, m->n_wk, m->n_k, m->n_items);
+        } else if (m->conj.kind == BIAS_MD) {
+            build_md_sent_kernel<<<grid_for(m->ctx, m->N * 32, threads), threads, 0, st>>>(
+                m->sent_ptr, m->sent_word, m->sent_count, m->z, m->N, m->Kpad, m->n_wk, m->n_k, m->n_items);
+        } else {
+            build_g1g1_kernel<<<grid_for(m->ctx, m->N, threads, 2), threads, (size_t)m->Kpad * 12, st>>>(
+                m->x, m->z, m->N, m->Kpad, m->sumx, m->n_items);
+        }
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+        if (m->group_rows) {
+            BIAS_CUDA_TRY(cudaMemsetAsync(m->group_rows, 0, (size_t)m->G * m->Kpad * sizeof(int32_t), st));
+            build_group_rows_kernel<<<grid_for(m->ctx, m->N, threads), threads, 0, st>>>(m->z, m->group_of, m->N,
+                                                                                         m->Kpad, m->group_rows);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+        }
+    }
+    return BIAS_OK;
+}
+
+static int validate(const bias_conjugate *c, const bias_data *d, int64_t G, const int64_t *ptr, const int32_t *zz,
+                    int32_t K, double alpha, int32_t model) {
+    if (!c || !d || !zz) return fail(BIAS_EINVAL, "null argument");
+    if (K < 1) return fail(BIAS_EINVAL, "KK must be >= 1");
+    if (!(alpha > 0.0)) return fail(BIAS_EINVAL, "aa must be > 0");
+    if (d->n_items < 0) return fail(BIAS_EINVAL, "negative item count");
+    if (c->kind == BIAS_MD) {
+        if (c->datum != BIAS_INT && c->datum != BIAS_SENT)
+            return fail(BIAS_EINVAL, "MultinomialDirichlet takes Int or Sent observations (src/conjugates.jl:153-198)");
+        if (c->dd < 1 || !(c->aa > 0.0)) return fail(BIAS_EINVAL, "MultinomialDirichlet: dd >= 1 and aa > 0 required");
+        if (c->datum == BIAS_INT && !d->word) return fail(BIAS_EINVAL, "data.word is null");
+        if (c->datum == BIAS_SENT && (!d->sent_ptr || !d->sent_word || !d->sent_count))
+            return fail(BIAS_EINVAL, "Sent data pointers are null");
+    } else if (c->kind == BIAS_G1G1) {
+        if (c->datum != BIAS_F64) return fail(BIAS_EINVAL, "Gaussian1DGaussian1D takes Float64 observations (src/conjugates.jl:60-103)");
+        if (!(c->v0 > 0.0) || !(c->vv > 0.0))
+            return fail(BIAS_EINVAL, "Gaussian1D: the condition vv > zero(vv) is not satisfied (src/distributions.jl:19)");
+        if (!d->x) return fail(BIAS_EINVAL, "data.x is null");
+    } else {
+        return fail(BIAS_EINVAL, "unknown conjugate kind %d", c->kind);
+    }
+    if (model != BIAS_MODEL_BMM) {
+        if (!ptr || G < 0) return fail(BIAS_EINVAL, "group_ptr is required for grouped models");
+        if (ptr[0] != 0 || ptr[G] != d->n_items) return fail(BIAS_EINVAL, "group_ptr must start at 0 and end at n_items");
+        for (int64_t j = 0; j < G; ++j)
+            if (ptr[j + 1] < ptr[j]) return fail(BIAS_EINVAL, "group_ptr must be non-decreasing");
+    }
+    for (int64_t i = 0; i < d->n_items; ++i)
+        if (zz[i] < 0 || zz[i] >= K) return fail(BIAS_EINVAL, "zz[%lld] = %d outside [0, %d)", (long long)i, zz[i], K);
+    if (c->kind == BIAS_MD && c->datum == BIAS_INT)
+        for (int64_t i = 0; i < d->n_items; ++i)
+            if (d->word[i] < 0 || d->word[i] >= c->dd)
+                return fail(BIAS_EINVAL, "word id %d outside [0, %lld) (reference: BoundsError)", d->word[i], (long long)c->dd);
+    if (c->kind == BIAS_MD && c->datum == BIAS_SENT) {
+        if (d->sent_ptr[0] != 0) return fail(BIAS_EINVAL, "sent_ptr must start at 0");
+        const int64_t nnz = d->sent_ptr[d->n_items];
+        for (int64_t t = 0; t < nnz; ++t)
+            if (d->sent_word[t] < 0 || d->sent_word[t] >= c->dd || d->sent_count[t] < 0)
+                return fail(BIAS_EINVAL, "Sent entry %lld invalid", (long long)t);
+    }
+    return BIAS_OK;
+}
+
+}  // namespace bias
+
+using namespace bias;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int bias_version(void) { return 100; }
+
+const char *bias_last_error(void) { return g_err.c_str(); }
+
+int bias_device_count(int *n_out) {
+    if (!n_out) return fail(BIAS_EINVAL, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *n_out = 0;
+        return fail(BIAS_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    *n_out = n;
+    return BIAS_OK;
+}
+
+int bias_ctx_create(int device, uint64_t seed, void *stream, bias_ctx **out) {
+    if (!out) return fail(BIAS_EINVAL, "null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(BIAS_ENODEV, "libbias_cuda has no CPU fallback and found no CUDA device (%s)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(BIAS_EINVAL, "device %d out of range (have %d)", device, n);
+    BIAS_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BIAS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(BIAS_ENODEV, "libbias_cuda is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    bias_ctx *c = new (std::nothrow) bias_ctx();
+    if (!c) return fail(BIAS_ENOMEM, "out of host memory");
+    c->device = device;
+    c->seed = seed;
+    c->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete c; return fail(BIAS_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(se)); }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev_a);
+    cudaEventCreate(&c->ev_b);
+    *out = c;
+    return BIAS_OK;
+}
+
+int bias_ctx_destroy(bias_ctx *ctx) {
+    if (!ctx) return BIAS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stirling) cudaFree(ctx->stirling);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return BIAS_OK;
+}
+
+int bias_ctx_sync(bias_ctx *ctx) {
+    if (!ctx) return fail(BIAS_EINVAL, "null context");
+    BIAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BIAS_OK;
+}
+
+int bias_ctx_num_sms(bias_ctx *ctx, int *n_out) {
+    if (!ctx || !n_out) return fail(BIAS_EINVAL, "null argument");
+    *n_out = ctx->num_sms;
+    return BIAS_OK;
+}
+
+int bias_ctx_launch_count(bias_ctx *ctx, int64_t *n_out) {
+    if (!ctx || !n_out) return fail(BIAS_EINVAL, "null argument");
+    *n_out = ctx->launches;
+    return BIAS_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+int bias_model_destroy(bias_model *m) {
+    if (!m) return BIAS_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    hdp_destroy(m);
+    void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
+                    m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
+                    m->delta_f64, m->scratch};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (m->h_scratch) cudaFreeHost(m->h_scratch);
+    delete m;
+    return BIAS_OK;
+}
+
+int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, const bias_data *data,
+                      int64_t n_groups, const int64_t *group_ptr, const int32_t *zz,
+                      int32_t K, double alpha, const bias_hdp_params *hdp, bias_model **out) {
+    if (!ctx || !out) return fail(BIAS_EINVAL, "null argument");
+    *out = nullptr;
+    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "unknown model %d", model);
+    if (model == BIAS_MODEL_HDP) {
+        if (!hdp) return fail(BIAS_EINVAL, "HDP parameters are required");
+        if (hdp->KK < 1 || hdp->Kmax < hdp->KK + 2) return fail(BIAS_EINVAL, "HDP: need 1 <= KK and Kmax >= KK + 2");
+        if (!(hdp->gg > 0.0) || !(hdp->aa > 0.0)) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
+        K = hdp->KK;
+        alpha = hdp->aa;
+    }
+    BIAS_TRY(validate(conj, data, n_groups, group_ptr, zz, K, alpha, model));
+    BIAS_CUDA_TRY(cudaSetDevice(ctx->device));
+
+    bias_model *m = new (std::nothrow) bias_model();
+    if (!m) return fail(BIAS_ENOMEM, "out of host memory");
+    m->ctx = ctx;
+    m->model = model;
+    m->conj = *conj;
+    m->N = data->n_items;
+    m->G = (model == BIAS_MODEL_BMM) ? 0 : n_groups;
+    m->K = K;
+    m->alpha = alpha;
+    m->V = (conj->kind == BIAS_MD) ? conj->dd : 0;
+    const int32_t Kcap = (model == BIAS_MODEL_HDP) ? hdp->Kmax : K;
+    // pad K to 128 * 2^j (the fast kernel's chunk tree); the generic kernels only need the stride
+    int32_t kp = 128;
+    while (kp < Kcap) kp *= 2;
+    m->Kpad = kp;
+    const char *force_generic = getenv("BIAS_FORCE_GENERIC");
+    m->fast = (model == BIAS_MODEL_LDA && conj->kind == BIAS_MD && conj->datum == BIAS_INT && kp <= 4096 &&
+               !(force_generic && force_generic[0] == '1'));
+    if (m->N >= (int64_t)1 << 31) { delete m; return fail(BIAS_EINVAL, "more than 2^31-1 items per device"); }
+
+    cudaStream_t st = ctx->stream;
+    int rc = BIAS_OK;
+#define M_TRY(expr) do { rc = (expr); if (rc != BIAS_OK) { bias_model_destroy(m); return rc; } } while (0)
+#define M_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { bias_model_destroy(m); \
+        return fail(_e == cudaErrorMemoryAllocation ? BIAS_ENOMEM : BIAS_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+
+    // observations
+    if (conj->datum == BIAS_INT) {
+        M_TRY(dev_alloc(&m->word, (size_t)m->N));
+        M_CUDA(cudaMemcpyAsync(m->word, data->word, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    } else if (conj->datum == BIAS_F64) {
+        M_TRY(dev_alloc(&m->x, (size_t)m->N));
+        M_CUDA(cudaMemcpyAsync(m->x, data->x, (size_t)m->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        m->nnz = data->sent_ptr[m->N];
+        M_TRY(dev_alloc(&m->sent_ptr, (size_t)m->N + 1));
+        M_TRY(dev_alloc(&m->sent_word, (size_t)m->nnz));
+        M_TRY(dev_alloc(&m->sent_count, (size_t)m->nnz));
+        M_CUDA(cudaMemcpyAsync(m->sent_ptr, data->sent_ptr, ((size_t)m->N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        M_CUDA(cudaMemcpyAsync(m->sent_word, data->sent_word, (size_t)m->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        M_CUDA(cudaMemcpyAsync(m->sent_count, data->sent_count, (size_t)m->nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    M_TRY(dev_alloc(&m->z, (size_t)m->N));
+    M_CUDA(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (model != BIAS_MODEL_BMM) {
+        M_TRY(dev_alloc(&m->group_ptr, (size_t)m->G + 1));
+        M_CUDA(cudaMemcpyAsync(m->group_ptr, group_ptr, ((size_t)m->G + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (!m->fast) {
+            M_TRY(dev_alloc(&m->group_of, (size_t)m->N));
+            if (m->N > 0) {
+                group_of_kernel<<<grid_for(ctx, m->N, 256), 256, 0, st>>>(m->group_ptr, m->G, m->N, m->group_of);
+                M_CUDA(cudaGetLastError());
+                ctx->launches += 1;
+            }
+            M_TRY(dev_alloc(&m->group_rows, (size_t)m->G * m->Kpad));
+        }
+    }
+    // component statistics
+    const int64_t n_wk_elems = (conj->kind == BIAS_MD) ? m->V * (int64_t)m->Kpad : 0;
+    m->n_i32 = n_wk_elems + 2 * (int64_t)m->Kpad;      // Kpad is a multiple of 128: stays 16-byte aligned
+    M_TRY(dev_alloc(&m->i32_block, (size_t)m->n_i32));
+    m->n_wk = m->i32_block;
+    m->n_k = m->i32_block + n_wk_elems;
+    m->n_items = m->n_k + m->Kpad;
+    if (conj->kind == BIAS_G1G1) {
+        m->n_f64 = m->Kpad;
+        M_TRY(dev_alloc(&m->f64_block, (size_t)m->n_f64));
+        m->sumx = m->f64_block;
+    }
+    M_TRY(dev_alloc(&m->scratch, 8));
+    M_CUDA(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
+    M_CUDA(cudaMallocHost((void **)&m->h_scratch, 8 * sizeof(unsigned long long)));
+    if (model == BIAS_MODEL_HDP) M_TRY(hdp_create(m, hdp));
+    M_TRY(rebuild_counts(m));
+    // the uploads came from caller-owned pageable memory: finish them before returning
+    M_CUDA(cudaStreamSynchronize(st));
+#undef M_TRY
+#undef M_CUDA
+    m->last.KK = K;
+    *out = m;
+    return BIAS_OK;
+}
+
+int bias_model_set_zz(bias_model *m, const int32_t *zz) {
+    if (!m || !zz) return fail(BIAS_EINVAL, "null argument");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    const int32_t Kcur = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    for (int64_t i = 0; i < m->N; ++i)
+        if (zz[i] < 0 || zz[i] >= Kcur) return fail(BIAS_EINVAL, "zz[%lld] = %d outside [0, %d)", (long long)i, zz[i], Kcur);
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
+    BIAS_TRY(rebuild_counts(m));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    return BIAS_OK;
+}
+
+int bias_model_get_zz(bias_model *m, int32_t *zz) {
+    if (!m || !zz) return fail(BIAS_EINVAL, "null argument");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(zz, m->z, (size_t)m->N * sizeof(int32_t), cudaMemcpyDeviceToHost, m->ctx->stream));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    return BIAS_OK;
+}
+
+static int one_sweep(bias_model *m) {
+    cudaStream_t st = m->ctx->stream;
+    if (m->model == BIAS_MODEL_HDP) return hdp_sweep(m);
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st));
+    if (m->fast) {
+        BIAS_TRY(launch_lda_fast(m, nullptr, 0, nullptr));
+    } else {
+        int32_t *prior = (m->model == BIAS_MODEL_BMM) ? m->n_items : m->group_rows;
+        const int32_t *row_of = (m->model == BIAS_MODEL_BMM) ? nullptr : m->group_of;
+        BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, row_of, prior, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                kStreamItemDraw));
+    }
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    return BIAS_OK;
+}
+
+int bias_model_sweep(bias_model *m, int32_t n_sweeps) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (n_sweeps < 0) return fail(BIAS_EINVAL, "n_sweeps < 0");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    const int64_t l0 = m->ctx->launches;
+    BIAS_CUDA_TRY(cudaEventRecord(m->ctx->ev_a, m->ctx->stream));
+    for (int32_t s = 0; s < n_sweeps; ++s) BIAS_TRY(one_sweep(m));
+    BIAS_CUDA_TRY(cudaEventRecord(m->ctx->ev_b, m->ctx->stream));
+    m->last_launches = (int32_t)(m->ctx->launches - l0);
+    m->timing_valid = true;
+    return BIAS_OK;
+}
+
+int bias_model_last_sweep_ms(bias_model *m, float *ms_out, int32_t *launches_out) {
+    if (!m || !ms_out) return fail(BIAS_EINVAL, "null argument");
+    if (!m->timing_valid) return fail(BIAS_ESTATE, "no sweep has been timed yet");
+    BIAS_CUDA_TRY(cudaEventSynchronize(m->ctx->ev_b));
+    BIAS_CUDA_TRY(cudaEventElapsedTime(ms_out, m->ctx->ev_a, m->ctx->ev_b));
+    if (launches_out) *launches_out = m->last_launches;
+    return BIAS_OK;
+}
+
+static int fetch_stats(bias_model *m) {
+    if (m->stats_pending) {
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->h_scratch, m->scratch, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                      m->ctx->stream));
+        BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+        double d;
+        memcpy(&d, &m->h_scratch[0], sizeof d);
+        m->last.log_likelihood = d;
+        m->last.n_moved = (int64_t)m->h_scratch[1];
+        m->stats_pending = false;
+    }
+    m->last.KK = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    m->last.gg = m->hdp.gg;
+    m->last.aa = (m->model == BIAS_MODEL_HDP) ? m->hdp.aa : m->alpha;
+    return BIAS_OK;
+}
+
+int bias_model_last_stats(bias_model *m, bias_sweep_stats *out) {
+    if (!m || !out) return fail(BIAS_EINVAL, "null argument");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(fetch_stats(m));
+    *out = m->last;
+    return BIAS_OK;
+}
+
+int bias_model_get_components(bias_model *m, int64_t *mi, int64_t *mm, double *mu, int64_t *nn) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    const int K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    std::vector<int32_t> h_nk(m->Kpad), h_ni(m->Kpad);
+    BIAS_CUDA_TRY(cudaMemcpyAsync(h_nk.data(), m->n_k, (size_t)m->Kpad * 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(h_ni.data(), m->n_items, (size_t)m->Kpad * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<double> h_sx;
+    if (m->conj.kind == BIAS_G1G1) {
+        h_sx.resize(m->Kpad);
+        BIAS_CUDA_TRY(cudaMemcpyAsync(h_sx.data(), m->sumx, (size_t)m->Kpad * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (mi && m->conj.kind == BIAS_MD) {
+        int64_t *d_mi = nullptr;
+        BIAS_TRY(dev_alloc(&d_mi, (size_t)(m->V * K)));
+        export_mi_kernel<<<grid_for(m->ctx, m->V * K, 256), 256, 0, st>>>(m->n_wk, m->V, K, m->Kpad, d_mi);
+        m->ctx->launches += 1;
+        cudaError_t e = cudaMemcpyAsync(mi, d_mi, (size_t)(m->V * K) * 8, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        cudaFree(d_mi);
+        if (e != cudaSuccess) return fail(BIAS_ECUDA, "export of mi failed: %s", cudaGetErrorString(e));
+    }
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    // the fp32 LDA kernel maintains n_k only; for word-id items nn == mm
+    const bool int_items = (m->conj.kind == BIAS_MD && m->conj.datum == BIAS_INT);
+    for (int k = 0; k < K; ++k) {
+        if (mm && m->conj.kind == BIAS_MD) mm[k] = h_nk[k];
+        if (nn) nn[k] = int_items ? h_nk[k] : h_ni[k];
+        if (mu && m->conj.kind == BIAS_G1G1) mu[k] = h_ni[k] > 0 ? h_sx[k] / (double)h_ni[k] : m->conj.m0;
+    }
+    return BIAS_OK;
+}
+
+int bias_model_get_group_counts(bias_model *m, int64_t *nn) {
+    if (!m || !nn) return fail(BIAS_EINVAL, "null argument");
+    if (m->model == BIAS_MODEL_BMM) return fail(BIAS_EINVAL, "BMM has no groups; use bias_model_get_components");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    // computed on the host from z: posterior() is outside the hot path
+    std::vector<int32_t> z((size_t)m->N);
+    std::vector<int64_t> ptr((size_t)m->G + 1);
+    BIAS_CUDA_TRY(cudaMemcpyAsync(z.data(), m->z, (size_t)m->N * 4, cudaMemcpyDeviceToHost, m->ctx->stream));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(ptr.data(), m->group_ptr, ((size_t)m->G + 1) * 8, cudaMemcpyDeviceToHost, m->ctx->stream));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    const int K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    std::fill(nn, nn + (size_t)m->G * K, (int64_t)0);
+    for (int64_t j = 0; j < m->G; ++j)
+        for (int64_t i = ptr[j]; i < ptr[j + 1]; ++i)
+            if (z[i] >= 0 && z[i] < K) nn[j * K + z[i]] += 1;
+    return BIAS_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// verification
+// -----------------------------------------------------------------------------------------
+int bias_model_conditionals(bias_model *m, int64_t n_query, const int64_t *item_idx, const double *uniforms,
+                            double *raw, double *prob, int32_t *draw) {
+    if (!m || !item_idx || !uniforms || !draw) return fail(BIAS_EINVAL, "null argument");
+    if (n_query <= 0) return BIAS_OK;
+    for (int64_t q = 0; q < n_query; ++q)
+        if (item_idx[q] < 0 || item_idx[q] >= m->N) return fail(BIAS_EINVAL, "query item out of range");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    const int K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    const int n_out = (m->model == BIAS_MODEL_HDP) ? K + 1 : K;
+    int64_t *d_idx = nullptr;
+    double *d_u = nullptr, *d_raw = nullptr, *d_prob = nullptr;
+    int32_t *d_draw = nullptr, *d_rows = nullptr, *d_rowof = nullptr;
+    int rc = BIAS_OK;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        for (void *p : {(void *)d_idx, (void *)d_u, (void *)d_raw, (void *)d_prob, (void *)d_draw, (void *)d_rows, (void *)d_rowof})
+            if (p) cudaFree(p);
+    };
+#define V_TRY(expr) do { rc = (expr); if (rc != BIAS_OK) { cleanup(); return rc; } } while (0)
+#define V_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(BIAS_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } } while (0)
+    V_TRY(dev_alloc(&d_idx, (size_t)n_query));
+    V_TRY(dev_alloc(&d_u, (size_t)n_query));
+    V_TRY(dev_alloc(&d_raw, (size_t)n_query * n_out));
+    V_TRY(dev_alloc(&d_prob, (size_t)n_query * n_out));
+    V_TRY(dev_alloc(&d_draw, (size_t)n_query));
+    V_CUDA(cudaMemcpyAsync(d_idx, item_idx, (size_t)n_query * 8, cudaMemcpyHostToDevice, st));
+    V_CUDA(cudaMemcpyAsync(d_u, uniforms, (size_t)n_query * 8, cudaMemcpyHostToDevice, st));
+    int32_t *prior = nullptr;
+    const int32_t *row_of = nullptr;
+    if (m->model == BIAS_MODEL_BMM) {
+        prior = m->n_items;
+    } else if (m->group_rows) {
+        prior = m->group_rows;
+        row_of = m->group_of;
+    } else {
+        // the fast LDA path keeps no n_jk table: build the rows of the queried items' groups
+        V_TRY(dev_alloc(&d_rows, (size_t)n_query * m->Kpad));
+        V_CUDA(cudaMemsetAsync(d_rows, 0, (size_t)n_query * m->Kpad * 4, st));
+        V_TRY(dev_alloc(&d_rowof, (size_t)n_query));
+        build_query_rows_kernel<<<grid_for(m->ctx, n_query * 32, 128), 128, 0, st>>>(d_idx, n_query, m->group_ptr, m->G,
+                                                                                    m->z, m->Kpad, d_rows, d_rowof);
+        V_CUDA(cudaGetLastError());
+        m->ctx->launches += 1;
+        prior = d_rows;
+        row_of = d_rowof;
+    }
+    V_TRY(launch_generic(m, n_query, d_idx, nullptr, row_of, prior, d_u, 1, 1, d_raw, d_prob, d_draw, kStreamItemDraw,
+                         row_of == d_rowof ? 1 : 0));
+    if (raw) V_CUDA(cudaMemcpyAsync(raw, d_raw, (size_t)n_query * n_out * 8, cudaMemcpyDeviceToHost, st));
+    if (prob) V_CUDA(cudaMemcpyAsync(prob, d_prob, (size_t)n_query * n_out * 8, cudaMemcpyDeviceToHost, st));
+    V_CUDA(cudaMemcpyAsync(draw, d_draw, (size_t)n_query * 4, cudaMemcpyDeviceToHost, st));
+#undef V_TRY
+#undef V_CUDA
+    cleanup();
+    return BIAS_OK;
+}
+
+int bias_model_frozen_draws(bias_model *m, const double *uniforms, int32_t *draws) {
+    if (!m || !uniforms || !draws) return fail(BIAS_EINVAL, "null argument");
+    if (m->model == BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "frozen draws are defined for LDA and BMM");
+    if (m->N == 0) return BIAS_OK;
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    double *d_u = nullptr;
+    int32_t *d_draw = nullptr;
+    BIAS_TRY(dev_alloc(&d_u, (size_t)m->N));
+    if (dev_alloc(&d_draw, (size_t)m->N) != BIAS_OK) { cudaFree(d_u); return BIAS_ENOMEM; }
+    int rc = BIAS_OK;
+    cudaError_t e = cudaMemcpyAsync(d_u, uniforms, (size_t)m->N * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->scratch + 2, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        if (m->fast) {
+            rc = launch_lda_fast(m, d_u, 1, d_draw);
+        } else {
+            int32_t *prior = (m->model == BIAS_MODEL_BMM) ? m->n_items : m->group_rows;
+            const int32_t *row_of = (m->model == BIAS_MODEL_BMM) ? nullptr : m->group_of;
+            rc = launch_generic(m, m->N, nullptr, nullptr, row_of, prior, d_u, 1, 0, nullptr, nullptr, d_draw, kStreamItemDraw);
+        }
+    }
+    if (e == cudaSuccess && rc == BIAS_OK) e = cudaMemcpyAsync(draws, d_draw, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(d_u);
+    cudaFree(d_draw);
+    if (e != cudaSuccess) return fail(BIAS_ECUDA, "frozen draws: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+// -----------------------------------------------------------------------------------------
+// multi-GPU exchange
+// -----------------------------------------------------------------------------------------
+static int ensure_exchange(bias_model *m) {
+    if (!m->base_i32) {
+        BIAS_TRY(dev_alloc(&m->base_i32, (size_t)m->n_i32));
+        BIAS_TRY(dev_alloc(&m->delta_i32, (size_t)m->n_i32));
+        if (m->n_f64) {
+            BIAS_TRY(dev_alloc(&m->base_f64, (size_t)m->n_f64));
+            BIAS_TRY(dev_alloc(&m->delta_f64, (size_t)m->n_f64));
+        }
+    }
+    return BIAS_OK;
+}
+
+int bias_model_delta_begin(bias_model *m) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(ensure_exchange(m));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->base_i32, m->i32_block, (size_t)m->n_i32 * 4, cudaMemcpyDeviceToDevice, m->ctx->stream));
+    if (m->n_f64)
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->base_f64, m->f64_block, (size_t)m->n_f64 * 8, cudaMemcpyDeviceToDevice, m->ctx->stream));
+    return BIAS_OK;
+}
+
+int bias_model_delta_pack(bias_model *m, void **delta_i32_dev, int64_t *n_i32, void **delta_f64_dev, int64_t *n_f64) {
+    if (!m || !delta_i32_dev || !n_i32) return fail(BIAS_EINVAL, "null argument");
+    if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    const int64_t n4 = m->n_i32 / 4;
+    delta_pack_i32_kernel<<<grid_for(m->ctx, n4, 256), 256, 0, st>>>(m->i32_block, m->base_i32, m->delta_i32, n4);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    if (m->n_f64) {
+        delta_pack_f64_kernel<<<grid_for(m->ctx, m->n_f64, 256), 256, 0, st>>>(m->f64_block, m->base_f64, m->delta_f64, m->n_f64);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+    }
+    *delta_i32_dev = m->delta_i32;
+    *n_i32 = m->n_i32;
+    if (delta_f64_dev) *delta_f64_dev = m->delta_f64;
+    if (n_f64) *n_f64 = m->n_f64;
+    return BIAS_OK;
+}
+
+int bias_model_delta_apply(bias_model *m) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    const int64_t n4 = m->n_i32 / 4;
+    delta_apply_i32_kernel<<<grid_for(m->ctx, n4, 256), 256, 0, st>>>(m->i32_block, m->base_i32, m->delta_i32, n4);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    if (m->n_f64) {
+        delta_apply_f64_kernel<<<grid_for(m->ctx, m->n_f64, 256), 256, 0, st>>>(m->f64_block, m->base_f64, m->delta_f64, m->n_f64);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+    }
+    return BIAS_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// one-call samplers
+// -----------------------------------------------------------------------------------------
+static int run_model(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, const bias_data *data, int64_t G,
+                     const int64_t *ptr, int32_t *zz, int32_t K, double alpha, bias_hdp_params *hp, int32_t n_sweeps,
+                     double *beta_out, bias_sweep_stats *stats) {
+    if (n_sweeps < 0) return fail(BIAS_EINVAL, "n_sweeps < 0");
+    bias_model *m = nullptr;
+    BIAS_TRY(bias_model_create(ctx, model, conj, data, G, ptr, zz, K, alpha, hp, &m));
+    int rc = BIAS_OK;
+    for (int32_t s = 0; s < n_sweeps && rc == BIAS_OK; ++s) {
+        rc = one_sweep(m);
+        if (rc == BIAS_OK && stats) {
+            rc = fetch_stats(m);
+            stats[s] = m->last;
+        }
+    }
+    if (rc == BIAS_OK) rc = bias_model_get_zz(m, zz);
+    if (rc == BIAS_OK && hp) rc = bias_model_get_hdp(m, hp, beta_out);
+    bias_model_destroy(m);
+    return rc;
+}
+
+int bias_lda_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int64_t n_groups,
+                 const int64_t *group_ptr, int32_t *zz, int32_t K, double alpha, int32_t n_sweeps,
+                 bias_sweep_stats *stats) {
+    return run_model(ctx, BIAS_MODEL_LDA, conj, data, n_groups, group_ptr, zz, K, alpha, nullptr, n_sweeps, nullptr, stats);
+}
+
+int bias_bmm_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int32_t *zz, int32_t K,
+                 double alpha, int32_t n_sweeps, bias_sweep_stats *stats) {
+    return run_model(ctx, BIAS_MODEL_BMM, conj, data, 0, nullptr, zz, K, alpha, nullptr, n_sweeps, nullptr, stats);
+}
+
+int bias_hdp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int64_t n_groups,
+                 const int64_t *group_ptr, int32_t *zz, bias_hdp_params *params, int32_t n_sweeps,
+                 double *beta_out, bias_sweep_stats *stats) {
+    if (!params) return fail(BIAS_EINVAL, "null HDP parameters");
+    return run_model(ctx, BIAS_MODEL_HDP, conj, data, n_groups, group_ptr, zz, params->KK, params->aa, params, n_sweeps,
+                     beta_out, stats);
+}
+
+}  // extern "C"

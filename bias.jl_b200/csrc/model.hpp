@@ -1,0 +1,82 @@
+// model.hpp — host-side state of libbias_cuda (context and resident sampler state).
+#pragma once
+#include <vector>
+#include <random>
+#include "common.cuh"
+
+struct bias_ctx {
+    int device = 0;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+    int64_t launches = 0;
+    // device-resident normalised log-Stirling table (packed lower triangle), built on first use
+    double *stirling = nullptr;
+    int32_t stirling_rows = 0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+};
+
+struct bias_model {
+    bias_ctx *ctx = nullptr;
+    int32_t model = 0;
+    bias_conjugate conj{};
+    int64_t N = 0, G = 0, nnz = 0, V = 0;
+    int32_t K = 0, Kpad = 0;
+    double alpha = 0.0;
+    bool fast = false;              // LDA x MD x Int on the fp32 warp-per-document kernel
+
+    // observations
+    int32_t *word = nullptr;
+    double *x = nullptr;
+    int64_t *sent_ptr = nullptr;
+    int32_t *sent_word = nullptr, *sent_count = nullptr;
+    int64_t *group_ptr = nullptr;
+    int32_t *group_of = nullptr;
+    int32_t *z = nullptr;
+
+    // shared component statistics: one int32 block [n_wk | n_k | n_items] and one f64 block [sumx]
+    int32_t *i32_block = nullptr;
+    int64_t n_i32 = 0;              // padded to a multiple of 4
+    int32_t *n_wk = nullptr, *n_k = nullptr, *n_items = nullptr;
+    double *f64_block = nullptr;
+    int64_t n_f64 = 0;
+    double *sumx = nullptr;
+    int32_t *group_rows = nullptr;  // [G][Kpad] n_jk for the generic LDA/HDP path
+
+    // multi-GPU exchange buffers (allocated on first use)
+    int32_t *base_i32 = nullptr, *delta_i32 = nullptr;
+    double *base_f64 = nullptr, *delta_f64 = nullptr;
+
+    // per-sweep scratch: [0] diag (double) [1] moved (u64) [2] doc counter (u64) [3] pending count (u32)
+    unsigned long long *scratch = nullptr;
+    unsigned long long *h_scratch = nullptr;   // pinned mirror
+    uint32_t sweep_index = 0;
+    bias_sweep_stats last{};
+    bool stats_pending = false;
+    int32_t last_launches = 0;
+    bool timing_valid = false;
+
+    // HDP
+    bias_hdp_params hdp{};
+    std::vector<double> h_beta;     // [Kmax+1]
+    double *d_beta = nullptr;
+    int32_t *pending = nullptr;     // [N] items that drew the new-component slot
+    int32_t *d_KK = nullptr;        // device copy of KK used by the serial birth pass
+    int64_t *d_tables = nullptr;    // [Kpad] sum_j M_jk, [Kpad] = total
+    double *d_hyper = nullptr;      // [0] sum log w, [1] sum s
+    int32_t *d_remap = nullptr;     // [Kpad] slot compaction map
+    std::mt19937_64 host_rng;
+};
+
+namespace bias {
+int ensure_stirling(bias_ctx *ctx, int32_t rows);
+int hdp_create(bias_model *m, const bias_hdp_params *hp);
+int hdp_sweep(bias_model *m);
+int hdp_destroy(bias_model *m);
+int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const int32_t *work_idx32,
+                   const int32_t *row_of, int32_t *prior_rows, const double *ext_uniforms, int frozen,
+                   int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,
+                   int row_by_work = 0);
+int rebuild_counts(bias_model *m);
+}  // namespace bias

@@ -1,0 +1,149 @@
+// util_kernels.cuh — initialisation pass (src/LDA.jl:91-98, src/BMM.jl:70-75, src/HDP.jl:217-224:
+// additem! for every item) and the count-delta kernels of the multi-GPU exchange.
+#pragma once
+#include "common.cuh"
+
+namespace bias {
+
+#ifdef __CUDACC__
+
+// item -> group id by binary search in the CSR offsets
+__global__ void group_of_kernel(const int64_t *ptr, int64_t G, int64_t N, int32_t *group_of) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = G;        // invariant: ptr[lo] <= i < ptr[hi]
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (ptr[mid] <= i) lo = mid; else hi = mid;
+        }
+        group_of[i] = (int32_t)lo;
+    }
+}
+
+// additem! for word-id items: n_wk[w][z] += 1, n_k[z] += 1 (block-private histogram for n_k)
+__global__ void build_md_int_kernel(const int32_t *word, const int32_t *z, int64_t N, int Kpad,
+                                    int32_t *n_wk, int32_t *n_k, int32_t *n_items) {
+    extern __shared__ int32_t hist[];
+    for (int k = threadIdx.x; k < Kpad; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = z[i];
+        atomicAdd(n_wk + (size_t)word[i] * Kpad + k, 1);
+        atomicAdd(&hist[k], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+        const int h = hist[k];
+        if (h) {
+            atomicAdd(n_k + k, h);
+            atomicAdd(n_items + k, h);
+        }
+    }
+}
+
+// additem! for Sent items: one warp per item
+__global__ void build_md_sent_kernel(const int64_t *sptr, const int32_t *sw, const int32_t *sc, const int32_t *z,
+                                     int64_t N, int Kpad, int32_t *n_wk, int32_t *n_k, int32_t *n_items) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += nw) {
+        const int k = z[i];
+        int m = 0;
+        for (int64_t t = sptr[i] + lane; t < sptr[i + 1]; t += 32) {
+            atomicAdd(n_wk + (size_t)sw[t] * Kpad + k, sc[t]);
+            m += sc[t];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(kFull, m, o);
+        if (lane == 0) {
+            atomicAdd(n_k + k, m);
+            atomicAdd(n_items + k, 1);
+        }
+    }
+}
+
+// additem! for Float64 items under Gaussian1DGaussian1D: (sum x, n) per component
+__global__ void build_g1g1_kernel(const double *x, const int32_t *z, int64_t N, int Kpad,
+                                  double *sumx, int32_t *n_items) {
+    extern __shared__ unsigned char sraw[];
+    double *hs = reinterpret_cast<double *>(sraw);
+    int32_t *hn = reinterpret_cast<int32_t *>(hs + Kpad);
+    for (int k = threadIdx.x; k < Kpad; k += blockDim.x) { hs[k] = 0.0; hn[k] = 0; }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = z[i];
+        atomicAdd(&hs[k], x[i]);
+        atomicAdd(&hn[k], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < Kpad; k += blockDim.x)
+        if (hn[k]) { atomicAdd(sumx + k, hs[k]); atomicAdd(n_items + k, hn[k]); }
+}
+
+// nn[j, k] (the reference's group-by-component matrix)
+__global__ void build_group_rows_kernel(const int32_t *z, const int32_t *group_of, int64_t N, int Kpad,
+                                        int32_t *rows) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = z[i];
+        if (k >= 0) atomicAdd(rows + (size_t)group_of[i] * Kpad + k, 1);
+    }
+}
+
+// group rows of a list of query items (verification of models that keep no n_jk table):
+// one warp per query, row q of `rows` <- histogram of z over the query item's group.
+__global__ void build_query_rows_kernel(const int64_t *item_idx, int64_t nq, const int64_t *ptr, int64_t G,
+                                        const int32_t *z, int Kpad, int32_t *rows, int32_t *row_of_query) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nw) {
+        const int64_t i = item_idx[q];
+        int64_t lo = 0, hi = G;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (ptr[mid] <= i) lo = mid; else hi = mid;
+        }
+        for (int64_t t = ptr[lo] + lane; t < ptr[lo + 1]; t += 32) atomicAdd(rows + (size_t)q * Kpad + z[t], 1);
+        if (lane == 0) row_of_query[q] = (int32_t)q;
+    }
+}
+
+// ---- multi-GPU exchange -----------------------------------------------------------------
+__global__ void delta_pack_i32_kernel(const int32_t *live, const int32_t *base, int32_t *delta, int64_t n4) {
+    // n4 = number of int4 groups (buffers are padded to 16 bytes)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 a = reinterpret_cast<const int4 *>(live)[i], b = reinterpret_cast<const int4 *>(base)[i];
+        reinterpret_cast<int4 *>(delta)[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    }
+}
+__global__ void delta_apply_i32_kernel(int32_t *live, int32_t *base, const int32_t *delta, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 b = reinterpret_cast<const int4 *>(base)[i], d = reinterpret_cast<const int4 *>(delta)[i];
+        const int4 v = make_int4(b.x + d.x, b.y + d.y, b.z + d.z, b.w + d.w);
+        reinterpret_cast<int4 *>(live)[i] = v;
+        reinterpret_cast<int4 *>(base)[i] = v;
+    }
+}
+__global__ void delta_pack_f64_kernel(const double *live, const double *base, double *delta, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        delta[i] = live[i] - base[i];
+}
+__global__ void delta_apply_f64_kernel(double *live, double *base, const double *delta, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = base[i] + delta[i];
+        live[i] = v;
+        base[i] = v;
+    }
+}
+
+// topic-major int64 export for posterior(): mi[k*V + w] = n_wk[w*Kpad + k]
+__global__ void export_mi_kernel(const int32_t *n_wk, int64_t V, int K, int Kpad, int64_t *mi) {
+    const int64_t total = V * (int64_t)K;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = idx / K;
+        const int k = (int)(idx - w * K);
+        mi[(int64_t)k * V + w] = (int64_t)n_wk[w * Kpad + k];
+    }
+}
+
+#endif
+
+}  // namespace bias

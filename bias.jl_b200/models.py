@@ -1,0 +1,393 @@
+"""Host-side mirror of the reference's sampler API for the assignment-sweep hot path.
+
+  LDA(c, KK, aa)                      src/LDA.jl:11-18
+  BMM(c, KK, aa)                      src/BMM.jl:11-18
+  HDP(c, KK, gg, g1, g2, aa, a1, a2)  src/HDP.jl:15-33
+  init_zz(model, zz)                  src/common.jl:25-34
+  collapsed_gibbs_sampler(model, xx, zz, n_burnins, n_lags, n_samples, ...)
+                                      src/LDA.jl:67-148, src/BMM.jl:46-130, src/HDP.jl:166-399
+  posterior(model, xx, zz)            src/LDA.jl:151-167, src/BMM.jl:134-151
+
+Everything below the sampler entry point runs in libbias_cuda on the GPU; this module only
+flattens the ragged Julia-style containers to CSR, calls the C ABI and writes zz back in place.
+Python indices are 0-based.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, check, lib, ptr
+from .conjugates import Gaussian1DGaussian1D, MultinomialDirichlet, Sent
+
+
+# ------------------------------------------------------------------ model types
+class LDA:
+    """Latent Dirichlet Allocation: finite KK, grouped data (src/LDA.jl:11-18)."""
+    model_id = _lib.MODEL_LDA
+
+    def __init__(self, component, KK: int, aa: float):
+        self.component, self.KK, self.aa = component, int(KK), float(aa)
+
+    def __repr__(self):
+        return f"Latent Dirichlet Allocation model with {self.KK} {type(self.component).__name__} components"
+
+
+class BMM:
+    """Bayesian (finite) mixture model over flat data (src/BMM.jl:11-18)."""
+    model_id = _lib.MODEL_BMM
+
+    def __init__(self, component, KK: int, aa: float):
+        self.component, self.KK, self.aa = component, int(KK), float(aa)
+
+    def __repr__(self):
+        return f"Finite Mixture Model with {self.KK} {type(self.component).__name__} components"
+
+
+class HDP:
+    """Hierarchical Dirichlet process mixture (src/HDP.jl:15-33). KK, gg and aa are updated in
+    place by the sampler, as on the Julia object.  Kmax is the engine's slot capacity."""
+    model_id = _lib.MODEL_HDP
+
+    def __init__(self, component, KK: int, gg: float, g1: float, g2: float, aa: float, a1: float, a2: float,
+                 Kmax: int = 256):
+        self.component, self.KK = component, int(KK)
+        self.gg, self.g1, self.g2 = float(gg), float(g1), float(g2)
+        self.aa, self.a1, self.a2 = float(aa), float(a1), float(a2)
+        self.Kmax = int(Kmax)
+
+    def __repr__(self):
+        return (f"Hierarchical Dirichlet Process Mixture Model with {self.KK} "
+                f"{type(self.component).__name__} components")
+
+
+def init_zz(model, zz, rng=None):
+    """src/common.jl:25-34 — uniform random initial assignments (0-based)."""
+    rng = rng or np.random.default_rng()
+    if isinstance(model, BMM):
+        zz[:] = rng.integers(0, model.KK, len(zz))
+    else:
+        for jj in range(len(zz)):
+            zz[jj] = rng.integers(0, model.KK, len(zz[jj])).astype(np.int64)
+    return zz
+
+
+# ------------------------------------------------------------------ flattening
+class FlatData:
+    """CSR view of the reference's containers: xx::Vector{T} or Vector{Vector{T}}."""
+
+    def __init__(self, component, xx, grouped: bool):
+        items = [x for g in xx for x in g] if grouped else list(xx)
+        if grouped:
+            lens = np.array([len(g) for g in xx], dtype=np.int64)
+            self.group_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            self.n_groups = len(xx)
+        else:
+            self.group_ptr, self.n_groups = None, 0
+        self.n_items = len(items)
+        probe = items[0] if items else (0.0 if isinstance(component, Gaussian1DGaussian1D) else 0)
+        self.datum = component.datum_kind(probe)
+        self.word = self.x = self.sent_ptr = self.sent_word = self.sent_count = None
+        if self.datum == _lib.INT:
+            if grouped and all(isinstance(g, np.ndarray) for g in xx) and len(xx):
+                self.word = _lib.as_i32(np.concatenate(xx)) if self.n_items else np.zeros(0, np.int32)
+            else:
+                self.word = _lib.as_i32(items)
+        elif self.datum == _lib.F64:
+            if grouped and all(isinstance(g, np.ndarray) for g in xx) and len(xx):
+                self.x = _lib.as_f64(np.concatenate(xx)) if self.n_items else np.zeros(0)
+            else:
+                self.x = _lib.as_f64(items)
+        else:
+            # merge duplicate words inside a Sent: the reference accumulates them into one
+            # vocabulary slot (lll[w] += c, src/conjugates.jl:186-191)
+            ws, cs, sp = [], [], [0]
+            for s in items:
+                uw, inv = np.unique(s.w, return_inverse=True)
+                uc = np.zeros(len(uw), dtype=np.int64)
+                np.add.at(uc, inv, s.c)
+                ws.append(uw)
+                cs.append(uc)
+                sp.append(sp[-1] + len(uw))
+            self.sent_ptr = np.asarray(sp, dtype=np.int64)
+            self.sent_word = _lib.as_i32(np.concatenate(ws)) if ws else np.zeros(0, np.int32)
+            self.sent_count = _lib.as_i32(np.concatenate(cs)) if cs else np.zeros(0, np.int32)
+        self.c = _lib.Data(self.n_items, ptr(self.word), ptr(self.x), ptr(self.sent_ptr), ptr(self.sent_word),
+                           ptr(self.sent_count))
+
+    @classmethod
+    def from_csr(cls, datum: int, n_items: int, group_ptr=None, word=None, x=None, sent_ptr=None, sent_word=None,
+                 sent_count=None):
+        """Already-flat inputs (what the Julia shim and bench.py hand over)."""
+        self = cls.__new__(cls)
+        self.datum, self.n_items = datum, int(n_items)
+        self.group_ptr = None if group_ptr is None else _lib.as_i64(group_ptr)
+        self.n_groups = 0 if group_ptr is None else len(self.group_ptr) - 1
+        self.word = None if word is None else _lib.as_i32(word)
+        self.x = None if x is None else _lib.as_f64(x)
+        self.sent_ptr = None if sent_ptr is None else _lib.as_i64(sent_ptr)
+        self.sent_word = None if sent_word is None else _lib.as_i32(sent_word)
+        self.sent_count = None if sent_count is None else _lib.as_i32(sent_count)
+        self.c = _lib.Data(self.n_items, ptr(self.word), ptr(self.x), ptr(self.sent_ptr), ptr(self.sent_word),
+                           ptr(self.sent_count))
+        return self
+
+
+def _flat_zz(zz, grouped: bool) -> np.ndarray:
+    if grouped:
+        return _lib.as_i32(np.concatenate([np.asarray(g) for g in zz])) if len(zz) else np.zeros(0, np.int32)
+    return _lib.as_i32(zz)
+
+
+def _scatter_zz(flat: np.ndarray, zz, grouped: bool, group_ptr):
+    if grouped:
+        for jj in range(len(zz)):
+            seg = flat[group_ptr[jj]:group_ptr[jj + 1]]
+            if isinstance(zz[jj], np.ndarray) and zz[jj].shape == seg.shape:
+                zz[jj][:] = seg
+            else:
+                zz[jj] = seg.astype(np.int64)
+    else:
+        zz[:] = flat
+
+
+def _hdp_params(hdp: HDP, sample_hyperparam=True, n_internals=10) -> _lib.HdpParams:
+    return _lib.HdpParams(hdp.KK, hdp.Kmax, hdp.gg, hdp.g1, hdp.g2, hdp.aa, hdp.a1, hdp.a2,
+                          int(bool(sample_hyperparam)), int(n_internals))
+
+
+_default_ctx: Context | None = None
+
+
+def default_context(seed: int = 0) -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0, seed)
+    return _default_ctx
+
+
+# ------------------------------------------------------------------ resident sampler state
+class ResidentSampler:
+    """bias_model: xx, zz and the component statistics live in HBM between sweeps."""
+
+    def __init__(self, ctx: Context, model, data: FlatData, zz_flat: np.ndarray, *, sample_hyperparam=True,
+                 n_internals=10):
+        self.ctx, self.model, self.data = ctx, model, data
+        self.spec = model.component.spec(data.datum)
+        self.h = C.c_void_p()
+        hp = _hdp_params(model, sample_hyperparam, n_internals) if isinstance(model, HDP) else None
+        self.zz = _lib.as_i32(zz_flat)
+        check(lib().bias_model_create(ctx.h, model.model_id, C.byref(self.spec), C.byref(data.c), data.n_groups,
+                                      ptr(data.group_ptr), ptr(self.zz), model.KK, model.aa,
+                                      C.byref(hp) if hp is not None else None, C.byref(self.h)))
+
+    # -- sweeps
+    def sweep(self, n: int = 1):
+        check(lib().bias_model_sweep(self.h, n))
+
+    def stats(self) -> _lib.SweepStats:
+        s = _lib.SweepStats()
+        check(lib().bias_model_last_stats(self.h, C.byref(s)))
+        return s
+
+    def last_sweep_ms(self):
+        ms, n = C.c_float(), C.c_int32()
+        check(lib().bias_model_last_sweep_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- state access
+    def get_zz(self) -> np.ndarray:
+        out = np.empty(self.data.n_items, dtype=np.int32)
+        check(lib().bias_model_get_zz(self.h, ptr(out)))
+        return out
+
+    def set_zz(self, zz_flat):
+        z = _lib.as_i32(zz_flat)
+        check(lib().bias_model_set_zz(self.h, ptr(z)))
+
+    def current_KK(self) -> int:
+        return int(self.stats().KK)
+
+    def components(self):
+        K = self.current_KK()
+        nn = np.zeros(K, dtype=np.int64)
+        if self.spec.kind == _lib.MD:
+            mi = np.zeros((K, self.spec.dd), dtype=np.int64)
+            mm = np.zeros(K, dtype=np.int64)
+            check(lib().bias_model_get_components(self.h, ptr(mi), ptr(mm), None, ptr(nn)))
+            return {"mi": mi, "mm": mm, "nn": nn}
+        mu = np.zeros(K)
+        check(lib().bias_model_get_components(self.h, None, None, ptr(mu), ptr(nn)))
+        return {"mu": mu, "nn": nn}
+
+    def group_counts(self) -> np.ndarray:
+        K = self.current_KK()
+        nn = np.zeros((self.data.n_groups, K), dtype=np.int64)
+        check(lib().bias_model_get_group_counts(self.h, ptr(nn)))
+        return nn
+
+    def hdp_state(self):
+        hp = _lib.HdpParams()
+        beta = np.zeros(self.model.Kmax + 1)
+        check(lib().bias_model_get_hdp(self.h, C.byref(hp), ptr(beta)))
+        return hp, beta[:hp.KK + 1].copy()
+
+    # -- verification
+    def conditionals(self, item_idx, uniforms):
+        idx, u = _lib.as_i64(item_idx), _lib.as_f64(uniforms)
+        n_out = self.current_KK() + (1 if isinstance(self.model, HDP) else 0)
+        raw, prob = np.zeros((len(idx), n_out)), np.zeros((len(idx), n_out))
+        draw = np.zeros(len(idx), dtype=np.int32)
+        check(lib().bias_model_conditionals(self.h, len(idx), ptr(idx), ptr(u), ptr(raw), ptr(prob), ptr(draw)))
+        return raw, prob, draw
+
+    def frozen_draws(self, uniforms) -> np.ndarray:
+        u = _lib.as_f64(uniforms)
+        assert len(u) == self.data.n_items
+        out = np.zeros(self.data.n_items, dtype=np.int32)
+        check(lib().bias_model_frozen_draws(self.h, ptr(u), ptr(out)))
+        return out
+
+    # -- multi-GPU exchange (AD-LDA)
+    def delta_begin(self):
+        check(lib().bias_model_delta_begin(self.h))
+
+    def delta_pack(self):
+        """-> [(device_ptr, n_elems, 'int32'), (device_ptr, n_elems, 'float64')] (second may be empty)"""
+        p32, p64, n32, n64 = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        check(lib().bias_model_delta_pack(self.h, C.byref(p32), C.byref(n32), C.byref(p64), C.byref(n64)))
+        out = [(p32.value, n32.value, "int32")]
+        if n64.value:
+            out.append((p64.value, n64.value, "float64"))
+        return out
+
+    def delta_apply(self):
+        check(lib().bias_model_delta_apply(self.h))
+
+    def close(self):
+        if self.h:
+            lib().bias_model_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ the reference entry points
+def _store(filename: str, i: int, **arrays):
+    """storesample (src/LDA.jl:45-64): the reference writes JLD (HDF5); no HDF5 tooling exists in
+    this image, so samples are stored as .npz with the same keys."""
+    name = f"{filename}{i}.npz" if filename.endswith("_") else f"{filename}_{i}.npz"
+    np.savez(name, **arrays)
+
+
+def collapsed_gibbs_sampler(model, xx, zz, n_burnins: int, n_lags: int, n_samples: int, *args,
+                            store_every: int = 100, filename: str | None = None, ctx: Context | None = None,
+                            verbose: bool = False, sample_hyperparam: bool = True, n_internals: int = 10,
+                            KK_list: Sequence[int] = (), KK_dict: dict | None = None):
+    """collapsed_gibbs_sampler!(model, xx, zz, n_burnins, n_lags, n_samples, ...).
+
+    LDA / BMM: mutates zz in place and returns None (src/LDA.jl:67-148, src/BMM.jl:46-130).
+    HDP: returns (KK_list, KK_dict, betas, gammas, alphas) (src/HDP.jl:398) and updates
+    hdp.KK / hdp.gg / hdp.aa.  Positional extras follow the reference's order
+    (HDP: sample_hyperparam, n_internals, store_every, filename; LDA/BMM: store_every, filename).
+    filename=None disables sample files.
+    """
+    if isinstance(model, HDP):
+        names = ["sample_hyperparam", "n_internals", "store_every", "filename"]
+    else:
+        names = ["store_every", "filename"]
+    if len(args) > len(names):
+        raise TypeError("too many positional arguments")
+    loc = {"sample_hyperparam": sample_hyperparam, "n_internals": n_internals, "store_every": store_every,
+           "filename": filename}
+    loc.update(dict(zip(names, args)))
+    sample_hyperparam, n_internals = loc["sample_hyperparam"], loc["n_internals"]
+    store_every, filename = loc["store_every"], loc["filename"]
+
+    ctx = ctx or default_context()
+    grouped = not isinstance(model, BMM)
+    data = FlatData(model.component, xx, grouped)
+    n_iterations = n_burnins + n_samples * (n_lags + 1)                 # src/LDA.jl:82
+    try:
+        rs = ResidentSampler(ctx, model, data, _flat_zz(zz, grouped), sample_hyperparam=sample_hyperparam,
+                             n_internals=n_internals)
+    except _lib.BiasError as e:
+        if e.code == _lib.EINVAL:
+            raise ValueError(str(e)) from None                          # the reference's ArgumentError
+        raise
+
+    is_hdp = isinstance(model, HDP)
+    if is_hdp:
+        n_old = len(KK_list)
+        KK_list = list(KK_list) + [0] * n_samples
+        KK_dict = {} if (KK_dict is None or n_old == 0) else KK_dict
+        betas, gammas, alphas = [None] * n_samples, np.zeros(n_samples), np.zeros(n_samples)
+    try:
+        for iteration in range(1, n_iterations + 1):
+            rs.sweep(1)
+            if verbose:
+                s = rs.stats()
+                burn = "Burning... " if iteration < n_burnins else ""
+                print(f"{burn}iteration: {iteration}, KK={s.KK}, likelihood={s.log_likelihood:.2f}")
+            if (iteration - n_burnins) % (n_lags + 1) == 0 and iteration > n_burnins:
+                i = (iteration - n_burnins) // (n_lags + 1)
+                if is_hdp:
+                    hp, beta = rs.hdp_state()
+                    flat = rs.get_zz()
+                    _scatter_zz(flat, zz, True, data.group_ptr)
+                    KK_list[n_old + i - 1] = hp.KK
+                    KK_dict[hp.KK] = [np.array(g, dtype=np.int64) for g in zz]
+                    alphas[i - 1], gammas[i - 1], betas[i - 1] = hp.aa, hp.gg, beta
+                if filename is not None and i % store_every == 0:
+                    _store(filename, i, zz=rs.get_zz(), iteration=iteration)
+        flat = rs.get_zz()
+        _scatter_zz(flat, zz, grouped, data.group_ptr)
+        if is_hdp:
+            hp, beta = rs.hdp_state()
+            model.KK, model.gg, model.aa = hp.KK, hp.gg, hp.aa
+            if n_samples > 0:                                           # src/HDP.jl:390-395
+                KK_list[n_old + n_samples - 1] = hp.KK
+                KK_dict[hp.KK] = [np.array(g, dtype=np.int64) for g in zz]
+                alphas[n_samples - 1], gammas[n_samples - 1], betas[n_samples - 1] = hp.aa, hp.gg, beta
+        if filename is not None:
+            _store(filename, (n_iterations - n_burnins) // (n_lags + 1), zz=flat, iteration=n_iterations)
+    finally:
+        rs.close()
+    if is_hdp:
+        return KK_list, KK_dict, betas, gammas, alphas
+    return None
+
+
+def posterior(model, xx, zz, ctx: Context | None = None):
+    """posterior(model, xx, zz) -> ([posterior(component_k)], nn)  (src/LDA.jl:151-167, src/BMM.jl:134-151).
+    The sufficient statistics are accumulated on the device by the initialisation pass."""
+    from .distributions import Dirichlet, Gaussian1D
+    ctx = ctx or default_context()
+    grouped = not isinstance(model, BMM)
+    data = FlatData(model.component, xx, grouped)
+    rs = ResidentSampler(ctx, model, data, _flat_zz(zz, grouped))
+    try:
+        comp = rs.components()
+        c0 = model.component
+        posts = []
+        for k in range(model.KK):
+            if isinstance(c0, MultinomialDirichlet):
+                posts.append(Dirichlet(comp["mi"][k] + c0.aa))
+            else:
+                n = int(comp["nn"][k])
+                if n > 0:
+                    denom = c0.vv + n * c0.v0
+                    posts.append(Gaussian1D((n * c0.v0 * comp["mu"][k] + c0.vv * c0.m0) / denom, c0.v0 * c0.vv / denom))
+                else:
+                    posts.append(Gaussian1D(c0.m0, c0.v0))
+        nn = rs.group_counts() if grouped else comp["nn"]
+    finally:
+        rs.close()
+    return posts, nn

@@ -1,0 +1,180 @@
+/*
+ * bias_cuda.h — C ABI of libbias_cuda, the B200 (sm_100a) collapsed-Gibbs engine that
+ * replaces the component-assignment sweep of BIAS.jl's LDA / BMM / HDP samplers.
+ *
+ * The reference has no FFI: its boundary is the exported Julia method set
+ * (src/BIAS.jl:8-14).  Each entry point below names the reference interface it
+ * replaces (file:line under the reference tree).  A Julia shim `ccall`s these
+ * (INTEGRATION.md); the tested caller is the ctypes binding in bias.jl_b200/_lib.py.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a BIAS_E* code; bias_last_error() gives the
+ *    thread-local message.  No C++ exception crosses the ABI.
+ *  - all buffers are caller-owned HOST memory unless a name ends in _dev.
+ *  - indices are 0-based: assignments zz in [0, K), word ids in [0, V).  Ragged Julia
+ *    arrays (Vector{Vector{T}}) arrive CSR-flattened: group_ptr[n_groups+1] offsets into
+ *    the item arrays.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with BIAS_ENODEV.
+ */
+#ifndef BIAS_CUDA_H
+#define BIAS_CUDA_H
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BIAS_API __attribute__((visibility("default")))
+#else
+#define BIAS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIAS_OK        0
+#define BIAS_EINVAL    1   /* bad argument (the reference's ArgumentError from @check_args, src/common.jl:233-240) */
+#define BIAS_ENODEV    2   /* no usable CUDA device */
+#define BIAS_ECUDA     3   /* CUDA runtime error */
+#define BIAS_ENOMEM    4
+#define BIAS_ERANGE    5   /* n_jk beyond the Stirling table (reference: BoundsError, src/HDP.jl:355) or Kmax exhausted */
+#define BIAS_ESTATE    6   /* e.g. delitem! on an empty Gaussian component (reference throws, src/conjugates.jl:66) */
+
+/* conjugate family (src/conjugates.jl) and datum type (src/common.jl:12-18) */
+#define BIAS_MD    0   /* MultinomialDirichlet, src/conjugates.jl:131-143 */
+#define BIAS_G1G1  1   /* Gaussian1DGaussian1D, src/conjugates.jl:30-47 */
+#define BIAS_INT   0   /* one word id per item */
+#define BIAS_SENT  1   /* sparse count vector (Sent) per item */
+#define BIAS_F64   2   /* one Float64 per item */
+
+typedef struct bias_ctx bias_ctx;
+typedef struct bias_model bias_model;    /* a device-resident LDA / BMM / HDP sampler state */
+
+/* The prototype component handed to LDA(c, K, aa) / BMM(...) / HDP(...) */
+typedef struct {
+    int32_t kind;      /* BIAS_MD | BIAS_G1G1 */
+    int32_t datum;     /* BIAS_INT | BIAS_SENT | BIAS_F64 */
+    int64_t dd;        /* MD: cardinality V */
+    double  aa;        /* MD: per-dimension concentration, i.e. the value the ctor stores (aa/dd, src/conjugates.jl:142) */
+    double  m0, v0, vv;/* G1G1: prior mean / prior variance / likelihood variance */
+} bias_conjugate;
+
+/* The observations xx.  Exactly one family of pointers is used, chosen by conjugate.datum. */
+typedef struct {
+    int64_t n_items;
+    const int32_t *word;        /* BIAS_INT  [n_items] */
+    const double  *x;           /* BIAS_F64  [n_items] */
+    const int64_t *sent_ptr;    /* BIAS_SENT [n_items+1] CSR offsets */
+    const int32_t *sent_word;   /* BIAS_SENT word ids (unique within an item, as sparsify_sentence makes them) */
+    const int32_t *sent_count;  /* BIAS_SENT counts */
+} bias_data;
+
+/* What the reference prints once per sweep (src/LDA.jl:108-109) plus engine counters. */
+typedef struct {
+    double  log_likelihood;   /* the reference's per-sweep diagnostic (posterior-mean sum for MD, src/conjugates.jl:205) */
+    int64_t n_moved;          /* items whose assignment changed */
+    int32_t KK;               /* components alive after the sweep (HDP); K otherwise */
+    int32_t reserved;
+    double  gg, aa;           /* HDP concentrations after the sweep */
+} bias_sweep_stats;
+
+/* HDP(c, KK, gg, g1, g2, aa, a1, a2), src/HDP.jl:15-33 — KK, gg, aa are updated in place like the Julia object */
+typedef struct {
+    int32_t KK;
+    int32_t Kmax;             /* slot capacity (engine parameter; the reference grows nn by copying) */
+    double  gg, g1, g2;
+    double  aa, a1, a2;
+    int32_t sample_hyperparam;/* src/HDP.jl:171 */
+    int32_t n_internals;      /* src/HDP.jl:171 */
+} bias_hdp_params;
+
+/* ---- context ------------------------------------------------------------------------- */
+BIAS_API int  bias_version(void);
+BIAS_API const char *bias_last_error(void);
+BIAS_API int  bias_device_count(int *n_out);
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
+BIAS_API int  bias_ctx_create(int device, uint64_t seed, void *stream, bias_ctx **out);
+BIAS_API int  bias_ctx_destroy(bias_ctx *ctx);
+BIAS_API int  bias_ctx_sync(bias_ctx *ctx);
+BIAS_API int  bias_ctx_num_sms(bias_ctx *ctx, int *n_out);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+BIAS_API int  bias_ctx_launch_count(bias_ctx *ctx, int64_t *n_out);
+
+/* ---- one-call samplers: what the Julia shim ccalls ------------------------------------ */
+/* collapsed_gibbs_sampler!(lda::LDA, xx, zz, n_burnins, n_lags, n_samples, ...)  src/LDA.jl:67-148.
+ * n_sweeps = n_burnins + n_samples*(n_lags+1) (src/LDA.jl:82).  zz is mutated in place.
+ * stats: NULL or n_sweeps entries. */
+BIAS_API int bias_lda_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data,
+                 int64_t n_groups, const int64_t *group_ptr, int32_t *zz,
+                 int32_t K, double alpha, int32_t n_sweeps, bias_sweep_stats *stats);
+/* collapsed_gibbs_sampler!(bmm::BMM, xx, zz, ...)  src/BMM.jl:46-130 */
+BIAS_API int bias_bmm_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data,
+                 int32_t *zz, int32_t K, double alpha, int32_t n_sweeps, bias_sweep_stats *stats);
+/* collapsed_gibbs_sampler!(hdp::HDP, xx, zz, ...)  src/HDP.jl:166-399.  params (KK, gg, aa) are
+ * updated like the Julia object; beta_out[Kmax+1] receives my_beta (src/HDP.jl:394); zz is
+ * renumbered to 0..KK-1 in slot order. */
+BIAS_API int bias_hdp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data,
+                 int64_t n_groups, const int64_t *group_ptr, int32_t *zz,
+                 bias_hdp_params *params, int32_t n_sweeps, double *beta_out, bias_sweep_stats *stats);
+
+/* ---- resident sampler state: same samplers, split into upload / sweep / download ------- */
+#define BIAS_MODEL_LDA 0
+#define BIAS_MODEL_BMM 1
+#define BIAS_MODEL_HDP 2
+/* Uploads xx and zz and runs the initialisation pass (src/LDA.jl:91-98, src/BMM.jl:70-75,
+ * src/HDP.jl:217-228).  For BMM pass n_groups = 0, group_ptr = NULL; hdp = NULL unless model is HDP. */
+BIAS_API int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, const bias_data *data,
+                      int64_t n_groups, const int64_t *group_ptr, const int32_t *zz,
+                      int32_t K, double alpha, const bias_hdp_params *hdp, bias_model **out);
+BIAS_API int bias_model_destroy(bias_model *m);
+/* n_sweeps asynchronous sweeps on the context stream (one iteration of the loop at src/LDA.jl:103). */
+BIAS_API int bias_model_sweep(bias_model *m, int32_t n_sweeps);
+/* Re-upload assignments (and rebuild counts) without re-uploading xx. */
+BIAS_API int bias_model_set_zz(bias_model *m, const int32_t *zz);
+BIAS_API int bias_model_get_zz(bias_model *m, int32_t *zz);
+BIAS_API int bias_model_last_stats(bias_model *m, bias_sweep_stats *out);
+/* posterior(model, xx, zz) support (src/LDA.jl:151-167): component sufficient statistics.
+ * MD:   mi[K*dd] topic-major int64 (the reference's per-topic mi), mm[K], nn[K].
+ * G1G1: mu[K] (mean of the assigned data), nn[K].  Unused outputs may be NULL. */
+BIAS_API int bias_model_get_components(bias_model *m, int64_t *mi, int64_t *mm, double *mu, int64_t *nn);
+/* nn[n_groups*K] row-major group-by-component counts (the reference's nn matrix). */
+BIAS_API int bias_model_get_group_counts(bias_model *m, int64_t *nn);
+BIAS_API int bias_model_get_hdp(bias_model *m, bias_hdp_params *params, double *beta /* [Kmax+1] */);
+
+/* ---- verification entry points (parity levels (a) and (b) of the north star) ----------- */
+/* Conditionals of n_query items on the CURRENT device state with the item itself removed
+ * (LDA_sample_zz, src/LDA.jl:26-42; src/BMM.jl:102-107; src/HDP.jl:312-317), evaluated in
+ * Float64 with the reference's operation order.  n_out = K (K+1 for HDP).
+ * raw[n_query*n_out]: unnormalised log scores; prob[...]: after lognormalize!;
+ * draw[n_query]: result of `sample` for the supplied uniforms.  State is not modified. */
+BIAS_API int bias_model_conditionals(bias_model *m, int64_t n_query, const int64_t *item_idx,
+                            const double *uniforms, double *raw, double *prob, int32_t *draw);
+/* One pass of the PRODUCTION sweep kernel with counts frozen and uniforms supplied
+ * (uniforms[n_items]); draws[n_items] out.  State is not modified. */
+BIAS_API int bias_model_frozen_draws(bias_model *m, const double *uniforms, int32_t *draws);
+/* HDP table-count conditional (src/HDP.jl:353-358) for n_query (n, a = aa*beta_k) pairs:
+ * prob[q*n_max + m-1] for m = 1..n, draws[q] in 1..n. */
+BIAS_API int bias_hdp_table_conditionals(bias_ctx *ctx, int64_t n_query, const int32_t *n, const double *a,
+                                const double *uniforms, int32_t n_max, double *prob, int32_t *draws);
+/* Device-resident normalised log-Stirling table (regenerates StirlingNums_10K.mat, src/HDP.jl:207-209).
+ * Copies rows 1..n_rows (packed lower triangle) to out; builds the table on first use. */
+BIAS_API int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out);
+
+/* ---- multi-GPU exchange (AD-LDA: one allreduce of count deltas per sweep) --------------- */
+/* Snapshot the shared component statistics (n_wk, n_k / sumx, n) as the base of the next delta. */
+BIAS_API int bias_model_delta_begin(bias_model *m);
+/* Compute delta = live - base into the exchange buffer and return its DEVICE address:
+ * n_i32 int32 values followed (8-byte aligned) by n_f64 doubles.  The caller all-reduces
+ * (sum) both segments in place across ranks, e.g. with NCCL on the same stream. */
+BIAS_API int bias_model_delta_pack(bias_model *m, void **delta_i32_dev, int64_t *n_i32,
+                          void **delta_f64_dev, int64_t *n_f64);
+/* live = base + (all-reduced) delta. */
+BIAS_API int bias_model_delta_apply(bias_model *m);
+
+/* ---- instrumentation ------------------------------------------------------------------ */
+/* Device time of the most recent bias_model_sweep call's sweep kernels, measured with CUDA
+ * events on the context stream: total ms and launches. */
+BIAS_API int bias_model_last_sweep_ms(bias_model *m, float *ms_out, int32_t *launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
