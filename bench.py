@@ -159,7 +159,7 @@ def cpu_baseline_run(n_docs: int, n_sweeps: int, warm: int = 0):
     ptr = np.arange(n_docs + 1, dtype=np.int64) * L_DOC
     rng = np.random.default_rng(7)
     z0 = rng.integers(0, K, len(words))
-    state = orc.LDAState(orc.Comps.md(K, V, BETA * V), orc.Data.words(words), ptr, z0, ALPHA)
+    state = orc.LDAState(orc.Comps.md(K, V, BETA * V), orc.Data.words(words), ptr, z0, ALPHA, with_diag=False)
     times = []
     for s in range(warm + n_sweeps):
         u = rng.random(len(words))

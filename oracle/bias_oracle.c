@@ -271,7 +271,7 @@ static double md_int_diag_fast(const orc_comps *c, int64_t k, int64_t w)
  * src/LDA.jl
  * ====================================================================== */
 double orc_lda_init(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
-                    const int64_t *z, int64_t *nn)
+                    const int64_t *z, int64_t *nn, int with_diag)
 {                                                   /* src/LDA.jl:91-98 */
     int64_t K = c->K;
     double ll = 0.0;
@@ -280,7 +280,7 @@ double orc_lda_init(orc_comps *c, const orc_data *d, int64_t D, const int64_t *p
             int64_t k = z[i];
             orc_additem(c, k, d, i);
             nn[j * K + k] += 1;
-            ll += orc_loglikelihood(c, k, d, i);
+            if (with_diag) ll += orc_loglikelihood(c, k, d, i);
         }
     return ll;
 }

@@ -74,7 +74,7 @@ void   orc_comps_move(orc_comps *c, int64_t dst, int64_t src); /* splice! suppor
 /* ---- src/LDA.jl ------------------------------------------------------- */
 /* Initialisation pass (src/LDA.jl:91-98). nn is [D*K] row-major. Returns the log_likelihood diagnostic. */
 double orc_lda_init(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
-                    const int64_t *z, int64_t *nn);
+                    const int64_t *z, int64_t *nn, int with_diag);
 /* One sweep (src/LDA.jl:113-133). doc_order[D] / tok_order[N] give the randperm
  * orders (global item indices, grouped by document in visiting order); NULL = identity.
  * uniforms[N] is indexed by global item index. Returns the log_likelihood diagnostic. */

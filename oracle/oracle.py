@@ -88,7 +88,7 @@ def lib():
         L.orc_g1g1_posterior.argtypes = [cp, i64, dp, dp]
         L.orc_comps_reset.argtypes = [cp, i64]
         L.orc_lda_init.restype = f64
-        L.orc_lda_init.argtypes = [cp, dpp, i64, vp, vp, vp]
+        L.orc_lda_init.argtypes = [cp, dpp, i64, vp, vp, vp, i32]
         L.orc_lda_sweep.restype = f64
         L.orc_lda_sweep.argtypes = [cp, dpp, i64, vp, vp, vp, f64, vp, vp, vp, i32]
         L.orc_lda_conditional.restype = i64
@@ -254,14 +254,15 @@ def loglikelihood(c: Comps, k, d: Data, i) -> float:
 class LDAState:
     """Serial LDA sampler state: components + nn[D,K] (src/LDA.jl:75-98)."""
 
-    def __init__(self, comps: Comps, data: Data, ptr, z, alpha: float):
+    def __init__(self, comps: Comps, data: Data, ptr, z, alpha: float, with_diag: bool = True):
         self.c, self.d = comps, data
         self.ptr = _i64(ptr)
         self.D = self.ptr.size - 1
         self.z = _i64(z).copy()
         self.alpha = float(alpha)
         self.nn = np.zeros((self.D, comps.K), dtype=np.int64)
-        self.loglik = lib().orc_lda_init(comps.ref(), data.ref(), self.D, _p(self.ptr), _p(self.z), _p(self.nn))
+        self.loglik = lib().orc_lda_init(comps.ref(), data.ref(), self.D, _p(self.ptr), _p(self.z), _p(self.nn),
+                                         int(with_diag))
 
     def sweep(self, uniforms, doc_order=None, tok_order=None, diag_mode=1) -> float:
         u = _f64(uniforms)
