@@ -232,7 +232,8 @@ def ours(args):
     ptr = np.arange(d1 - d0 + 1, dtype=np.int64) * L_DOC
     gen_s = time.perf_counter() - t_gen
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)     # a real (non-null) stream: the library launches on it and the events time it
+    torch.cuda.set_stream(stream)
     ctx = b.Context(local, seed=SEED + rank, stream=stream.cuda_stream)
     lda = b.LDA(b.MultinomialDirichlet(V, BETA * V), K, ALPHA)
     data = b.FlatData.from_csr(b._lib.INT, n_local, group_ptr=ptr, word=words_h.numpy())
