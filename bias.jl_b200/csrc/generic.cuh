@@ -113,6 +113,195 @@ __device__ __forceinline__ double g1g1_loglik(double n, double sx, double x, dou
     return log(exp(-(x - mu) * (x - mu) / (2.0 * vp)) / sqrt(2.0 * 3.141592653589793 * vp));
 }
 
+// ---- building blocks shared by the sweep kernel and the serial HDP birth pass --------------
+struct Datum {
+    int w;
+    double xv;
+    int64_t s0, s1;
+    double m_tot, coef;
+};
+
+__device__ __forceinline__ Datum load_datum(const GenericParams &p, int64_t i, int lane) {
+    Datum d{0, 0.0, 0, 0, 0.0, 0.0};
+    if (p.datum == BIAS_INT) {
+        d.w = p.word[i];
+    } else if (p.datum == BIAS_F64) {
+        d.xv = p.x[i];
+    } else {
+        d.s0 = p.sent_ptr[i];
+        d.s1 = p.sent_ptr[i + 1];
+        double mloc = 0.0, lg = 0.0;
+        for (int64_t t = d.s0 + lane; t < d.s1; t += 32) {
+            const double c = (double)p.sent_count[t];
+            mloc += c;
+            lg += lgamma(c + 1.0);
+        }
+        d.m_tot = warp_sum(mloc);
+        d.coef = lgamma(d.m_tot + 1.0) - warp_sum(lg);   // k-independent, src/conjugates.jl:193
+    }
+    return d;
+}
+
+// K (+1) unnormalised log scores into sc[]; returns the warp-wide maximum.
+// zold < 0: the item is currently unassigned (nothing to remove).
+__device__ __forceinline__ double score_all(const GenericParams &p, const Datum &d, int zold, int K, int n_out,
+                                            const int32_t *prow, const double *hdp_beta, double alpha,
+                                            double *sc, int lane) {
+    const bool is_hdp = p.model == BIAS_MODEL_HDP;
+    const int Kpad = p.Kpad;
+    double lmax = -INFINITY;
+    for (int k = lane; k < n_out; k += 32) {
+        const bool own = (k == zold);
+        const bool fresh = (k >= K);                  // HDP new-component slot: the empty prototype
+        double prior;
+        if (is_hdp) {
+            prior = fresh ? log(alpha * hdp_beta[K])
+                          : log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha * hdp_beta[k]);
+        } else {
+            prior = log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha);
+        }
+        double lp;
+        if (p.kind == BIAS_G1G1) {
+            double n = 0.0, sx = 0.0;
+            if (!fresh) {
+                n = (double)(__ldcg(p.n_items + k) - (own ? 1 : 0));
+                sx = __ldcg(p.sumx + k) - (own ? d.xv : 0.0);
+            }
+            lp = g1g1_logpred(n, sx, d.xv, p.m0, p.v0, p.vv);
+        } else if (p.datum == BIAS_INT) {
+            double nw = 0.0, nk = 0.0;
+            if (!fresh) {
+                nw = (double)(__ldcg(p.n_wk + (size_t)d.w * Kpad + k) - (own ? 1 : 0));
+                nk = (double)(__ldcg(p.n_k + k) - (own ? 1 : 0));
+            }
+            lp = log((p.beta + nw) / (p.beta * (double)p.V + nk));       // src/conjugates.jl:180
+        } else {
+            double nk = 0.0;
+            if (!fresh) nk = (double)__ldcg(p.n_k + k) - (own ? d.m_tot : 0.0);
+            double acc = 0.0;
+            for (int64_t t = d.s0; t < d.s1; ++t) {
+                const int wt = p.sent_word[t];
+                const double ct = (double)p.sent_count[t];
+                double nw = 0.0;
+                if (!fresh) nw = (double)__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0.0);
+                acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
+            }
+            const double bv = p.beta * (double)p.V;
+            lp = d.coef + lgamma(bv + nk) - lgamma(bv + nk + d.m_tot) + acc; // src/conjugates.jl:193-195
+        }
+        const double s = prior + lp;
+        sc[k] = s;
+        lmax = fmax(lmax, s);
+    }
+    lmax = warp_max(lmax);
+    __syncwarp();
+    return lmax;
+}
+
+// lognormalize! + sample in the reference's operation order, by lane 0 (src/common.jl:42-52, 69-79).
+// Leaves the normalised probabilities in sc[].
+__device__ __forceinline__ int draw_faithful(double *sc, int n_out, double lmax, double u, int lane) {
+    int knew = 0;
+    if (lane == 0) {
+        for (int k = 0; k < n_out; ++k) sc[k] = exp(sc[k] - lmax);
+        const double tot = jsum_dev(sc, 0, n_out - 1);
+        for (int k = 0; k < n_out; ++k) sc[k] /= tot;
+        int idx = 0;
+        double cw = sc[0];
+        while (cw < u && idx < n_out - 1) {
+            idx += 1;
+            cw += sc[idx];
+        }
+        knew = idx;
+    }
+    knew = __shfl_sync(kFull, knew, 0);
+    __syncwarp();
+    return knew;
+}
+
+// Production draw: exp in parallel, CDF by 32-wide chunk scans in k order, first k with cdf >= u * total.
+__device__ __forceinline__ int draw_parallel(double *sc, int n_out, double lmax, double u, int lane) {
+    double total = 0.0;
+    for (int b = 0; b < n_out; b += 32) {
+        const int k = b + lane;
+        double e = 0.0;
+        if (k < n_out) {
+            e = exp(sc[k] - lmax);
+            sc[k] = e;
+        }
+        total += warp_sum(e);
+    }
+    __syncwarp();
+    const double target = u * total;
+    double base = 0.0;
+    int knew = n_out - 1;
+    for (int b = 0; b < n_out; b += 32) {
+        const int k = b + lane;
+        const double e = (k < n_out) ? sc[k] : 0.0;
+        const double incl = base + warp_incl_scan(e, lane);
+        const unsigned bal = __ballot_sync(kFull, (k < n_out) && (incl >= target));
+        if (bal) {
+            knew = b + __ffs(bal) - 1;
+            break;
+        }
+        base = __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
+    return knew;
+}
+
+// delitem! from zold (if >= 0) and additem! to kdst (if >= 0) on the shared tables.
+__device__ __forceinline__ void apply_move(const GenericParams &p, const Datum &d, int zold, int kdst,
+                                           int32_t *prow, int lane) {
+    const int Kpad = p.Kpad;
+    if (p.kind == BIAS_MD) {
+        if (p.datum == BIAS_INT) {
+            if (lane == 0) {
+                if (zold >= 0) { atomicAdd(p.n_wk + (size_t)d.w * Kpad + zold, -1); atomicAdd(p.n_k + zold, -1); }
+                if (kdst >= 0) { atomicAdd(p.n_wk + (size_t)d.w * Kpad + kdst, 1); atomicAdd(p.n_k + kdst, 1); }
+            }
+        } else {
+            for (int64_t t = d.s0 + lane; t < d.s1; t += 32) {
+                const int wt = p.sent_word[t], ct = p.sent_count[t];
+                if (zold >= 0) atomicAdd(p.n_wk + (size_t)wt * Kpad + zold, -ct);
+                if (kdst >= 0) atomicAdd(p.n_wk + (size_t)wt * Kpad + kdst, ct);
+            }
+            if (lane == 0) {
+                if (zold >= 0) atomicAdd(p.n_k + zold, -(int)d.m_tot);
+                if (kdst >= 0) atomicAdd(p.n_k + kdst, (int)d.m_tot);
+            }
+        }
+    } else if (lane == 0) {
+        if (zold >= 0) atomicAdd(p.sumx + zold, -d.xv);
+        if (kdst >= 0) atomicAdd(p.sumx + kdst, d.xv);
+    }
+    if (lane == 0) {
+        if (zold >= 0) atomicAdd(p.n_items + zold, -1);
+        if (kdst >= 0) atomicAdd(p.n_items + kdst, 1);
+        if (!p.prior_is_items) {
+            if (zold >= 0) atomicAdd(prow + zold, -1);
+            if (kdst >= 0) atomicAdd(prow + kdst, 1);
+        }
+    }
+}
+
+// loglikelihood(components[kk], x) after the add (src/LDA.jl:131): valid on lane 0.
+__device__ __forceinline__ double diag_after(const GenericParams &p, const Datum &d, int knew, int lane) {
+    const int Kpad = p.Kpad;
+    if (p.kind == BIAS_G1G1)
+        return g1g1_loglik((double)__ldcg(p.n_items + knew), __ldcg(p.sumx + knew), d.xv, p.m0, p.v0, p.vv);
+    if (p.datum == BIAS_INT)
+        return ((double)__ldcg(p.n_wk + (size_t)d.w * Kpad + knew) + p.beta) /
+               ((double)__ldcg(p.n_k + knew) + p.beta * (double)p.V);
+    double part = 0.0;
+    const double den = (double)__ldcg(p.n_k + knew) + p.beta * (double)p.V;
+    for (int64_t t = d.s0 + lane; t < d.s1; t += 32)
+        part += (double)p.sent_count[t] *
+                (((double)__ldcg(p.n_wk + (size_t)p.sent_word[t] * Kpad + knew) + p.beta) / den);
+    return warp_sum(part);
+}
+
+#ifdef BIAS_GENERIC_KERNEL_IMPL      // the kernel itself is emitted by model.cu only
 __global__ void __launch_bounds__(kGenThreads)
 generic_sweep_kernel(const GenericParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -130,76 +319,8 @@ generic_sweep_kernel(const GenericParams p) {
         const int64_t i = p.item_idx ? p.item_idx[q] : (p.work_idx32 ? (int64_t)p.work_idx32[q] : q);
         const int zold = p.z[i];                      // -1: the item is currently unassigned (HDP pending)
         int32_t *prow = p.prior_rows + (p.row_of ? (size_t)p.row_of[p.row_by_work ? q : i] * Kpad : 0);
-
-        // ---- the datum ----
-        int w = 0;
-        double xv = 0.0;
-        int64_t s0 = 0, s1 = 0;
-        double m_tot = 0.0, coef = 0.0;
-        if (p.datum == BIAS_INT) {
-            w = p.word[i];
-        } else if (p.datum == BIAS_F64) {
-            xv = p.x[i];
-        } else {
-            s0 = p.sent_ptr[i];
-            s1 = p.sent_ptr[i + 1];
-            double mloc = 0.0, lg = 0.0;
-            for (int64_t t = s0 + lane; t < s1; t += 32) {
-                const double c = (double)p.sent_count[t];
-                mloc += c;
-                lg += lgamma(c + 1.0);
-            }
-            m_tot = warp_sum(mloc);
-            coef = lgamma(m_tot + 1.0) - warp_sum(lg);   // k-independent, src/conjugates.jl:193
-        }
-
-        // ---- K (+1) scores ----
-        double lmax = -INFINITY;
-        for (int k = lane; k < n_out; k += 32) {
-            const bool own = (k == zold);
-            const bool fresh = (k >= K);                  // HDP new-component slot: the empty prototype
-            double prior;
-            if (is_hdp) {
-                prior = fresh ? log(p.alpha * p.hdp_beta[K])
-                              : log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + p.alpha * p.hdp_beta[k]);
-            } else {
-                prior = log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + p.alpha);
-            }
-            double lp;
-            if (p.kind == BIAS_G1G1) {
-                double n = 0.0, sx = 0.0;
-                if (!fresh) {
-                    n = (double)(__ldcg(p.n_items + k) - (own ? 1 : 0));
-                    sx = __ldcg(p.sumx + k) - (own ? xv : 0.0);
-                }
-                lp = g1g1_logpred(n, sx, xv, p.m0, p.v0, p.vv);
-            } else if (p.datum == BIAS_INT) {
-                double nw = 0.0, nk = 0.0;
-                if (!fresh) {
-                    nw = (double)(__ldcg(p.n_wk + (size_t)w * Kpad + k) - (own ? 1 : 0));
-                    nk = (double)(__ldcg(p.n_k + k) - (own ? 1 : 0));
-                }
-                lp = log((p.beta + nw) / (p.beta * (double)p.V + nk));       // src/conjugates.jl:180
-            } else {
-                double nk = 0.0;
-                if (!fresh) nk = (double)__ldcg(p.n_k + k) - (own ? m_tot : 0.0);
-                double acc = 0.0;
-                for (int64_t t = s0; t < s1; ++t) {
-                    const int wt = p.sent_word[t];
-                    const double ct = (double)p.sent_count[t];
-                    double nw = 0.0;
-                    if (!fresh) nw = (double)__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0.0);
-                    acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
-                }
-                const double bv = p.beta * (double)p.V;
-                lp = coef + lgamma(bv + nk) - lgamma(bv + nk + m_tot) + acc; // src/conjugates.jl:193-195
-            }
-            const double s = prior + lp;
-            sc[k] = s;
-            lmax = fmax(lmax, s);
-        }
-        lmax = warp_max(lmax);
-        __syncwarp();
+        const Datum d = load_datum(p, i, lane);
+        const double lmax = score_all(p, d, zold, K, n_out, prow, p.hdp_beta, p.alpha, sc, lane);
 
         const int64_t uidx = (p.item_idx || p.work_idx32) ? q : i;
         double u;
@@ -211,54 +332,16 @@ generic_sweep_kernel(const GenericParams p) {
             u = u01_double(o[0], o[1]);
         }
 
-        int knew = 0;
+        int knew;
         if (p.faithful) {
             if (p.raw_out)
                 for (int k = lane; k < n_out; k += 32) p.raw_out[(size_t)q * n_out + k] = sc[k];
             __syncwarp();
-            if (lane == 0) {
-                for (int k = 0; k < n_out; ++k) sc[k] = exp(sc[k] - lmax);
-                const double tot = jsum_dev(sc, 0, n_out - 1);
-                for (int k = 0; k < n_out; ++k) sc[k] /= tot;
-                int idx = 0;
-                double cw = sc[0];
-                while (cw < u && idx < n_out - 1) {
-                    idx += 1;
-                    cw += sc[idx];
-                }
-                knew = idx;
-            }
-            knew = __shfl_sync(kFull, knew, 0);
-            __syncwarp();
+            knew = draw_faithful(sc, n_out, lmax, u, lane);
             if (p.prob_out)
                 for (int k = lane; k < n_out; k += 32) p.prob_out[(size_t)q * n_out + k] = sc[k];
         } else {
-            // production: exp in parallel, CDF by 32-wide chunk scans in k order
-            double carry = 0.0;
-            for (int b = 0; b < n_out; b += 32) {
-                const int k = b + lane;
-                double e = 0.0;
-                if (k < n_out) {
-                    e = exp(sc[k] - lmax);
-                    sc[k] = e;
-                }
-                carry += warp_sum(e);
-            }
-            __syncwarp();
-            const double target = u * carry;
-            double base = 0.0;
-            knew = n_out - 1;
-            for (int b = 0; b < n_out; b += 32) {
-                const int k = b + lane;
-                const double e = (k < n_out) ? sc[k] : 0.0;
-                const double incl = base + warp_incl_scan(e, lane);
-                const unsigned bal = __ballot_sync(kFull, (k < n_out) && (incl >= target));
-                if (bal) {
-                    knew = b + __ffs(bal) - 1;
-                    break;
-                }
-                base = __shfl_sync(kFull, incl, 31);
-            }
+            knew = draw_parallel(sc, n_out, lmax, u, lane);
         }
         __syncwarp();
 
@@ -267,69 +350,26 @@ generic_sweep_kernel(const GenericParams p) {
             continue;
         }
 
-        // ---- HDP: a draw of the new-component slot is deferred to the serial birth pass ----
+        // HDP: a draw of the new-component slot is deferred to the serial birth pass
         const bool born = is_hdp && knew >= K;
-        const int kdst = born ? -1 : knew;
-        if (kdst != zold) {
-            // remove from zold (if assigned), add to kdst (if not deferred)
-            if (p.kind == BIAS_MD) {
-                if (p.datum == BIAS_INT) {
-                    if (lane == 0) {
-                        if (zold >= 0) { atomicAdd(p.n_wk + (size_t)w * Kpad + zold, -1); atomicAdd(p.n_k + zold, -1); }
-                        if (kdst >= 0) { atomicAdd(p.n_wk + (size_t)w * Kpad + kdst, 1); atomicAdd(p.n_k + kdst, 1); }
-                    }
-                } else {
-                    for (int64_t t = s0 + lane; t < s1; t += 32) {
-                        const int wt = p.sent_word[t], ct = p.sent_count[t];
-                        if (zold >= 0) atomicAdd(p.n_wk + (size_t)wt * Kpad + zold, -ct);
-                        if (kdst >= 0) atomicAdd(p.n_wk + (size_t)wt * Kpad + kdst, ct);
-                    }
-                    if (lane == 0) {
-                        if (zold >= 0) atomicAdd(p.n_k + zold, -(int)m_tot);
-                        if (kdst >= 0) atomicAdd(p.n_k + kdst, (int)m_tot);
-                    }
-                }
-            } else if (lane == 0) {
-                if (zold >= 0) atomicAdd(p.sumx + zold, -xv);
-                if (kdst >= 0) atomicAdd(p.sumx + kdst, xv);
-            }
+        if (born) {
+            // leave the item unassigned and queue it (also when it was already unassigned)
+            if (zold >= 0) apply_move(p, d, zold, -1, prow, lane);
             if (lane == 0) {
-                if (zold >= 0) atomicAdd(p.n_items + zold, -1);
-                if (kdst >= 0) atomicAdd(p.n_items + kdst, 1);
-                if (!p.prior_is_items) {
-                    if (zold >= 0) atomicAdd(prow + zold, -1);
-                    if (kdst >= 0) atomicAdd(prow + kdst, 1);
-                }
-                p.z[i] = kdst;
-                if (born) {
-                    const unsigned slot = atomicAdd(p.pending_count, 1u);
-                    p.pending_list[slot] = (int32_t)i;
-                } else {
-                    moved_acc += 1;
-                }
+                p.z[i] = -1;
+                const unsigned slot = atomicAdd(p.pending_count, 1u);
+                p.pending_list[slot] = (int32_t)i;
+            }
+        } else if (knew != zold) {
+            apply_move(p, d, zold, knew, prow, lane);
+            if (lane == 0) {
+                p.z[i] = knew;
+                moved_acc += 1;
             }
         }
-
-        // ---- the reference's per-item diagnostic, evaluated after the add (src/LDA.jl:131) ----
         if (!born && p.diag_sum) {
-            if (p.kind == BIAS_G1G1) {
-                if (lane == 0) {
-                    const double n = (double)__ldcg(p.n_items + knew);
-                    diag_acc += g1g1_loglik(n, __ldcg(p.sumx + knew), xv, p.m0, p.v0, p.vv);
-                }
-            } else if (p.datum == BIAS_INT) {
-                if (lane == 0)
-                    diag_acc += ((double)__ldcg(p.n_wk + (size_t)w * Kpad + knew) + p.beta) /
-                                ((double)__ldcg(p.n_k + knew) + p.beta * (double)p.V);
-            } else {
-                double part = 0.0;
-                const double den = (double)__ldcg(p.n_k + knew) + p.beta * (double)p.V;
-                for (int64_t t = s0 + lane; t < s1; t += 32)
-                    part += (double)p.sent_count[t] *
-                            (((double)__ldcg(p.n_wk + (size_t)p.sent_word[t] * Kpad + knew) + p.beta) / den);
-                part = warp_sum(part);
-                if (lane == 0) diag_acc += part;
-            }
+            const double dv = diag_after(p, d, knew, lane);
+            if (lane == 0) diag_acc += dv;
         }
     }
 
@@ -338,6 +378,8 @@ generic_sweep_kernel(const GenericParams p) {
         if (p.moved && moved_acc) atomicAdd(p.moved, moved_acc);
     }
 }
+
+#endif  // BIAS_GENERIC_KERNEL_IMPL
 
 #endif  // __CUDACC__
 

@@ -1,14 +1,659 @@
-// hdp.cu — placeholder until the HDP kernels land (replaced later in this round).
+// hdp.cu — direct-assignment HDP sampler (reference src/HDP.jl:166-399) on the GPU.
+//
+// One sweep =
+//   1. parallel assignment pass over all items with K+1 outcomes (generic_sweep_kernel,
+//      src/HDP.jl:285-317).  A draw of the (K+1)-th outcome cannot be resolved in parallel —
+//      a birth changes K and splits the stick for everyone after it (src/HDP.jl:320-331) —
+//      so such items are left unassigned and queued;
+//   2. serial birth pass: one warp walks a bounded slice of the queue with the reference's exact
+//      sequential semantics (K+1 conditional on the live state, b ~ Beta(1, gamma), stick split);
+//      the rest of the queue is then re-sampled in parallel against the enlarged component set,
+//      and so on until the queue is empty;
+//   3. prune: components that lost their last item are removed, every zz above them shifts down
+//      and their stick returns to the unrepresented mass (src/HDP.jl:291-307, 248-264) — done
+//      once per sweep as a column compaction instead of at each death;
+//   4. n_internals x { table counts from the device-resident Stirling table (src/HDP.jl:348-361),
+//      beta ~ Dirichlet (:362-364, host, K+1 gamma draws), alpha0 / gamma resampling
+//      (:369-372 -> :124-159; the O(groups) auxiliary draws run on the device) }.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
 #include "model.hpp"
-using namespace bias;
+#include "generic.cuh"
+
 namespace bias {
-int ensure_stirling(bias_ctx *, int32_t) { return fail(BIAS_EINVAL, "HDP not built yet"); }
-int hdp_create(bias_model *, const bias_hdp_params *) { return fail(BIAS_EINVAL, "HDP not built yet"); }
-int hdp_sweep(bias_model *) { return fail(BIAS_EINVAL, "HDP not built yet"); }
-int hdp_destroy(bias_model *) { return BIAS_OK; }
+
+// ---------------------------------------------------------------------------------------
+// Stirling table: normalised log unsigned Stirling numbers of the first kind, packed lower
+// triangle, row n (1-based) at offset n(n-1)/2.  s(n+1,m) = n s(n,m) + s(n,m-1) in log space;
+// every row is shifted so that its maximum is 0 (any row scaling cancels in lognormalize!).
+// Regenerates the reference's missing StirlingNums_10K.mat (src/HDP.jl:207-209).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) stirling_build_kernel(double *tab, int nmax) {
+    __shared__ double red[32];
+    __shared__ double row_max;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) tab[0] = 0.0;
+    __syncthreads();
+    for (int n = 1; n < nmax; ++n) {
+        const double *prev = tab + (size_t)n * (n - 1) / 2;
+        double *cur = tab + (size_t)(n + 1) * n / 2;
+        const double logn = log((double)n);
+        double mx = -INFINITY;
+        for (int m = tid + 1; m <= n + 1; m += 1024) {
+            const double a = (m <= n) ? logn + prev[m - 1] : -INFINITY;
+            const double b = (m >= 2) ? prev[m - 2] : -INFINITY;
+            const double hi = a > b ? a : b, lo = a > b ? b : a;
+            const double v = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
+            cur[m - 1] = v;
+            mx = fmax(mx, v);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) red[wid] = mx;
+        __syncthreads();
+        if (wid == 0) {
+            double v = red[lane];
+            v = warp_max(v);
+            if (lane == 0) row_max = v;
+        }
+        __syncthreads();
+        const double rm = row_max;
+        for (int m = tid + 1; m <= n + 1; m += 1024) cur[m - 1] -= rm;
+        __syncthreads();
+    }
 }
+
+int ensure_stirling(bias_ctx *ctx, int32_t rows) {
+    if (rows < 1) rows = 1;
+    if (ctx->stirling && ctx->stirling_rows >= rows) return BIAS_OK;
+    if (rows > 10000) rows = 10000;             // the reference's table is 10k x 10k (src/HDP.jl:207)
+    if (ctx->stirling && ctx->stirling_rows >= rows) return BIAS_OK;
+    BIAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stirling) cudaFree(ctx->stirling);
+    ctx->stirling = nullptr;
+    ctx->stirling_rows = 0;
+    const size_t n = (size_t)rows * (rows + 1) / 2;
+    BIAS_CUDA_TRY(cudaMalloc((void **)&ctx->stirling, n * sizeof(double)));
+    stirling_build_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->stirling, rows);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->stirling_rows = rows;
+    return BIAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// small counter-based random stream for device-side Gamma / Beta draws
+// ---------------------------------------------------------------------------------------
+struct PhiloxStream {
+    Philox ph;
+    uint32_t c0, c1, c2, ctr;
+    uint32_t buf[4];
+    int have;
+    __device__ PhiloxStream(uint64_t seed, uint32_t a, uint32_t b, uint32_t c) : ph(seed), c0(a), c1(b), c2(c), ctr(0), have(0) {}
+    __device__ double u01() {
+        if (have < 2) {
+            ph(c0, c1, c2, ctr++, buf);
+            have = 4;
+        }
+        const double u = u01_double(buf[have - 1], buf[have - 2]);
+        have -= 2;
+        return u;
+    }
+    __device__ double normal() {
+        const double u1 = u01(), u2 = u01();
+        return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+    }
+    __device__ double gamma(double shape) {     // Marsaglia-Tsang
+        double boost = 1.0;
+        if (shape < 1.0) {
+            boost = pow(u01(), 1.0 / shape);
+            shape += 1.0;
+        }
+        const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (int it = 0; it < 64; ++it) {
+            double x, v;
+            do {
+                x = normal();
+                v = 1.0 + c * x;
+            } while (v <= 0.0);
+            v = v * v * v;
+            const double u = u01();
+            if (u < 1.0 - 0.0331 * x * x * x * x || log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return boost * d * v;
+        }
+        return boost * d;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// table counts: M_jk ~ p(m | n_jk, alpha0 beta_k) ∝ s(n_jk, m) (alpha0 beta_k)^m   (src/HDP.jl:348-361)
+// one warp per group; sums of M over groups accumulate in tables[k], the grand total in tables[Kpad]
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int table_draw(const double *row, int n, double la, double u, int lane, bool faithful,
+                                          double *prob_out) {
+    // scores v_m = row[m-1] + m*la, m = 1..n
+    double lmax = -INFINITY;
+    for (int m = lane + 1; m <= n; m += 32) lmax = fmax(lmax, row[m - 1] + (double)m * la);
+    lmax = warp_max(lmax);
+    if (faithful) {
+        // lane 0 alone, reference operation order (lognormalize! then sample)
+        int res = 1;
+        if (lane == 0) {
+            double tot = 0.0;
+            // Base.sum association for n <= 1024 is left to right; above that pairwise halves
+            if (n <= 1024) {
+                for (int m = 1; m <= n; ++m) {
+                    const double e = exp(row[m - 1] + (double)m * la - lmax);
+                    prob_out[m - 1] = e;
+                    tot = (m == 1) ? e : tot + e;
+                }
+            } else {
+                for (int m = 1; m <= n; ++m) prob_out[m - 1] = exp(row[m - 1] + (double)m * la - lmax);
+                tot = jsum_dev(prob_out, 0, n - 1);
+            }
+            for (int m = 1; m <= n; ++m) prob_out[m - 1] /= tot;
+            int idx = 0;
+            double cw = prob_out[0];
+            while (cw < u && idx < n - 1) {
+                idx += 1;
+                cw += prob_out[idx];
+            }
+            res = idx + 1;
+        }
+        return __shfl_sync(kFull, res, 0);
+    }
+    double total = 0.0;
+    for (int b = 0; b < n; b += 32) {
+        const int m = b + lane + 1;
+        const double e = (m <= n) ? exp(row[m - 1] + (double)m * la - lmax) : 0.0;
+        total += warp_sum(e);
+    }
+    const double target = u * total;
+    double base = 0.0;
+    int res = n;
+    for (int b = 0; b < n; b += 32) {
+        const int m = b + lane + 1;
+        const double e = (m <= n) ? exp(row[m - 1] + (double)m * la - lmax) : 0.0;
+        const double incl = base + warp_incl_scan(e, lane);
+        const unsigned bal = __ballot_sync(kFull, (m <= n) && (incl >= target));
+        if (bal) {
+            res = b + __ffs(bal);
+            break;
+        }
+        base = __shfl_sync(kFull, incl, 31);
+    }
+    return res;
+}
+
+__global__ void __launch_bounds__(128)
+hdp_tables_kernel(const int32_t *rows, int64_t G, int Kpad, int KK, const double *beta, double aa,
+                  const double *stirling, int stirling_rows, uint64_t seed, uint32_t sweep, uint32_t internal,
+                  unsigned long long *tables, int *err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const Philox philox(seed);
+    for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < G; j += nw) {
+        for (int k = 0; k < KK; ++k) {
+            const int n = rows[(size_t)j * Kpad + k];
+            if (n <= 0) continue;
+            if (n > stirling_rows) {            // the reference indexes past its 10k table: BoundsError
+                if (lane == 0) *err = 1;
+                continue;
+            }
+            uint32_t o[4];
+            philox((uint32_t)j, (uint32_t)((uint64_t)j >> 32) ^ ((uint32_t)k << 8), sweep * 64u + internal, kStreamTable, o);
+            const double u = u01_double(o[0], o[1]);
+            const double *row = stirling + (size_t)n * (n - 1) / 2;
+            const int mjk = table_draw(row, n, log(aa * beta[k]), u, lane, false, nullptr);
+            if (lane == 0) {
+                atomicAdd(tables + k, (unsigned long long)mjk);
+                atomicAdd(tables + Kpad, (unsigned long long)mjk);
+            }
+        }
+    }
+}
+
+__global__ void hdp_table_conditionals_kernel(const int32_t *n_arr, const double *a_arr, const double *u_arr,
+                                              int64_t nq, int n_max, const double *stirling, double *prob,
+                                              int32_t *draws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nw) {
+        const int n = n_arr[q];
+        const double *row = stirling + (size_t)n * (n - 1) / 2;
+        const int m = table_draw(row, n, log(a_arr[q]), u_arr[q], lane, true, prob + (size_t)q * n_max);
+        if (lane == 0) draws[q] = m;
+    }
+}
+
+// alpha0 auxiliaries (src/HDP.jl:133-147): w_j ~ Beta(aa+1, n_j), s_j ~ Bernoulli(n_j / (n_j + aa)).
+// out[0] += sum_j log w_j, out[1] += sum_j s_j
+__global__ void hdp_hyper_kernel(const int64_t *group_ptr, int64_t G, double aa, uint64_t seed, uint32_t sweep,
+                                 uint32_t internal, double *out) {
+    double lw = 0.0, ss = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G; j += (int64_t)gridDim.x * blockDim.x) {
+        const double nj = (double)(group_ptr[j + 1] - group_ptr[j]);
+        PhiloxStream rs(seed, (uint32_t)j, (uint32_t)((uint64_t)j >> 32), (sweep * 64u + internal) * 8u + kStreamHyper);
+        if (nj > 0.0) {
+            const double ga = rs.gamma(aa + 1.0), gb = rs.gamma(nj);
+            lw += log(ga / (ga + gb));
+            ss += (rs.u01() < nj / (nj + aa)) ? 1.0 : 0.0;
+        }
+    }
+    lw = warp_sum(lw);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, lw);
+        atomicAdd(out + 1, ss);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// serial birth pass (src/HDP.jl:312-338 with the reference's sequential semantics): one warp
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK, double *beta, double gg,
+                 int Kmax, int *err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sc = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    int KK = *d_KK;
+    double diag_acc = 0.0;
+    unsigned long long moved = 0;
+    for (int q = 0; q < n_list; ++q) {
+        const int64_t i = list[q];
+        int32_t *prow = p.prior_rows + (size_t)p.row_of[i] * p.Kpad;
+        const Datum d = load_datum(p, i, lane);
+        const double lmax = score_all(p, d, -1, KK, KK + 1, prow, beta, p.alpha, sc, lane);
+        PhiloxStream rs(p.seed, (uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep * 8u + kStreamBirth);
+        const double u = rs.u01();
+        int knew = draw_parallel(sc, KK + 1, lmax, u, lane);
+        if (knew == KK) {
+            if (KK + 2 > Kmax) {                 // slot capacity exhausted
+                if (lane == 0) *err = 2;
+                knew = KK - 1;
+            } else {
+                const double b = 1.0 - pow(1.0 - rs.u01(), 1.0 / gg);      // Beta(1, gg), src/HDP.jl:325
+                if (lane == 0) {
+                    const double b_new = beta[KK];
+                    beta[KK] = b * b_new;                                   // :326-328
+                    beta[KK + 1] = (1.0 - b) * b_new;
+                }
+                KK += 1;
+                __syncwarp();
+            }
+        }
+        apply_move(p, d, -1, knew, prow, lane);
+        if (lane == 0) p.z[i] = knew;
+        __threadfence();
+        __syncwarp();
+        const double dv = diag_after(p, d, knew, lane);
+        if (lane == 0) diag_acc += dv;
+        moved += 1;
+    }
+    if (lane == 0) {
+        *d_KK = KK;
+        atomicAdd(p.diag_sum, diag_acc);
+        atomicAdd(p.moved, moved);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// prune: column compaction of an int32 table [rows][Kpad] with remap[k] = new index or -1
+// ---------------------------------------------------------------------------------------
+__global__ void compact_columns_kernel(int32_t *tab, int64_t rows, int Kpad, int KK_old, const int32_t *remap) {
+    extern __shared__ int32_t buf[];
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        int32_t *row = tab + (size_t)r * Kpad;
+        for (int k = threadIdx.x; k < KK_old; k += blockDim.x) buf[k] = row[k];
+        __syncthreads();
+        for (int k = threadIdx.x; k < KK_old; k += blockDim.x) row[k] = 0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < KK_old; k += blockDim.x) {
+            const int nk = remap[k];
+            if (nk >= 0) row[nk] = buf[k];
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void remap_z_kernel(int32_t *z, int64_t N, const int32_t *remap) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = z[i];
+        if (k >= 0) z[i] = remap[k];
+    }
+}
+
+static int grid1d(bias_ctx *ctx, int64_t n, int threads, int per_sm = 8) {
+    int64_t blocks = (n + threads - 1) / threads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)ctx->num_sms * per_sm));
+}
+
+static int hdp_prune(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int KK = m->hdp.KK, Kpad = m->Kpad;
+    std::vector<int32_t> ni(Kpad), nk(Kpad);
+    std::vector<double> sx;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(ni.data(), m->n_items, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(nk.data(), m->n_k, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
+    if (m->sumx) {
+        sx.resize(Kpad);
+        BIAS_CUDA_TRY(cudaMemcpyAsync(sx.data(), m->sumx, (size_t)Kpad * 8, cudaMemcpyDeviceToHost, st));
+    }
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int32_t> remap(Kpad, -1);
+    int alive = 0;
+    for (int k = 0; k < KK; ++k)
+        if (ni[k] > 0) remap[k] = alive++;
+    if (alive == KK) return BIAS_OK;
+    if (alive == 0) {            // keep one (empty) component: the reference cannot reach KK = 0 with data present
+        remap[0] = 0;
+        alive = 1;
+    }
+    // sticks of the removed components return to the unrepresented mass (src/HDP.jl:303-305)
+    std::vector<double> nb(m->h_beta.size(), 0.0);
+    double rest = m->h_beta[KK];
+    std::vector<int32_t> n_ni(Kpad, 0), n_nk(Kpad, 0);
+    std::vector<double> n_sx(Kpad, 0.0);
+    for (int k = 0; k < KK; ++k) {
+        if (remap[k] >= 0) {
+            nb[remap[k]] = m->h_beta[k];
+            n_ni[remap[k]] = ni[k];
+            n_nk[remap[k]] = nk[k];
+            if (m->sumx) n_sx[remap[k]] = sx[k];
+        } else {
+            rest += m->h_beta[k];
+        }
+    }
+    nb[alive] = rest;
+    m->h_beta = nb;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_remap, remap.data(), (size_t)Kpad * 4, cudaMemcpyHostToDevice, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->n_items, n_ni.data(), (size_t)Kpad * 4, cudaMemcpyHostToDevice, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->n_k, n_nk.data(), (size_t)Kpad * 4, cudaMemcpyHostToDevice, st));
+    if (m->sumx) BIAS_CUDA_TRY(cudaMemcpyAsync(m->sumx, n_sx.data(), (size_t)Kpad * 8, cudaMemcpyHostToDevice, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), m->h_beta.size() * 8, cudaMemcpyHostToDevice, st));
+    if (m->N > 0) {
+        remap_z_kernel<<<grid1d(ctx, m->N, 256), 256, 0, st>>>(m->z, m->N, m->d_remap);
+        ctx->launches += 1;
+    }
+    if (m->G > 0) {
+        compact_columns_kernel<<<grid1d(ctx, m->G * 128, 128), 128, (size_t)KK * 4, st>>>(m->group_rows, m->G, Kpad, KK, m->d_remap);
+        ctx->launches += 1;
+    }
+    if (m->conj.kind == BIAS_MD) {
+        compact_columns_kernel<<<grid1d(ctx, m->V * 128, 128), 128, (size_t)KK * 4, st>>>(m->n_wk, m->V, Kpad, KK, m->d_remap);
+        ctx->launches += 1;
+    }
+    BIAS_CUDA_TRY(cudaGetLastError());
+    // the host vectors above must outlive the async copies
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->hdp.KK = alive;
+    return BIAS_OK;
+}
+
+int hdp_create(bias_model *m, const bias_hdp_params *hp) {
+    m->hdp = *hp;
+    const int Kpad = m->Kpad;
+    m->h_beta.assign((size_t)Kpad + 1, 0.0);
+    for (int k = 0; k <= hp->KK; ++k) m->h_beta[k] = 1.0 / (double)(hp->KK + 1);       // src/HDP.jl:228
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_beta, ((size_t)Kpad + 1) * 8));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, m->ctx->stream));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->pending, (size_t)std::max<int64_t>(1, m->N) * 2 * 4));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_KK, 4 * sizeof(int32_t)));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->d_KK, 0, 4 * sizeof(int32_t), m->ctx->stream));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_tables, ((size_t)Kpad + 1) * 8));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_hyper, 2 * 8));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_remap, (size_t)Kpad * 4));
+    m->host_rng.seed(m->ctx->seed ^ 0x9E3779B97F4A7C15ull);
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    return BIAS_OK;
+}
+
+int hdp_destroy(bias_model *m) {
+    for (void *p : {(void *)m->d_beta, (void *)m->pending, (void *)m->d_KK, (void *)m->d_tables, (void *)m->d_hyper,
+                    (void *)m->d_remap})
+        if (p) cudaFree(p);
+    m->d_beta = nullptr;
+    m->pending = nullptr;
+    m->d_KK = nullptr;
+    m->d_tables = nullptr;
+    m->d_hyper = nullptr;
+    m->d_remap = nullptr;
+    return BIAS_OK;
+}
+
+static GenericParams birth_params(bias_model *m) {
+    GenericParams p{};
+    p.model = BIAS_MODEL_HDP;
+    p.kind = m->conj.kind;
+    p.datum = m->conj.datum;
+    p.K = m->hdp.KK;
+    p.Kpad = m->Kpad;
+    p.n_out = p.K + 1;
+    p.row_of = m->group_of;
+    p.prior_rows = m->group_rows;
+    p.word = m->word;
+    p.x = m->x;
+    p.sent_ptr = m->sent_ptr;
+    p.sent_word = m->sent_word;
+    p.sent_count = m->sent_count;
+    p.z = m->z;
+    p.n_wk = m->n_wk;
+    p.n_k = m->n_k;
+    p.n_items = m->n_items;
+    p.sumx = m->sumx;
+    p.V = m->V;
+    p.beta = m->conj.aa;
+    p.m0 = m->conj.m0;
+    p.v0 = m->conj.v0;
+    p.vv = m->conj.vv;
+    p.alpha = m->hdp.aa;
+    p.seed = m->ctx->seed;
+    p.sweep = m->sweep_index;
+    p.diag_sum = reinterpret_cast<double *>(m->scratch);
+    p.moved = m->scratch + 1;
+    return p;
+}
+
+int hdp_sweep(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int Kpad = m->Kpad, Kmax = m->hdp.Kmax;
+    unsigned int *d_pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
+    int *d_err = reinterpret_cast<int *>(m->scratch + 4);
+
+    BIAS_TRY(hdp_prune(m));                       // src/HDP.jl:248-264
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 6 * sizeof(unsigned long long), st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+
+    // 1. parallel assignment pass
+    int32_t *list_cur = m->pending, *list_next = m->pending + std::max<int64_t>(1, m->N);
+    m->pending = list_cur;
+    BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, m->group_of, m->group_rows, nullptr, 0, 0, nullptr, nullptr,
+                            nullptr, kStreamItemDraw));
+    // 2. births
+    uint32_t round = 0;
+    for (;;) {
+        unsigned int n_pending = 0;
+        int err = 0;
+        BIAS_CUDA_TRY(cudaMemcpyAsync(&n_pending, d_pending_count, 4, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (n_pending == 0) break;
+        const int n_serial = (int)std::min<unsigned int>(n_pending, 256u);
+        GenericParams bp = birth_params(m);
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
+        hdp_birth_kernel<<<1, 32, ((size_t)Kmax + 4) * 8, st>>>(bp, list_cur, n_serial, m->d_KK, m->d_beta, m->hdp.gg,
+                                                                 Kmax, d_err);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+        int32_t kk_new = 0;
+        BIAS_CUDA_TRY(cudaMemcpyAsync(&kk_new, m->d_KK, 4, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->h_beta.data(), m->d_beta, ((size_t)Kpad + 1) * 8, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+        m->hdp.KK = kk_new;
+        if (err == 2)
+            return fail(BIAS_ERANGE, "HDP: Kmax = %d component slots exhausted (KK = %d); construct the model with a larger Kmax",
+                        Kmax, kk_new);
+        const int64_t rest = (int64_t)n_pending - n_serial;
+        BIAS_CUDA_TRY(cudaMemsetAsync(d_pending_count, 0, 4, st));
+        if (rest > 0) {
+            // re-sample the remainder of the queue in parallel against the enlarged component set;
+            // items that draw the new slot again land in the other half of the queue buffer
+            m->pending = list_next;
+            round += 1;
+            const uint32_t saved = m->sweep_index;
+            BIAS_TRY(launch_generic(m, rest, nullptr, list_cur + n_serial, m->group_of, m->group_rows, nullptr, 0, 0,
+                                    nullptr, nullptr, nullptr, kStreamBirth + 8 * round));
+            m->sweep_index = saved;
+            std::swap(list_cur, list_next);
+        }
+    }
+    m->pending = std::min(list_cur, list_next);
+    // 3. prune components that died during the pass (src/HDP.jl:291-307)
+    BIAS_TRY(hdp_prune(m));
+    const int KK = m->hdp.KK;
+
+    // 4. beta, alpha0, gamma (src/HDP.jl:343-373)
+    const int64_t max_len = m->max_group_len;
+    BIAS_TRY(ensure_stirling(ctx, (int32_t)std::min<int64_t>(max_len, 10000)));
+    std::vector<unsigned long long> tables((size_t)Kpad + 1);
+    for (int hh = 0; hh < m->hdp.n_internals; ++hh) {
+        BIAS_CUDA_TRY(cudaMemsetAsync(m->d_tables, 0, ((size_t)Kpad + 1) * 8, st));
+        BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (m->G > 0) {
+            hdp_tables_kernel<<<grid1d(ctx, m->G * 32, 128, 16), 128, 0, st>>>(
+                m->group_rows, m->G, Kpad, KK, m->d_beta, m->hdp.aa, ctx->stirling, ctx->stirling_rows, ctx->seed,
+                m->sweep_index, (uint32_t)hh, reinterpret_cast<unsigned long long *>(m->d_tables), d_err);
+            ctx->launches += 1;
+            if (m->hdp.sample_hyperparam) {
+                hdp_hyper_kernel<<<grid1d(ctx, m->G, 128, 4), 128, 0, st>>>(m->group_ptr, m->G, m->hdp.aa, ctx->seed,
+                                                                           m->sweep_index, (uint32_t)hh, m->d_hyper);
+                ctx->launches += 1;
+            }
+            BIAS_CUDA_TRY(cudaGetLastError());
+        }
+        double hyper[2] = {0.0, 0.0};
+        int err = 0;
+        BIAS_CUDA_TRY(cudaMemcpyAsync(tables.data(), m->d_tables, ((size_t)Kpad + 1) * 8, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+        if (err == 1)
+            return fail(BIAS_ERANGE, "HDP: some n_jk exceeds the %d-row Stirling table (the reference throws BoundsError, src/HDP.jl:355)",
+                        ctx->stirling_rows);
+        // beta ~ Dirichlet([sum_j M_jk ..., gg])  (src/HDP.jl:362-364)
+        double tot = 0.0;
+        for (int k = 0; k <= KK; ++k) {
+            const double a = (k < KK) ? (double)tables[k] : m->hdp.gg;
+            double g = 0.0;
+            if (a > 0.0) {
+                std::gamma_distribution<double> gd(a, 1.0);
+                g = gd(m->host_rng);
+            }
+            m->h_beta[k] = g;
+            tot += g;
+        }
+        for (int k = 0; k <= KK; ++k) m->h_beta[k] = tot > 0.0 ? m->h_beta[k] / tot : 1.0 / (KK + 1);
+        for (size_t k = (size_t)KK + 1; k < m->h_beta.size(); ++k) m->h_beta[k] = 0.0;
+        if (m->hdp.sample_hyperparam) {            // src/HDP.jl:124-159
+            const double mt = (double)tables[Kpad];
+            const double aa_shape = m->hdp.a1 + mt - hyper[1];
+            const double aa_rate = m->hdp.a2 - hyper[0];
+            if (aa_shape > 0.0 && aa_rate > 0.0) {
+                std::gamma_distribution<double> ga(aa_shape, 1.0);
+                m->hdp.aa = ga(m->host_rng) / aa_rate;
+            }
+            std::gamma_distribution<double> g1(m->hdp.gg + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
+            const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
+            const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
+            const double le = std::log(eta);
+            const double pi_eta = 1.0 / (1.0 + (mt * (m->hdp.g2 - le)) / (m->hdp.g1 + KK - 1.0));   // :152
+            std::uniform_real_distribution<double> ud(0.0, 1.0);
+            const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
+            if (shape > 0.0) {
+                std::gamma_distribution<double> gg(shape, 1.0);
+                m->hdp.gg = gg(m->host_rng) / (m->hdp.g2 - le);
+            }
+        }
+    }
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    return BIAS_OK;
+}
+
+}  // namespace bias
+
+using namespace bias;
+
 extern "C" {
-int bias_model_get_hdp(bias_model *, bias_hdp_params *, double *) { return fail(BIAS_EINVAL, "HDP not built yet"); }
-int bias_hdp_table_conditionals(bias_ctx *, int64_t, const int32_t *, const double *, const double *, int32_t, double *, int32_t *) { return fail(BIAS_EINVAL, "HDP not built yet"); }
-int bias_stirling_rows(bias_ctx *, int32_t, double *) { return fail(BIAS_EINVAL, "HDP not built yet"); }
+
+int bias_model_get_hdp(bias_model *m, bias_hdp_params *params, double *beta) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (m->model != BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "not an HDP model");
+    if (params) *params = m->hdp;
+    if (beta) {
+        const int n = m->hdp.Kmax + 1;
+        for (int k = 0; k < n; ++k) beta[k] = (k < (int)m->h_beta.size()) ? m->h_beta[k] : 0.0;
+    }
+    return BIAS_OK;
 }
+
+int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out) {
+    if (!ctx || !out) return fail(BIAS_EINVAL, "null argument");
+    if (n_rows < 1 || n_rows > 10000) return fail(BIAS_EINVAL, "n_rows must be in [1, 10000]");
+    BIAS_CUDA_TRY(cudaSetDevice(ctx->device));
+    BIAS_TRY(ensure_stirling(ctx, n_rows));
+    const size_t n = (size_t)n_rows * (n_rows + 1) / 2;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(out, ctx->stirling, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return BIAS_OK;
+}
+
+int bias_hdp_table_conditionals(bias_ctx *ctx, int64_t n_query, const int32_t *n, const double *a,
+                                const double *uniforms, int32_t n_max, double *prob, int32_t *draws) {
+    if (!ctx || !n || !a || !uniforms || !prob || !draws) return fail(BIAS_EINVAL, "null argument");
+    if (n_query <= 0) return BIAS_OK;
+    int32_t need = 1;
+    for (int64_t q = 0; q < n_query; ++q) {
+        if (n[q] < 1 || n[q] > n_max) return fail(BIAS_EINVAL, "n[%lld] = %d outside [1, n_max]", (long long)q, n[q]);
+        if (n[q] > 10000) return fail(BIAS_ERANGE, "n = %d exceeds the 10k Stirling table (reference: BoundsError)", n[q]);
+        if (!(a[q] > 0.0)) return fail(BIAS_EINVAL, "a must be > 0");
+        need = std::max(need, n[q]);
+    }
+    BIAS_CUDA_TRY(cudaSetDevice(ctx->device));
+    BIAS_TRY(ensure_stirling(ctx, need));
+    cudaStream_t st = ctx->stream;
+    int32_t *d_n = nullptr, *d_draw = nullptr;
+    double *d_a = nullptr, *d_u = nullptr, *d_prob = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void **)&d_n, (size_t)n_query * 4);
+    A((void **)&d_draw, (size_t)n_query * 4);
+    A((void **)&d_a, (size_t)n_query * 8);
+    A((void **)&d_u, (size_t)n_query * 8);
+    A((void **)&d_prob, (size_t)n_query * n_max * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_prob, 0, (size_t)n_query * n_max * 8, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_n, n, (size_t)n_query * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_a, a, (size_t)n_query * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_u, uniforms, (size_t)n_query * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        hdp_table_conditionals_kernel<<<grid1d(ctx, n_query * 32, 128), 128, 0, st>>>(d_n, d_a, d_u, n_query, n_max,
+                                                                                      ctx->stirling, d_prob, d_draw);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(prob, d_prob, (size_t)n_query * n_max * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(draws, d_draw, (size_t)n_query * 4, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    for (void *p : {(void *)d_n, (void *)d_draw, (void *)d_a, (void *)d_u, (void *)d_prob})
+        if (p) cudaFree(p);
+    if (e != cudaSuccess) return fail(BIAS_ECUDA, "table conditionals: %s", cudaGetErrorString(e));
+    return BIAS_OK;
+}
+
+}  // extern "C"

@@ -6,6 +6,7 @@
 #include <new>
 #include "model.hpp"
 #include "lda_fast.cuh"
+#define BIAS_GENERIC_KERNEL_IMPL
 #include "generic.cuh"
 #include "util_kernels.cuh"
 
@@ -357,6 +358,8 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
         if (!hdp) return fail(BIAS_EINVAL, "HDP parameters are required");
         if (hdp->KK < 1 || hdp->Kmax < hdp->KK + 2) return fail(BIAS_EINVAL, "HDP: need 1 <= KK and Kmax >= KK + 2");
         if (!(hdp->gg > 0.0) || !(hdp->aa > 0.0)) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
+        if (hdp->Kmax > 4096) return fail(BIAS_EINVAL, "HDP: Kmax is limited to 4096 component slots");
+        if (hdp->n_internals < 0) return fail(BIAS_EINVAL, "HDP: n_internals < 0");
         K = hdp->KK;
         alpha = hdp->aa;
     }
@@ -373,6 +376,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     m->K = K;
     m->alpha = alpha;
     m->V = (conj->kind == BIAS_MD) ? conj->dd : 0;
+    for (int64_t j = 0; j < m->G; ++j) m->max_group_len = std::max(m->max_group_len, group_ptr[j + 1] - group_ptr[j]);
     const int32_t Kcap = (model == BIAS_MODEL_HDP) ? hdp->Kmax : K;
     // pad K to 128 * 2^j (the fast kernel's chunk tree); the generic kernels only need the stride
     int32_t kp = 128;

@@ -391,3 +391,21 @@ def posterior(model, xx, zz, ctx: Context | None = None):
     finally:
         rs.close()
     return posts, nn
+
+
+# ------------------------------------------------------------------ HDP verification helpers
+def stirling_rows(ctx: Context, n_rows: int) -> np.ndarray:
+    """Rows 1..n_rows of the device-resident normalised log-Stirling table (packed lower triangle)."""
+    out = np.zeros(n_rows * (n_rows + 1) // 2)
+    check(lib().bias_stirling_rows(ctx.h, n_rows, ptr(out)))
+    return out
+
+
+def hdp_table_conditionals(ctx: Context, n, a, uniforms):
+    """p(m | n, a) for each query and the draw for the supplied uniform (src/HDP.jl:353-358)."""
+    n, a, u = _lib.as_i32(n), _lib.as_f64(a), _lib.as_f64(uniforms)
+    n_max = int(n.max()) if len(n) else 1
+    prob = np.zeros((len(n), n_max))
+    draws = np.zeros(len(n), dtype=np.int32)
+    check(lib().bias_hdp_table_conditionals(ctx.h, len(n), ptr(n), ptr(a), ptr(u), n_max, ptr(prob), ptr(draws)))
+    return prob, draws

@@ -1,0 +1,176 @@
+"""GPU parity tests for the generic Float64 kernel: every (model, conjugate, datum) combination the
+reference has a demo for, LDA and BMM.  Same three levels as test_gpu_lda.py."""
+import numpy as np
+import pytest
+
+import bias_jl_b200 as b
+from oracle import oracle as orc
+from helpers import assert_conditionals_close, assert_draws_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b.Context(0, seed=99)
+    yield c
+    c.close()
+
+
+def _sent_corpus(n, n_tokens, KK, V, seed):
+    xx, true_zz, topics = b.data.bars_bmm_sentences(n, n_tokens, KK, V, seed)
+    sp = np.concatenate([[0], np.cumsum([len(s) for s in xx])])
+    sw = np.concatenate([s.w for s in xx])
+    sc = np.concatenate([s.c for s in xx])
+    return xx, true_zz, orc.Data.sents(sp, sw, sc)
+
+
+def _make(kind, grouped, seed=0):
+    """-> (model, xx, oracle Data, oracle Comps factory, K, extra)"""
+    rng = np.random.default_rng(seed)
+    if kind == "sent":
+        K, V = 4, 25
+        xx, true_zz, odata = _sent_corpus(160, 15, K, V, seed + 1)
+        comp = b.MultinomialDirichlet(V, 1.0)
+        ocomp = lambda: orc.Comps.md(K, V, 1.0)
+    elif kind == "f64":
+        K = 5
+        x, true_zz, atoms = b.data.gaussian_mixture(200, K, 0.01, seed + 1)
+        xx = list(x)
+        odata = orc.Data.reals(x)
+        m0 = float(np.mean(x))
+        comp = b.Gaussian1DGaussian1D(m0, 2.0, 0.01)
+        ocomp = lambda: orc.Comps.g1g1(K, m0, 2.0, 0.01)
+    else:
+        K, V = 6, 16
+        w = rng.integers(0, V, 180)
+        xx = list(w)
+        true_zz = None
+        odata = orc.Data.words(w)
+        comp = b.MultinomialDirichlet(V, 1.6)
+        ocomp = lambda: orc.Comps.md(K, V, 1.6)
+    n = len(xx)
+    if grouped:
+        cuts = [0, 37, 37, 90, n]           # ragged groups, one empty
+        xg = [xx[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+        if kind != "sent":
+            xg = [np.asarray(g, dtype=np.float64 if kind == "f64" else np.int64) for g in xg]
+        model = b.LDA(comp, K, 0.3)
+        return model, xg, odata, ocomp, K, np.array(cuts, dtype=np.int64)
+    model = b.BMM(comp, K, 0.3)
+    if kind != "sent":
+        xx = np.asarray(xx, dtype=np.float64 if kind == "f64" else np.int64)
+    return model, xx, odata, ocomp, K, None
+
+
+@pytest.mark.parametrize("kind", ["sent", "f64", "int"])
+@pytest.mark.parametrize("grouped", [True, False])
+def test_conditionals_draws_and_conservation(ctx, kind, grouped):
+    if kind == "int" and grouped:
+        pytest.skip("LDA x Int is covered by test_gpu_lda.py")
+    model, xx, odata, ocomp, K, ptr = _make(kind, grouped)
+    rng = np.random.default_rng(5)
+    data = b.FlatData(model.component, xx, grouped)
+    N = data.n_items
+    z0 = rng.integers(0, K, N).astype(np.int32)
+    rs = b.ResidentSampler(ctx, model, data, z0)
+    if grouped:
+        st = orc.LDAState(ocomp(), odata, ptr, z0, model.aa)
+        grp = np.searchsorted(ptr, np.arange(N), side="right") - 1
+        cond = lambda i, r: st.conditional(int(grp[i]), int(i), float(r))
+    else:
+        st = orc.BMMState(ocomp(), odata, z0, model.aa)
+        cond = lambda i, r: st.conditional(int(i), float(r))
+    u = rng.random(N)
+    idx = np.arange(N)
+    raw, prob, draw = rs.conditionals(idx, u)
+    oraw, oprob, odraw = np.zeros((N, K)), np.zeros((N, K)), np.zeros(N, dtype=np.int64)
+    for i in range(N):
+        odraw[i], oraw[i], oprob[i] = cond(i, u[i])
+    assert_conditionals_close(raw, oraw, f"{kind} grouped={grouped}")
+    assert np.allclose(raw, oraw, rtol=1e-9, atol=1e-8), np.abs(raw - oraw).max()
+    assert_draws_match(draw, odraw, oprob, u, 1e-9, "verification draws")
+    fdraw = rs.frozen_draws(u)
+    assert_draws_match(fdraw, odraw, oprob, u, 1e-9, "production draws")
+    assert np.array_equal(rs.get_zz(), z0)
+
+    # sweeps: integer statistics conserved exactly, Gaussian sums to rounding
+    rs.sweep(6)
+    z = rs.get_zz()
+    assert ((z >= 0) & (z < K)).all() and rs.stats().n_moved >= 0
+    comp = rs.components()
+    assert np.array_equal(comp["nn"], np.bincount(z, minlength=K))
+    if kind == "f64":
+        x = np.asarray(odata.x)
+        for k in range(K):
+            if comp["nn"][k]:
+                assert abs(comp["mu"][k] - x[z == k].mean()) < 1e-9
+    else:
+        V = model.component.dd
+        mi = np.zeros((K, V), dtype=np.int64)
+        if kind == "int":
+            np.add.at(mi, (z, np.asarray(odata.w)), 1)
+        else:
+            item = np.repeat(np.arange(N), np.diff(odata.sptr))
+            np.add.at(mi, (z[item], odata.sw), odata.sc)
+        assert np.array_equal(comp["mi"], mi) and np.array_equal(comp["mm"], mi.sum(1))
+    if grouped:
+        nn = rs.group_counts()
+        assert nn.shape == (len(ptr) - 1, K)
+        for j in range(len(ptr) - 1):
+            assert np.array_equal(nn[j], np.bincount(z[ptr[j]:ptr[j + 1]], minlength=K))
+    rs.close()
+
+
+def test_bmm_gaussian_recovers_clusters(ctx, golden):
+    """demo_BMM_Gaussian1DGaussian1D: cluster sizes match the generating ones up to permutation and the
+    posterior variances follow v0*vv/(vv+n*v0) (doc/examples/demo_BMM_Gaussian1DGaussian1D.rst:139-167)."""
+    K, vv = 5, 0.01
+    x, true_zz, atoms = b.data.gaussian_mixture(500, K, vv, seed=3)
+    bmm = b.BMM(b.Gaussian1DGaussian1D(float(x.mean()), 2.0, vv), K, 1.0)
+    zz = np.zeros(len(x), dtype=np.int64)
+    b.init_zz(bmm, zz, np.random.default_rng(1))
+    assert b.collapsed_gibbs_sampler(bmm, x, zz, 100, 2, 50, ctx=ctx) is None
+    posts, nn = b.posterior(bmm, x, zz, ctx=ctx)
+    assert nn.sum() == 500
+    true_nn = np.bincount(true_zz, minlength=K)
+    # a Gibbs chain may leave two atoms merged; require most clusters recovered exactly
+    assert len(set(nn.tolist()) & set(true_nn.tolist())) >= 3, (sorted(nn), sorted(true_nn))
+    for p, n in zip(posts, nn):
+        if n:
+            assert abs(p.vv - 2.0 * vv / (vv + n * 2.0)) < 1e-18
+    g = golden["bmm_gaussian_posterior_variances"]
+    got = [b.Gaussian1DGaussian1D(0.0, g["v0"], g["vv"]) for _ in g["nn"]]
+    for q, n, pv in zip(got, g["nn"], g["post_vv"]):
+        q.nn = n
+        assert q.posterior().vv == pv
+
+
+def test_bmm_sentences_recover_bars(ctx):
+    """demo_BMM_MultinomialDirichlet: 4 bar topics, 200 sentences of 15 tokens."""
+    xx, true_zz, topics = b.data.bars_bmm_sentences(200, 15, 4, 25, seed=123)
+    bmm = b.BMM(b.MultinomialDirichlet(25, 1.0), 4, 0.1)
+    zz = np.zeros(len(xx), dtype=np.int64)
+    b.init_zz(bmm, zz, np.random.default_rng(0))
+    b.collapsed_gibbs_sampler(bmm, xx, zz, 100, 2, 50, ctx=ctx)
+    posts, nn = b.posterior(bmm, xx, zz, ctx=ctx)
+    est = np.stack([p.mean() for p in posts])
+    got = sum(np.min(np.abs(est - t).sum(1)) < 0.3 for t in topics)
+    assert got >= 3, got
+    # clusters are pure: sentences with the same true topic share a label
+    purity = sum(np.bincount(zz[true_zz == k], minlength=4).max() for k in range(4)) / len(zz)
+    assert purity > 0.9
+
+
+def test_lda_gaussian_groups(ctx):
+    """demo_LDA_Gaussian1DGaussian1D: grouped Gaussian data; counts conserved and atoms recovered."""
+    xx, true_zz, atoms = b.data.gaussian_groups(40, 100, 5, 0.01, seed=5)
+    allx = np.concatenate(xx)
+    lda = b.LDA(b.Gaussian1DGaussian1D(float(allx.mean()), 2.0, 0.01), 5, 0.1)
+    zz = [np.zeros(len(x), dtype=np.int64) for x in xx]
+    b.init_zz(lda, zz, np.random.default_rng(2))
+    b.collapsed_gibbs_sampler(lda, xx, zz, 60, 1, 20, ctx=ctx)
+    posts, nn = b.posterior(lda, xx, zz, ctx=ctx)
+    assert nn.sum() == len(allx)
+    mus = sorted(p.mu for p, n in zip(posts, nn.sum(0)) if n > 50)
+    assert sum(any(abs(m - a) < 0.05 for m in mus) for a in atoms) >= 4
