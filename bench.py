@@ -292,12 +292,13 @@ def ours(args):
 
     # ---- end-to-end arm: host buffers in, host assignments out, every step ----
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    zz_out_h = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         rs2, sh2 = make_sampler()              # H2D: words, zz, doc offsets; initialisation pass
         sh2.sweep(1)
-        out = rs2.get_zz()                     # D2H: zz
+        out = rs2.get_zz(out=zz_out_h.numpy())   # D2H: zz into pinned host memory
         rs2.close()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)

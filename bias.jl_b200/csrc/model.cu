@@ -202,6 +202,25 @@ int rebuild_counts(bias_model *m) {
     return BIAS_OK;
 }
 
+// zz / word / Sent range checks on the uploaded arrays; one small D2H + sync
+static int validate_on_device(bias_model *m, int32_t K) {
+    if (m->N == 0) return BIAS_OK;
+    cudaStream_t st = m->ctx->stream;
+    int *flag = reinterpret_cast<int *>(m->scratch + 5);
+    validate_kernel<<<grid_for(m->ctx, std::max<int64_t>(m->N, m->nnz), 256), 256, 0, st>>>(
+        m->z, m->N, K, m->word, m->V, m->sent_word, m->sent_count, m->nnz, flag);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    int h = 0;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    BIAS_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    if (h & 1) return fail(BIAS_EINVAL, "zz holds a value outside [0, %d)", K);
+    if (h & 2) return fail(BIAS_EINVAL, "a word id lies outside [0, %lld) (reference: BoundsError)", (long long)m->V);
+    if (h & 4) return fail(BIAS_EINVAL, "a Sent entry has a word id outside [0, %lld) or a negative count", (long long)m->V);
+    return BIAS_OK;
+}
+
 static int validate(const bias_conjugate *c, const bias_data *d, int64_t G, const int64_t *ptr, const int32_t *zz,
                     int32_t K, double alpha, int32_t model) {
     if (!c || !d || !zz) return fail(BIAS_EINVAL, "null argument");
@@ -229,19 +248,8 @@ static int validate(const bias_conjugate *c, const bias_data *d, int64_t G, cons
         for (int64_t j = 0; j < G; ++j)
             if (ptr[j + 1] < ptr[j]) return fail(BIAS_EINVAL, "group_ptr must be non-decreasing");
     }
-    for (int64_t i = 0; i < d->n_items; ++i)
-        if (zz[i] < 0 || zz[i] >= K) return fail(BIAS_EINVAL, "zz[%lld] = %d outside [0, %d)", (long long)i, zz[i], K);
-    if (c->kind == BIAS_MD && c->datum == BIAS_INT)
-        for (int64_t i = 0; i < d->n_items; ++i)
-            if (d->word[i] < 0 || d->word[i] >= c->dd)
-                return fail(BIAS_EINVAL, "word id %d outside [0, %lld) (reference: BoundsError)", d->word[i], (long long)c->dd);
-    if (c->kind == BIAS_MD && c->datum == BIAS_SENT) {
-        if (d->sent_ptr[0] != 0) return fail(BIAS_EINVAL, "sent_ptr must start at 0");
-        const int64_t nnz = d->sent_ptr[d->n_items];
-        for (int64_t t = 0; t < nnz; ++t)
-            if (d->sent_word[t] < 0 || d->sent_word[t] >= c->dd || d->sent_count[t] < 0)
-                return fail(BIAS_EINVAL, "Sent entry %lld invalid", (long long)t);
-    }
+    if (c->kind == BIAS_MD && c->datum == BIAS_SENT && d->sent_ptr[0] != 0) return fail(BIAS_EINVAL, "sent_ptr must start at 0");
+    // the O(N) range checks on zz / word ids / Sent entries run on the device (validate_kernel)
     return BIAS_OK;
 }
 
@@ -440,6 +448,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     M_CUDA(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
     M_CUDA(cudaMallocHost((void **)&m->h_scratch, 8 * sizeof(unsigned long long)));
     if (model == BIAS_MODEL_HDP) M_TRY(hdp_create(m, hdp));
+    M_TRY(validate_on_device(m, K));
     M_TRY(rebuild_counts(m));
     // the uploads came from caller-owned pageable memory: finish them before returning
     M_CUDA(cudaStreamSynchronize(st));
@@ -454,9 +463,8 @@ int bias_model_set_zz(bias_model *m, const int32_t *zz) {
     if (!m || !zz) return fail(BIAS_EINVAL, "null argument");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     const int32_t Kcur = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
-    for (int64_t i = 0; i < m->N; ++i)
-        if (zz[i] < 0 || zz[i] >= Kcur) return fail(BIAS_EINVAL, "zz[%lld] = %d outside [0, %d)", (long long)i, zz[i], Kcur);
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
+    BIAS_TRY(validate_on_device(m, Kcur));
     BIAS_TRY(rebuild_counts(m));
     BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
     return BIAS_OK;
@@ -699,6 +707,15 @@ int bias_model_delta_begin(bias_model *m) {
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->base_i32, m->i32_block, (size_t)m->n_i32 * 4, cudaMemcpyDeviceToDevice, m->ctx->stream));
     if (m->n_f64)
         BIAS_CUDA_TRY(cudaMemcpyAsync(m->base_f64, m->f64_block, (size_t)m->n_f64 * 8, cudaMemcpyDeviceToDevice, m->ctx->stream));
+    return BIAS_OK;
+}
+
+int bias_model_delta_begin_zero(bias_model *m) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(ensure_exchange(m));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->base_i32, 0, (size_t)m->n_i32 * 4, m->ctx->stream));
+    if (m->n_f64) BIAS_CUDA_TRY(cudaMemsetAsync(m->base_f64, 0, (size_t)m->n_f64 * 8, m->ctx->stream));
     return BIAS_OK;
 }
 

@@ -7,6 +7,26 @@ namespace bias {
 
 #ifdef __CUDACC__
 
+// Range checks the reference gets from Julia's bounds checking (BoundsError) and @check_args:
+// flag bit 0: zz outside [0, K); bit 1: word id outside [0, V); bit 2: bad Sent entry.
+__global__ void validate_kernel(const int32_t *z, int64_t N, int K, const int32_t *word, int64_t V,
+                                const int32_t *sent_word, const int32_t *sent_count, int64_t nnz, int *flag) {
+    int bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const int k = z[i];
+        if (k < 0 || k >= K) bad |= 1;
+        if (word) {
+            const int w = word[i];
+            if (w < 0 || w >= V) bad |= 2;
+        }
+    }
+    if (sent_word)
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride)
+            if (sent_word[t] < 0 || sent_word[t] >= V || sent_count[t] < 0) bad |= 4;
+    if (bad) atomicOr(flag, bad);
+}
+
 // item -> group id by binary search in the CSR offsets
 __global__ void group_of_kernel(const int64_t *ptr, int64_t G, int64_t N, int32_t *group_of) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {

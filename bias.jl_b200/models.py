@@ -199,8 +199,10 @@ class ResidentSampler:
         return ms.value, n.value
 
     # -- state access
-    def get_zz(self) -> np.ndarray:
-        out = np.empty(self.data.n_items, dtype=np.int32)
+    def get_zz(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.data.n_items, dtype=np.int32)
+        assert out.dtype == np.int32 and out.size == self.data.n_items and out.flags.c_contiguous
         check(lib().bias_model_get_zz(self.h, ptr(out)))
         return out
 
@@ -254,6 +256,9 @@ class ResidentSampler:
     # -- multi-GPU exchange (AD-LDA)
     def delta_begin(self):
         check(lib().bias_model_delta_begin(self.h))
+
+    def delta_begin_zero(self):
+        check(lib().bias_model_delta_begin_zero(self.h))
 
     def delta_pack(self):
         """-> [(device_ptr, n_elems, 'int32'), (device_ptr, n_elems, 'float64')] (second may be empty)"""

@@ -46,7 +46,7 @@ def device_tensor(ptr: int, n: int, dtype: str, device):
 class ShardedSampler:
     """Drives one rank's shard: delta_begin -> sweep -> delta_pack -> all_reduce -> delta_apply.
 
-    `shard` is anything with delta_begin(), sweep(n), delta_tensors() -> [torch.Tensor] and
+    `shard` is anything with delta_begin(), delta_begin_zero(), sweep(n), delta_tensors() -> [torch.Tensor] and
     delta_apply(): bias.jl_b200.models.ResidentSampler (through GpuShard) on B200s, or the
     oracle-backed stand-in the CPU tests use to check this logic under gloo.
     """
@@ -55,15 +55,21 @@ class ShardedSampler:
         import torch.distributed as dist
         self.shard, self.group, self.dist = shard, group, dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 1:
+            # every rank built its counts from its own shard: sum them into the global replica
+            self.shard.delta_begin_zero()
+            self._exchange()
 
-    def sweep(self, n_sweeps: int = 1, syncs_per_sweep: int = 1):
+    def _exchange(self):
+        for t in self.shard.delta_tensors():
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.shard.delta_apply()
+
+    def sweep(self, n_sweeps: int = 1):
         for _ in range(n_sweeps):
-            self.shard.delta_begin()
             self.shard.sweep(1)
             if self.world > 1:
-                for t in self.shard.delta_tensors():
-                    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-                self.shard.delta_apply()
+                self._exchange()        # delta_apply leaves base == live, ready for the next sweep
 
 
 class GpuShard:
@@ -75,6 +81,9 @@ class GpuShard:
 
     def delta_begin(self):
         self.rs.delta_begin()
+
+    def delta_begin_zero(self):
+        self.rs.delta_begin_zero()
 
     def sweep(self, n):
         self.rs.sweep(n)

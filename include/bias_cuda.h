@@ -161,6 +161,9 @@ BIAS_API int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out);
 /* ---- multi-GPU exchange (AD-LDA: one allreduce of count deltas per sweep) --------------- */
 /* Snapshot the shared component statistics (n_wk, n_k / sumx, n) as the base of the next delta. */
 BIAS_API int bias_model_delta_begin(bias_model *m);
+/* Base = 0: the next pack/all-reduce/apply merges the ranks' LOCAL initial counts into the global ones
+ * (call once after bias_model_create on every rank). */
+BIAS_API int bias_model_delta_begin_zero(bias_model *m);
 /* Compute delta = live - base into the exchange buffer and return its DEVICE address:
  * n_i32 int32 values followed (8-byte aligned) by n_f64 doubles.  The caller all-reduces
  * (sum) both segments in place across ranks, e.g. with NCCL on the same stream. */
