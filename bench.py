@@ -295,11 +295,18 @@ def ours(args):
     zz_out_h = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
     barrier()
     t0 = time.perf_counter()
+    phases = []
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         rs2, sh2 = make_sampler()              # H2D: words, zz, doc offsets; initialisation pass
+        tb = time.perf_counter()
         sh2.sweep(1)
-        out = rs2.get_zz(out=zz_out_h.numpy())   # D2H: zz into pinned host memory
+        out = rs2.get_zz(out=zz_out_h.numpy())   # D2H: zz into pinned host memory (waits for the sweep)
+        tc = time.perf_counter()
         rs2.close()
+        phases.append((tb - ta, tc - tb, time.perf_counter() - tc))
+    if os.environ.get("BIAS_BENCH_VERBOSE") and rank == 0:
+        print("e2e phases (upload+init, sweep+download, free) s:", phases, file=sys.stderr)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = n_local * 4 * 2 + ptr.nbytes

@@ -160,11 +160,12 @@ def test_hdp_gaussian_finds_the_number_of_atoms(ctx):
         st.resample_beta(tab, 128, 5, True, r)
     # (the serial chain tends to carry a few more small components this early; the parallel one must not over-create)
     assert st.KK >= len(used) - 2 and hdp.KK <= st.KK + 2, (hdp.KK, st.KK, len(used))
-    # cluster purity against the generating labels
+    # every inferred component is (almost) pure in the generating labels; duplicates of one atom are
+    # allowed this early in the chain, merged atoms are not
     z = np.concatenate(zz)
     zt = np.concatenate(zz_true)
-    purity = sum(np.bincount(z[zt == k]).max() for k in used) / len(z)
-    assert purity > 0.95
+    homogeneity = sum(np.bincount(zt[z == c]).max() for c in np.unique(z)) / len(z)
+    assert homogeneity > 0.97, homogeneity
 
 
 def test_kmax_exhaustion_is_an_error(ctx):

@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the bench.py line): sweep times of the other BASELINE configs
+on one B200, with the serial oracle timed on a bounded sample next to each.
+
+  C1  LDA bars K=10 V=25, 1k docs x 100 tokens
+  C2  BMM x Sent, K=64, V=1024, 1M sentences x 64 tokens
+  C4  HDP x Gaussian, groups of 100 points (size set by --hdp-groups)
+Writes one JSON object per config to stdout."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bias_jl_b200 as b          # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def timed_sweeps(rs, n, warm=2):
+    rs.sweep(warm)
+    rs.ctx.sync()
+    t0 = time.perf_counter()
+    rs.sweep(n)
+    rs.ctx.sync()
+    return (time.perf_counter() - t0) / n
+
+
+def c1(ctx):
+    xx, _, _ = b.data.bars_lda_corpus(1000, 100, 10, 25, seed=123)
+    lda = b.LDA(b.MultinomialDirichlet(25, 2.5), 10, 0.1)
+    data = b.FlatData(lda.component, xx, True)
+    z0 = np.random.default_rng(0).integers(0, 10, data.n_items).astype(np.int32)
+    rs = b.ResidentSampler(ctx, lda, data, z0)
+    t = timed_sweeps(rs, 50)
+    rs.close()
+    st = orc.LDAState(orc.Comps.md(10, 25, 2.5), orc.Data.words(np.concatenate(xx)), data.group_ptr, z0, 0.1, with_diag=False)
+    u = np.random.default_rng(1).random(data.n_items)
+    t0 = time.perf_counter()
+    st.sweep(u, diag_mode=0)
+    tc = time.perf_counter() - t0
+    return {"config": "C1 LDA bars K=10 V=25 1000x100", "items": data.n_items, "gpu_ms_per_sweep": 1e3 * t,
+            "gpu_items_per_s": data.n_items / t, "cpu_items_per_s": data.n_items / tc, "cpu_sample": "full corpus, 1 sweep"}
+
+
+def c2(ctx, n_sent):
+    K, V, L = 64, 1024, 64
+    sp, sw, sc, _, _ = b.data.bars_bmm_sentences_csr(n_sent, L, K, V, seed=123)
+    bmm = b.BMM(b.MultinomialDirichlet(V, 1.0), K, 0.1)
+    data = b.FlatData.from_csr(b._lib.SENT, n_sent, sent_ptr=sp, sent_word=sw, sent_count=sc)
+    z0 = np.random.default_rng(0).integers(0, K, n_sent).astype(np.int32)
+    rs = b.ResidentSampler(ctx, bmm, data, z0)
+    t = timed_sweeps(rs, 5, warm=2)
+    moved = rs.stats().n_moved
+    rs.close()
+    ns = 300
+    od = orc.Data.sents(sp[:ns + 1], sw[:sp[ns]], sc[:sp[ns]])
+    st = orc.BMMState(orc.Comps.md(K, V, 1.0), od, z0[:ns], 0.1)
+    u = np.random.default_rng(1).random(ns)
+    t0 = time.perf_counter()
+    st.sweep(u)
+    tc = time.perf_counter() - t0
+    return {"config": f"C2 BMM x Sent K=64 V=1024 {n_sent} sentences x 64 tokens", "items": n_sent, "tokens": n_sent * L,
+            "gpu_ms_per_sweep": 1e3 * t, "gpu_items_per_s": n_sent / t, "gpu_tokens_per_s": n_sent * L / t,
+            "n_moved_last": int(moved), "cpu_items_per_s": ns / tc,
+            "cpu_sample": f"first {ns} sentences, 1 sweep of the serial sampler (dense O(V K) predictive as in the reference)"}
+
+
+def c4(ctx, n_groups):
+    rng = np.random.default_rng(123)
+    # CRF-like groups without the O(N^2) python seating loop: each group mixes a few of 20 atoms
+    n_atoms = 20
+    xx = []
+    for _ in range(n_groups):
+        ks = rng.permutation(n_atoms)[:int(rng.integers(1, 5))]
+        z = ks[rng.integers(0, len(ks), 100)]
+        xx.append(2.0 * (z + 1) + np.sqrt(0.001) * rng.standard_normal(100))
+    allx = np.concatenate(xx)
+    hdp = b.HDP(b.Gaussian1DGaussian1D(float(allx.mean()), 10.0, 0.001), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=256)
+    ptr = np.arange(n_groups + 1, dtype=np.int64) * 100
+    data = b.FlatData.from_csr(b._lib.F64, len(allx), group_ptr=ptr, x=allx)
+    rs = b.ResidentSampler(ctx, hdp, data, np.zeros(len(allx), dtype=np.int32), sample_hyperparam=True, n_internals=10)
+    ctx.sync()
+    t0 = time.perf_counter()
+    rs.sweep(3)
+    ctx.sync()
+    t_first = (time.perf_counter() - t0) / 3
+    t = timed_sweeps(rs, 5, warm=2)
+    s = rs.stats()
+    rs.close()
+    ng = min(n_groups, 40)
+    st = orc.HDPState(orc.Comps.g1g1(256, float(allx.mean()), 10.0, 0.001), orc.Data.reals(allx[:ng * 100]), ptr[:ng + 1],
+                      np.zeros(ng * 100, dtype=np.int64), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
+    r = orc.Rng(1)
+    tab = orc.stirling_table(128)
+    for _ in range(3):
+        st.sweep(r)
+        st.resample_beta(tab, 128, 10, True, r)
+    t0 = time.perf_counter()
+    st.sweep(r)
+    st.resample_beta(tab, 128, 10, True, r)
+    tc = time.perf_counter() - t0
+    return {"config": f"C4 HDP x Gaussian {n_groups} groups x 100 points, n_internals=10", "items": len(allx),
+            "gpu_ms_per_sweep": 1e3 * t, "gpu_ms_per_sweep_first3": 1e3 * t_first, "gpu_items_per_s": len(allx) / t,
+            "KK": int(s.KK), "cpu_items_per_s": ng * 100 / tc, "cpu_sample": f"first {ng} groups, 4th sweep of the serial sampler"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sentences", type=int, default=1_000_000)
+    ap.add_argument("--hdp-groups", type=int, default=100_000)
+    args = ap.parse_args()
+    ctx = b.Context(0, seed=123)
+    for fn in (lambda: c1(ctx), lambda: c2(ctx, args.sentences), lambda: c4(ctx, args.hdp_groups)):
+        print(json.dumps(fn()), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
