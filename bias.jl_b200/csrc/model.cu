@@ -767,6 +767,16 @@ static int run_model(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, c
     bias_model *m = nullptr;
     BIAS_TRY(bias_model_create(ctx, model, conj, data, G, ptr, zz, K, alpha, hp, &m));
     int rc = BIAS_OK;
+    if (hp && beta_out && beta_out[0] > 0.0) {
+        // resume: the caller hands back the my_beta of an earlier call (src/HDP.jl:173-174 resume path)
+        double tot = 0.0;
+        for (int k = 0; k <= hp->KK; ++k) tot += beta_out[k];
+        if (tot > 0.0) {
+            for (int k = 0; k <= hp->KK; ++k) m->h_beta[k] = beta_out[k] / tot;
+            cudaMemcpyAsync(m->d_beta, m->h_beta.data(), m->h_beta.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+    }
     for (int32_t s = 0; s < n_sweeps && rc == BIAS_OK; ++s) {
         rc = one_sweep(m);
         if (rc == BIAS_OK && stats) {

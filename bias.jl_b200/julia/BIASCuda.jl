@@ -1,0 +1,184 @@
+#=
+BIASCuda.jl — the reference-side binding: routes BIAS.jl's sampler entry points to libbias_cuda.
+
+Written in the reference's own dialect (Julia 0.4, REQUIRE:1).  For Julia >= 0.7 replace
+`immutable` -> `struct`, `type` -> `mutable struct`, `Ptr{Void}` -> `Ptr{Cvoid}`,
+`Array(T, n)` -> `Vector{T}(undef, n)`.  Julia is not available in the build image, so this file is
+untested there; the same C ABI is exercised by the ctypes binding (bias.jl_b200/_lib.py) that the
+test-suite drives.
+
+Usage inside BIAS.jl (src/BIAS.jl, after the includes):
+
+    include("BIASCuda.jl")          # defines BIASCuda
+    # collapsed_gibbs_sampler!(lda, xx, zz, ...) now dispatches to the GPU when
+    # BIASCuda.enabled() is true; the Julia API (model constructors, conjugate types, zz mutated
+    # in place, HDP's return tuple) is unchanged.
+=#
+module BIASCuda
+
+const LIB = get(ENV, "BIAS_CUDA_LIB", "libbias_cuda")
+
+# mirrors include/bias_cuda.h
+const BIAS_MD, BIAS_G1G1 = Int32(0), Int32(1)
+const BIAS_INT, BIAS_SENT, BIAS_F64 = Int32(0), Int32(1), Int32(2)
+
+immutable Conjugate            # bias_conjugate
+    kind::Int32
+    datum::Int32
+    dd::Int64
+    aa::Float64
+    m0::Float64
+    v0::Float64
+    vv::Float64
+end
+
+immutable Data                 # bias_data
+    n_items::Int64
+    word::Ptr{Int32}
+    x::Ptr{Float64}
+    sent_ptr::Ptr{Int64}
+    sent_word::Ptr{Int32}
+    sent_count::Ptr{Int32}
+end
+
+immutable SweepStats           # bias_sweep_stats
+    log_likelihood::Float64
+    n_moved::Int64
+    KK::Int32
+    reserved::Int32
+    gg::Float64
+    aa::Float64
+end
+
+type HdpParams                 # bias_hdp_params (mutable: KK, gg, aa come back updated)
+    KK::Int32
+    Kmax::Int32
+    gg::Float64
+    g1::Float64
+    g2::Float64
+    aa::Float64
+    a1::Float64
+    a2::Float64
+    sample_hyperparam::Int32
+    n_internals::Int32
+end
+
+last_error() = bytestring(ccall((:bias_last_error, LIB), Ptr{UInt8}, ()))
+
+function check(rc::Cint)
+    rc == 0 && return
+    msg = last_error()
+    rc == 1 && throw(ArgumentError(msg))          # BIAS_EINVAL <-> @check_args (src/common.jl:233-240)
+    rc == 5 && throw(BoundsError())               # BIAS_ERANGE <-> the 10k Stirling table (src/HDP.jl:355)
+    error("libbias_cuda error $rc: $msg")
+end
+
+function enabled()
+    n = Cint[0]
+    rc = try ccall((:bias_device_count, LIB), Cint, (Ptr{Cint},), n) catch; Cint(2) end
+    rc == 0 && n[1] > 0
+end
+
+const CTX = Ptr{Void}[C_NULL]
+function context(seed::Integer=0, device::Integer=0)
+    if CTX[1] == C_NULL
+        h = Ptr{Void}[C_NULL]
+        check(ccall((:bias_ctx_create, LIB), Cint, (Cint, UInt64, Ptr{Void}, Ptr{Ptr{Void}}),
+                    device, seed, C_NULL, h))
+        CTX[1] = h[1]
+    end
+    CTX[1]
+end
+
+# ---- flattening of the reference's containers (1-based -> 0-based) -------------------------
+flat_ptr(zz) = (p = zeros(Int64, length(zz) + 1); for j = 1:length(zz) p[j+1] = p[j] + length(zz[j]) end; p)
+flat_zz(zz::Vector{Vector{Int}}) = Int32[z - 1 for g in zz for z in g]
+flat_zz(zz::Vector{Int}) = Int32[z - 1 for z in zz]
+
+conj_spec(c, datum) = isa(c, Main.BIAS.MultinomialDirichlet) ?
+    Conjugate(BIAS_MD, datum, c.dd, c.aa, 0.0, 1.0, 1.0) :              # c.aa is already aa/dd (src/conjugates.jl:142)
+    Conjugate(BIAS_G1G1, datum, 0, 0.0, c.m0, c.v0, c.vv)
+
+# returns (Data, keepalive arrays)
+function flat_data(items::Vector{Int})
+    w = Int32[x - 1 for x in items]
+    Data(length(w), pointer(w), C_NULL, C_NULL, C_NULL, C_NULL), (w,), BIAS_INT
+end
+function flat_data(items::Vector{Float64})
+    Data(length(items), C_NULL, pointer(items), C_NULL, C_NULL, C_NULL), (items,), BIAS_F64
+end
+function flat_data(items::Vector{Main.BIAS.Sent})
+    sp = zeros(Int64, length(items) + 1)
+    for i = 1:length(items) sp[i+1] = sp[i] + length(items[i].w) end
+    sw = Int32[w - 1 for s in items for w in s.w]
+    sc = Int32[c for s in items for c in s.c]
+    Data(length(items), C_NULL, C_NULL, pointer(sp), pointer(sw), pointer(sc)), (sp, sw, sc), BIAS_SENT
+end
+
+scatter!(zz::Vector{Int}, flat::Vector{Int32}) = (for i = 1:length(zz) zz[i] = flat[i] + 1 end)
+function scatter!(zz::Vector{Vector{Int}}, flat::Vector{Int32})
+    t = 0
+    for g in zz, i = 1:length(g)
+        t += 1; g[i] = flat[t] + 1
+    end
+end
+
+# ---- collapsed_gibbs_sampler!(lda::LDA, xx, zz, n_burnins, n_lags, n_samples, ...)  src/LDA.jl:67-148
+function lda!(lda, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int; seed=0)
+    n_sweeps = n_burnins + n_samples * (n_lags + 1)                     # src/LDA.jl:82
+    items = vcat(xx...)
+    d, keep, datum = flat_data(items)
+    c = conj_spec(lda.component, datum)
+    ptr = flat_ptr(zz)
+    z = flat_zz(zz)
+    stats = Array(SweepStats, n_sweeps)
+    check(ccall((:bias_lda_run, LIB), Cint,
+                (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Int32, Float64, Int32, Ptr{SweepStats}),
+                context(seed), [c], [d], length(zz), ptr, z, lda.KK, lda.aa, n_sweeps, stats))
+    scatter!(zz, z)
+    stats
+end
+
+# ---- collapsed_gibbs_sampler!(bmm::BMM, xx, zz, ...)  src/BMM.jl:46-130
+function bmm!(bmm, xx, zz::Vector{Int}, n_burnins::Int, n_lags::Int, n_samples::Int; seed=0)
+    n_sweeps = n_burnins + n_samples * (n_lags + 1)
+    d, keep, datum = flat_data(xx)
+    c = conj_spec(bmm.component, datum)
+    z = flat_zz(zz)
+    stats = Array(SweepStats, n_sweeps)
+    check(ccall((:bias_bmm_run, LIB), Cint,
+                (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Ptr{Int32}, Int32, Float64, Int32, Ptr{SweepStats}),
+                context(seed), [c], [d], z, bmm.KK, bmm.aa, n_sweeps, stats))
+    scatter!(zz, z)
+    stats
+end
+
+# ---- collapsed_gibbs_sampler!(hdp::HDP, xx, zz, ...)  src/HDP.jl:166-399
+# One call per kept sample reproduces the (KK_list, KK_dict, betas, gammas, alphas) return value.
+function hdp!(hdp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
+              sample_hyperparam::Bool=true, n_internals::Int=10; Kmax::Int=256, seed=0)
+    items = vcat(xx...)
+    d, keep, datum = flat_data(items)
+    c = conj_spec(hdp.component, datum)
+    ptr = flat_ptr(zz)
+    z = flat_zz(zz)
+    hp = HdpParams(hdp.KK, Kmax, hdp.gg, hdp.g1, hdp.g2, hdp.aa, hdp.a1, hdp.a2, sample_hyperparam, n_internals)
+    KK_list = zeros(Int, n_samples); KK_dict = Dict{Int, Vector{Vector{Int}}}()
+    betas = Array(Vector{Float64}, n_samples); gammas = zeros(n_samples); alphas = zeros(n_samples)
+    beta = zeros(Float64, Kmax + 1)
+    run(n) = check(ccall((:bias_hdp_run, LIB), Cint,
+                (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{HdpParams}, Int32, Ptr{Float64}, Ptr{Void}),
+                context(seed), [c], [d], length(zz), ptr, z, pointer_from_objref(hp), n, beta, C_NULL))
+    run(n_burnins)
+    for s = 1:n_samples
+        run(n_lags + 1)
+        scatter!(zz, z)
+        KK_list[s] = hp.KK; KK_dict[hp.KK] = deepcopy(zz)
+        betas[s] = beta[1:hp.KK+1]; gammas[s] = hp.gg; alphas[s] = hp.aa
+    end
+    scatter!(zz, z)
+    hdp.KK, hdp.gg, hdp.aa = hp.KK, hp.gg, hp.aa
+    KK_list, KK_dict, betas, gammas, alphas
+end
+
+end # module

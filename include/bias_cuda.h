@@ -110,7 +110,8 @@ BIAS_API int bias_bmm_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_
                  int32_t *zz, int32_t K, double alpha, int32_t n_sweeps, bias_sweep_stats *stats);
 /* collapsed_gibbs_sampler!(hdp::HDP, xx, zz, ...)  src/HDP.jl:166-399.  params (KK, gg, aa) are
  * updated like the Julia object; beta_out[Kmax+1] receives my_beta (src/HDP.jl:394); zz is
- * renumbered to 0..KK-1 in slot order. */
+ * renumbered to 0..KK-1 in slot order.  If beta_out[0] > 0 on entry, beta_out[0..KK] is taken as the
+ * initial my_beta (resuming a chain across calls); otherwise my_beta starts uniform (src/HDP.jl:228). */
 BIAS_API int bias_hdp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data,
                  int64_t n_groups, const int64_t *group_ptr, int32_t *zz,
                  bias_hdp_params *params, int32_t n_sweeps, double *beta_out, bias_sweep_stats *stats);
