@@ -6,6 +6,7 @@
 #include <new>
 #include "model.hpp"
 #include "lda_fast.cuh"
+#include "lda_tma.cuh"
 #define BIAS_GENERIC_KERNEL_IMPL
 #include "generic.cuh"
 #include "util_kernels.cuh"
@@ -70,6 +71,31 @@ static int launch_lda_fast_t(bias_model *m, const LdaFastParams &p) {
     return BIAS_OK;
 }
 
+template <int NCH>
+static int launch_lda_tma_t(bias_model *m, const LdaFastParams &p) {
+    static bool configured = false;
+    const size_t smem = lda_tma_smem_bytes(NCH);
+    if (!configured) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_tma_kernel<NCH>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int64_t want = (p.D + kTmaWarps - 1) / kTmaWarps;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms));
+    lda_md_int_sweep_tma_kernel<NCH><<<grid, kTmaWarps * 32, smem, m->ctx->stream>>>(p);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    return BIAS_OK;
+}
+
+// which LDA x MD x Int kernel: rows staged in shared memory by bulk async copies (default when
+// K <= 1024 and every document is shorter than 65,536 tokens) or kept in registers
+static bool use_tma_kernel(const bias_model *m) {
+    const char *force = getenv("BIAS_LDA_KERNEL");
+    if (force && force[0] == 'r') return false;
+    return m->Kpad <= 1024 && m->max_group_len <= 65535;
+}
+
 static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen, int32_t *draws_out) {
     LdaFastParams p{};
     p.doc_ptr = m->group_ptr;
@@ -92,6 +118,14 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.frozen = frozen;
     p.diag_sum = reinterpret_cast<double *>(m->scratch);
     p.moved = m->scratch + 1;
+    if (use_tma_kernel(m)) {
+        switch (m->Kpad / 128) {
+            case 1: return launch_lda_tma_t<1>(m, p);
+            case 2: return launch_lda_tma_t<2>(m, p);
+            case 4: return launch_lda_tma_t<4>(m, p);
+            case 8: return launch_lda_tma_t<8>(m, p);
+        }
+    }
     switch (m->Kpad / 128) {
         case 1: return launch_lda_fast_t<1>(m, p);
         case 2: return launch_lda_fast_t<2>(m, p);
