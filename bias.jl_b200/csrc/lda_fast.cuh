@@ -52,7 +52,7 @@ struct LdaFastParams {
 
 // warps per CTA: 8 up to K = 1024, 4 above (the per-warp rows are 8*Kpad bytes of shared memory)
 __host__ __device__ constexpr int lda_fast_warps(int nch) { return nch <= 8 ? 8 : 4; }
-__host__ __device__ constexpr int lda_fast_min_ctas(int nch) { return nch <= 8 ? 2 : 1; }
+__host__ __device__ constexpr int lda_fast_min_ctas(int nch) { return nch <= 8 ? 3 : 1; }
 
 __host__ __device__ inline size_t lda_fast_smem_bytes(int nch) {
     // per warp: r[Kpad] float + cnt[Kpad] int32 + R[Kpad/128] float (padded to 32 floats)
@@ -240,10 +240,17 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
                 // ---- pass 2: CDF inside the selected chunk ----
                 int4 cs;
                 if constexpr (KEEP_ROW) {
-                    cs = c[0];
-#pragma unroll
-                    for (int j = 1; j < NCH; ++j)
-                        if (j == jsel) cs = c[j];
+                    // jsel is warp-uniform: a jump table instead of a 4 x (NCH-1) select chain
+                    switch (jsel) {
+                        default: cs = c[0]; break;
+                        case 1: if constexpr (NCH > 1) cs = c[1 % NCH]; break;
+                        case 2: if constexpr (NCH > 2) cs = c[2 % NCH]; break;
+                        case 3: if constexpr (NCH > 2) cs = c[3 % NCH]; break;
+                        case 4: if constexpr (NCH > 4) cs = c[4 % NCH]; break;
+                        case 5: if constexpr (NCH > 4) cs = c[5 % NCH]; break;
+                        case 6: if constexpr (NCH > 4) cs = c[6 % NCH]; break;
+                        case 7: if constexpr (NCH > 4) cs = c[7 % NCH]; break;
+                    }
                 } else {
                     cs = __ldcg(row + jsel * 32 + lane);
                 }
