@@ -280,6 +280,7 @@ def ours(args):
     launches = ctx.launches - launches0
     clock_rec = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     stats = rs.stats()
+    ll_sum, ll_n = rs.log_likelihood()           # training log-likelihood per token of the local shard (not timed)
 
     # dominant-kernel duration: the sweep kernel alone, CUDA events on the launching stream
     barrier()
@@ -352,7 +353,8 @@ def ours(args):
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clock_rec,
-            "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood},
+            "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood,
+                            "train_loglik_per_token_rank0": ll_sum / max(1, ll_n), "sweeps_done": args.warmup + args.steps},
         }
         print(json.dumps(line))
     ctx.close()

@@ -27,7 +27,7 @@ SYMBOLS = [
     "bias_model_create", "bias_model_destroy", "bias_model_sweep", "bias_model_set_zz", "bias_model_get_zz",
     "bias_model_last_stats", "bias_model_get_components", "bias_model_get_group_counts", "bias_model_get_hdp",
     "bias_model_conditionals", "bias_model_frozen_draws", "bias_hdp_table_conditionals", "bias_stirling_rows",
-    "bias_model_delta_begin", "bias_model_delta_begin_zero", "bias_model_delta_pack", "bias_model_delta_apply", "bias_model_last_sweep_ms",
+    "bias_model_log_likelihood", "bias_model_delta_begin", "bias_model_delta_begin_zero", "bias_model_delta_pack", "bias_model_delta_apply", "bias_model_last_sweep_ms",
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
     L.bias_model_frozen_draws.argtypes = [vp, vp, vp]
     L.bias_hdp_table_conditionals.argtypes = [vp, i64, vp, vp, vp, i32, vp, vp]
     L.bias_stirling_rows.argtypes = [vp, i32, vp]
+    L.bias_model_log_likelihood.argtypes = [vp, C.POINTER(f64), C.POINTER(i64)]
     L.bias_model_delta_begin.argtypes = [vp]
     L.bias_model_delta_begin_zero.argtypes = [vp]
     L.bias_model_delta_pack.argtypes = [vp, pp, C.POINTER(i64), pp, C.POINTER(i64)]

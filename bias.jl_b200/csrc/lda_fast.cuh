@@ -46,6 +46,8 @@ struct LdaFastParams {
     const double *ext_uniforms; // nullable: uniforms[N] supplied by the caller (verification)
     int32_t *draws_out;         // frozen mode: draws[N]
     int32_t frozen;             // 1: do not touch z or counts
+    int32_t eval;               // 1: no sampling; accumulate sum_t log p(w_t | theta_d, phi) into eval_sum
+    double *eval_sum;
     double *diag_sum;           // sum of posterior-mean probabilities (src/conjugates.jl:205)
     unsigned long long *moved;  // tokens whose assignment changed
 };
@@ -109,6 +111,7 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
     const float alpha = p.alpha, beta = p.beta, vbeta = p.vbeta;
     float diag_acc = 0.f;
     unsigned moved_acc = 0;
+    double eval_acc = 0.0, eval_log_norm = 0.0;
 
     for (;;) {
         // ---- fetch the next document (one atomic per document) ----
@@ -118,6 +121,7 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
         if (doc >= (unsigned long long)p.D) break;
         const int64_t t_begin = p.doc_ptr[doc], t_end = p.doc_ptr[doc + 1];
         if (t_end <= t_begin) continue;
+        eval_log_norm = (double)logf((float)(t_end - t_begin) + (float)p.K * alpha);
 
         // ---- rebuild n_dk from z, then r = (n_dk + alpha) / (n_k + V beta) ----
 #pragma unroll
@@ -191,7 +195,7 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
                 // ---- delitem!: n_dk[kold] -= 1, n_k[kold] -= 1 folded into r[kold] ----
                 const int jo = kold >> 7;
                 float r_saved = 0.f, R_saved = 0.f, r_rm = 0.f;
-                if (lane == 0) {
+                if (lane == 0 && !p.eval) {
                     const int cn = cnt_s[kold];
                     r_saved = r_s[kold];
                     R_saved = R_s[jo];
@@ -221,7 +225,7 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
                 float T = transpose_reduce<NCH>(acc, lane);      // lane l: chunk (l >> GSHIFT)
                 const int myj = lane >> GSHIFT;
                 T = fmaf(beta, R_s[myj], T);
-                if (myj == jo) T -= r_rm;                        // the row still counts this token
+                if (myj == jo && !p.eval) T -= r_rm;             // the row still counts this token
                 T = fmaxf(T, 0.f);
                 // inclusive scan over chunks (in chunk order)
                 float P = T;
@@ -231,6 +235,11 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
                     if (myj >= d) P += y;
                 }
                 const float total = __shfl_sync(kFull, P, 31);
+                if (p.eval) {
+                    // point-estimate predictive: sum_k theta_dk phi_kw = total / (L_d + K alpha)
+                    if (lane == 0) eval_acc += (double)logf(total) - eval_log_norm;
+                    continue;
+                }
                 const float target = u * total;
                 unsigned bal = __ballot_sync(kFull, P >= target);
                 int src_lane = bal ? (__ffs(bal) - 1) : 31;
@@ -325,7 +334,9 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
                 __syncwarp();
             }  // tokens of the batch
 
-            if (p.frozen) {
+            if (p.eval) {
+                // nothing to write back
+            } else if (p.frozen) {
                 if (lane < nb) p.draws_out[t0 + lane] = my_new;
             } else if (lane < nb && my_new != my_z) {
                 p.z[t0 + lane] = my_new;
@@ -333,6 +344,10 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
         }  // batches
     }  // documents
 
+    if (p.eval) {
+        if (lane == 0) atomicAdd(p.eval_sum, eval_acc);
+        return;
+    }
     if (!p.frozen) {
         // lane 0 of each warp holds the warp's diagnostics
         if (lane == 0) {

@@ -98,8 +98,10 @@ static bool use_tma_kernel(const bias_model *m) {
     return m->Kpad <= 1024 && m->max_group_len <= 65535;
 }
 
-static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen, int32_t *draws_out) {
+static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen, int32_t *draws_out, int eval = 0) {
     LdaFastParams p{};
+    p.eval = eval;
+    p.eval_sum = reinterpret_cast<double *>(m->scratch + 6);
     p.doc_ptr = m->group_ptr;
     p.word = m->word;
     p.z = m->z;
@@ -120,7 +122,7 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.frozen = frozen;
     p.diag_sum = reinterpret_cast<double *>(m->scratch);
     p.moved = m->scratch + 1;
-    if (use_tma_kernel(m)) {
+    if (use_tma_kernel(m) && !eval) {
         switch (m->Kpad / 128) {
             case 1: return launch_lda_tma_t<1>(m, p);
             case 2: return launch_lda_tma_t<2>(m, p);
@@ -719,6 +721,22 @@ int bias_model_frozen_draws(bias_model *m, const double *uniforms, int32_t *draw
     cudaFree(d_draw);
     if (e != cudaSuccess) return fail(BIAS_ECUDA, "frozen draws: %s", cudaGetErrorString(e));
     return rc;
+}
+
+int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t *n_items) {
+    if (!m || !sum_log_p) return fail(BIAS_EINVAL, "null argument");
+    if (!m->fast) return fail(BIAS_EINVAL, "the log-likelihood evaluator covers LDA x MultinomialDirichlet x word ids");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch + 2, 0, sizeof(unsigned long long), st));      // document counter
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch + 6, 0, sizeof(double), st));
+    BIAS_TRY(launch_lda_fast(m, nullptr, 1, nullptr, 1));
+    double h = 0.0;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&h, m->scratch + 6, sizeof(double), cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    *sum_log_p = h;
+    if (n_items) *n_items = m->N;
+    return BIAS_OK;
 }
 
 // -----------------------------------------------------------------------------------------

@@ -253,6 +253,12 @@ class ResidentSampler:
         check(lib().bias_model_frozen_draws(self.h, ptr(u), ptr(out)))
         return out
 
+    def log_likelihood(self):
+        """(sum_i log p(x_i | point estimates), n_items); perplexity = exp(-sum / n)."""
+        s, n = C.c_double(), C.c_int64()
+        check(lib().bias_model_log_likelihood(self.h, C.byref(s), C.byref(n)))
+        return s.value, n.value
+
     # -- multi-GPU exchange (AD-LDA)
     def delta_begin(self):
         check(lib().bias_model_delta_begin(self.h))

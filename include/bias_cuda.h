@@ -159,6 +159,12 @@ BIAS_API int bias_hdp_table_conditionals(bias_ctx *ctx, int64_t n_query, const i
  * Copies rows 1..n_rows (packed lower triangle) to out; builds the table on first use. */
 BIAS_API int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out);
 
+/* Sum over items of log p(x_i | theta_group, phi) under the point estimates of the current state,
+ * theta_jk = (n_jk + aa)/(n_j + K aa), phi = posterior mean of each component (LDA x MD x Int).
+ * The reference has no perplexity function (src/notes.md:30); perplexity = exp(-sum / n_items).
+ * On a sharded run every rank reports its own shard's sum. */
+BIAS_API int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t *n_items);
+
 /* ---- multi-GPU exchange (AD-LDA: one allreduce of count deltas per sweep) --------------- */
 /* Snapshot the shared component statistics (n_wk, n_k / sumx, n) as the base of the next delta. */
 BIAS_API int bias_model_delta_begin(bias_model *m);

@@ -163,6 +163,18 @@ def test_bars_trajectory_tracks_the_serial_oracle(ctx):
     rs.close()
 
 
+def test_device_log_likelihood_matches_host_evaluator(ctx):
+    xx, _, _ = b.data.bars_lda_corpus(n_groups=120, n_tokens=60, seed=4)
+    rs, state, data, z0, words, rng = _setup(ctx, xx, 10, 25, 0.1, 2.5, seed=2)
+    for n in (0, 15):
+        rs.sweep(n)
+        s, cnt = rs.log_likelihood()
+        ref = lda_token_loglik(data.group_ptr, words, rs.get_zz().astype(np.int64), 10, 25, 0.1, 0.1)
+        assert cnt == data.n_items and abs(s / cnt - ref) < 2e-5 * abs(ref) + 1e-6, (s / cnt, ref)
+    assert np.array_equal(rs.get_zz(), rs.get_zz())
+    rs.close()
+
+
 def test_generic_path_agrees_with_fast_path(ctx, monkeypatch):
     """The Float64 generic kernel (used for Sent / Gaussian items and HDP) run on LDA x Int must
     reproduce the same conditionals and conserve counts."""
