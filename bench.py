@@ -324,7 +324,7 @@ def ours(args):
     tp = os.path.join(ROOT, "profiles", "lda_sweep_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_token") * tokens_per_launch   # ncu capture scaled to this launch
         except Exception:
             traffic = None
 

@@ -1,0 +1,96 @@
+"""The multi-GPU exchange kernels on ONE GPU: two shards of a corpus live in two resident samplers on
+the same device; their count deltas are summed (what the NCCL all-reduce does across ranks) and
+applied.  Replicas must stay identical and equal the counts recomputed from the gathered zz."""
+import numpy as np
+import pytest
+import torch
+
+import bias_jl_b200 as b
+from bias_jl_b200.sharding import device_tensor, shard_csr, shard_items
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = b.Context(0, seed=77)
+    yield c
+    c.close()
+
+
+def _exchange(samplers, first=False):
+    dev = torch.device("cuda", 0)
+    if first:
+        for rs in samplers:
+            rs.delta_begin_zero()
+    packs = [rs.delta_pack() for rs in samplers]
+    samplers[0].ctx.sync()
+    for seg in range(len(packs[0])):
+        ts = [device_tensor(*p[seg], dev) for p in packs]
+        total = ts[0].clone()
+        for t in ts[1:]:
+            total += t
+        for t in ts:
+            t.copy_(total)
+    torch.cuda.synchronize()
+    for rs in samplers:
+        rs.delta_apply()
+
+
+def test_two_lda_shards_on_one_gpu(ctx):
+    K, V = 10, 25
+    xx, _, _ = b.data.bars_lda_corpus(n_groups=61, n_tokens=40, seed=9)
+    words = np.concatenate(xx)
+    ptr = np.concatenate([[0], np.cumsum([len(x) for x in xx])]).astype(np.int64)
+    z0 = np.random.default_rng(1).integers(0, K, len(words)).astype(np.int32)
+    lda = b.LDA(b.MultinomialDirichlet(V, 2.5), K, 0.1)
+    samplers, spans = [], []
+    for r in range(2):
+        lo, hi, i0, i1, lptr = shard_csr(ptr, r, 2)
+        data = b.FlatData.from_csr(b._lib.INT, i1 - i0, group_ptr=lptr, word=words[i0:i1])
+        samplers.append(b.ResidentSampler(ctx, lda, data, z0[i0:i1]))
+        spans.append((i0, i1))
+    _exchange(samplers, first=True)
+    mi0 = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi0, (z0, words), 1)
+    for rs in samplers:
+        assert np.array_equal(rs.components()["mi"], mi0)
+    for _ in range(5):
+        for rs in samplers:
+            rs.sweep(1)
+        _exchange(samplers)
+    z = np.concatenate([rs.get_zz() for rs in samplers])
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, words), 1)
+    assert (z != z0).any()
+    for rs in samplers:
+        comp = rs.components()
+        assert np.array_equal(comp["mi"], mi) and np.array_equal(comp["mm"], mi.sum(1))
+        rs.close()
+
+
+def test_two_bmm_gaussian_shards_on_one_gpu(ctx):
+    K = 5
+    x, _, _ = b.data.gaussian_mixture(400, K, 0.01, seed=2)
+    z0 = np.random.default_rng(3).integers(0, K, len(x)).astype(np.int32)
+    bmm = b.BMM(b.Gaussian1DGaussian1D(float(x.mean()), 2.0, 0.01), K, 1.0)
+    samplers = []
+    for r in range(2):
+        i0, i1 = shard_items(len(x), r, 2)
+        data = b.FlatData.from_csr(b._lib.F64, i1 - i0, x=x[i0:i1])
+        samplers.append(b.ResidentSampler(ctx, bmm, data, z0[i0:i1]))
+    _exchange(samplers, first=True)
+    for rs in samplers:
+        assert np.array_equal(rs.components()["nn"], np.bincount(z0, minlength=K))
+    for _ in range(5):
+        for rs in samplers:
+            rs.sweep(1)
+        _exchange(samplers)
+    z = np.concatenate([rs.get_zz() for rs in samplers])
+    for rs in samplers:
+        comp = rs.components()
+        assert np.array_equal(comp["nn"], np.bincount(z, minlength=K))
+        for k in range(K):
+            if comp["nn"][k]:
+                assert abs(comp["mu"][k] - x[z == k].mean()) < 1e-9
+        rs.close()
