@@ -121,11 +121,12 @@ struct Datum {
     double m_tot, coef;
 };
 
+template <int KIND, int DATUM>
 __device__ __forceinline__ Datum load_datum(const GenericParams &p, int64_t i, int lane) {
     Datum d{0, 0.0, 0, 0, 0.0, 0.0};
-    if (p.datum == BIAS_INT) {
+    if (DATUM == BIAS_INT) {
         d.w = p.word[i];
-    } else if (p.datum == BIAS_F64) {
+    } else if (DATUM == BIAS_F64) {
         d.xv = p.x[i];
     } else {
         d.s0 = p.sent_ptr[i];
@@ -134,16 +135,18 @@ __device__ __forceinline__ Datum load_datum(const GenericParams &p, int64_t i, i
         for (int64_t t = d.s0 + lane; t < d.s1; t += 32) {
             const double c = (double)p.sent_count[t];
             mloc += c;
-            lg += lgamma(c + 1.0);
+            if (p.faithful) lg += lgamma(c + 1.0);
         }
         d.m_tot = warp_sum(mloc);
-        d.coef = lgamma(d.m_tot + 1.0) - warp_sum(lg);   // k-independent, src/conjugates.jl:193
+        // the multinomial coefficient is k-independent (src/conjugates.jl:193): kept only where raw scores are compared
+        if (p.faithful) d.coef = lgamma(d.m_tot + 1.0) - warp_sum(lg);
     }
     return d;
 }
 
 // K (+1) unnormalised log scores into sc[]; returns the warp-wide maximum.
 // zold < 0: the item is currently unassigned (nothing to remove).
+template <int KIND, int DATUM>
 __device__ __forceinline__ double score_all(const GenericParams &p, const Datum &d, int zold, int K, int n_out,
                                             const int32_t *prow, const double *hdp_beta, double alpha,
                                             double *sc, int lane) {
@@ -161,14 +164,14 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
             prior = log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha);
         }
         double lp;
-        if (p.kind == BIAS_G1G1) {
+        if (KIND == BIAS_G1G1) {
             double n = 0.0, sx = 0.0;
             if (!fresh) {
                 n = (double)(__ldcg(p.n_items + k) - (own ? 1 : 0));
                 sx = __ldcg(p.sumx + k) - (own ? d.xv : 0.0);
             }
             lp = g1g1_logpred(n, sx, d.xv, p.m0, p.v0, p.vv);
-        } else if (p.datum == BIAS_INT) {
+        } else if (DATUM == BIAS_INT) {
             double nw = 0.0, nk = 0.0;
             if (!fresh) {
                 nw = (double)(__ldcg(p.n_wk + (size_t)d.w * Kpad + k) - (own ? 1 : 0));
@@ -179,12 +182,31 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
             double nk = 0.0;
             if (!fresh) nk = (double)__ldcg(p.n_k + k) - (own ? d.m_tot : 0.0);
             double acc = 0.0;
-            for (int64_t t = d.s0; t < d.s1; ++t) {
-                const int wt = p.sent_word[t];
-                const double ct = (double)p.sent_count[t];
-                double nw = 0.0;
-                if (!fresh) nw = (double)__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0.0);
-                acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
+            if (p.faithful) {
+                // the reference's form: lgamma differences, summed in item order
+                for (int64_t t = d.s0; t < d.s1; ++t) {
+                    const int wt = p.sent_word[t];
+                    const double ct = (double)p.sent_count[t];
+                    double nw = 0.0;
+                    if (!fresh) nw = (double)__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0.0);
+                    acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
+                }
+            } else {
+                // lgamma(b+n+c) - lgamma(b+n) = sum_{i<c} log(b+n+i): rising-factorial products, one log per
+                // ~1e250 of accumulated magnitude instead of two lgamma calls per non-zero
+                double prod = 1.0;
+                for (int64_t t = d.s0; t < d.s1; ++t) {
+                    const int wt = p.sent_word[t];
+                    const int ct = p.sent_count[t];
+                    double base = p.beta;
+                    if (!fresh) base += (double)(__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0));
+                    for (int i = 0; i < ct; ++i) prod *= base + (double)i;
+                    if (prod > 1e250) {
+                        acc += log(prod);
+                        prod = 1.0;
+                    }
+                }
+                acc += log(prod);
             }
             const double bv = p.beta * (double)p.V;
             lp = d.coef + lgamma(bv + nk) - lgamma(bv + nk + d.m_tot) + acc; // src/conjugates.jl:193-195
@@ -251,11 +273,12 @@ __device__ __forceinline__ int draw_parallel(double *sc, int n_out, double lmax,
 }
 
 // delitem! from zold (if >= 0) and additem! to kdst (if >= 0) on the shared tables.
+template <int KIND, int DATUM>
 __device__ __forceinline__ void apply_move(const GenericParams &p, const Datum &d, int zold, int kdst,
                                            int32_t *prow, int lane) {
     const int Kpad = p.Kpad;
-    if (p.kind == BIAS_MD) {
-        if (p.datum == BIAS_INT) {
+    if (KIND == BIAS_MD) {
+        if (DATUM == BIAS_INT) {
             if (lane == 0) {
                 if (zold >= 0) { atomicAdd(p.n_wk + (size_t)d.w * Kpad + zold, -1); atomicAdd(p.n_k + zold, -1); }
                 if (kdst >= 0) { atomicAdd(p.n_wk + (size_t)d.w * Kpad + kdst, 1); atomicAdd(p.n_k + kdst, 1); }
@@ -286,11 +309,12 @@ __device__ __forceinline__ void apply_move(const GenericParams &p, const Datum &
 }
 
 // loglikelihood(components[kk], x) after the add (src/LDA.jl:131): valid on lane 0.
+template <int KIND, int DATUM>
 __device__ __forceinline__ double diag_after(const GenericParams &p, const Datum &d, int knew, int lane) {
     const int Kpad = p.Kpad;
-    if (p.kind == BIAS_G1G1)
+    if (KIND == BIAS_G1G1)
         return g1g1_loglik((double)__ldcg(p.n_items + knew), __ldcg(p.sumx + knew), d.xv, p.m0, p.v0, p.vv);
-    if (p.datum == BIAS_INT)
+    if (DATUM == BIAS_INT)
         return ((double)__ldcg(p.n_wk + (size_t)d.w * Kpad + knew) + p.beta) /
                ((double)__ldcg(p.n_k + knew) + p.beta * (double)p.V);
     double part = 0.0;
@@ -302,7 +326,8 @@ __device__ __forceinline__ double diag_after(const GenericParams &p, const Datum
 }
 
 #ifdef BIAS_GENERIC_KERNEL_IMPL      // the kernel itself is emitted by model.cu only
-__global__ void __launch_bounds__(kGenThreads)
+template <int KIND, int DATUM>
+__global__ void __launch_bounds__(kGenThreads, (KIND == BIAS_G1G1 || DATUM == BIAS_INT) ? 8 : 4)
 generic_sweep_kernel(const GenericParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -319,8 +344,8 @@ generic_sweep_kernel(const GenericParams p) {
         const int64_t i = p.item_idx ? p.item_idx[q] : (p.work_idx32 ? (int64_t)p.work_idx32[q] : q);
         const int zold = p.z[i];                      // -1: the item is currently unassigned (HDP pending)
         int32_t *prow = p.prior_rows + (p.row_of ? (size_t)p.row_of[p.row_by_work ? q : i] * Kpad : 0);
-        const Datum d = load_datum(p, i, lane);
-        const double lmax = score_all(p, d, zold, K, n_out, prow, p.hdp_beta, p.alpha, sc, lane);
+        const Datum d = load_datum<KIND, DATUM>(p, i, lane);
+        const double lmax = score_all<KIND, DATUM>(p, d, zold, K, n_out, prow, p.hdp_beta, p.alpha, sc, lane);
 
         const int64_t uidx = (p.item_idx || p.work_idx32) ? q : i;
         double u;
@@ -354,21 +379,21 @@ generic_sweep_kernel(const GenericParams p) {
         const bool born = is_hdp && knew >= K;
         if (born) {
             // leave the item unassigned and queue it (also when it was already unassigned)
-            if (zold >= 0) apply_move(p, d, zold, -1, prow, lane);
+            if (zold >= 0) apply_move<KIND, DATUM>(p, d, zold, -1, prow, lane);
             if (lane == 0) {
                 p.z[i] = -1;
                 const unsigned slot = atomicAdd(p.pending_count, 1u);
                 p.pending_list[slot] = (int32_t)i;
             }
         } else if (knew != zold) {
-            apply_move(p, d, zold, knew, prow, lane);
+            apply_move<KIND, DATUM>(p, d, zold, knew, prow, lane);
             if (lane == 0) {
                 p.z[i] = knew;
                 moved_acc += 1;
             }
         }
         if (!born && p.diag_sum) {
-            const double dv = diag_after(p, d, knew, lane);
+            const double dv = diag_after<KIND, DATUM>(p, d, knew, lane);
             if (lane == 0) diag_acc += dv;
         }
     }

@@ -251,6 +251,7 @@ __global__ void hdp_hyper_kernel(const int64_t *group_ptr, int64_t G, double aa,
 // ---------------------------------------------------------------------------------------
 // serial birth pass (src/HDP.jl:312-338 with the reference's sequential semantics): one warp
 // ---------------------------------------------------------------------------------------
+template <int KIND, int DATUM>
 __global__ void __launch_bounds__(32)
 hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK, double *beta, double gg,
                  int Kmax, int *err) {
@@ -263,8 +264,8 @@ hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK
     for (int q = 0; q < n_list; ++q) {
         const int64_t i = list[q];
         int32_t *prow = p.prior_rows + (size_t)p.row_of[i] * p.Kpad;
-        const Datum d = load_datum(p, i, lane);
-        const double lmax = score_all(p, d, -1, KK, KK + 1, prow, beta, p.alpha, sc, lane);
+        const Datum d = load_datum<KIND, DATUM>(p, i, lane);
+        const double lmax = score_all<KIND, DATUM>(p, d, -1, KK, KK + 1, prow, beta, p.alpha, sc, lane);
         PhiloxStream rs(p.seed, (uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep * 8u + kStreamBirth);
         const double u = rs.u01();
         int knew = draw_parallel(sc, KK + 1, lmax, u, lane);
@@ -283,11 +284,11 @@ hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK
                 __syncwarp();
             }
         }
-        apply_move(p, d, -1, knew, prow, lane);
+        apply_move<KIND, DATUM>(p, d, -1, knew, prow, lane);
         if (lane == 0) p.z[i] = knew;
         __threadfence();
         __syncwarp();
-        const double dv = diag_after(p, d, knew, lane);
+        const double dv = diag_after<KIND, DATUM>(p, d, knew, lane);
         if (lane == 0) diag_acc += dv;
         moved += 1;
     }
@@ -483,8 +484,13 @@ int hdp_sweep(bias_model *m) {
         const int n_serial = (int)std::min<unsigned int>(n_pending, 256u);
         GenericParams bp = birth_params(m);
         BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
-        hdp_birth_kernel<<<1, 32, ((size_t)Kmax + 4) * 8, st>>>(bp, list_cur, n_serial, m->d_KK, m->d_beta, m->hdp.gg,
-                                                                 Kmax, d_err);
+        const size_t bsm = ((size_t)Kmax + 4) * 8;
+        if (bp.kind == BIAS_G1G1)
+            hdp_birth_kernel<BIAS_G1G1, BIAS_F64><<<1, 32, bsm, st>>>(bp, list_cur, n_serial, m->d_KK, m->d_beta, m->hdp.gg, Kmax, d_err);
+        else if (bp.datum == BIAS_INT)
+            hdp_birth_kernel<BIAS_MD, BIAS_INT><<<1, 32, bsm, st>>>(bp, list_cur, n_serial, m->d_KK, m->d_beta, m->hdp.gg, Kmax, d_err);
+        else
+            hdp_birth_kernel<BIAS_MD, BIAS_SENT><<<1, 32, bsm, st>>>(bp, list_cur, n_serial, m->d_KK, m->d_beta, m->hdp.gg, Kmax, d_err);
         BIAS_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
         int32_t kk_new = 0;

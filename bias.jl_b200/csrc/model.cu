@@ -144,6 +144,26 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
 // ---------------------------------------------------------------------------------------
 // generic kernel launch
 // ---------------------------------------------------------------------------------------
+template <int KIND, int DATUM>
+static int launch_generic_t(bias_model *m, const GenericParams &p) {
+    const size_t smem = generic_smem_bytes(p.n_out);
+    static size_t smem_set = 0;
+    static int ctas_per_sm = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(generic_sweep_kernel<KIND, DATUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    int occ = 0;
+    BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, generic_sweep_kernel<KIND, DATUM>, kGenThreads, smem));
+    ctas_per_sm = std::max(1, occ);
+    const int64_t blocks = (p.n_work + kGenWarps - 1) / kGenWarps;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)m->ctx->num_sms * ctas_per_sm));
+    generic_sweep_kernel<KIND, DATUM><<<grid, kGenThreads, smem, m->ctx->stream>>>(p);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    return BIAS_OK;
+}
+
 int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const int32_t *work_idx32,
                    const int32_t *row_of, int32_t *prior_rows, const double *ext_uniforms, int frozen,
                    int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,
@@ -194,18 +214,9 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
     p.pending_list = m->pending;
     p.pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
 
-    const size_t smem = generic_smem_bytes(p.n_out);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        BIAS_CUDA_TRY(cudaFuncSetAttribute(generic_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-    int64_t blocks = (n_work + kGenWarps - 1) / kGenWarps;
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)m->ctx->num_sms * 12));
-    generic_sweep_kernel<<<grid, kGenThreads, smem, m->ctx->stream>>>(p);
-    BIAS_CUDA_TRY(cudaGetLastError());
-    m->ctx->launches += 1;
-    return BIAS_OK;
+    if (p.kind == BIAS_G1G1) return launch_generic_t<BIAS_G1G1, BIAS_F64>(m, p);
+    if (p.datum == BIAS_INT) return launch_generic_t<BIAS_MD, BIAS_INT>(m, p);
+    return launch_generic_t<BIAS_MD, BIAS_SENT>(m, p);
 }
 
 // ---------------------------------------------------------------------------------------
