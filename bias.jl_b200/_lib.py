@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbias_cuda.so")
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE, ESTATE = range(7)
 MD, G1G1 = 0, 1
 INT, SENT, F64 = 0, 1, 2
-MODEL_LDA, MODEL_BMM, MODEL_HDP = 0, 1, 2
+MODEL_LDA, MODEL_BMM, MODEL_HDP, MODEL_RCRP = 0, 1, 2, 3
 
 # every symbol include/bias_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -28,6 +28,7 @@ SYMBOLS = [
     "bias_model_last_stats", "bias_model_get_components", "bias_model_get_group_counts", "bias_model_get_hdp",
     "bias_model_conditionals", "bias_model_frozen_draws", "bias_hdp_table_conditionals", "bias_stirling_rows",
     "bias_model_log_likelihood", "bias_model_delta_begin", "bias_model_delta_begin_zero", "bias_model_delta_pack", "bias_model_delta_apply", "bias_model_last_sweep_ms",
+    "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam",
 ]
 
 
@@ -55,6 +56,11 @@ class SweepStats(C.Structure):
 class HdpParams(C.Structure):
     _fields_ = [("KK", C.c_int32), ("Kmax", C.c_int32), ("gg", C.c_double), ("g1", C.c_double),
                 ("g2", C.c_double), ("aa", C.c_double), ("a1", C.c_double), ("a2", C.c_double),
+                ("sample_hyperparam", C.c_int32), ("n_internals", C.c_int32)]
+
+
+class RcrpParams(C.Structure):
+    _fields_ = [("KK", C.c_int32), ("Kmax", C.c_int32), ("a1", C.c_double), ("a2", C.c_double),
                 ("sample_hyperparam", C.c_int32), ("n_internals", C.c_int32)]
 
 
@@ -104,6 +110,11 @@ def lib():
     L.bias_model_delta_pack.argtypes = [vp, pp, C.POINTER(i64), pp, C.POINTER(i64)]
     L.bias_model_delta_apply.argtypes = [vp]
     L.bias_model_last_sweep_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+    rp = C.POINTER(RcrpParams)
+    L.bias_rcrp_run.argtypes = [vp, cj, dt, i64, vp, vp, rp, vp, i32, i32, st]
+    L.bias_rcrp_create.argtypes = [vp, cj, dt, i64, vp, vp, rp, vp, pp]
+    L.bias_model_get_rcrp.argtypes = [vp, rp, vp]
+    L.bias_model_set_sample_hyperparam.argtypes = [vp, i32]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int

@@ -50,6 +50,10 @@ struct GenericParams {
     double m0, v0, vv;
     double alpha;               // LDA/BMM aa; HDP aa (alpha0)
     const double *hdp_beta;     // HDP my_beta[KK+1]
+    // RCRP (src/RCRP.jl): groups are epochs; the prior couples epoch t with t-1 and t+1
+    int32_t rcrp_T;             // number of epochs
+    const double *rcrp_aa;      // [T] per-epoch concentration
+    int64_t work_base;          // first item of the launch when no index list is given
     // RNG
     uint64_t seed;
     uint32_t sweep;
@@ -149,10 +153,28 @@ __device__ __forceinline__ Datum load_datum(const GenericParams &p, int64_t i, i
 template <int KIND, int DATUM>
 __device__ __forceinline__ double score_all(const GenericParams &p, const Datum &d, int zold, int K, int n_out,
                                             const int32_t *prow, const double *hdp_beta, double alpha,
-                                            double *sc, int lane) {
+                                            double *sc, int lane, int epoch = 0) {
     const bool is_hdp = p.model == BIAS_MODEL_HDP;
+    const bool is_rcrp = p.model == BIAS_MODEL_RCRP;
     const int Kpad = p.Kpad;
     double lmax = -INFINITY;
+    // RCRP: rows of the neighbouring epochs and a = aa[t] / (1 + #components alive in the window)
+    const int32_t *rprev = nullptr, *rnext = nullptr;
+    double rc_a = 0.0;
+    if (is_rcrp) {
+        if (epoch > 0) rprev = prow - Kpad;
+        if (epoch < p.rcrp_T - 1) rnext = prow + Kpad;
+        if (rnext) {                                   // src/RCRP.jl:196-198, :267-269
+            int alive = 0;
+            for (int k = lane; k < K; k += 32) {
+                const int tot = __ldcg(prow + k) - (k == zold ? 1 : 0) + (rprev ? __ldcg(rprev + k) : 0) + __ldcg(rnext + k);
+                alive += (tot > 0) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) alive += __shfl_xor_sync(kFull, alive, o);
+            rc_a = alpha / (double)(alive + 1);
+        }
+    }
     for (int k = lane; k < n_out; k += 32) {
         const bool own = (k == zold);
         const bool fresh = (k >= K);                  // HDP new-component slot: the empty prototype
@@ -160,6 +182,24 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
         if (is_hdp) {
             prior = fresh ? log(alpha * hdp_beta[K])
                           : log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha * hdp_beta[k]);
+        } else if (is_rcrp) {
+            if (fresh) {
+                prior = log(alpha);                                        // src/RCRP.jl:217
+            } else {
+                const int cur = __ldcg(prow + k) - (own ? 1 : 0);
+                const int cnt = cur + (rprev ? __ldcg(rprev + k) : 0);   // :213 (first epoch), :283
+                if (cnt <= 0) {
+                    prior = -INFINITY;                                     // not in kk_idx_precur
+                } else {
+                    prior = log((double)cnt);
+                    if (rnext) {
+                        // sum(L1) - L2 is common to every outcome; what differs is L1[k] evaluated with
+                        // n_tk + 1 (:209-211), and sum_{i<n'} log(i+n+1+a) - log(i+n+a) telescopes:
+                        const double nx = (double)__ldcg(rnext + k);
+                        prior += log(((double)cur + nx + rc_a) / ((double)cur + rc_a));
+                    }
+                }
+            }
         } else {
             prior = log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha);
         }
@@ -341,11 +381,13 @@ generic_sweep_kernel(const GenericParams p) {
     unsigned long long moved_acc = 0;
 
     for (int64_t q = (int64_t)blockIdx.x * kGenWarps + warp; q < p.n_work; q += n_warps) {
-        const int64_t i = p.item_idx ? p.item_idx[q] : (p.work_idx32 ? (int64_t)p.work_idx32[q] : q);
+        const int64_t i = p.item_idx ? p.item_idx[q] : (p.work_idx32 ? (int64_t)p.work_idx32[q] : p.work_base + q);
         const int zold = p.z[i];                      // -1: the item is currently unassigned (HDP pending)
         int32_t *prow = p.prior_rows + (p.row_of ? (size_t)p.row_of[p.row_by_work ? q : i] * Kpad : 0);
         const Datum d = load_datum<KIND, DATUM>(p, i, lane);
-        const double lmax = score_all<KIND, DATUM>(p, d, zold, K, n_out, prow, p.hdp_beta, p.alpha, sc, lane);
+        const int epoch = (p.model == BIAS_MODEL_RCRP) ? p.row_of[i] : 0;
+        const double alpha_i = (p.model == BIAS_MODEL_RCRP) ? p.rcrp_aa[epoch] : p.alpha;
+        const double lmax = score_all<KIND, DATUM>(p, d, zold, K, n_out, prow, p.hdp_beta, alpha_i, sc, lane, epoch);
 
         const int64_t uidx = (p.item_idx || p.work_idx32) ? q : i;
         double u;
@@ -376,7 +418,7 @@ generic_sweep_kernel(const GenericParams p) {
         }
 
         // HDP: a draw of the new-component slot is deferred to the serial birth pass
-        const bool born = is_hdp && knew >= K;
+        const bool born = (is_hdp || p.model == BIAS_MODEL_RCRP) && knew >= K;
         if (born) {
             // leave the item unassigned and queue it (also when it was already unassigned)
             if (zold >= 0) apply_move<KIND, DATUM>(p, d, zold, -1, prow, lane);

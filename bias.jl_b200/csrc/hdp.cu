@@ -265,7 +265,9 @@ hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK
         const int64_t i = list[q];
         int32_t *prow = p.prior_rows + (size_t)p.row_of[i] * p.Kpad;
         const Datum d = load_datum<KIND, DATUM>(p, i, lane);
-        const double lmax = score_all<KIND, DATUM>(p, d, -1, KK, KK + 1, prow, beta, p.alpha, sc, lane);
+        const int epoch = (p.model == BIAS_MODEL_RCRP) ? p.row_of[i] : 0;
+        const double alpha_i = (p.model == BIAS_MODEL_RCRP) ? p.rcrp_aa[epoch] : p.alpha;
+        const double lmax = score_all<KIND, DATUM>(p, d, -1, KK, KK + 1, prow, beta, alpha_i, sc, lane, epoch);
         PhiloxStream rs(p.seed, (uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep * 8u + kStreamBirth);
         const double u = rs.u01();
         int knew = draw_parallel(sc, KK + 1, lmax, u, lane);
@@ -275,7 +277,7 @@ hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK
                 knew = KK - 1;
             } else {
                 const double b = 1.0 - pow(1.0 - rs.u01(), 1.0 / gg);      // Beta(1, gg), src/HDP.jl:325
-                if (lane == 0) {
+                if (lane == 0 && p.model == BIAS_MODEL_HDP) {
                     const double b_new = beta[KK];
                     beta[KK] = b * b_new;                                   // :326-328
                     beta[KK + 1] = (1.0 - b) * b_new;
@@ -426,7 +428,9 @@ int hdp_destroy(bias_model *m) {
 
 static GenericParams birth_params(bias_model *m) {
     GenericParams p{};
-    p.model = BIAS_MODEL_HDP;
+    p.model = m->model;
+    p.rcrp_T = (int32_t)m->G;
+    p.rcrp_aa = m->d_aa_t;
     p.kind = m->conj.kind;
     p.datum = m->conj.datum;
     p.K = m->hdp.KK;
@@ -457,23 +461,13 @@ static GenericParams birth_params(bias_model *m) {
     return p;
 }
 
-int hdp_sweep(bias_model *m) {
+// Serial birth pass + parallel re-sampling of the rest of the queue, until the queue is empty.
+static int resolve_births(bias_model *m, int32_t *&list_cur, int32_t *&list_next) {
     bias_ctx *ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     const int Kpad = m->Kpad, Kmax = m->hdp.Kmax;
     unsigned int *d_pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
     int *d_err = reinterpret_cast<int *>(m->scratch + 4);
-
-    BIAS_TRY(hdp_prune(m));                       // src/HDP.jl:248-264
-    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 6 * sizeof(unsigned long long), st));
-    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
-
-    // 1. parallel assignment pass
-    int32_t *list_cur = m->pending, *list_next = m->pending + std::max<int64_t>(1, m->N);
-    m->pending = list_cur;
-    BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, m->group_of, m->group_rows, nullptr, 0, 0, nullptr, nullptr,
-                            nullptr, kStreamItemDraw));
-    // 2. births
     uint32_t round = 0;
     for (;;) {
         unsigned int n_pending = 0;
@@ -516,6 +510,27 @@ int hdp_sweep(bias_model *m) {
             std::swap(list_cur, list_next);
         }
     }
+    return BIAS_OK;
+}
+
+int hdp_sweep(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int Kpad = m->Kpad, Kmax = m->hdp.Kmax;
+    unsigned int *d_pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
+    int *d_err = reinterpret_cast<int *>(m->scratch + 4);
+
+    BIAS_TRY(hdp_prune(m));                       // src/HDP.jl:248-264
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 6 * sizeof(unsigned long long), st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+
+    // 1. parallel assignment pass
+    int32_t *list_cur = m->pending, *list_next = m->pending + std::max<int64_t>(1, m->N);
+    m->pending = list_cur;
+    BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, m->group_of, m->group_rows, nullptr, 0, 0, nullptr, nullptr,
+                            nullptr, kStreamItemDraw));
+    // 2. births
+    BIAS_TRY(resolve_births(m, list_cur, list_next));
     m->pending = std::min(list_cur, list_next);
     // 3. prune components that died during the pass (src/HDP.jl:291-307)
     BIAS_TRY(hdp_prune(m));
@@ -587,6 +602,121 @@ int hdp_sweep(bias_model *m) {
     }
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    return BIAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// RCRP (reference src/RCRP.jl:77-416): epochs are visited serially, the items of an epoch in parallel
+// ---------------------------------------------------------------------------------------
+template <int KIND, int DATUM>
+__global__ void rcrp_split_kernel(GenericParams p, int64_t i0, int64_t i1, int k_from, int k_to) {
+    // src/RCRP.jl:309-331: everything chain k_from holds from epoch t+1 on moves to the new component k_to
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = i0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < i1; i += nw) {
+        if (p.z[i] != k_from) continue;
+        int32_t *prow = p.prior_rows + (size_t)p.row_of[i] * p.Kpad;
+        const Datum d = load_datum<KIND, DATUM>(p, i, lane);
+        apply_move<KIND, DATUM>(p, d, k_from, k_to, prow, lane);
+        if (lane == 0) p.z[i] = k_to;
+    }
+}
+
+int rcrp_create(bias_model *m, const bias_rcrp_params *rp, const double *aa) {
+    m->h_aa_t.assign(aa, aa + m->G);
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_aa_t, (size_t)m->G * 8));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)m->G * 8, cudaMemcpyHostToDevice, m->ctx->stream));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    (void)rp;
+    return BIAS_OK;
+}
+
+static void rcrp_host_hyper(bias_model *m, int64_t t, int KK_t) {
+    // src/RCRP.jl:60-74.  The reference's loop variable `for n = 1:iters` (:62) shadows the epoch size it
+    // was handed, so the "n" of the Escobar-West update is the iteration number; kept as is.
+    std::uniform_real_distribution<double> ud(0.0, 1.0);
+    for (int it = 1; it <= m->hdp.n_internals; ++it) {
+        const double n = (double)it;
+        std::gamma_distribution<double> g1(m->h_aa_t[t] + 1.0, 1.0), g2(n, 1.0);
+        const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
+        const double eta = x1 / (x1 + x2);                                   // Beta(aa + 1, n)
+        const double le = std::log(eta);
+        const double rr = (m->hdp.a1 + KK_t - 1.0) / (n * (m->hdp.a2 - le));
+        const double pi_eta = rr / (1.0 + rr);
+        const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.a1 + KK_t : m->hdp.a1 + KK_t - 1.0;
+        if (shape > 0.0) {
+            std::gamma_distribution<double> gs(shape, 1.0);
+            m->h_aa_t[t] = gs(m->host_rng) / (m->hdp.a2 - le);
+        }
+    }
+}
+
+int rcrp_sweep(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int Kpad = m->Kpad, Kmax = m->hdp.Kmax;
+    const int64_t TT = m->G;
+    BIAS_TRY(hdp_prune(m));                       // src/RCRP.jl:116-128 (and the in-loop deletions, once per sweep)
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 6 * sizeof(unsigned long long), st));
+    int32_t *list_cur = m->pending, *list_next = m->pending + std::max<int64_t>(1, m->N);
+    int32_t *const list_base = m->pending;
+    std::vector<int32_t> rows((size_t)TT * Kpad);
+    for (int64_t t = 0; t < TT; ++t) {
+        const int64_t i0 = m->h_group_ptr[t], i1 = m->h_group_ptr[t + 1];
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)TT * 8, cudaMemcpyHostToDevice, st));
+        if (i1 > i0) {
+            m->pending = list_cur;
+            m->work_base = i0;
+            int rc = launch_generic(m, i1 - i0, nullptr, nullptr, m->group_of, m->group_rows, nullptr, 0, 0, nullptr,
+                                    nullptr, nullptr, kStreamItemDraw);
+            m->work_base = 0;
+            BIAS_TRY(rc);
+            BIAS_TRY(resolve_births(m, list_cur, list_next));
+        }
+        const bool middle = (t > 0 && t < TT - 1);
+        if (middle || m->hdp.sample_hyperparam) {
+            BIAS_CUDA_TRY(cudaMemcpyAsync(rows.data(), m->group_rows, rows.size() * 4, cudaMemcpyDeviceToHost, st));
+            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        if (middle) {
+            const int KK0 = m->hdp.KK;
+            for (int k = 0; k < KK0; ++k) {
+                if (rows[(size_t)t * Kpad + k] != 0 || rows[(size_t)(t + 1) * Kpad + k] == 0) continue;
+                int64_t before = 0;
+                for (int64_t tt = 0; tt <= t; ++tt) before += rows[(size_t)tt * Kpad + k];
+                if (before == 0) continue;
+                if (m->hdp.KK + 2 > Kmax)
+                    return fail(BIAS_ERANGE, "RCRP: Kmax = %d component slots exhausted while splitting a chain", Kmax);
+                const int kn = m->hdp.KK;
+                GenericParams bp = birth_params(m);
+                const int64_t j0 = m->h_group_ptr[t + 1], j1 = m->N;
+                const int grid = grid1d(ctx, (j1 - j0) * 32, 128, 8);
+                if (bp.kind == BIAS_G1G1) rcrp_split_kernel<BIAS_G1G1, BIAS_F64><<<grid, 128, 0, st>>>(bp, j0, j1, k, kn);
+                else if (bp.datum == BIAS_INT) rcrp_split_kernel<BIAS_MD, BIAS_INT><<<grid, 128, 0, st>>>(bp, j0, j1, k, kn);
+                else rcrp_split_kernel<BIAS_MD, BIAS_SENT><<<grid, 128, 0, st>>>(bp, j0, j1, k, kn);
+                BIAS_CUDA_TRY(cudaGetLastError());
+                ctx->launches += 1;
+                m->hdp.KK += 1;
+                // keep the host copy of the table in step for the remaining checks of this epoch
+                for (int64_t tt = t + 1; tt < TT; ++tt) {
+                    rows[(size_t)tt * Kpad + kn] = rows[(size_t)tt * Kpad + k];
+                    rows[(size_t)tt * Kpad + k] = 0;
+                }
+            }
+        }
+        if (m->hdp.sample_hyperparam) {
+            int KK_t = 0;
+            for (int k = 0; k < m->hdp.KK; ++k) KK_t += rows[(size_t)t * Kpad + k] != 0;
+            rcrp_host_hyper(m, t, KK_t);
+        }
+    }
+    m->pending = list_base;
+    BIAS_TRY(hdp_prune(m));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)TT * 8, cudaMemcpyHostToDevice, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->hdp.aa = m->h_aa_t[0];
     m->sweep_index += 1;
     m->stats_pending = true;
     return BIAS_OK;

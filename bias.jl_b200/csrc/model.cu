@@ -15,6 +15,8 @@ namespace bias {
 
 static thread_local std::string g_err;
 
+bool is_dynamic_K(const bias_model *m) { return m->model == BIAS_MODEL_HDP || m->model == BIAS_MODEL_RCRP; }
+
 void set_error(const char *fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -173,9 +175,12 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
     p.model = m->model;
     p.kind = m->conj.kind;
     p.datum = m->conj.datum;
-    p.K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    p.K = is_dynamic_K(m) ? m->hdp.KK : m->K;
     p.Kpad = m->Kpad;
-    p.n_out = (m->model == BIAS_MODEL_HDP) ? p.K + 1 : p.K;
+    p.n_out = is_dynamic_K(m) ? p.K + 1 : p.K;
+    p.rcrp_T = (int32_t)m->G;
+    p.rcrp_aa = m->d_aa_t;
+    p.work_base = m->work_base;
     p.n_work = n_work;
     p.item_idx = item_idx;
     p.work_idx32 = work_idx32;
@@ -397,7 +402,7 @@ int bias_model_destroy(bias_model *m) {
     hdp_destroy(m);
     void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
                     m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
-                    m->delta_f64, m->scratch};
+                    m->delta_f64, m->scratch, m->d_aa_t};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
@@ -410,11 +415,11 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
                       int32_t K, double alpha, const bias_hdp_params *hdp, bias_model **out) {
     if (!ctx || !out) return fail(BIAS_EINVAL, "null argument");
     *out = nullptr;
-    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "unknown model %d", model);
-    if (model == BIAS_MODEL_HDP) {
-        if (!hdp) return fail(BIAS_EINVAL, "HDP parameters are required");
+    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_RCRP) return fail(BIAS_EINVAL, "unknown model %d", model);
+    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP) {
+        if (!hdp) return fail(BIAS_EINVAL, "HDP / RCRP parameters are required");
         if (hdp->KK < 1 || hdp->Kmax < hdp->KK + 2) return fail(BIAS_EINVAL, "HDP: need 1 <= KK and Kmax >= KK + 2");
-        if (!(hdp->gg > 0.0) || !(hdp->aa > 0.0)) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
+        if (model == BIAS_MODEL_HDP && (!(hdp->gg > 0.0) || !(hdp->aa > 0.0))) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
         if (hdp->Kmax > 4096) return fail(BIAS_EINVAL, "HDP: Kmax is limited to 4096 component slots");
         if (hdp->n_internals < 0) return fail(BIAS_EINVAL, "HDP: n_internals < 0");
         K = hdp->KK;
@@ -434,7 +439,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     m->alpha = alpha;
     m->V = (conj->kind == BIAS_MD) ? conj->dd : 0;
     for (int64_t j = 0; j < m->G; ++j) m->max_group_len = std::max(m->max_group_len, group_ptr[j + 1] - group_ptr[j]);
-    const int32_t Kcap = (model == BIAS_MODEL_HDP) ? hdp->Kmax : K;
+    const int32_t Kcap = (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP) ? hdp->Kmax : K;
     // pad K to 128 * 2^j (the fast kernel's chunk tree); the generic kernels only need the stride
     int32_t kp = 128;
     while (kp < Kcap) kp *= 2;
@@ -496,7 +501,8 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     M_TRY(dev_alloc(&m->scratch, 8));
     M_CUDA(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
     M_CUDA(cudaMallocHost((void **)&m->h_scratch, 8 * sizeof(unsigned long long)));
-    if (model == BIAS_MODEL_HDP) M_TRY(hdp_create(m, hdp));
+    if (model != BIAS_MODEL_BMM) m->h_group_ptr.assign(group_ptr, group_ptr + m->G + 1);
+    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP) M_TRY(hdp_create(m, hdp));
     M_TRY(validate_on_device(m, K));
     M_TRY(rebuild_counts(m));
     // the uploads came from caller-owned pageable memory: finish them before returning
@@ -511,7 +517,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
 int bias_model_set_zz(bias_model *m, const int32_t *zz) {
     if (!m || !zz) return fail(BIAS_EINVAL, "null argument");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
-    const int32_t Kcur = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    const int32_t Kcur = is_dynamic_K(m) ? m->hdp.KK : m->K;
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
     BIAS_TRY(validate_on_device(m, Kcur));
     BIAS_TRY(rebuild_counts(m));
@@ -530,6 +536,7 @@ int bias_model_get_zz(bias_model *m, int32_t *zz) {
 static int one_sweep(bias_model *m) {
     cudaStream_t st = m->ctx->stream;
     if (m->model == BIAS_MODEL_HDP) return hdp_sweep(m);
+    if (m->model == BIAS_MODEL_RCRP) return rcrp_sweep(m);
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st));
     if (m->fast) {
         BIAS_TRY(launch_lda_fast(m, nullptr, 0, nullptr));
@@ -577,7 +584,7 @@ static int fetch_stats(bias_model *m) {
         m->last.n_moved = (int64_t)m->h_scratch[1];
         m->stats_pending = false;
     }
-    m->last.KK = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    m->last.KK = is_dynamic_K(m) ? m->hdp.KK : m->K;
     m->last.gg = m->hdp.gg;
     m->last.aa = (m->model == BIAS_MODEL_HDP) ? m->hdp.aa : m->alpha;
     return BIAS_OK;
@@ -595,7 +602,7 @@ int bias_model_get_components(bias_model *m, int64_t *mi, int64_t *mm, double *m
     if (!m) return fail(BIAS_EINVAL, "null model");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
-    const int K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    const int K = is_dynamic_K(m) ? m->hdp.KK : m->K;
     std::vector<int32_t> h_nk(m->Kpad), h_ni(m->Kpad);
     BIAS_CUDA_TRY(cudaMemcpyAsync(h_nk.data(), m->n_k, (size_t)m->Kpad * 4, cudaMemcpyDeviceToHost, st));
     BIAS_CUDA_TRY(cudaMemcpyAsync(h_ni.data(), m->n_items, (size_t)m->Kpad * 4, cudaMemcpyDeviceToHost, st));
@@ -635,7 +642,7 @@ int bias_model_get_group_counts(bias_model *m, int64_t *nn) {
     BIAS_CUDA_TRY(cudaMemcpyAsync(z.data(), m->z, (size_t)m->N * 4, cudaMemcpyDeviceToHost, m->ctx->stream));
     BIAS_CUDA_TRY(cudaMemcpyAsync(ptr.data(), m->group_ptr, ((size_t)m->G + 1) * 8, cudaMemcpyDeviceToHost, m->ctx->stream));
     BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
-    const int K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
+    const int K = is_dynamic_K(m) ? m->hdp.KK : m->K;
     std::fill(nn, nn + (size_t)m->G * K, (int64_t)0);
     for (int64_t j = 0; j < m->G; ++j)
         for (int64_t i = ptr[j]; i < ptr[j + 1]; ++i)
@@ -654,8 +661,8 @@ int bias_model_conditionals(bias_model *m, int64_t n_query, const int64_t *item_
         if (item_idx[q] < 0 || item_idx[q] >= m->N) return fail(BIAS_EINVAL, "query item out of range");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
-    const int K = (m->model == BIAS_MODEL_HDP) ? m->hdp.KK : m->K;
-    const int n_out = (m->model == BIAS_MODEL_HDP) ? K + 1 : K;
+    const int K = is_dynamic_K(m) ? m->hdp.KK : m->K;
+    const int n_out = is_dynamic_K(m) ? K + 1 : K;
     int64_t *d_idx = nullptr;
     double *d_u = nullptr, *d_raw = nullptr, *d_prob = nullptr;
     int32_t *d_draw = nullptr, *d_rows = nullptr, *d_rowof = nullptr;
@@ -706,7 +713,7 @@ int bias_model_conditionals(bias_model *m, int64_t n_query, const int64_t *item_
 
 int bias_model_frozen_draws(bias_model *m, const double *uniforms, int32_t *draws) {
     if (!m || !uniforms || !draws) return fail(BIAS_EINVAL, "null argument");
-    if (m->model == BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "frozen draws are defined for LDA and BMM");
+    if (is_dynamic_K(m)) return fail(BIAS_EINVAL, "frozen draws are defined for LDA and BMM");
     if (m->N == 0) return BIAS_OK;
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
@@ -851,6 +858,74 @@ static int run_model(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, c
     }
     if (rc == BIAS_OK) rc = bias_model_get_zz(m, zz);
     if (rc == BIAS_OK && hp) rc = bias_model_get_hdp(m, hp, beta_out);
+    bias_model_destroy(m);
+    return rc;
+}
+
+int bias_rcrp_create(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int64_t n_epochs,
+                     const int64_t *epoch_ptr, const int32_t *zz, const bias_rcrp_params *params, const double *aa,
+                     bias_model **out) {
+    if (!params || !aa || !out) return fail(BIAS_EINVAL, "null argument");
+    if (n_epochs < 2) return fail(BIAS_EINVAL, "RCRP needs at least two epochs (src/RCRP.jl:174-398 has first and last epoch blocks)");
+    for (int64_t t = 0; t < n_epochs; ++t)
+        if (!(aa[t] > 0.0)) return fail(BIAS_EINVAL, "RCRP: aa[%lld] must be > 0", (long long)t);
+    bias_hdp_params hp{};
+    hp.KK = params->KK;
+    hp.Kmax = params->Kmax;
+    hp.gg = 1.0;
+    hp.aa = aa[0];
+    hp.a1 = params->a1;
+    hp.a2 = params->a2;
+    hp.sample_hyperparam = params->sample_hyperparam;
+    hp.n_internals = params->n_internals;
+    BIAS_TRY(bias_model_create(ctx, BIAS_MODEL_RCRP, conj, data, n_epochs, epoch_ptr, zz, params->KK, aa[0], &hp, out));
+    int rc = rcrp_create(*out, params, aa);
+    if (rc != BIAS_OK) {
+        bias_model_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int bias_model_get_rcrp(bias_model *m, bias_rcrp_params *params, double *aa) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (m->model != BIAS_MODEL_RCRP) return fail(BIAS_EINVAL, "not an RCRP model");
+    if (params) {
+        params->KK = m->hdp.KK;
+        params->Kmax = m->hdp.Kmax;
+        params->a1 = m->hdp.a1;
+        params->a2 = m->hdp.a2;
+        params->sample_hyperparam = m->hdp.sample_hyperparam;
+        params->n_internals = m->hdp.n_internals;
+    }
+    if (aa) std::copy(m->h_aa_t.begin(), m->h_aa_t.end(), aa);
+    return BIAS_OK;
+}
+
+int bias_model_set_sample_hyperparam(bias_model *m, int32_t on) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    m->hdp.sample_hyperparam = on ? 1 : 0;
+    return BIAS_OK;
+}
+
+int bias_rcrp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int64_t n_epochs,
+                  const int64_t *epoch_ptr, int32_t *zz, bias_rcrp_params *params, double *aa, int32_t n_burnins,
+                  int32_t n_sweeps, bias_sweep_stats *stats) {
+    if (!params || !aa) return fail(BIAS_EINVAL, "null argument");
+    if (n_sweeps < 0) return fail(BIAS_EINVAL, "n_sweeps < 0");
+    bias_model *m = nullptr;
+    BIAS_TRY(bias_rcrp_create(ctx, conj, data, n_epochs, epoch_ptr, zz, params, aa, &m));
+    int rc = BIAS_OK;
+    for (int32_t s = 0; s < n_sweeps && rc == BIAS_OK; ++s) {
+        if (s >= n_burnins) m->hdp.sample_hyperparam = 0;        // src/RCRP.jl:166-168
+        rc = one_sweep(m);
+        if (rc == BIAS_OK && stats) {
+            rc = fetch_stats(m);
+            stats[s] = m->last;
+        }
+    }
+    if (rc == BIAS_OK) rc = bias_model_get_zz(m, zz);
+    if (rc == BIAS_OK) rc = bias_model_get_rcrp(m, params, aa);
     bias_model_destroy(m);
     return rc;
 }

@@ -67,6 +67,12 @@ struct bias_model {
     double *d_hyper = nullptr;      // [0] sum log w, [1] sum s
     int32_t *d_remap = nullptr;     // [Kpad] slot compaction map
     std::mt19937_64 host_rng;
+
+    // RCRP (epochs are the groups)
+    std::vector<double> h_aa_t;     // [T] per-epoch concentration
+    double *d_aa_t = nullptr;
+    std::vector<int64_t> h_group_ptr;
+    int64_t work_base = 0;          // first item of the next generic launch (per-epoch passes)
 };
 
 namespace bias {
@@ -74,6 +80,9 @@ int ensure_stirling(bias_ctx *ctx, int32_t rows);
 int hdp_create(bias_model *m, const bias_hdp_params *hp);
 int hdp_sweep(bias_model *m);
 int hdp_destroy(bias_model *m);
+int rcrp_create(bias_model *m, const bias_rcrp_params *rp, const double *aa);
+int rcrp_sweep(bias_model *m);
+bool is_dynamic_K(const bias_model *m);
 int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const int32_t *work_idx32,
                    const int32_t *row_of, int32_t *prior_rows, const double *ext_uniforms, int frozen,
                    int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,

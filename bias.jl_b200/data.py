@@ -165,3 +165,30 @@ def dirichlet_lda_corpus(D, L, K, V, beta_conc=0.01, alpha_conc=0.1, seed=123):
         words[d0 * L:d1 * L] = out
     doc_ptr = np.arange(D + 1, dtype=np.int64) * L
     return doc_ptr, words
+
+
+def gen_rcrp_data(N_t, aa: float, seed=123):
+    """Recurrent-CRP seating (src/generate_data.jl:57-113): epoch 1 is a plain CRP; a customer of epoch t
+    joins cluster k with weight n[t-1,k] + n[t,k] and opens a new one with weight aa.
+    Returns (nn [T x KK], zz list of 0-based label arrays, KK)."""
+    rng = np.random.default_rng(seed)
+    TT = len(N_t)
+    counts: list[np.ndarray] = []        # one length-TT column per cluster
+    zz = []
+    for tt in range(TT):
+        z = np.empty(N_t[tt], dtype=np.int64)
+        for ii in range(N_t[tt]):
+            if tt == 0 and ii == 0:
+                k = 0                                           # :66-70
+                counts.append(np.zeros(TT, dtype=np.int64))
+            else:
+                w = np.array([c[tt] + (c[tt - 1] if tt > 0 else 0) for c in counts] + [aa], dtype=np.float64)
+                w /= w.sum()
+                k = int(min(np.searchsorted(np.cumsum(w), rng.random()), len(w) - 1))
+                if k == len(counts):
+                    counts.append(np.zeros(TT, dtype=np.int64))
+            counts[k][tt] += 1
+            z[ii] = k
+        zz.append(z)
+    nn = np.stack(counts, axis=1) if counts else np.zeros((TT, 0), dtype=np.int64)
+    return nn, zz, len(counts)

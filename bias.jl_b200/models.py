@@ -7,6 +7,9 @@
   collapsed_gibbs_sampler(model, xx, zz, n_burnins, n_lags, n_samples, ...)
                                       src/LDA.jl:67-148, src/BMM.jl:46-130, src/HDP.jl:166-399
   posterior(model, xx, zz)            src/LDA.jl:151-167, src/BMM.jl:134-151
+  RCRP(c, KK, aa, TT, a1, a2)         src/RCRP.jl:18-28
+  RCRP_gibbs_sampler(rcrp, xx, zz, n_burnins, n_lags, n_samples, ...)   src/RCRP.jl:77-416
+  posterior(rcrp, xx, KK_dict, KK)    src/RCRP.jl:418-453
 
 Everything below the sampler entry point runs in libbias_cuda on the GPU; this module only
 flattens the ragged Julia-style containers to CSR, calls the C ABI and writes zz back in place.
@@ -61,6 +64,27 @@ class HDP:
 
     def __repr__(self):
         return (f"Hierarchical Dirichlet Process Mixture Model with {self.KK} "
+                f"{type(self.component).__name__} components")
+
+
+class RCRP:
+    """Recurrent Chinese restaurant process over TT epochs (src/RCRP.jl:18-28).  aa holds one concentration
+    per epoch; KK and aa are updated in place by the sampler.  Kmax is the engine's slot capacity."""
+    model_id = _lib.MODEL_RCRP
+
+    def __init__(self, component, KK: int, aa, TT: int | None = None, a1: float = 1.0, a2: float = 1.0,
+                 Kmax: int = 256):
+        self.component, self.KK = component, int(KK)
+        if np.isscalar(aa):
+            if TT is None:
+                raise ValueError("RCRP(c, KK, aa, TT, a1, a2): TT is required when aa is a scalar")
+            self.aa = np.full(int(TT), float(aa))
+        else:
+            self.aa = np.array(aa, dtype=np.float64)
+        self.a1, self.a2, self.Kmax = float(a1), float(a2), int(Kmax)
+
+    def __repr__(self):
+        return (f"Recurrent Chinese Restaurant Process with {self.KK} "
                 f"{type(self.component).__name__} components")
 
 
@@ -180,6 +204,15 @@ class ResidentSampler:
         self.h = C.c_void_p()
         hp = _hdp_params(model, sample_hyperparam, n_internals) if isinstance(model, HDP) else None
         self.zz = _lib.as_i32(zz_flat)
+        if isinstance(model, RCRP):
+            rp = _lib.RcrpParams(model.KK, model.Kmax, model.a1, model.a2, int(bool(sample_hyperparam)),
+                                 int(n_internals))
+            aa = _lib.as_f64(model.aa)
+            if len(aa) != data.n_groups:
+                raise ValueError(f"RCRP: aa has {len(aa)} entries for {data.n_groups} epochs")
+            check(lib().bias_rcrp_create(ctx.h, C.byref(self.spec), C.byref(data.c), data.n_groups,
+                                         ptr(data.group_ptr), ptr(self.zz), C.byref(rp), ptr(aa), C.byref(self.h)))
+            return
         check(lib().bias_model_create(ctx.h, model.model_id, C.byref(self.spec), C.byref(data.c), data.n_groups,
                                       ptr(data.group_ptr), ptr(self.zz), model.KK, model.aa,
                                       C.byref(hp) if hp is not None else None, C.byref(self.h)))
@@ -237,10 +270,19 @@ class ResidentSampler:
         check(lib().bias_model_get_hdp(self.h, C.byref(hp), ptr(beta)))
         return hp, beta[:hp.KK + 1].copy()
 
+    def rcrp_state(self):
+        rp = _lib.RcrpParams()
+        aa = np.zeros(self.data.n_groups)
+        check(lib().bias_model_get_rcrp(self.h, C.byref(rp), ptr(aa)))
+        return rp, aa
+
+    def set_sample_hyperparam(self, on: bool):
+        check(lib().bias_model_set_sample_hyperparam(self.h, int(bool(on))))
+
     # -- verification
     def conditionals(self, item_idx, uniforms):
         idx, u = _lib.as_i64(item_idx), _lib.as_f64(uniforms)
-        n_out = self.current_KK() + (1 if isinstance(self.model, HDP) else 0)
+        n_out = self.current_KK() + (1 if isinstance(self.model, (HDP, RCRP)) else 0)
         raw, prob = np.zeros((len(idx), n_out)), np.zeros((len(idx), n_out))
         draw = np.zeros(len(idx), dtype=np.int32)
         check(lib().bias_model_conditionals(self.h, len(idx), ptr(idx), ptr(u), ptr(raw), ptr(prob), ptr(draw)))
@@ -376,11 +418,65 @@ def collapsed_gibbs_sampler(model, xx, zz, n_burnins: int, n_lags: int, n_sample
     return None
 
 
-def posterior(model, xx, zz, ctx: Context | None = None):
+def RCRP_gibbs_sampler(rcrp: RCRP, xx, zz, n_burnins: int, n_lags: int, n_samples: int,
+                       sample_hyperparam: bool = True, n_internals: int = 10, store_every: int = 100,
+                       filename: str | None = None, KK_list: Sequence[int] = (), KK_dict: dict | None = None,
+                       ctx: Context | None = None, verbose: bool = False):
+    """RCRP_gibbs_sampler!(rcrp, xx, zz, n_burnins, n_lags, n_samples, sample_hyperparam, n_internals,
+    store_every, filename, KK_list, KK_dict) -> (KK_list, KK_dict)   (src/RCRP.jl:77-416).
+    xx / zz are lists over epochs; zz, rcrp.KK and rcrp.aa are updated in place."""
+    ctx = ctx or default_context()
+    data = FlatData(rcrp.component, xx, True)
+    n_iterations = n_burnins + n_samples * (n_lags + 1)                 # src/RCRP.jl:159
+    n_old = len(KK_list)
+    KK_list = list(KK_list) + [0] * n_samples
+    KK_dict = {} if (KK_dict is None or n_old == 0) else KK_dict
+    try:
+        rs = ResidentSampler(ctx, rcrp, data, _flat_zz(zz, True), sample_hyperparam=sample_hyperparam,
+                             n_internals=n_internals)
+    except _lib.BiasError as e:
+        if e.code == _lib.EINVAL:
+            raise ValueError(str(e)) from None
+        raise
+    try:
+        if n_samples > 0:
+            KK_list[0] = rs.current_KK()                                # :147 (KK after the inactive-chain prune)
+        for iteration in range(1, n_iterations + 1):
+            if iteration > n_burnins:                                   # :166-168
+                rs.set_sample_hyperparam(False)
+            rs.sweep(1)
+            if verbose:
+                s = rs.stats()
+                burn = "Burning... " if iteration < n_burnins else ""
+                print(f"{burn}iteration: {iteration}, KK={s.KK}, likelihood={s.log_likelihood:.2f}")
+            if (iteration - n_burnins) % (n_lags + 1) == 0 and iteration > n_burnins:
+                i = n_old + (iteration - n_burnins) // (n_lags + 1)
+                KK = rs.current_KK()
+                _scatter_zz(rs.get_zz(), zz, True, data.group_ptr)
+                KK_list[i - 1] = KK
+                KK_dict[KK] = [np.array(g, dtype=np.int64) for g in zz]
+                if filename is not None and i % store_every == 0:
+                    _store(filename, i, zz=np.concatenate(zz), KK_list=np.asarray(KK_list), iteration=iteration)
+        _scatter_zz(rs.get_zz(), zz, True, data.group_ptr)
+        rp, aa = rs.rcrp_state()
+        rcrp.KK, rcrp.aa = int(rp.KK), aa
+    finally:
+        rs.close()
+    return KK_list, KK_dict
+
+
+def posterior(model, xx, zz, KK: int | None = None, ctx: Context | None = None):
     """posterior(model, xx, zz) -> ([posterior(component_k)], nn)  (src/LDA.jl:151-167, src/BMM.jl:134-151).
+    RCRP: posterior(rcrp, xx, KK_dict, KK) (src/RCRP.jl:418-453).
     The sufficient statistics are accumulated on the device by the initialisation pass."""
     from .distributions import Dirichlet, Gaussian1D
     ctx = ctx or default_context()
+    if isinstance(model, RCRP):
+        if KK is None:
+            raise TypeError("posterior(rcrp, xx, KK_dict, KK): KK is required")
+        zz = zz[KK]
+        sized = RCRP(model.component, KK, model.aa, None, model.a1, model.a2, max(model.Kmax, KK + 2))
+        model = sized
     grouped = not isinstance(model, BMM)
     data = FlatData(model.component, xx, grouped)
     rs = ResidentSampler(ctx, model, data, _flat_zz(zz, grouped))
@@ -388,7 +484,7 @@ def posterior(model, xx, zz, ctx: Context | None = None):
         comp = rs.components()
         c0 = model.component
         posts = []
-        for k in range(model.KK):
+        for k in range(rs.current_KK()):
             if isinstance(c0, MultinomialDirichlet):
                 posts.append(Dirichlet(comp["mi"][k] + c0.aa))
             else:

@@ -86,6 +86,16 @@ typedef struct {
     int32_t n_internals;      /* src/HDP.jl:171 */
 } bias_hdp_params;
 
+/* RCRP(c, KK, aa, TT, a1, a2), src/RCRP.jl:18-28.  aa (one concentration per epoch) travels as a
+ * separate array; KK is updated in place like the Julia object. */
+typedef struct {
+    int32_t KK;
+    int32_t Kmax;             /* slot capacity (engine parameter) */
+    double  a1, a2;
+    int32_t sample_hyperparam;/* src/RCRP.jl:81; the sampler switches it off after the burn-in (:166-168) */
+    int32_t n_internals;
+} bias_rcrp_params;
+
 /* ---- context ------------------------------------------------------------------------- */
 BIAS_API int  bias_version(void);
 BIAS_API const char *bias_last_error(void);
@@ -116,15 +126,30 @@ BIAS_API int bias_hdp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_
                  int64_t n_groups, const int64_t *group_ptr, int32_t *zz,
                  bias_hdp_params *params, int32_t n_sweeps, double *beta_out, bias_sweep_stats *stats);
 
+/* RCRP_gibbs_sampler!(rcrp::RCRP, xx, zz, n_burnins, n_lags, n_samples, sample_hyperparam, n_internals, ...)
+ * src/RCRP.jl:77-416.  Epochs arrive as CSR groups (epoch_ptr[n_epochs+1]); aa[n_epochs] and params->KK are
+ * updated in place; hyper-parameters are resampled only during the first n_burnins of the n_sweeps sweeps. */
+BIAS_API int bias_rcrp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data,
+                  int64_t n_epochs, const int64_t *epoch_ptr, int32_t *zz,
+                  bias_rcrp_params *params, double *aa, int32_t n_burnins, int32_t n_sweeps, bias_sweep_stats *stats);
+
 /* ---- resident sampler state: same samplers, split into upload / sweep / download ------- */
 #define BIAS_MODEL_LDA 0
 #define BIAS_MODEL_BMM 1
 #define BIAS_MODEL_HDP 2
+#define BIAS_MODEL_RCRP 3
 /* Uploads xx and zz and runs the initialisation pass (src/LDA.jl:91-98, src/BMM.jl:70-75,
  * src/HDP.jl:217-228).  For BMM pass n_groups = 0, group_ptr = NULL; hdp = NULL unless model is HDP. */
 BIAS_API int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, const bias_data *data,
                       int64_t n_groups, const int64_t *group_ptr, const int32_t *zz,
                       int32_t K, double alpha, const bias_hdp_params *hdp, bias_model **out);
+/* Same for an RCRP model (epochs are the groups). */
+BIAS_API int bias_rcrp_create(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data,
+                     int64_t n_epochs, const int64_t *epoch_ptr, const int32_t *zz,
+                     const bias_rcrp_params *params, const double *aa, bias_model **out);
+BIAS_API int bias_model_get_rcrp(bias_model *m, bias_rcrp_params *params, double *aa /* [n_epochs] */);
+/* Switch hyper-parameter resampling on/off between sweeps (HDP, RCRP). */
+BIAS_API int bias_model_set_sample_hyperparam(bias_model *m, int32_t on);
 BIAS_API int bias_model_destroy(bias_model *m);
 /* n_sweeps asynchronous sweeps on the context stream (one iteration of the loop at src/LDA.jl:103). */
 BIAS_API int bias_model_sweep(bias_model *m, int32_t n_sweeps);

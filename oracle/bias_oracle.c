@@ -711,3 +711,179 @@ int orc_hdp_resample_beta(orc_hdp *h, int64_t D, const int64_t *ptr, const int64
     free(rr); free(MM);
     return 0;
 }
+
+/* ======================================================================
+ * src/RCRP.jl — recurrent Chinese restaurant process
+ * ====================================================================== */
+void orc_rcrp_init(orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, const int64_t *z, int64_t *nn)
+{                                                   /* src/RCRP.jl:98-104, :131-143 */
+    int64_t S = h->Kmax;
+    for (int64_t t = 0; t < h->TT; ++t)
+        for (int64_t i = ptr[t]; i < ptr[t + 1]; ++i) {
+            nn[t * S + z[i]] += 1;
+            orc_additem(c, z[i], d, i);
+        }
+}
+
+static int64_t rcrp_colsum(const int64_t *nn, int64_t S, int64_t t0, int64_t t1, int64_t k)
+{
+    int64_t s = 0;
+    for (int64_t t = t0; t <= t1; ++t) s += nn[t * S + k];
+    return s;
+}
+
+static void rcrp_delete_component(orc_rcrp *h, orc_comps *c, const int64_t *ptr, int64_t *z, int64_t *nn, int64_t kk)
+{                                                   /* :184-193 (and the same block in the other epochs) */
+    int64_t S = h->Kmax, KK = h->KK, TT = h->TT;
+    for (int64_t i = 0; i < ptr[TT]; ++i) if (z[i] > kk) z[i] -= 1;
+    for (int64_t k = kk; k < KK - 1; ++k) orc_comps_move(c, k, k + 1);
+    orc_comps_reset(c, KK - 1);
+    for (int64_t t = 0; t < TT; ++t) {
+        for (int64_t k = kk; k < KK - 1; ++k) nn[t * S + k] = nn[t * S + k + 1];
+        nn[t * S + KK - 1] = 0;
+    }
+    h->KK -= 1;
+}
+
+/* sum(log(collect(0:n-1) + base)) as the reference writes it (:176, :201-204, :211) */
+static double rcrp_logsum(int64_t n, double base)
+{
+    if (n <= 0) return 0.0;
+    double *v = (double *)malloc((size_t)n * sizeof(double));
+    for (int64_t i = 0; i < n; ++i) v[i] = log((double)i + base);
+    double s = orc_julia_sum(v, n);
+    free(v);
+    return s;
+}
+
+/* Scores of one item of epoch t (0-based) on the current (item-removed) state.  pp has KK+1 entries. */
+static void rcrp_scores(const orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, int64_t t, int64_t i,
+                        const int64_t *nn, double *pp)
+{
+    int64_t S = h->Kmax, KK = h->KK, TT = h->TT;
+    int first = (t == 0), last = (t == TT - 1);
+    for (int64_t k = 0; k <= KK; ++k) pp[k] = -INFINITY;           /* pp = fill(-Inf, KK+1) */
+    if (last) {                                                     /* :366-377 */
+        for (int64_t k = 0; k < KK; ++k) {
+            int64_t cnt = nn[(t - 1) * S + k] + nn[t * S + k];
+            if (cnt > 0) pp[k] = log((double)cnt) + orc_logpredictive(c, k, d, i);
+        }
+        pp[KK] = log(h->aa[t]) + orc_logpredictive(c, c->K - 1, d, i);
+        return;
+    }
+    int64_t N_t = ptr[t + 1] - ptr[t], N_next = ptr[t + 2] - ptr[t + 1];
+    double L2 = rcrp_logsum(N_next, (double)N_t + h->aa[t]);       /* :176, :246 (N_t is the full epoch size) */
+    int64_t KK_curnex = 1;
+    for (int64_t k = 0; k < KK; ++k)
+        if (rcrp_colsum(nn, S, first ? t : t - 1, t + 1, k) > 0) KK_curnex += 1;      /* :196-198, :267-269 */
+    double a = h->aa[t] / (double)KK_curnex;
+    double *L1 = (double *)calloc((size_t)(KK > 0 ? KK : 1), sizeof(double));
+    for (int64_t k = 0; k < KK; ++k)
+        if (rcrp_colsum(nn, S, first ? t : t - 1, t + 1, k) > 0)
+            L1[k] = rcrp_logsum(nn[(t + 1) * S + k], (double)nn[t * S + k] + a);     /* :200-203 */
+    for (int64_t k = 0; k < KK; ++k) {
+        int64_t cnt = first ? nn[t * S + k] : nn[(t - 1) * S + k] + nn[t * S + k];
+        if (cnt <= 0) continue;                                     /* kk_idx_precur */
+        double old = L1[k];
+        L1[k] = rcrp_logsum(nn[(t + 1) * S + k], (double)nn[t * S + k] + 1.0 + a);   /* :209-211 */
+        pp[k] = log((double)cnt) + orc_logpredictive(c, k, d, i) + orc_julia_sum(L1, KK) - L2;
+        L1[k] = old;
+    }
+    pp[KK] = log(h->aa[t]) + orc_logpredictive(c, c->K - 1, d, i) + orc_julia_sum(L1, KK) - L2;   /* :217 */
+    free(L1);
+}
+
+static void rcrp_sample_hyperparam(orc_rcrp *h, int64_t t, int64_t n_items, int64_t KK, int iters, orc_rng *g)
+{                                                   /* src/RCRP.jl:60-74 */
+    /* Reference quirk, reproduced: the loop at :62 is `for n = 1:iters`, which rebinds the argument n
+     * (the epoch size), so inside the body n is the iteration number 1..iters, not N_t[tt]. */
+    (void)n_items;
+    for (int it = 1; it <= iters; ++it) {
+        double n = (double)it;
+        double eta = orc_rand_beta(g, h->aa[t] + 1.0, n);
+        double rr = (h->a1 + (double)KK - 1.0) / (n * (h->a2 - log(eta)));
+        double pi_eta = rr / (1.0 + rr);
+        if (orc_rand(g) < pi_eta) h->aa[t] = orc_rand_gamma(g, h->a1 + (double)KK) / (h->a2 - log(eta));
+        else h->aa[t] = orc_rand_gamma(g, h->a1 + (double)KK - 1.0) / (h->a2 - log(eta));
+    }
+}
+
+double orc_rcrp_sweep(orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, int64_t *z, int64_t *nn,
+                      orc_rng *g, const double *uniforms, int shuffle, int sample_hyper, int n_internals)
+{
+    int64_t S = h->Kmax, TT = h->TT;
+    double *pp = (double *)malloc((size_t)(S + 1) * sizeof(double));
+    double ll = 0.0;
+    for (int64_t t = 0; t < TT; ++t) {
+        if (t == 0 || t == TT - 1) ll = (t == 0) ? 0.0 : ll;       /* the reference resets the diagnostic at the first epoch only (:171) */
+        int64_t len = ptr[t + 1] - ptr[t];
+        int64_t *order = (int64_t *)malloc((size_t)(len > 0 ? len : 1) * sizeof(int64_t));
+        if (shuffle) orc_randperm(g, len, order); else for (int64_t q = 0; q < len; ++q) order[q] = q;
+        for (int64_t q = 0; q < len; ++q) {
+            int64_t i = ptr[t] + order[q];
+            int64_t kk = z[i];
+            orc_delitem(c, kk, d, i);
+            nn[t * S + kk] -= 1;
+            if (rcrp_colsum(nn, S, 0, TT - 1, kk) == 0) rcrp_delete_component(h, c, ptr, z, nn, kk);
+            rcrp_scores(h, c, d, ptr, t, i, nn, pp);
+            orc_lognormalize(pp, h->KK + 1);
+            kk = orc_sample(pp, h->KK + 1, uniforms ? uniforms[i] : orc_rand(g));
+            if (kk == h->KK) {                                      /* :222-226 */
+                if (h->KK + 1 >= S) { free(order); free(pp); return NAN; }
+                orc_comps_reset(c, h->KK);
+                h->KK += 1;
+            }
+            z[i] = kk;
+            nn[t * S + kk] += 1;
+            orc_additem(c, kk, d, i);
+            ll += orc_loglikelihood(c, kk, d, i);
+        }
+        free(order);
+        if (t > 0 && t < TT - 1) {
+            /* :309-331 — a chain that is empty at t but alive before and after is split: everything it holds
+             * from t+1 on becomes a new component */
+            for (int64_t kk = 0; kk < h->KK; ++kk) {
+                if (nn[t * S + kk] == 0 && nn[(t + 1) * S + kk] != 0 && rcrp_colsum(nn, S, 0, t, kk) != 0) {
+                    if (h->KK + 1 >= S) { free(pp); return NAN; }
+                    int64_t kn = h->KK;
+                    orc_comps_reset(c, kn);
+                    for (int64_t tt = t + 1; tt < TT; ++tt) {
+                        for (int64_t i = ptr[tt]; i < ptr[tt + 1]; ++i)
+                            if (z[i] == kk) {
+                                z[i] = kn;
+                                orc_delitem(c, kk, d, i);
+                                orc_additem(c, kn, d, i);
+                            }
+                        nn[tt * S + kn] = nn[tt * S + kk];
+                        nn[tt * S + kk] = 0;
+                    }
+                    h->KK += 1;
+                }
+            }
+        }
+        if (sample_hyper) {
+            int64_t KK_t = 0;
+            for (int64_t k = 0; k < h->KK; ++k) if (nn[t * S + k] != 0) KK_t += 1;
+            rcrp_sample_hyperparam(h, t, len, KK_t, n_internals, g);
+        }
+    }
+    free(pp);
+    return ll;
+}
+
+int64_t orc_rcrp_conditional(const orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, int64_t t,
+                             int64_t i, int64_t zi, int64_t *nn, double r, double *raw, double *prob)
+{
+    int64_t S = h->Kmax, n = h->KK + 1;
+    double mu_saved = (c->kind == ORC_G1G1) ? c->mu[zi] : 0.0;
+    orc_delitem(c, zi, d, i);
+    nn[t * S + zi] -= 1;
+    rcrp_scores(h, c, d, ptr, t, i, nn, raw);
+    memcpy(prob, raw, (size_t)n * sizeof(double));
+    orc_lognormalize(prob, n);
+    int64_t k = orc_sample(prob, n, r);
+    orc_additem(c, zi, d, i);
+    nn[t * S + zi] += 1;
+    if (c->kind == ORC_G1G1) c->mu[zi] = mu_saved;
+    return k;
+}

@@ -133,6 +133,26 @@ int orc_hdp_resample_beta(orc_hdp *h, int64_t D, const int64_t *ptr, const int64
                           orc_rng *g, int64_t *M_out);
 void orc_hdp_sample_hyperparam(orc_hdp *h, int64_t D, const int64_t *ptr, int64_t m, orc_rng *g); /* :124-159 */
 
+/* ---- src/RCRP.jl (recurrent Chinese restaurant process, :77-416) ---------------------------
+ * Epochs are the groups: ptr[TT+1] offsets, nn[TT*Kmax] row-major epoch-by-component counts,
+ * aa[TT] per-epoch concentration.  Components are shared by all epochs. */
+typedef struct {
+    int64_t KK, Kmax, TT;
+    double *aa;        /* [TT] */
+    double a1, a2;
+} orc_rcrp;
+void orc_rcrp_init(orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, const int64_t *z, int64_t *nn); /* :98-143 */
+/* One iteration of the MCMC loop (:174-398): first / middle / last epoch blocks, deaths, births,
+ * chain splits (:309-331), optional hyper-parameter resampling (:60-74).  uniforms may be NULL.
+ * Returns the log_likelihood diagnostic of the last epoch block structure (sum over all epochs), NaN on capacity. */
+double orc_rcrp_sweep(orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, int64_t *z, int64_t *nn,
+                      orc_rng *g, const double *uniforms, int shuffle, int sample_hyper, int n_internals);
+/* Conditional of item i of epoch t on the current state with the item removed (:191-215, :263-287, :366-377).
+ * raw/prob have KK+1 entries; components that are not alive in the window get -Inf / 0.  No deletion is
+ * performed when the removal empties a component (it simply has probability 0).  State restored. */
+int64_t orc_rcrp_conditional(const orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, int64_t t,
+                             int64_t i, int64_t zi, int64_t *nn, double r, double *raw, double *prob);
+
 /* Normalised log unsigned Stirling numbers of the first kind, rows n = 1..nmax, packed:
  * entry (n, m), 1 <= m <= n, at index n*(n-1)/2 + (m-1); each row shifted so its maximum is 0.
  * Regenerates the missing src/StirlingNums_10K.mat (snumbersNormalizedSparse, src/HDP.jl:207-209). */

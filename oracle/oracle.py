@@ -54,6 +54,11 @@ class _Hdp(C.Structure):
                 ("beta", C.c_void_p)]
 
 
+class _Rcrp(C.Structure):
+    _fields_ = [("KK", C.c_int64), ("Kmax", C.c_int64), ("TT", C.c_int64), ("aa", C.c_void_p),
+                ("a1", C.c_double), ("a2", C.c_double)]
+
+
 class _Rng(C.Structure):
     _fields_ = [("s", C.c_uint64 * 4)]
 
@@ -120,6 +125,12 @@ def lib():
         L.orc_hdp_resample_beta.argtypes = [hp, i64, vp, vp, vp, i64, i32, i32, rp, vp]
         L.orc_hdp_sample_hyperparam.argtypes = [hp, i64, vp, i64, rp]
         L.orc_stirling_table.argtypes = [i64, vp]
+        rcp = C.POINTER(_Rcrp)
+        L.orc_rcrp_init.argtypes = [rcp, cp, dpp, vp, vp, vp]
+        L.orc_rcrp_sweep.restype = f64
+        L.orc_rcrp_sweep.argtypes = [rcp, cp, dpp, vp, vp, vp, rp, vp, i32, i32, i32]
+        L.orc_rcrp_conditional.restype = i64
+        L.orc_rcrp_conditional.argtypes = [rcp, cp, dpp, vp, i64, i64, i64, vp, f64, vp, vp]
         _lib = L
     return _lib
 
@@ -376,3 +387,35 @@ class HDPState:
         if rc != 0:
             raise IndexError("n_jk exceeds the Stirling table (the reference throws BoundsError)")
         return M
+
+
+# ------------------------------------------------------------------ RCRP.jl
+class RCRPState:
+    """Recurrent CRP state (src/RCRP.jl:77-143). comps.K == Kmax; the last slot stays empty (prototype)."""
+
+    def __init__(self, comps: Comps, data: Data, ptr, z, KK, aa, a1, a2):
+        self.c, self.d = comps, data
+        self.ptr = _i64(ptr)
+        self.TT = self.ptr.size - 1
+        self.z = _i64(z).copy()
+        self.Kmax = comps.K
+        self.aa = _f64(np.full(self.TT, aa) if np.isscalar(aa) else aa).copy()
+        self.h = _Rcrp(KK, self.Kmax, self.TT, _p(self.aa), a1, a2)
+        self.nn = np.zeros((self.TT, self.Kmax), dtype=np.int64)
+        lib().orc_rcrp_init(C.byref(self.h), comps.ref(), data.ref(), _p(self.ptr), _p(self.z), _p(self.nn))
+
+    @property
+    def KK(self):
+        return int(self.h.KK)
+
+    def sweep(self, rng: Rng, uniforms=None, shuffle=False, sample_hyper=False, n_internals=10) -> float:
+        u = None if uniforms is None else _f64(uniforms)
+        return lib().orc_rcrp_sweep(C.byref(self.h), self.c.ref(), self.d.ref(), _p(self.ptr), _p(self.z), _p(self.nn),
+                                    rng.ref(), _p(u), int(shuffle), int(sample_hyper), int(n_internals))
+
+    def conditional(self, t, i, r):
+        n = self.KK + 1
+        raw, prob = np.zeros(n), np.zeros(n)
+        k = lib().orc_rcrp_conditional(C.byref(self.h), self.c.ref(), self.d.ref(), _p(self.ptr), t, i, int(self.z[i]),
+                                       _p(self.nn), float(r), _p(raw), _p(prob))
+        return int(k), raw, prob
