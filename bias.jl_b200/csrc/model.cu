@@ -7,6 +7,7 @@
 #include "model.hpp"
 #include "lda_fast.cuh"
 #include "lda_tma.cuh"
+#include "lda_half.cuh"
 #define BIAS_GENERIC_KERNEL_IMPL
 #include "generic.cuh"
 #include "util_kernels.cuh"
@@ -90,6 +91,35 @@ static int launch_lda_tma_t(bias_model *m, const LdaFastParams &p) {
     return BIAS_OK;
 }
 
+template <int NCK>
+static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
+    static int ctas_per_sm = 0;
+    const size_t smem = lda_half_smem_bytes(NCK);
+    const int threads = kHalfWarps * 32;
+    if (ctas_per_sm == 0) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half_kernel<NCK>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half_kernel<NCK>, threads, smem));
+        if (occ < 1) return fail(BIAS_ECUDA, "LDA half-warp sweep kernel does not fit on an SM (K padded to %d)", NCK * 64);
+        ctas_per_sm = occ;
+    }
+    const int64_t want = (p.D + kHalfWarps * 2 - 1) / (kHalfWarps * 2);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms * ctas_per_sm));
+    lda_md_int_sweep_half_kernel<NCK><<<grid, threads, smem, m->ctx->stream>>>(p);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    return BIAS_OK;
+}
+
+// two documents per warp (lda_half.cuh): the default for K <= 1024 and documents shorter than 65,536 tokens;
+// BIAS_LDA_KERNEL=reg selects the one-document-per-warp kernel, =tma the shared-memory staged one
+static bool use_half_kernel(const bias_model *m) {
+    const char *force = getenv("BIAS_LDA_KERNEL");
+    if (force && (force[0] == 't' || force[0] == 'r')) return false;
+    return m->Kpad <= 1024 && m->max_group_len <= 65535;
+}
+
 // which LDA x MD x Int kernel: rows kept in registers (default: measured faster on B200, r01:
 // 57.0 ms vs 73.4 ms per 100M-token sweep — the sweep is bound by the LSU/shared-memory data pipe, and
 // staging rows in shared memory doubles their trips through it) or staged in shared memory by bulk
@@ -124,6 +154,14 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.frozen = frozen;
     p.diag_sum = reinterpret_cast<double *>(m->scratch);
     p.moved = m->scratch + 1;
+    if (use_half_kernel(m) && !eval) {
+        switch (m->Kpad / 64) {
+            case 2: return launch_lda_half_t<2>(m, p);
+            case 4: return launch_lda_half_t<4>(m, p);
+            case 8: return launch_lda_half_t<8>(m, p);
+            case 16: return launch_lda_half_t<16>(m, p);
+        }
+    }
     if (use_tma_kernel(m) && !eval) {
         switch (m->Kpad / 128) {
             case 1: return launch_lda_tma_t<1>(m, p);
