@@ -28,12 +28,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, V, D_TOTAL, L_DOC = 1024, 50_000, 500_000, 200
+K, V, D_TOTAL, L_DOC = 1024, int(os.environ.get("BIAS_BENCH_V", 50_000)), 500_000, 200   # BIAS_BENCH_V: experiments only
 ALPHA, BETA = 0.1, 0.1          # aa_total = BETA * V
 PHI_CONC, THETA_CONC = 0.01, 0.1
 B_ALG = 4 * K + 12              # algorithmic bytes per token-sample
 SEED = 123
 CHUNK_DOCS = 10_000             # corpus is generated chunk by chunk, seeded by chunk index
+
+
+def sweep_kernel_name():
+    """The kernel bias_model_sweep launches for this workload (csrc/model.cu: use_half_kernel / use_tma_kernel)."""
+    force = os.environ.get("BIAS_LDA_KERNEL", "")
+    if force.startswith("r"):
+        return "lda_md_int_sweep_kernel<8>"
+    if force.startswith("t"):
+        return "lda_md_int_sweep_tma_kernel<8>"
+    return "lda_md_int_sweep_half_kernel<16>"
 
 
 def peaks():
@@ -292,27 +302,55 @@ def ours(args):
     rs.close()
 
     # ---- end-to-end arm: host buffers in, host assignments out, every step ----
-    e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    zz_out_h = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+    # Streaming use of the public API: two resident models on two contexts (streams) are re-fed in turn
+    # (ResidentSampler.reload: H2D of the step's words / zz / offsets from pinned host memory + the
+    # initialisation pass, no allocation), swept once, and read back (get_zz: D2H into pinned host memory).
+    # The upload of step s+1 and the download of step s run on the copy engines while step s / s+1 is swept.
+    e2e_steps = max(1, args.e2e_steps)
+    streams = [stream, torch.cuda.Stream(device=dev)]
+    ctxs = [ctx, b.Context(local, seed=SEED + 1000 + rank, stream=streams[1].cuda_stream)]
+    zz_out_h = [torch.empty(n_local, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    pipes = []
+    for i in range(2):
+        with torch.cuda.stream(streams[i]):
+            rs_i = b.ResidentSampler(ctxs[i], lda, data, z_h.numpy())
+            pipes.append((rs_i, ShardedSampler(GpuShard(rs_i, dev))))
+
+    def e2e_upload(i):
+        with torch.cuda.stream(streams[i]):
+            pipes[i][0].reload(data, z_h.numpy())
+            pipes[i][1].merge_local_counts()
+
+    def e2e_sweep(i):
+        with torch.cuda.stream(streams[i]):
+            pipes[i][1].sweep(1)
+
+    def e2e_download(i):
+        return pipes[i][0].get_zz(out=zz_out_h[i].numpy())      # waits for the model's own stream only
+
+    def e2e_run(n_steps):
+        e2e_upload(0)
+        e2e_sweep(0)
+        for s_ in range(n_steps):
+            cur, nxt = s_ % 2, 1 - (s_ % 2)
+            if s_ + 1 < n_steps:
+                e2e_upload(nxt)
+                e2e_sweep(nxt)
+            e2e_download(cur)
+
+    e2e_run(2)                                   # warm both pipelines (first-touch of the pinned buffers, NCCL)
     barrier()
     t0 = time.perf_counter()
-    phases = []
-    for _ in range(e2e_steps):
-        ta = time.perf_counter()
-        rs2, sh2 = make_sampler()              # H2D: words, zz, doc offsets; initialisation pass
-        tb = time.perf_counter()
-        sh2.sweep(1)
-        out = rs2.get_zz(out=zz_out_h.numpy())   # D2H: zz into pinned host memory (waits for the sweep)
-        tc = time.perf_counter()
-        rs2.close()
-        phases.append((tb - ta, tc - tb, time.perf_counter() - tc))
-    if os.environ.get("BIAS_BENCH_VERBOSE") and rank == 0:
-        print("e2e phases (upload+init, sweep+download, free) s:", phases, file=sys.stderr)
+    e2e_run(e2e_steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    moved_e2e = int(pipes[(e2e_steps - 1) % 2][0].stats().n_moved)
+    assert moved_e2e > 0 and int(zz_out_h[(e2e_steps - 1) % 2].max()) < K
     h2d = n_local * 4 * 2 + ptr.nbytes
     d2h = n_local * 4
-    del out
+    for rs_i, _ in pipes:
+        rs_i.close()
+    ctxs[1].close()
 
     n_total = n_docs_total * L_DOC
     value = n_total * args.steps / (ms_total * 1e-3)
@@ -346,11 +384,13 @@ def ours(args):
                        "l2": "inputs larger than L2 (n_wk 205 MB + tokens 800 MB per sweep vs 126 MB L2)",
                        "corpus_gen_s": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "lda_md_int_sweep_kernel<8>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": sweep_kernel_name(),
                          "kernel_ms": kern_ms, "alg_bytes_per_token": B_ALG, "tokens_per_launch": tokens_per_launch},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps,
+                    "how": "2 resident models on 2 streams, re-fed in turn (reload = H2D + init pass, sweep, get_zz = D2H); "
+                           "wall clock over the steps, barrier + synchronize both sides, max over ranks"},
             "gpu_launches": int(launches),
             "clocks": clock_rec,
             "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood,
@@ -370,7 +410,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--docs", type=int, default=D_TOTAL, help="documents in the corpus (default: the full 100M-token workload)")
     ap.add_argument("--ref-docs", type=int, default=1000, help="documents in the CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--kernel-timing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

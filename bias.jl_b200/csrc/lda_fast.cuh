@@ -50,6 +50,7 @@ struct LdaFastParams {
     double *eval_sum;
     double *diag_sum;           // sum of posterior-mean probabilities (src/conjugates.jl:205)
     unsigned long long *moved;  // tokens whose assignment changed
+    int32_t pf_dist;            // lda_half.cuh: rows are pulled into L2 this many tokens ahead (0: off; at most 16)
 };
 
 // warps per CTA: 8 up to K = 1024, 4 above (the per-warp rows are 8*Kpad bytes of shared memory)

@@ -168,6 +168,7 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
             }
             __syncwarp();
         }
+        const bool first_batch = __any_sync(kFull, fetched);
         const int nb = (int)min((int64_t)16, t_end - t_cur);      // 0 when this half has run out of documents
         const int nb_both = max(nb, __shfl_xor_sync(kFull, nb, 16));
         if (nb_both == 0) break;
@@ -188,8 +189,13 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
             }
         }
         int my_new = my_z;
+        // words of the following batch, so that rows can be pulled into L2 across the batch boundary
+        int nxt_w = 0;
+        const int rem = (int)min((int64_t)64, t_end - t_cur);          // tokens of this document still ahead (capped)
+        if (16 + l16 < rem) nxt_w = p.word[t_cur + 16 + l16];
+        const int pf = p.pf_dist;
 
-        // operands and row of the first token; the rows of the next two are pulled into L2
+        // operands and row of the first token
         int w = __shfl_sync(kFull, my_w, 0, 16);
         int kold = __shfl_sync(kFull, my_z, 0, 16);
         float u = __shfl_sync(kFull, my_u, 0, 16);
@@ -200,10 +206,12 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
             for (int j = 0; j < NCK; ++j) c[j] = __ldcg(reinterpret_cast<const int4 *>(row32) + j * 16 + l16);
         }
         int c_own = __ldcg(p.n_wk + (size_t)w * KPAD + kold);
-        {
-            const int w1 = __shfl_sync(kFull, my_w, 1, 16), w2 = __shfl_sync(kFull, my_w, 2, 16);
-            if (nb > 1) prefetch_row_half<NCK>(p.n_wk + (size_t)w1 * KPAD, l16);
-            if (nb > 2) prefetch_row_half<NCK>(p.n_wk + (size_t)w2 * KPAD, l16);
+        if (first_batch) {
+            // a new document: nothing was prefetched for its first rows
+            for (int d = 1; d < pf; ++d) {
+                const int wd = __shfl_sync(kFull, my_w, d & 15, 16);
+                if (d < nb) prefetch_row_half<NCK>(p.n_wk + (size_t)wd * KPAD, l16);
+            }
         }
 
         for (int i = 0; i < nb_both; ++i) {
@@ -263,8 +271,11 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
 #pragma unroll
                 for (int j = 0; j < NCK; ++j) c[j] = __ldcg(reinterpret_cast<const int4 *>(rown) + j * 16 + l16);
                 c_own_n = __ldcg(rown + kold_n);
-                const int w3 = __shfl_sync(kFull, my_w, (i + 3) & 15, 16);
-                if (i + 3 < nb) prefetch_row_half<NCK>(p.n_wk + (size_t)w3 * KPAD, l16);
+                if (pf > 0) {
+                    const int ip = i + pf;
+                    const int wa = __shfl_sync(kFull, my_w, ip & 15, 16), wb = __shfl_sync(kFull, nxt_w, ip & 15, 16);
+                    if (ip < rem) prefetch_row_half<NCK>(p.n_wk + (size_t)(ip < 16 ? wa : wb) * KPAD, l16);
+                }
             }
 
             // ---- pass 2: CDF inside the selected chunk ----

@@ -154,6 +154,10 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.frozen = frozen;
     p.diag_sum = reinterpret_cast<double *>(m->scratch);
     p.moved = m->scratch + 1;
+    {
+        const char *pf = getenv("BIAS_LDA_PF");
+        p.pf_dist = pf ? std::max(0, std::min(16, atoi(pf))) : 3;
+    }
     if (use_half_kernel(m) && !eval) {
         switch (m->Kpad / 64) {
             case 2: return launch_lda_half_t<2>(m, p);
@@ -548,7 +552,56 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
 #undef M_TRY
 #undef M_CUDA
     m->last.KK = K;
+    m->N_cap = m->N;
+    m->G_cap = m->G;
+    m->nnz_cap = m->nnz;
     *out = m;
+    return BIAS_OK;
+}
+
+int bias_model_reload(bias_model *m, const bias_data *data, int64_t n_groups, const int64_t *group_ptr, const int32_t *zz) {
+    if (!m || !data || !zz) return fail(BIAS_EINVAL, "null argument");
+    if (is_dynamic_K(m)) return fail(BIAS_EINVAL, "reload is defined for the fixed-K models (LDA, BMM)");
+    const int64_t G = (m->model == BIAS_MODEL_BMM) ? 0 : n_groups;
+    BIAS_TRY(validate(&m->conj, data, G, group_ptr, zz, m->K, m->alpha, m->model));
+    const int64_t nnz = (m->conj.datum == BIAS_SENT) ? data->sent_ptr[data->n_items] : 0;
+    if (data->n_items > m->N_cap || G > m->G_cap || nnz > m->nnz_cap)
+        return fail(BIAS_ERANGE, "reload: %lld items / %lld groups / %lld Sent entries exceed the capacity the model was "
+                    "created with (%lld / %lld / %lld)", (long long)data->n_items, (long long)G, (long long)nnz,
+                    (long long)m->N_cap, (long long)m->G_cap, (long long)m->nnz_cap);
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    m->N = data->n_items;
+    m->G = G;
+    m->nnz = nnz;
+    if (m->conj.datum == BIAS_INT) {
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->word, data->word, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    } else if (m->conj.datum == BIAS_F64) {
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->x, data->x, (size_t)m->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->sent_ptr, data->sent_ptr, ((size_t)m->N + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->sent_word, data->sent_word, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->sent_count, data->sent_count, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (m->model != BIAS_MODEL_BMM) {
+        m->max_group_len = 1;
+        for (int64_t j = 0; j < G; ++j) m->max_group_len = std::max(m->max_group_len, group_ptr[j + 1] - group_ptr[j]);
+        m->h_group_ptr.assign(group_ptr, group_ptr + G + 1);
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->group_ptr, group_ptr, ((size_t)G + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (m->group_of && m->N > 0) {
+            group_of_kernel<<<grid_for(m->ctx, m->N, 256), 256, 0, st>>>(m->group_ptr, m->G, m->N, m->group_of);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+        }
+    }
+    BIAS_TRY(validate_on_device(m, m->K));
+    BIAS_TRY(rebuild_counts(m));
+    m->sweep_index = 0;
+    m->stats_pending = false;
+    m->timing_valid = false;
+    // the uploads came from caller-owned memory: finish them before returning
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
     return BIAS_OK;
 }
 

@@ -22,6 +22,7 @@ struct bias_model {
     int32_t model = 0;
     bias_conjugate conj{};
     int64_t N = 0, G = 0, nnz = 0, V = 0, max_group_len = 1;
+    int64_t N_cap = 0, G_cap = 0, nnz_cap = 0;      // allocated capacities (bias_model_reload re-feeds up to these)
     int32_t K = 0, Kpad = 0;
     double alpha = 0.0;
     bool fast = false;              // LDA x MD x Int on the fp32 warp-per-document kernel

@@ -217,6 +217,12 @@ class ResidentSampler:
                                       ptr(data.group_ptr), ptr(self.zz), model.KK, model.aa,
                                       C.byref(hp) if hp is not None else None, C.byref(self.h)))
 
+    def reload(self, data: FlatData, zz_flat: np.ndarray):
+        """Re-feed the resident model with a new batch (LDA / BMM): no allocation, buffers are reused."""
+        self.data = data
+        self.zz = _lib.as_i32(zz_flat)
+        check(lib().bias_model_reload(self.h, C.byref(data.c), data.n_groups, ptr(data.group_ptr), ptr(self.zz)))
+
     # -- sweeps
     def sweep(self, n: int = 1):
         check(lib().bias_model_sweep(self.h, n))

@@ -55,8 +55,11 @@ class ShardedSampler:
         import torch.distributed as dist
         self.shard, self.group, self.dist = shard, group, dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.merge_local_counts()
+
+    def merge_local_counts(self):
+        """After (re)building the counts from the local shard only: sum them into the global replica."""
         if self.world > 1:
-            # every rank built its counts from its own shard: sum them into the global replica
             self.shard.delta_begin_zero()
             self._exchange()
 

@@ -150,6 +150,12 @@ BIAS_API int bias_rcrp_create(bias_ctx *ctx, const bias_conjugate *conj, const b
 BIAS_API int bias_model_get_rcrp(bias_model *m, bias_rcrp_params *params, double *aa /* [n_epochs] */);
 /* Switch hyper-parameter resampling on/off between sweeps (HDP, RCRP). */
 BIAS_API int bias_model_set_sample_hyperparam(bias_model *m, int32_t on);
+/* Re-feeds a resident LDA / BMM model with a new batch (same conjugate, K, alpha): uploads xx and zz into the
+ * buffers the model already owns (no allocation; the batch may be smaller than the one the model was created
+ * with, BIAS_ERANGE if larger) and reruns the initialisation pass.  Streaming callers alternate two models on
+ * two contexts so that one batch uploads while the other is swept. */
+BIAS_API int bias_model_reload(bias_model *m, const bias_data *data, int64_t n_groups, const int64_t *group_ptr,
+                      const int32_t *zz);
 BIAS_API int bias_model_destroy(bias_model *m);
 /* n_sweeps asynchronous sweeps on the context stream (one iteration of the loop at src/LDA.jl:103). */
 BIAS_API int bias_model_sweep(bias_model *m, int32_t n_sweeps);

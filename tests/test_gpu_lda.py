@@ -221,3 +221,39 @@ def test_collapsed_gibbs_sampler_entry_point_recovers_bars(ctx):
     ref = (st.c.mi + 0.1) / (st.c.mi + 0.1).sum(1, keepdims=True)
     want = sum(np.min(np.abs(ref - t).sum(1)) < 0.25 for t in topics)
     assert got >= 7 and got >= want - 2, (got, want)
+
+
+def test_reload_refeeds_a_resident_model(ctx):
+    """bias_model_reload: a new (smaller) batch goes into the buffers the model owns; the initialisation pass is
+    rerun, so counts equal those recomputed from the new xx / zz; a larger batch is BIAS_ERANGE."""
+    K, V = 12, 40
+    rng = np.random.default_rng(5)
+    mk = lambda lens: [rng.integers(0, V, n).astype(np.int64) for n in lens]
+    xx1, xx2, xx3 = mk([50, 0, 70, 33]), mk([20, 64, 9]), mk([200, 200])
+    lda = b.LDA(b.MultinomialDirichlet(V, 4.0), K, 0.3)
+    d1 = b.FlatData(lda.component, xx1, True)
+    rs = b.ResidentSampler(ctx, lda, d1, rng.integers(0, K, d1.n_items).astype(np.int32))
+    rs.sweep(3)
+    d2 = b.FlatData(lda.component, xx2, True)
+    z2 = rng.integers(0, K, d2.n_items).astype(np.int32)
+    rs.reload(d2, z2)
+    assert np.array_equal(rs.get_zz(), z2)
+    w2 = np.concatenate(xx2)
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z2, w2), 1)
+    comp = rs.components()
+    assert np.array_equal(comp["mi"], mi) and comp["mm"].sum() == d2.n_items
+    rs.sweep(4)
+    z = rs.get_zz()
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, w2), 1)
+    assert np.array_equal(rs.components()["mi"], mi)
+    nn = rs.group_counts()
+    assert nn.shape == (3, K) and np.array_equal(nn[1], np.bincount(z[20:84], minlength=K))
+    d3 = b.FlatData(lda.component, xx3, True)
+    with pytest.raises(b.BiasError) as e:
+        rs.reload(d3, np.zeros(d3.n_items, dtype=np.int32))
+    assert e.value.code == 5
+    with pytest.raises(b.BiasError):
+        rs.reload(d2, np.full(d2.n_items, K, dtype=np.int32))          # zz out of range is still rejected
+    rs.close()
