@@ -28,7 +28,7 @@ SYMBOLS = [
     "bias_model_last_stats", "bias_model_get_components", "bias_model_get_group_counts", "bias_model_get_hdp",
     "bias_model_conditionals", "bias_model_frozen_draws", "bias_hdp_table_conditionals", "bias_stirling_rows",
     "bias_model_log_likelihood", "bias_model_delta_begin", "bias_model_delta_begin_zero", "bias_model_delta_pack", "bias_model_delta_apply", "bias_model_last_sweep_ms",
-    "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload",
+    "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload", "bias_model_heldout_log_likelihood",
 ]
 
 
@@ -116,6 +116,7 @@ def lib():
     L.bias_model_get_rcrp.argtypes = [vp, rp, vp]
     L.bias_model_set_sample_hyperparam.argtypes = [vp, i32]
     L.bias_model_reload.argtypes = [vp, dt, i64, vp, vp]
+    L.bias_model_heldout_log_likelihood.argtypes = [vp, vp, vp, C.POINTER(f64), C.POINTER(i64)]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int

@@ -50,6 +50,8 @@ struct LdaFastParams {
     double *eval_sum;
     double *diag_sum;           // sum of posterior-mean probabilities (src/conjugates.jl:205)
     unsigned long long *moved;  // tokens whose assignment changed
+    const int64_t *eval_ptr;    // eval mode, nullable: CSR of held-out tokens per document (document completion)
+    const int32_t *eval_word;   //   their word ids; theta_d still comes from the document's training tokens (z)
     int32_t pf_dist;            // lda_half.cuh: rows are pulled into L2 this many tokens ahead (0: off; at most 16)
 };
 
@@ -121,7 +123,10 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
         doc = __shfl_sync(kFull, doc, 0);
         if (doc >= (unsigned long long)p.D) break;
         const int64_t t_begin = p.doc_ptr[doc], t_end = p.doc_ptr[doc + 1];
-        if (t_end <= t_begin) continue;
+        // tokens that are scored / resampled: the document's own, or its held-out tokens in evaluation mode
+        const int64_t s_begin = p.eval_ptr ? p.eval_ptr[doc] : t_begin, s_end = p.eval_ptr ? p.eval_ptr[doc + 1] : t_end;
+        const int32_t *s_word = p.eval_ptr ? p.eval_word : p.word;
+        if (s_end <= s_begin) continue;
         eval_log_norm = (double)logf((float)(t_end - t_begin) + (float)p.K * alpha);
 
         // ---- rebuild n_dk from z, then r = (n_dk + alpha) / (n_k + V beta) ----
@@ -148,13 +153,13 @@ lda_md_int_sweep_kernel(const LdaFastParams p) {
         __syncwarp();
 
         // ---- tokens of the document, 32 at a time ----
-        for (int64_t t0 = t_begin; t0 < t_end; t0 += 32) {
-            const int nb = (int)min((int64_t)32, t_end - t0);
+        for (int64_t t0 = s_begin; t0 < s_end; t0 += 32) {
+            const int nb = (int)min((int64_t)32, s_end - t0);
             int my_w = 0, my_z = 0;
             float my_u = 0.5f;
             if (lane < nb) {
-                my_w = p.word[t0 + lane];
-                my_z = p.z[t0 + lane];
+                my_w = s_word[t0 + lane];
+                my_z = p.eval_ptr ? 0 : p.z[t0 + lane];
                 const uint64_t tid = (uint64_t)(t0 + lane);
                 if (p.ext_uniforms) {
                     my_u = (float)p.ext_uniforms[tid];

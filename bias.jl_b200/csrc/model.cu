@@ -130,9 +130,12 @@ static bool use_tma_kernel(const bias_model *m) {
     return m->Kpad <= 1024 && m->max_group_len <= 65535;
 }
 
-static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen, int32_t *draws_out, int eval = 0) {
+static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen, int32_t *draws_out, int eval = 0,
+                           const int64_t *eval_ptr = nullptr, const int32_t *eval_word = nullptr) {
     LdaFastParams p{};
     p.eval = eval;
+    p.eval_ptr = eval_ptr;
+    p.eval_word = eval_word;
     p.eval_sum = reinterpret_cast<double *>(m->scratch + 6);
     p.doc_ptr = m->group_ptr;
     p.word = m->word;
@@ -845,6 +848,47 @@ int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t *n_items
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
     *sum_log_p = h;
     if (n_items) *n_items = m->N;
+    return BIAS_OK;
+}
+
+int bias_model_heldout_log_likelihood(bias_model *m, const int64_t *heldout_ptr, const int32_t *heldout_word,
+                                      double *sum_log_p, int64_t *n_tokens) {
+    if (!m || !heldout_ptr || !sum_log_p) return fail(BIAS_EINVAL, "null argument");
+    if (!m->fast) return fail(BIAS_EINVAL, "the held-out evaluator covers LDA x MultinomialDirichlet x word ids");
+    const int64_t nh = heldout_ptr[m->G];
+    if (heldout_ptr[0] != 0 || nh < 0) return fail(BIAS_EINVAL, "heldout_ptr must start at 0");
+    for (int64_t j = 0; j < m->G; ++j)
+        if (heldout_ptr[j + 1] < heldout_ptr[j]) return fail(BIAS_EINVAL, "heldout_ptr must be non-decreasing");
+    if (nh > 0 && !heldout_word) return fail(BIAS_EINVAL, "heldout_word is null");
+    for (int64_t t = 0; t < nh; ++t)
+        if (heldout_word[t] < 0 || heldout_word[t] >= m->V)
+            return fail(BIAS_EINVAL, "held-out word id %d at %lld is outside 0..%lld", heldout_word[t], (long long)t, (long long)m->V - 1);
+    *sum_log_p = 0.0;
+    if (n_tokens) *n_tokens = nh;
+    if (nh == 0) return BIAS_OK;
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    int64_t *d_ptr = nullptr;
+    int32_t *d_word = nullptr;
+    BIAS_TRY(dev_alloc(&d_ptr, (size_t)m->G + 1));
+    int rc = dev_alloc(&d_word, (size_t)nh);
+    if (rc != BIAS_OK) { cudaFree(d_ptr); return rc; }
+    double h = 0.0;
+    cudaError_t e = cudaMemcpyAsync(d_ptr, heldout_ptr, ((size_t)m->G + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_word, heldout_word, (size_t)nh * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->scratch + 2, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->scratch + 6, 0, sizeof(double), st);
+    if (e == cudaSuccess) {
+        rc = launch_lda_fast(m, nullptr, 1, nullptr, 1, d_ptr, d_word);
+        if (rc == BIAS_OK) e = cudaMemcpyAsync(&h, m->scratch + 6, sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_ptr);
+    cudaFree(d_word);
+    if (rc != BIAS_OK) return rc;
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(BIAS_ECUDA, "held-out evaluation: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    *sum_log_p = h;
     return BIAS_OK;
 }
 

@@ -307,6 +307,17 @@ class ResidentSampler:
         check(lib().bias_model_log_likelihood(self.h, C.byref(s), C.byref(n)))
         return s.value, n.value
 
+    def heldout_log_likelihood(self, heldout):
+        """Document completion: heldout[j] = held-out word ids of group j.  -> (sum log p, n_tokens);
+        held-out perplexity = exp(-sum / n_tokens)."""
+        lens = np.array([len(h) for h in heldout], dtype=np.int64)
+        hp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        hw = _lib.as_i32(np.concatenate([np.asarray(h) for h in heldout])) if hp[-1] else np.zeros(0, np.int32)
+        assert len(hp) == self.data.n_groups + 1
+        s, n = C.c_double(), C.c_int64()
+        check(lib().bias_model_heldout_log_likelihood(self.h, ptr(hp), ptr(hw), C.byref(s), C.byref(n)))
+        return s.value, n.value
+
     # -- multi-GPU exchange (AD-LDA)
     def delta_begin(self):
         check(lib().bias_model_delta_begin(self.h))

@@ -195,6 +195,11 @@ BIAS_API int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out);
  * The reference has no perplexity function (src/notes.md:30); perplexity = exp(-sum / n_items).
  * On a sharded run every rank reports its own shard's sum. */
 BIAS_API int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t *n_items);
+/* Document completion: the same sum over HELD-OUT tokens (CSR over the model's groups: heldout_ptr[n_groups+1],
+ * heldout_word[heldout_ptr[n_groups]], host buffers); theta_j comes from the group's training tokens, phi from the
+ * training counts.  Held-out perplexity = exp(-sum / n_tokens) (north_star level (c)). */
+BIAS_API int bias_model_heldout_log_likelihood(bias_model *m, const int64_t *heldout_ptr, const int32_t *heldout_word,
+                      double *sum_log_p, int64_t *n_tokens);
 
 /* ---- multi-GPU exchange (AD-LDA: one allreduce of count deltas per sweep) --------------- */
 /* Snapshot the shared component statistics (n_wk, n_k / sumx, n) as the base of the next delta. */

@@ -47,3 +47,21 @@ def lda_token_loglik(ptr, words, z, K, V, alpha, beta):
         theta = (n_dk + alpha) / (e - s + K * alpha)
         total += np.log(theta @ phi[:, words[s:e]]).sum()
     return total / max(1, ptr[-1])
+
+
+def lda_heldout_loglik(ptr, words, z, heldout, K, V, alpha, beta):
+    """Document completion: sum over held-out tokens of log sum_k theta_dk phi_kw with theta from the training
+    tokens of the document and phi from the training counts (same point estimates as lda_token_loglik)."""
+    n_kw = np.zeros((K, V))
+    np.add.at(n_kw, (z, words), 1)
+    phi = (n_kw + beta) / (n_kw.sum(1, keepdims=True) + V * beta)
+    total, n = 0.0, 0
+    for j, h in enumerate(heldout):
+        if len(h) == 0:
+            continue
+        s, e = ptr[j], ptr[j + 1]
+        n_dk = np.bincount(z[s:e], minlength=K)
+        theta = (n_dk + alpha) / (e - s + K * alpha)
+        total += np.log(theta @ phi[:, np.asarray(h)]).sum()
+        n += len(h)
+    return total, n

@@ -257,3 +257,54 @@ def test_reload_refeeds_a_resident_model(ctx):
     with pytest.raises(b.BiasError):
         rs.reload(d2, np.full(d2.n_items, K, dtype=np.int32))          # zz out of range is still rejected
     rs.close()
+
+
+def _heldout_case(seed, D=300, L=100, L_held=25, K=16, V=300):
+    ptr, words = b.data.dirichlet_lda_corpus(D, L + L_held, K, V, beta_conc=0.05, alpha_conc=0.2, seed=seed)
+    docs = [words[ptr[j]:ptr[j + 1]].astype(np.int64) for j in range(D)]
+    train = [d[:L] for d in docs]
+    held = [d[L:] for d in docs]
+    held[3] = held[3][:0]                              # a document without held-out tokens
+    train[5], held[5] = train[5][:0], docs[5][:7]      # and one with no training tokens (theta = prior)
+    return train, held, K, V
+
+
+def test_heldout_log_likelihood_matches_numpy(ctx):
+    from helpers import lda_heldout_loglik
+    train, held, K, V = _heldout_case(2)
+    alpha, aa = 0.2, 0.05 * V
+    rs, state, data, z0, words, rng = _setup(ctx, train, K, V, alpha, aa, seed=9)
+    rs.sweep(5)
+    z = rs.get_zz().astype(np.int64)
+    s_gpu, n_gpu = rs.heldout_log_likelihood(held)
+    s_ref, n_ref = lda_heldout_loglik(data.group_ptr, words, z, held, K, V, alpha, aa / V)
+    assert n_gpu == n_ref == sum(len(h) for h in held)
+    assert abs(s_gpu - s_ref) <= 1e-5 * abs(s_ref), (s_gpu, s_ref)
+    with pytest.raises(b.BiasError):
+        rs.heldout_log_likelihood([np.array([V])] + [np.zeros(0, dtype=np.int64)] * (len(train) - 1))
+    rs.close()
+
+
+def test_heldout_perplexity_converges_to_the_serial_samplers(ctx):
+    """north_star level (c): held-out perplexity after a fixed number of sweeps within 1% of the serial reference
+    sampler's (several serial chains give the spread)."""
+    from helpers import lda_heldout_loglik
+    train, held, K, V = _heldout_case(4)
+    alpha, aa = 0.2, 0.05 * V
+    rs, state0, data, z0, words, rng = _setup(ctx, train, K, V, alpha, aa, seed=13)
+    n_sweeps = 100
+    ppl_refs = []
+    for seed in range(3):
+        st = orc.LDAState(orc.Comps.md(K, V, aa), orc.Data.words(words), data.group_ptr, z0, alpha)
+        r = np.random.default_rng(40 + seed)
+        for _ in range(n_sweeps):
+            st.sweep(r.random(data.n_items), diag_mode=0)
+        s, n = lda_heldout_loglik(data.group_ptr, words, st.z, held, K, V, alpha, aa / V)
+        ppl_refs.append(np.exp(-s / n))
+    rs.sweep(n_sweeps)
+    s, n = rs.heldout_log_likelihood(held)
+    ppl_gpu = np.exp(-s / n)
+    s0, n0 = lda_heldout_loglik(data.group_ptr, words, z0.astype(np.int64), held, K, V, alpha, aa / V)
+    assert ppl_gpu < 0.8 * np.exp(-s0 / n0)                      # far below the random initial state
+    assert min(ppl_refs) * 0.99 <= ppl_gpu <= max(ppl_refs) * 1.01, (ppl_gpu, ppl_refs)
+    rs.close()

@@ -5,6 +5,7 @@ on one B200, with the serial oracle timed on a bounded sample next to each.
   C1  LDA bars K=10 V=25, 1k docs x 100 tokens
   C2  BMM x Sent, K=64, V=1024, 1M sentences x 64 tokens
   C4  HDP x Gaussian, groups of 100 points (size set by --hdp-groups)
+  C5  RCRP x Gaussian, 100 epochs x 500 points (gen_RCRP_data, demo_RCRP_Gaussian1DGaussian1D.jl)
 Writes one JSON object per config to stdout."""
 import argparse
 import json
@@ -108,13 +109,45 @@ def c4(ctx, n_groups):
             "KK": int(s.KK), "cpu_items_per_s": ng * 100 / tc, "cpu_sample": f"first {ng} groups, 4th sweep of the serial sampler"}
 
 
+def c5(ctx, n_epochs, n_per):
+    _, zz_true, _ = b.data.gen_rcrp_data([n_per] * n_epochs, 0.5, seed=123)
+    rng = np.random.default_rng(5)
+    xx = [10.0 * (z + 1) + 0.1 * rng.standard_normal(len(z)) for z in zz_true]
+    allx = np.concatenate(xx)
+    rcrp = b.RCRP(b.Gaussian1DGaussian1D(float(xx[0].mean()), 2.0, 0.01), 1, 1.0, n_epochs, 1.0, 1.0, Kmax=256)
+    data = b.FlatData(rcrp.component, xx, True)
+    rs = b.ResidentSampler(ctx, rcrp, data, np.zeros(len(allx), dtype=np.int32), sample_hyperparam=True, n_internals=10)
+    rs.sweep(10)                       # burn-in with hyper-parameter resampling (src/RCRP.jl:166-168)
+    rs.set_sample_hyperparam(False)
+    t = timed_sweeps(rs, 10, warm=2)
+    KK = rs.stats().KK
+    z = rs.get_zz()
+    rs.close()
+    zt = np.concatenate(zz_true)
+    homog = sum(np.bincount(zt[z == c]).max() for c in np.unique(z)) / len(z)
+    ptr = np.arange(n_epochs + 1, dtype=np.int64) * n_per
+    st = orc.RCRPState(orc.Comps.g1g1(256, float(xx[0].mean()), 2.0, 0.01), orc.Data.reals(allx), ptr,
+                       np.zeros(len(allx), dtype=np.int64), 1, 1.0, 1.0, 1.0)
+    r = orc.Rng(1)
+    for _ in range(3):
+        st.sweep(r, shuffle=True, sample_hyper=True)
+    t0 = time.perf_counter()
+    st.sweep(r, shuffle=True)
+    tc = time.perf_counter() - t0
+    return {"config": f"C5 RCRP x Gaussian {n_epochs} epochs x {n_per} points", "items": len(allx),
+            "gpu_ms_per_sweep": 1e3 * t, "gpu_items_per_s": len(allx) / t, "KK": int(KK), "KK_true": int(len(np.unique(zt))),
+            "KK_serial": st.KK, "homogeneity": homog, "cpu_items_per_s": len(allx) / tc,
+            "cpu_sample": "full data, 4th sweep of the serial sampler (O(n_{t+1,k}) look-ahead loops as in the reference)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sentences", type=int, default=1_000_000)
     ap.add_argument("--hdp-groups", type=int, default=100_000)
     args = ap.parse_args()
     ctx = b.Context(0, seed=123)
-    for fn in (lambda: c1(ctx), lambda: c2(ctx, args.sentences), lambda: c4(ctx, args.hdp_groups)):
+    for fn in (lambda: c1(ctx), lambda: c2(ctx, args.sentences), lambda: c4(ctx, args.hdp_groups),
+               lambda: c5(ctx, 100, 500)):
         print(json.dumps(fn()), flush=True)
     ctx.close()
 
