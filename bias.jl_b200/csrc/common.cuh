@@ -110,6 +110,13 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
     }
     return v;
 }
+// fire-and-forget reductions (no value returns to the SM)
+__device__ __forceinline__ void red_add(int32_t *p, int32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(unsigned *p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -52,8 +52,19 @@ struct LdaFastParams {
     unsigned long long *moved;  // tokens whose assignment changed
     const int64_t *eval_ptr;    // eval mode, nullable: CSR of held-out tokens per document (document completion)
     const int32_t *eval_word;   //   their word ids; theta_d still comes from the document's training tokens (z)
+    uint16_t *n_wk16;           // lda_half16.cuh: 16-bit shadow of n_wk, [V][Kpad]
+    const int32_t *gate;        // nullable: the kernel runs only when *gate == gate_expect (16-bit / 32-bit hand-over)
+    int32_t gate_expect;
+    int32_t *nk_rep;            // half-warp kernels: [kNkRep][Kpad] replicas collecting this sweep's changes of n_k
+    int32_t exp_flags;          // experiments only (BIAS_LDA_EXP): 1 = skip the global atomics, 2 = weak (L1-cached) row loads
     int32_t pf_dist;            // lda_half.cuh: rows are pulled into L2 this many tokens ahead (0: off; at most 16)
 };
+
+// n_k is Kpad addresses that every document in flight on the GPU updates twice per moved token: RED traffic on those
+// few L2 lines costs 8 ms of a 47 ms sweep (the hot slices back up and delay the row loads too).  The half-warp kernels
+// therefore send their n_k updates to one of kNkRep zero-initialised replicas (chosen by CTA index), read
+// n_k + sum of the replicas when a document starts, and a small kernel folds the replicas into n_k after the sweep.
+constexpr int kNkRep = 8;
 
 // warps per CTA: 8 up to K = 1024, 4 above (the per-warp rows are 8*Kpad bytes of shared memory)
 __host__ __device__ constexpr int lda_fast_warps(int nch) { return nch <= 8 ? 8 : 4; }

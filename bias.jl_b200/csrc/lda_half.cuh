@@ -22,10 +22,15 @@
 
 namespace bias {
 
-constexpr int kHalfWarps = 8;       // warps per CTA = 16 documents in flight per CTA
+constexpr int kHalfWarps = 8;       // default warps per CTA = 16 documents in flight per CTA
 
 __host__ __device__ inline size_t lda_half_doc_bytes(int nck) { return (size_t)nck * 64 * 6 + 64; }
-__host__ __device__ inline size_t lda_half_smem_bytes(int nck) { return (size_t)kHalfWarps * 2 * lda_half_doc_bytes(nck); }
+// 8 warps x 2 CTAs at K = 1024: 2 x (99,328 + 1,024 reserved) = 200,704 B = exactly the 196 KB shared-memory carve-out,
+// which leaves 60 KB of L1.  That matters: the rows in flight (32 documents x 4 KB) pass through L1, and with the next
+// carve-out (228 KB, 28 KB of L1) the same kernel runs 30 % slower (measured, profiles/r01b_*).
+__host__ __device__ inline size_t lda_half_smem_bytes(int nck, int warps = kHalfWarps) {
+    return (size_t)warps * 2 * lda_half_doc_bytes(nck);
+}
 
 #ifdef __CUDACC__
 
@@ -96,12 +101,14 @@ __device__ __forceinline__ int4 pick_chunk(const int4 (&c)[NCK], int j) {
     return r;
 }
 
-template <int NCK>
-__global__ void __launch_bounds__(kHalfWarps * 32, 2)
+template <int NCK, int WARPS = kHalfWarps>
+__global__ void __launch_bounds__(WARPS * 32, 2)
 lda_md_int_sweep_half_kernel(const LdaFastParams p) {
     constexpr int LOG_NCK = (NCK == 2) ? 1 : (NCK == 4) ? 2 : (NCK == 8) ? 3 : 4;
     constexpr int GSHIFT = 4 - LOG_NCK;     // l16 >> GSHIFT = chunk held by the lane after the transposing reduction
     constexpr int KPAD = NCK * 64;
+
+    if (p.gate && *p.gate != p.gate_expect) return;     // the 16-bit kernel (lda_half16.cuh) took this sweep
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
@@ -109,6 +116,7 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
     float *r_s = reinterpret_cast<float *>(hbase);
     uint16_t *cnt_s = reinterpret_cast<uint16_t *>(hbase + (size_t)KPAD * 4);
     float *R_s = reinterpret_cast<float *>(hbase + (size_t)KPAD * 6);
+    int32_t *const my_nk = p.nk_rep + (blockIdx.x % kNkRep) * KPAD;
 
     const Philox philox(p.seed);
     const float alpha = p.alpha, beta = p.beta, vbeta = p.vbeta;
@@ -153,7 +161,12 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
 #pragma unroll
             for (int j = 0; j < NCK; ++j) {
                 const int k0 = j * 64 + l16 * 4;
-                const int4 nk = __ldcg(reinterpret_cast<const int4 *>(p.n_k) + j * 16 + l16);
+                int4 nk = __ldcg(reinterpret_cast<const int4 *>(p.n_k) + j * 16 + l16);
+#pragma unroll
+                for (int r = 0; r < kNkRep; ++r) {
+                    const int4 d = __ldcg(reinterpret_cast<const int4 *>(p.nk_rep + r * KPAD) + j * 16 + l16);
+                    nk.x += d.x; nk.y += d.y; nk.z += d.z; nk.w += d.w;
+                }
                 const uint2 cc = reinterpret_cast<const uint2 *>(cnt_s)[j * 16 + l16];
                 float4 rv;
                 rv.x = (k0 + 0 < p.K) ? __fdividef((float)(cc.x & 0xffffu) + alpha, (float)nk.x + vbeta) : 0.f;
@@ -319,27 +332,32 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
                 const float r_new = ((float)(cn2 + 1) + alpha) * inv_new;
                 if (knew == kold) inv_new = inv;
                 __syncwarp();
-                if (l16 == 0 && on) {
-                    if (moved) {
+                if (moved) {
+                    // the document's row: lane 0; the global counts: ONE fire-and-forget RED instruction with four active
+                    // lanes (a single lane issuing four atomics back to back sits on the token's critical path)
+                    if (l16 == 0) {
                         cnt_s[kold] = (uint16_t)(cn - 1);
                         r_s[kold] = r_rm;
                         R_s[jo] += r_rm - r_old;
                         cnt_s[knew] = (uint16_t)(cn2 + 1);
                         r_s[knew] = r_new;
                         R_s[knew >> 6] += r_new - r2;
-                        atomicAdd(row32 + kold, -1);
-                        atomicAdd(row32 + knew, 1);
-                        atomicAdd(p.n_k + kold, -1);
-                        atomicAdd(p.n_k + knew, 1);
-                        moved_acc += 1;
                     }
+                    if (l16 >= 8 && l16 < 12) {
+                        // lanes 8..11: n_wk[kold]--, n_wk[knew]++, n_k[kold]--, n_k[knew]++
+                        const int which = l16 - 8, kk = (which & 1) ? knew : kold;
+                        red_add((which < 2 ? row32 : my_nk) + kk, (which & 1) ? 1 : -1);
+                    }
+                    if (l16 == 0) moved_acc += 1;
+                }
+                if (l16 == 0 && on) {
                     // loglikelihood(components[kk], x) after the add: posterior mean of the word
                     if (nsel < 0.f) nsel = (float)__ldcg(row32 + knew) - (knew == kold ? 1.f : 0.f);
                     diag_acc += (nsel + 1.f + beta) * inv_new;
                 }
                 // the next token's row was read before this update: when it is the same word, read it again
                 if (__any_sync(kFull, moved && w_n == w && i + 1 < nb)) {
-                    if (l16 == 0) __threadfence();
+                    if (l16 >= 8 && l16 < 12) __threadfence();
                     __syncwarp();
                     if (moved && w_n == w && i + 1 < nb) {
                         const int32_t *rown = p.n_wk + (size_t)w_n * KPAD;

@@ -1,0 +1,394 @@
+// lda_half16.cuh — LDA x MultinomialDirichlet x word-id sweep over a 16-bit shadow of the count table (sm_100a).
+//
+// Same sampler, mapping and arithmetic as lda_half.cuh (two documents per warp, reference src/LDA.jl:113-133);
+// what changes is where a token's row comes from.  The canonical table n_wk stays int32 [V][Kpad] (the generic
+// kernels, the exchange and the exports read it), and at the start of every sweep `shadow_build_kernel` copies
+// it into n_wk16 uint16 [V][Kpad].  The sweep reads the 2*Kpad-byte shadow rows — half the L2->SM bytes and half
+// the LSU wavefronts of the int32 rows, 32 instead of 64 registers per lane for the row, and a 102 MB table at
+// K = 1024, V = 50k that the 126 MB L2 can hold — and applies every move to both tables with RED atomics.
+//
+// Exactness: the shadow is used only while no count can leave 16 bits during the sweep.  shadow_build_kernel
+// raises `wide` when max_k n_wk[w][k] + freq[w] > 65535 for any word (freq[w] = occurrences of w in this rank's
+// shard = the most a cell of the row can grow by within one sweep); the 16-bit kernel then exits at once and
+// the int32 kernel of lda_half.cuh, launched right behind it with the opposite gate, does the sweep.
+//
+// Chunks are 128 topics wide (16 lanes x 8 uint16 = one LDG.128 per lane); r is stored in shared memory with
+// the two float4 halves of a lane's 8 topics de-interleaved, so that both LDS.128 of a chunk are conflict-free.
+#pragma once
+#include "lda_half.cuh"
+
+namespace bias {
+
+constexpr int kH16Warps = 6;        // warps per CTA = 12 documents per CTA, 3 CTAs per SM
+
+__host__ __device__ inline size_t lda_half16_doc_bytes(int nc8) { return (size_t)nc8 * 128 * 6 + 64; }
+__host__ __device__ inline size_t lda_half16_smem_bytes(int nc8, int warps = kH16Warps) { return (size_t)warps * 2 * lda_half16_doc_bytes(nc8); }
+
+#ifdef __CUDACC__
+
+// position of topic k's r inside the shared-memory vector (see the header comment)
+__device__ __forceinline__ int r_pos(int k) {
+    return (k & ~127) | (((k >> 2) & 1) << 6) | (((k >> 3) & 15) << 2) | (k & 3);
+}
+
+// One warp per word: int32 row -> uint16 row, and the sweep-wide overflow check.
+__global__ void shadow_build_kernel(const int32_t *n_wk, const int32_t *freq, int64_t V, int Kpad, uint16_t *n_wk16,
+                                    int32_t *wide) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int bad = 0;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < V; w += nw) {
+        const int4 *src = reinterpret_cast<const int4 *>(n_wk + (size_t)w * Kpad);
+        uint4 *dst = reinterpret_cast<uint4 *>(n_wk16 + (size_t)w * Kpad);
+        int mx = 0;
+        for (int q = lane; q < Kpad / 8; q += 32) {
+            const int4 a = __ldcg(src + 2 * q), b = __ldcg(src + 2 * q + 1);
+            mx = max(mx, max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w))));
+            uint4 o;
+            o.x = (unsigned)(a.x & 0xffff) | ((unsigned)a.y << 16);
+            o.y = (unsigned)(a.z & 0xffff) | ((unsigned)a.w << 16);
+            o.z = (unsigned)(b.x & 0xffff) | ((unsigned)b.y << 16);
+            o.w = (unsigned)(b.z & 0xffff) | ((unsigned)b.w << 16);
+            dst[q] = o;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+        if ((int64_t)mx + (int64_t)freq[w] > 65535) bad = 1;
+    }
+    if (__any_sync(kFull, bad) && lane == 0) atomicOr(wide, 1);
+}
+
+// freq[w] = occurrences of word w in the local shard (row sums of the freshly built local counts)
+__global__ void word_freq_kernel(const int32_t *n_wk, int64_t V, int Kpad, int32_t *freq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < V; w += nw) {
+        const int4 *src = reinterpret_cast<const int4 *>(n_wk + (size_t)w * Kpad);
+        long long s = 0;
+        for (int q = lane; q < Kpad / 4; q += 32) {
+            const int4 a = __ldcg(src + q);
+            s += (long long)a.x + a.y + a.z + a.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        if (lane == 0) freq[w] = (int32_t)min(s, (long long)INT32_MAX);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ uint4 pick_chunk16(const uint4 (&c)[N], int j) {
+    uint4 r = c[0];
+    switch (j) {
+        default: break;
+        case 1: if constexpr (N > 1) r = c[1 % N]; break;
+        case 2: if constexpr (N > 2) r = c[2 % N]; break;
+        case 3: if constexpr (N > 2) r = c[3 % N]; break;
+        case 4: if constexpr (N > 4) r = c[4 % N]; break;
+        case 5: if constexpr (N > 4) r = c[5 % N]; break;
+        case 6: if constexpr (N > 4) r = c[6 % N]; break;
+        case 7: if constexpr (N > 4) r = c[7 % N]; break;
+    }
+    return r;
+}
+
+__device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float4 b) {
+    float s = (float)(x.x & 0xffffu) * a.x;
+    s = fmaf((float)(x.x >> 16), a.y, s);
+    s = fmaf((float)(x.y & 0xffffu), a.z, s);
+    s = fmaf((float)(x.y >> 16), a.w, s);
+    float t = (float)(x.z & 0xffffu) * b.x;
+    t = fmaf((float)(x.z >> 16), b.y, t);
+    t = fmaf((float)(x.w & 0xffffu), b.z, t);
+    t = fmaf((float)(x.w >> 16), b.w, t);
+    return s + t;
+}
+
+template <int NC8, int WARPS = kH16Warps, int CTAS = 3>
+__global__ void __launch_bounds__(WARPS * 32, CTAS)
+lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
+    constexpr int LOG_NC = (NC8 == 1) ? 0 : (NC8 == 2) ? 1 : (NC8 == 4) ? 2 : 3;
+    constexpr int GSHIFT = 4 - LOG_NC;      // l16 >> GSHIFT = chunk held by the lane after the transposing reduction
+    constexpr int KPAD = NC8 * 128;
+
+    if (*p.gate != p.gate_expect) return;   // a count may leave 16 bits this sweep: the int32 kernel runs instead
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+    unsigned char *hbase = smem_raw + (size_t)(warp * 2 + half) * lda_half16_doc_bytes(NC8);
+    float *r_s = reinterpret_cast<float *>(hbase);                                  // permuted, see r_pos
+    uint16_t *cnt_s = reinterpret_cast<uint16_t *>(hbase + (size_t)KPAD * 4);
+    float *R_s = reinterpret_cast<float *>(hbase + (size_t)KPAD * 6);
+    const float4 *r4 = reinterpret_cast<const float4 *>(r_s);
+
+    int32_t *const my_nk = p.nk_rep + (blockIdx.x % kNkRep) * KPAD;
+
+    const Philox philox(p.seed);
+    const float alpha = p.alpha, beta = p.beta, vbeta = p.vbeta;
+    float diag_acc = 0.f;
+    unsigned moved_acc = 0;
+    int64_t t_cur = 0, t_end = 0;
+    bool live = true;
+
+    for (;;) {
+        // ---- a half whose document is finished fetches the next one and rebuilds its row ----
+        bool need = live && t_cur >= t_end;
+        bool fetched = false;
+        while (__any_sync(kFull, need)) {
+            unsigned long long doc = 0;
+            if (l16 == 0 && need) doc = atomicAdd(p.doc_counter, 1ull);
+            doc = __shfl_sync(kFull, doc, 0, 16);
+            if (need) {
+                if (doc >= (unsigned long long)p.D) {
+                    live = false;
+                    need = false;
+                } else {
+                    t_cur = p.doc_ptr[doc];
+                    t_end = p.doc_ptr[doc + 1];
+                    need = t_end <= t_cur;
+                    fetched = !need;
+                }
+            }
+        }
+        if (__any_sync(kFull, fetched)) {
+            if (fetched)
+                for (int q = l16; q < KPAD / 8; q += 16) reinterpret_cast<uint4 *>(cnt_s)[q] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            if (fetched)
+                for (int64_t t = t_cur + l16; t < t_end; t += 16) {
+                    const int k = p.z[t];
+                    atomicAdd(reinterpret_cast<unsigned *>(cnt_s) + (k >> 1), 1u << ((k & 1) * 16));
+                }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NC8; ++j) {
+                const int k0 = j * 128 + l16 * 8;
+                int4 na = __ldcg(reinterpret_cast<const int4 *>(p.n_k) + j * 32 + l16 * 2);
+                int4 nb4 = __ldcg(reinterpret_cast<const int4 *>(p.n_k) + j * 32 + l16 * 2 + 1);
+#pragma unroll
+                for (int r = 0; r < kNkRep; ++r) {
+                    const int4 da = __ldcg(reinterpret_cast<const int4 *>(p.nk_rep + r * KPAD) + j * 32 + l16 * 2);
+                    const int4 db = __ldcg(reinterpret_cast<const int4 *>(p.nk_rep + r * KPAD) + j * 32 + l16 * 2 + 1);
+                    na.x += da.x; na.y += da.y; na.z += da.z; na.w += da.w;
+                    nb4.x += db.x; nb4.y += db.y; nb4.z += db.z; nb4.w += db.w;
+                }
+                const uint4 cc = reinterpret_cast<const uint4 *>(cnt_s)[j * 16 + l16];
+                float4 ra, rb;
+                ra.x = (k0 + 0 < p.K) ? __fdividef((float)(cc.x & 0xffffu) + alpha, (float)na.x + vbeta) : 0.f;
+                ra.y = (k0 + 1 < p.K) ? __fdividef((float)(cc.x >> 16) + alpha, (float)na.y + vbeta) : 0.f;
+                ra.z = (k0 + 2 < p.K) ? __fdividef((float)(cc.y & 0xffffu) + alpha, (float)na.z + vbeta) : 0.f;
+                ra.w = (k0 + 3 < p.K) ? __fdividef((float)(cc.y >> 16) + alpha, (float)na.w + vbeta) : 0.f;
+                rb.x = (k0 + 4 < p.K) ? __fdividef((float)(cc.z & 0xffffu) + alpha, (float)nb4.x + vbeta) : 0.f;
+                rb.y = (k0 + 5 < p.K) ? __fdividef((float)(cc.z >> 16) + alpha, (float)nb4.y + vbeta) : 0.f;
+                rb.z = (k0 + 6 < p.K) ? __fdividef((float)(cc.w & 0xffffu) + alpha, (float)nb4.z + vbeta) : 0.f;
+                rb.w = (k0 + 7 < p.K) ? __fdividef((float)(cc.w >> 16) + alpha, (float)nb4.w + vbeta) : 0.f;
+                const float s = half_sum(((ra.x + ra.y) + (ra.z + ra.w)) + ((rb.x + rb.y) + (rb.z + rb.w)));
+                if (fetched) {
+                    reinterpret_cast<float4 *>(r_s)[j * 32 + l16] = ra;
+                    reinterpret_cast<float4 *>(r_s)[j * 32 + 16 + l16] = rb;
+                    if (l16 == 0) R_s[j] = s;
+                }
+            }
+            __syncwarp();
+        }
+        const int nb = (int)min((int64_t)16, t_end - t_cur);      // 0 when this half has run out of documents
+        const int nb_both = max(nb, __shfl_xor_sync(kFull, nb, 16));
+        if (nb_both == 0) break;
+
+        // ---- up to 16 tokens of each half's document ----
+        int my_w = 0, my_z = 0;
+        float my_u = 0.5f;
+        if (l16 < nb) {
+            my_w = p.word[t_cur + l16];
+            my_z = p.z[t_cur + l16];
+            const uint64_t tid = (uint64_t)(t_cur + l16);
+            if (p.ext_uniforms) {
+                my_u = (float)p.ext_uniforms[tid];
+            } else {
+                uint32_t o[4];
+                philox((uint32_t)tid, (uint32_t)(tid >> 32), p.sweep, kStreamItemDraw, o);
+                my_u = u01_float(o[0]);
+            }
+        }
+        int my_new = my_z;
+
+        // operands and row of the first token
+        int w = __shfl_sync(kFull, my_w, 0, 16);
+        int kold = __shfl_sync(kFull, my_z, 0, 16);
+        float u = __shfl_sync(kFull, my_u, 0, 16);
+        uint4 c[NC8];
+        {
+            const uint4 *row = reinterpret_cast<const uint4 *>(p.n_wk16 + (size_t)w * KPAD);
+#pragma unroll
+            for (int j = 0; j < NC8; ++j) c[j] = __ldcg(row + j * 16 + l16);
+        }
+        int c_own = __ldcg(p.n_wk16 + (size_t)w * KPAD + kold);
+
+        for (int i = 0; i < nb_both; ++i) {
+            const bool on = i < nb;
+
+            // ---- delitem!, arithmetically: r[kold] with n_dk and n_k one lower; nothing is stored ----
+            const int jo = kold >> 7;
+            const int cn = cnt_s[kold];
+            const float r_old = r_s[r_pos(kold)];
+            const float inv = __fdividef(r_old, (float)cn + alpha);            // 1/(n_k + V beta)
+            const float inv_rm = __fdividef(inv, 1.f - inv);                   // 1/(n_k - 1 + V beta)
+            const float r_rm = ((float)(cn - 1) + alpha) * inv_rm;
+
+            // ---- pass 1: chunk sums of n_wk * r (beta * sum r is added per chunk) ----
+            float acc[NC8];
+#pragma unroll
+            for (int j = 0; j < NC8; ++j) acc[j] = dot8(c[j], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
+            float T = transpose_reduce_half<NC8>(acc, l16);                    // lane l: chunk (l >> GSHIFT)
+            const int myj = l16 >> GSHIFT;
+            T = fmaf(beta, R_s[myj], T);
+            if (myj == jo) {
+                const float co = (float)c_own;
+                T -= (co + beta) * r_old - (fmaxf(co - 1.f, 0.f) + beta) * r_rm;
+            }
+            T = fmaxf(T, 0.f);
+            float P = T;                                                       // inclusive scan in chunk order
+#pragma unroll
+            for (int d = 1; d < NC8; d <<= 1) {
+                const float y = __shfl_up_sync(kFull, P, d << GSHIFT, 16);
+                if (myj >= d) P += y;
+            }
+            const float total = __shfl_sync(kFull, P, 15, 16);
+            const float target = u * total;
+            unsigned bal = (__ballot_sync(kFull, P >= target) >> (half * 16)) & 0xffffu;
+            const int src_lane = bal ? (__ffs(bal) - 1) : 15;
+            const int jsel = src_lane >> GSHIFT;
+            const float base = __shfl_sync(kFull, P - T, src_lane, 16);
+            const uint4 cs = pick_chunk16<NC8>(c, jsel);
+
+            // ---- the next token's operands and row: in flight during pass 2 and the update ----
+            const int inext = (i + 1) & 15;
+            const int w_n = __shfl_sync(kFull, my_w, inext, 16);
+            const int kold_n = __shfl_sync(kFull, my_z, inext, 16);
+            const float u_n = __shfl_sync(kFull, my_u, inext, 16);
+            int c_own_n = 0;
+            if (i + 1 < nb_both) {
+                const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
+                if (p.exp_flags & 2) {
+#pragma unroll
+                    for (int j = 0; j < NC8; ++j) c[j] = reinterpret_cast<const uint4 *>(rown)[j * 16 + l16];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
+                }
+                c_own_n = __ldcg(rown + kold_n);
+            }
+
+            // ---- pass 2: CDF inside the selected chunk (8 topics per lane) ----
+            const float4 qa = r4[jsel * 32 + l16], qb = r4[jsel * 32 + 16 + l16];
+            const int kb = jsel * 128 + l16 * 8;
+            float n[8] = {(float)(cs.x & 0xffffu), (float)(cs.x >> 16), (float)(cs.y & 0xffffu), (float)(cs.y >> 16),
+                          (float)(cs.z & 0xffffu), (float)(cs.z >> 16), (float)(cs.w & 0xffffu), (float)(cs.w >> 16)};
+            float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const int eo = kold - kb;           // own token excluded (the clamp only matters for a count caught mid-update)
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (eo == e) { n[e] = fmaxf(n[e] - 1.f, 0.f); q[e] = r_rm; }
+            float wgt[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) wgt[e] = (n[e] + beta) * q[e];
+            const float s = ((wgt[0] + wgt[1]) + (wgt[2] + wgt[3])) + ((wgt[4] + wgt[5]) + (wgt[6] + wgt[7]));
+            const float incl = base + half_incl_scan(s, l16);
+            bal = (__ballot_sync(kFull, incl >= target) >> (half * 16)) & 0xffffu;
+            const int lsel = bal ? (__ffs(bal) - 1) : 15;
+            // walk the (at most) eight entries of the selected lane: first e whose running sum reaches the target
+            float cw = incl - s;
+            int csel = 7;
+            float nsel = n[7];
+            float pre[7];
+#pragma unroll
+            for (int e = 0; e < 7; ++e) { cw += wgt[e]; pre[e] = cw; }
+#pragma unroll
+            for (int e = 6; e >= 0; --e)
+                if (!(pre[e] < target)) { csel = e; nsel = n[e]; }
+            int knew = __shfl_sync(kFull, kb + csel, lsel, 16);
+            nsel = __shfl_sync(kFull, nsel, lsel, 16);
+            if (knew >= p.K) {           // rounding pushed the target past the last real topic
+                knew = p.K - 1;
+                nsel = -1.f;             // diagnostic recomputed below from memory
+            }
+            if (on && l16 == i) my_new = knew;
+
+            const bool moved = on && !p.frozen && knew != kold;
+            if (!p.frozen) {
+                // ---- additem!: the document's row changes only when the topic does ----
+                const int cn2 = cnt_s[knew];
+                const float r2 = r_s[r_pos(knew)];
+                const float inv2 = __fdividef(r2, (float)cn2 + alpha);
+                float inv_new = __fdividef(inv2, 1.f + inv2);                      // 1/(n_k + 1 + V beta)
+                const float r_new = ((float)(cn2 + 1) + alpha) * inv_new;
+                if (knew == kold) inv_new = inv;
+                __syncwarp();
+                int32_t *row32 = p.n_wk + (size_t)w * KPAD;
+                if (moved) {
+                    // the document's row: lane 0; the global counts: ONE fire-and-forget RED instruction with six active
+                    // lanes (a single lane issuing six atomics back to back sits on the token's critical path)
+                    if (l16 == 0) {
+                        cnt_s[kold] = (uint16_t)(cn - 1);
+                        r_s[r_pos(kold)] = r_rm;
+                        R_s[jo] += r_rm - r_old;
+                        cnt_s[knew] = (uint16_t)(cn2 + 1);
+                        r_s[r_pos(knew)] = r_new;
+                        R_s[knew >> 7] += r_new - r2;
+                    }
+                    if (l16 >= 8 && l16 < 14 && !(p.exp_flags & 1)) {
+                        // lanes 8..13: n_wk16[kold]--, n_wk16[knew]++, n_wk[kold]--, n_wk[knew]++, n_k[kold]--, n_k[knew]++
+                        const int which = l16 - 8, kk = (which & 1) ? knew : kold;
+                        unsigned *ptr;
+                        unsigned val;
+                        if (which < 2) {
+                            ptr = reinterpret_cast<unsigned *>(p.n_wk16 + (size_t)w * KPAD) + (kk >> 1);
+                            val = 1u << ((kk & 1) * 16);
+                        } else {
+                            ptr = reinterpret_cast<unsigned *>(which < 4 ? row32 : my_nk) + kk;
+                            val = 1u;
+                        }
+                        if (!((p.exp_flags & 4) && which >= 4) && !((p.exp_flags & 8) && which < 4))
+                            red_add(ptr, (which & 1) ? val : 0u - val);
+                    }
+                    if (l16 == 0) moved_acc += 1;
+                }
+                if (l16 == 0 && on) {
+                    if (nsel < 0.f) nsel = (float)__ldcg(row32 + knew) - (knew == kold ? 1.f : 0.f);
+                    diag_acc += (nsel + 1.f + beta) * inv_new;
+                }
+                // the next token's row was read before this update: when it is the same word, read it again
+                if (__any_sync(kFull, moved && w_n == w && i + 1 < nb)) {
+                    if (l16 >= 8 && l16 < 14) __threadfence();
+                    __syncwarp();
+                    if (moved && w_n == w && i + 1 < nb) {
+                        const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
+#pragma unroll
+                        for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
+                        c_own_n = __ldcg(rown + kold_n);
+                    }
+                }
+                __syncwarp();
+            }
+            w = w_n;
+            kold = kold_n;
+            u = u_n;
+            c_own = c_own_n;
+        }  // tokens of the batch
+
+        if (p.frozen) {
+            if (l16 < nb) p.draws_out[t_cur + l16] = my_new;
+        } else if (l16 < nb && my_new != my_z) {
+            p.z[t_cur + l16] = my_new;
+        }
+        t_cur += nb;
+    }  // batches
+
+    if (!p.frozen && l16 == 0) {
+        atomicAdd(p.diag_sum, (double)diag_acc);
+        atomicAdd(p.moved, (unsigned long long)moved_acc);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bias

@@ -8,6 +8,7 @@
 #include "lda_fast.cuh"
 #include "lda_tma.cuh"
 #include "lda_half.cuh"
+#include "lda_half16.cuh"
 #define BIAS_GENERIC_KERNEL_IMPL
 #include "generic.cuh"
 #include "util_kernels.cuh"
@@ -91,25 +92,58 @@ static int launch_lda_tma_t(bias_model *m, const LdaFastParams &p) {
     return BIAS_OK;
 }
 
-template <int NCK>
+template <int NCK, int WARPS = kHalfWarps>
 static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
     static int ctas_per_sm = 0;
-    const size_t smem = lda_half_smem_bytes(NCK);
-    const int threads = kHalfWarps * 32;
+    const size_t smem = lda_half_smem_bytes(NCK, WARPS);
+    const int threads = WARPS * 32;
     if (ctas_per_sm == 0) {
-        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half_kernel<NCK>,
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half_kernel<NCK, WARPS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const char *co = getenv("BIAS_LDA_CARVEOUT");
+        if (co)
+            BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half_kernel<NCK, WARPS>,
+                                               cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
         int occ = 0;
-        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half_kernel<NCK>, threads, smem));
+        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half_kernel<NCK, WARPS>, threads, smem));
         if (occ < 1) return fail(BIAS_ECUDA, "LDA half-warp sweep kernel does not fit on an SM (K padded to %d)", NCK * 64);
         ctas_per_sm = occ;
     }
-    const int64_t want = (p.D + kHalfWarps * 2 - 1) / (kHalfWarps * 2);
+    const int64_t want = (p.D + WARPS * 2 - 1) / (WARPS * 2);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms * ctas_per_sm));
-    lda_md_int_sweep_half_kernel<NCK><<<grid, threads, smem, m->ctx->stream>>>(p);
+    lda_md_int_sweep_half_kernel<NCK, WARPS><<<grid, threads, smem, m->ctx->stream>>>(p);
     BIAS_CUDA_TRY(cudaGetLastError());
     m->ctx->launches += 1;
     return BIAS_OK;
+}
+
+template <int NC8, int WARPS = kH16Warps, int CTAS = 3>
+static int launch_lda_half16_t(bias_model *m, const LdaFastParams &p) {
+    static int ctas_per_sm = 0;
+    const size_t smem = lda_half16_smem_bytes(NC8, WARPS);
+    const int threads = WARPS * 32;
+    if (ctas_per_sm == 0) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS>, threads, smem));
+        if (occ < 1) return fail(BIAS_ECUDA, "LDA 16-bit sweep kernel does not fit on an SM (K padded to %d)", NC8 * 128);
+        ctas_per_sm = std::min(occ, CTAS);
+    }
+    const int64_t want = (p.D + WARPS * 2 - 1) / (WARPS * 2);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms * ctas_per_sm));
+    lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS><<<grid, threads, smem, m->ctx->stream>>>(p);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    return BIAS_OK;
+}
+
+// 16-bit shadow rows (lda_half16.cuh): the default whenever the half-warp kernel applies and the shadow table was
+// allocated; BIAS_LDA_KERNEL=half keeps the int32 rows
+static bool use_half16_kernel(const bias_model *m) {
+    const char *force = getenv("BIAS_LDA_KERNEL");
+    if (force && (force[0] == 't' || force[0] == 'r' || force[0] == 'h')) return false;
+    return m->n_wk16 && m->Kpad <= 1024 && m->max_group_len <= 65535;
 }
 
 // two documents per warp (lda_half.cuh): the default for K <= 1024 and documents shorter than 65,536 tokens;
@@ -159,15 +193,45 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.moved = m->scratch + 1;
     {
         const char *pf = getenv("BIAS_LDA_PF");
-        p.pf_dist = pf ? std::max(0, std::min(16, atoi(pf))) : 3;
+        p.pf_dist = pf ? std::max(0, std::min(16, atoi(pf))) : 2;
+        const char *ex = getenv("BIAS_LDA_EXP");
+        p.exp_flags = ex ? atoi(ex) : 0;
     }
-    if (use_half_kernel(m) && !eval) {
-        switch (m->Kpad / 64) {
-            case 2: return launch_lda_half_t<2>(m, p);
-            case 4: return launch_lda_half_t<4>(m, p);
-            case 8: return launch_lda_half_t<8>(m, p);
-            case 16: return launch_lda_half_t<16>(m, p);
+    p.nk_rep = m->nk_rep;
+    const bool half_path = use_half_kernel(m) && !eval && m->nk_rep;
+    if (use_half16_kernel(m) && !eval && m->V > 0) {
+        // refresh the 16-bit shadow; the 16-bit kernel runs unless a count may leave 16 bits during this sweep,
+        // in which case it exits at once and the int32 kernel behind it does the work
+        cudaStream_t st = m->ctx->stream;
+        BIAS_CUDA_TRY(cudaMemsetAsync(m->wide_flag, 0, sizeof(int32_t), st));
+        shadow_build_kernel<<<grid_for(m->ctx, m->V * 32, 256), 256, 0, st>>>(m->n_wk, m->word_freq, m->V, m->Kpad,
+                                                                             m->n_wk16, m->wide_flag);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+        p.n_wk16 = m->n_wk16;
+        p.gate = m->wide_flag;
+        p.gate_expect = 0;
+        switch (m->Kpad / 128) {
+            case 1: BIAS_TRY(launch_lda_half16_t<1>(m, p)); break;
+            case 2: BIAS_TRY(launch_lda_half16_t<2>(m, p)); break;
+            case 4: BIAS_TRY(launch_lda_half16_t<4>(m, p)); break;
+            case 8: BIAS_TRY(launch_lda_half16_t<8>(m, p)); break;
         }
+        p.gate_expect = 1;
+    }
+    if (half_path) {
+        switch (m->Kpad / 64) {
+            case 2: BIAS_TRY(launch_lda_half_t<2>(m, p)); break;
+            case 4: BIAS_TRY(launch_lda_half_t<4>(m, p)); break;
+            case 8: BIAS_TRY(launch_lda_half_t<8>(m, p)); break;
+            default: BIAS_TRY(launch_lda_half_t<16>(m, p)); break;
+        }
+        if (!frozen) {
+            fold_nk_kernel<<<(m->Kpad + 255) / 256, 256, 0, m->ctx->stream>>>(m->n_k, m->nk_rep, m->Kpad, kNkRep);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+        }
+        return BIAS_OK;
     }
     if (use_tma_kernel(m) && !eval) {
         switch (m->Kpad / 128) {
@@ -276,6 +340,7 @@ int rebuild_counts(bias_model *m) {
     cudaStream_t st = m->ctx->stream;
     BIAS_CUDA_TRY(cudaMemsetAsync(m->i32_block, 0, (size_t)m->n_i32 * sizeof(int32_t), st));
     if (m->n_f64) BIAS_CUDA_TRY(cudaMemsetAsync(m->f64_block, 0, (size_t)m->n_f64 * sizeof(double), st));
+    if (m->word_freq) BIAS_CUDA_TRY(cudaMemsetAsync(m->word_freq, 0, (size_t)std::max<int64_t>(1, m->V) * sizeof(int32_t), st));
     const int threads = 256;
     if (m->N > 0) {
         if (m->conj.kind == BIAS_MD && m->conj.datum == BIAS_INT) {
@@ -290,6 +355,12 @@ int rebuild_counts(bias_model *m) {
         }
         BIAS_CUDA_TRY(cudaGetLastError());
         m->ctx->launches += 1;
+        if (m->word_freq) {
+            // occurrences of each word in the local shard: the bound on how far a cell of its row can grow in a sweep
+            word_freq_kernel<<<grid_for(m->ctx, m->V * 32, 256), 256, 0, st>>>(m->n_wk, m->V, m->Kpad, m->word_freq);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+        }
         if (m->group_rows) {
             BIAS_CUDA_TRY(cudaMemsetAsync(m->group_rows, 0, (size_t)m->G * m->Kpad * sizeof(int32_t), st));
             build_group_rows_kernel<<<grid_for(m->ctx, m->N, threads), threads, 0, st>>>(m->z, m->group_of, m->N,
@@ -447,7 +518,7 @@ int bias_model_destroy(bias_model *m) {
     hdp_destroy(m);
     void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
                     m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
-                    m->delta_f64, m->scratch, m->d_aa_t};
+                    m->delta_f64, m->scratch, m->d_aa_t, m->n_wk16, m->word_freq, m->wide_flag, m->nk_rep};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
@@ -542,6 +613,13 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
         m->n_f64 = m->Kpad;
         M_TRY(dev_alloc(&m->f64_block, (size_t)m->n_f64));
         m->sumx = m->f64_block;
+    }
+    if (m->fast && m->Kpad <= 1024) {
+        M_TRY(dev_alloc(&m->n_wk16, (size_t)n_wk_elems));
+        M_TRY(dev_alloc(&m->word_freq, (size_t)std::max<int64_t>(1, m->V)));
+        M_TRY(dev_alloc(&m->wide_flag, 4));
+        M_TRY(dev_alloc(&m->nk_rep, (size_t)kNkRep * m->Kpad));
+        M_CUDA(cudaMemsetAsync(m->nk_rep, 0, (size_t)kNkRep * m->Kpad * sizeof(int32_t), st));
     }
     M_TRY(dev_alloc(&m->scratch, 8));
     M_CUDA(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));

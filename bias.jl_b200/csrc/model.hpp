@@ -44,6 +44,10 @@ struct bias_model {
     int64_t n_f64 = 0;
     double *sumx = nullptr;
     int32_t *group_rows = nullptr;  // [G][Kpad] n_jk for the generic LDA/HDP path
+    uint16_t *n_wk16 = nullptr;     // fast LDA path: 16-bit shadow of n_wk, rebuilt at the start of every sweep
+    int32_t *word_freq = nullptr;   // [V] occurrences of each word in the local shard
+    int32_t *nk_rep = nullptr;      // [kNkRep][Kpad] replicas collecting a sweep's changes of n_k (half-warp kernels)
+    int32_t *wide_flag = nullptr;   // [1] set by shadow_build_kernel when a count may leave 16 bits this sweep
 
     // multi-GPU exchange buffers (allocated on first use)
     int32_t *base_i32 = nullptr, *delta_i32 = nullptr;

@@ -166,4 +166,16 @@ __global__ void export_mi_kernel(const int32_t *n_wk, int64_t V, int K, int Kpad
 
 #endif
 
+// n_k += sum of the replicas that collected this sweep's changes (lda_fast.cuh: kNkRep); the replicas are cleared
+__global__ void fold_nk_kernel(int32_t *n_k, int32_t *nk_rep, int Kpad, int n_rep) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Kpad; k += gridDim.x * blockDim.x) {
+        int s = 0;
+        for (int r = 0; r < n_rep; ++r) {
+            s += nk_rep[r * Kpad + k];
+            nk_rep[r * Kpad + k] = 0;
+        }
+        if (s) n_k[k] += s;
+    }
+}
+
 }  // namespace bias
