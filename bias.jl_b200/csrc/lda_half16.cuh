@@ -5,7 +5,8 @@
 // kernels, the exchange and the exports read it), and at the start of every sweep `shadow_build_kernel` copies
 // it into n_wk16 uint16 [V][Kpad].  The sweep reads the 2*Kpad-byte shadow rows — half the L2->SM bytes and half
 // the LSU wavefronts of the int32 rows, 32 instead of 64 registers per lane for the row, and a 102 MB table at
-// K = 1024, V = 50k that the 126 MB L2 can hold — and applies every move to both tables with RED atomics.
+// K = 1024, V = 50k that the 126 MB L2 can hold — applies every move to the shadow with RED atomics, and
+// `shadow_fold_kernel` rewrites the int32 table from the shadow when the sweep is over.
 //
 // Exactness: the shadow is used only while no count can leave 16 bits during the sweep.  shadow_build_kernel
 // raises `wide` when max_k n_wk[w][k] + freq[w] > 65535 for any word (freq[w] = occurrences of w in this rank's
@@ -56,6 +57,20 @@ __global__ void shadow_build_kernel(const int32_t *n_wk, const int32_t *freq, in
         if ((int64_t)mx + (int64_t)freq[w] > 65535) bad = 1;
     }
     if (__any_sync(kFull, bad) && lane == 0) atomicOr(wide, 1);
+}
+
+// After a 16-bit sweep: the int32 table is rewritten from the shadow (runs only when the 16-bit kernel did).
+__global__ void shadow_fold_kernel(const uint16_t *n_wk16, int64_t V, int Kpad, int32_t *n_wk, const int32_t *wide) {
+    if (*wide != 0) return;
+    const int64_t n8 = V * (int64_t)Kpad / 8;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 x = __ldcg(reinterpret_cast<const uint4 *>(n_wk16) + q);
+        int4 a, b;
+        a.x = (int)(x.x & 0xffffu); a.y = (int)(x.x >> 16); a.z = (int)(x.y & 0xffffu); a.w = (int)(x.y >> 16);
+        b.x = (int)(x.z & 0xffffu); b.y = (int)(x.z >> 16); b.z = (int)(x.w & 0xffffu); b.w = (int)(x.w >> 16);
+        reinterpret_cast<int4 *>(n_wk)[2 * q] = a;
+        reinterpret_cast<int4 *>(n_wk)[2 * q + 1] = b;
+    }
 }
 
 // freq[w] = occurrences of word w in the local shard (row sums of the freshly built local counts)
@@ -323,7 +338,6 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 const float r_new = ((float)(cn2 + 1) + alpha) * inv_new;
                 if (knew == kold) inv_new = inv;
                 __syncwarp();
-                int32_t *row32 = p.n_wk + (size_t)w * KPAD;
                 if (moved) {
                     // the document's row: lane 0; the global counts: ONE fire-and-forget RED instruction with six active
                     // lanes (a single lane issuing six atomics back to back sits on the token's critical path)
@@ -335,8 +349,9 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                         r_s[r_pos(knew)] = r_new;
                         R_s[knew >> 7] += r_new - r2;
                     }
-                    if (l16 >= 8 && l16 < 14 && !(p.exp_flags & 1)) {
-                        // lanes 8..13: n_wk16[kold]--, n_wk16[knew]++, n_wk[kold]--, n_wk[knew]++, n_k[kold]--, n_k[knew]++
+                    if (l16 >= 8 && l16 < 12 && !(p.exp_flags & 1)) {
+                        // lanes 8..11: n_wk16[kold]--, n_wk16[knew]++, n_k[kold]--, n_k[knew]++ (the int32 table is
+                        // rewritten from the shadow after the sweep, shadow_fold_kernel)
                         const int which = l16 - 8, kk = (which & 1) ? knew : kold;
                         unsigned *ptr;
                         unsigned val;
@@ -344,21 +359,20 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                             ptr = reinterpret_cast<unsigned *>(p.n_wk16 + (size_t)w * KPAD) + (kk >> 1);
                             val = 1u << ((kk & 1) * 16);
                         } else {
-                            ptr = reinterpret_cast<unsigned *>(which < 4 ? row32 : my_nk) + kk;
+                            ptr = reinterpret_cast<unsigned *>(my_nk) + kk;
                             val = 1u;
                         }
-                        if (!((p.exp_flags & 4) && which >= 4) && !((p.exp_flags & 8) && which < 4))
-                            red_add(ptr, (which & 1) ? val : 0u - val);
+                        red_add(ptr, (which & 1) ? val : 0u - val);
                     }
                     if (l16 == 0) moved_acc += 1;
                 }
                 if (l16 == 0 && on) {
-                    if (nsel < 0.f) nsel = (float)__ldcg(row32 + knew) - (knew == kold ? 1.f : 0.f);
+                    if (nsel < 0.f) nsel = (float)__ldcg(p.n_wk16 + (size_t)w * KPAD + knew) - (knew == kold ? 1.f : 0.f);
                     diag_acc += (nsel + 1.f + beta) * inv_new;
                 }
                 // the next token's row was read before this update: when it is the same word, read it again
                 if (__any_sync(kFull, moved && w_n == w && i + 1 < nb)) {
-                    if (l16 >= 8 && l16 < 14) __threadfence();
+                    if (l16 >= 8 && l16 < 12) __threadfence();
                     __syncwarp();
                     if (moved && w_n == w && i + 1 < nb) {
                         const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;

@@ -226,6 +226,12 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
             case 8: BIAS_TRY(launch_lda_half_t<8>(m, p)); break;
             default: BIAS_TRY(launch_lda_half_t<16>(m, p)); break;
         }
+        if (!frozen && p.n_wk16) {
+            shadow_fold_kernel<<<grid_for(m->ctx, m->V * (int64_t)m->Kpad / 8, 256), 256, 0, m->ctx->stream>>>(
+                m->n_wk16, m->V, m->Kpad, m->n_wk, m->wide_flag);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+        }
         if (!frozen) {
             fold_nk_kernel<<<(m->Kpad + 255) / 256, 256, 0, m->ctx->stream>>>(m->n_k, m->nk_rep, m->Kpad, kNkRep);
             BIAS_CUDA_TRY(cudaGetLastError());
