@@ -317,3 +317,35 @@ def test_heldout_perplexity_converges_to_the_serial_samplers(ctx):
     se = np.sqrt(np.var(ppl_refs, ddof=1) / n_chains + np.var(ppl_gpu, ddof=1) / n_chains)
     assert abs(m_gpu - m_ref) <= 0.01 * m_ref + 2 * se, (ppl_gpu, ppl_refs)
     assert min(ppl_refs) * 0.97 <= min(ppl_gpu) and max(ppl_gpu) <= max(ppl_refs) * 1.03, (ppl_gpu, ppl_refs)
+
+
+def test_counts_beyond_16_bits_fall_back_to_the_int32_rows(ctx):
+    """The 16-bit shadow rows are used only while no count can leave 16 bits during a sweep (lda_half16.cuh);
+    a word with more than 65,535 occurrences makes shadow_build_kernel hand the sweep to the int32 kernel.
+    Either way the tables must equal the counts recomputed from zz."""
+    K, V = 4, 6
+    rng = np.random.default_rng(8)
+    hot = np.zeros(140_000, dtype=np.int64)                        # word 0: 140k occurrences > 65,535
+    rest = rng.integers(1, V, 20_000)
+    words = rng.permutation(np.concatenate([hot, rest]))
+    xx = [words[i:i + 400] for i in range(0, len(words), 400)]
+    rs, state, data, z0, w, _ = _setup(ctx, xx, K, V, 0.5, 1.2, seed=2)
+    for _ in range(3):
+        rs.sweep(1)
+        assert rs.stats().n_moved > 0
+    z = rs.get_zz()
+    comp = rs.components()
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, w), 1)
+    assert comp["mi"].max() > 65535 or mi[:, 0].max() <= 65535      # the hot word really exceeds 16 bits in some topic
+    assert np.array_equal(comp["mi"], mi) and np.array_equal(comp["mm"], mi.sum(1))
+    # frozen-count draws agree with the oracle on this state too
+    u = rng.random(data.n_items)
+    idx = rng.choice(data.n_items, 200, replace=False)
+    raw, prob, draw = rs.conditionals(idx, u[idx])
+    fd = rs.frozen_draws(u)
+    st = orc.LDAState(orc.Comps.md(K, V, 1.2), orc.Data.words(w), data.group_ptr, z, 0.5)
+    oraw, oprob, odraw = _oracle_conditionals(st, data, idx, u[idx])
+    assert_draws_match(draw, odraw, oprob, u[idx], 1e-12)
+    assert_draws_match(fd[idx], odraw, oprob, u[idx], 2e-5)
+    rs.close()
