@@ -50,6 +50,15 @@ immutable SweepStats           # bias_sweep_stats
     aa::Float64
 end
 
+type RcrpParams                # bias_rcrp_params (mutable: KK comes back updated)
+    KK::Int32
+    Kmax::Int32
+    a1::Float64
+    a2::Float64
+    sample_hyperparam::Int32
+    n_internals::Int32
+end
+
 type HdpParams                 # bias_hdp_params (mutable: KK, gg, aa come back updated)
     KK::Int32
     Kmax::Int32
@@ -179,6 +188,47 @@ function hdp!(hdp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
     scatter!(zz, z)
     hdp.KK, hdp.gg, hdp.aa = hp.KK, hp.gg, hp.aa
     KK_list, KK_dict, betas, gammas, alphas
+end
+
+# ---- RCRP_gibbs_sampler!(rcrp::RCRP, xx, zz, ...)  src/RCRP.jl:77-416
+# Resident model: upload once, one bias_model_sweep per iteration, zz read back at every kept sample.
+function rcrp!(rcrp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
+               sample_hyperparam::Bool=true, n_internals::Int=10; Kmax::Int=256, seed=0)
+    items = vcat(xx...)
+    d, keep, datum = flat_data(items)
+    c = conj_spec(rcrp.component, datum)
+    ptr = flat_ptr(zz)
+    z = flat_zz(zz)
+    rp = RcrpParams(rcrp.KK, Kmax, rcrp.a1, rcrp.a2, sample_hyperparam, n_internals)
+    aa = copy(rcrp.aa)
+    m = Ptr{Void}[C_NULL]
+    check(ccall((:bias_rcrp_create, LIB), Cint,
+                (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{RcrpParams}, Ptr{Float64}, Ptr{Ptr{Void}}),
+                context(seed), [c], [d], length(zz), ptr, z, pointer_from_objref(rp), aa, m))
+    KK_list = zeros(Int, n_samples); KK_dict = Dict{Int, Vector{Vector{Int}}}()
+    try
+        for iteration = 1:(n_burnins + n_samples * (n_lags + 1))                 # src/RCRP.jl:159
+            if iteration > n_burnins                                            # :166-168
+                check(ccall((:bias_model_set_sample_hyperparam, LIB), Cint, (Ptr{Void}, Int32), m[1], 0))
+            end
+            check(ccall((:bias_model_sweep, LIB), Cint, (Ptr{Void}, Int32), m[1], 1))
+            if (iteration - n_burnins) % (n_lags + 1) == 0 && iteration > n_burnins
+                check(ccall((:bias_model_get_zz, LIB), Cint, (Ptr{Void}, Ptr{Int32}), m[1], z))
+                check(ccall((:bias_model_get_rcrp, LIB), Cint, (Ptr{Void}, Ptr{RcrpParams}, Ptr{Float64}), m[1], pointer_from_objref(rp), aa))
+                scatter!(zz, z)
+                s = div(iteration - n_burnins, n_lags + 1)
+                KK_list[s] = rp.KK; KK_dict[rp.KK] = deepcopy(zz)
+            end
+        end
+        check(ccall((:bias_model_get_zz, LIB), Cint, (Ptr{Void}, Ptr{Int32}), m[1], z))
+        check(ccall((:bias_model_get_rcrp, LIB), Cint, (Ptr{Void}, Ptr{RcrpParams}, Ptr{Float64}), m[1], pointer_from_objref(rp), aa))
+        scatter!(zz, z)
+        rcrp.KK = rp.KK
+        rcrp.aa[:] = aa
+    finally
+        ccall((:bias_model_destroy, LIB), Cint, (Ptr{Void},), m[1])
+    end
+    KK_list, KK_dict
 end
 
 end # module
