@@ -29,6 +29,8 @@ SYMBOLS = [
     "bias_model_conditionals", "bias_model_frozen_draws", "bias_hdp_table_conditionals", "bias_stirling_rows",
     "bias_model_log_likelihood", "bias_model_delta_begin", "bias_model_delta_begin_zero", "bias_model_delta_pack", "bias_model_delta_apply", "bias_model_last_sweep_ms",
     "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload", "bias_model_heldout_log_likelihood",
+    "bias_model_set_host_seed", "bias_hdp_shard_pass", "bias_hdp_shard_births", "bias_hdp_shard_adopt", "bias_hdp_shard_prune",
+    "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
 ]
 
 
@@ -117,6 +119,14 @@ def lib():
     L.bias_model_set_sample_hyperparam.argtypes = [vp, i32]
     L.bias_model_reload.argtypes = [vp, dt, i64, vp, vp]
     L.bias_model_heldout_log_likelihood.argtypes = [vp, vp, vp, C.POINTER(f64), C.POINTER(i64)]
+    L.bias_model_set_host_seed.argtypes = [vp, C.c_uint64]
+    L.bias_hdp_shard_pass.argtypes = [vp]
+    L.bias_hdp_shard_births.argtypes = [vp, C.POINTER(i32), vp]
+    L.bias_hdp_shard_adopt.argtypes = [vp, i32, vp]
+    L.bias_hdp_shard_prune.argtypes = [vp]
+    L.bias_hdp_shard_tables.argtypes = [vp, i32, pp, C.POINTER(i64), pp]
+    L.bias_hdp_shard_draw.argtypes = [vp]
+    L.bias_hdp_shard_end.argtypes = [vp]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int

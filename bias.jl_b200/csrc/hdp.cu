@@ -513,98 +513,128 @@ static int resolve_births(bias_model *m, int32_t *&list_cur, int32_t *&list_next
     return BIAS_OK;
 }
 
-int hdp_sweep(bias_model *m) {
+// ---- the phases of one HDP sweep (hdp_sweep runs them back to back; the sharded driver puts exchanges between) ----
+
+// parallel assignment pass (src/HDP.jl:279-341); items that draw the new-component slot are queued.  Does not prune.
+static int hdp_phase_pass(bias_model *m) {
     bias_ctx *ctx = m->ctx;
     cudaStream_t st = ctx->stream;
-    const int Kpad = m->Kpad, Kmax = m->hdp.Kmax;
-    unsigned int *d_pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
-    int *d_err = reinterpret_cast<int *>(m->scratch + 4);
-
-    BIAS_TRY(hdp_prune(m));                       // src/HDP.jl:248-264
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 6 * sizeof(unsigned long long), st));
-    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
-
-    // 1. parallel assignment pass
-    int32_t *list_cur = m->pending, *list_next = m->pending + std::max<int64_t>(1, m->N);
-    m->pending = list_cur;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)m->Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+    m->pending_base = m->pending;
     BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, m->group_of, m->group_rows, nullptr, 0, 0, nullptr, nullptr,
                             nullptr, kStreamItemDraw));
-    // 2. births
-    BIAS_TRY(resolve_births(m, list_cur, list_next));
-    m->pending = std::min(list_cur, list_next);
-    // 3. prune components that died during the pass (src/HDP.jl:291-307)
-    BIAS_TRY(hdp_prune(m));
-    const int KK = m->hdp.KK;
+    return BIAS_OK;
+}
 
-    // 4. beta, alpha0, gamma (src/HDP.jl:343-373)
-    const int64_t max_len = m->max_group_len;
-    BIAS_TRY(ensure_stirling(ctx, (int32_t)std::min<int64_t>(max_len, 10000)));
-    std::vector<unsigned long long> tables((size_t)Kpad + 1);
-    for (int hh = 0; hh < m->hdp.n_internals; ++hh) {
-        BIAS_CUDA_TRY(cudaMemsetAsync(m->d_tables, 0, ((size_t)Kpad + 1) * 8, st));
-        BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
-        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (m->G > 0) {
-            hdp_tables_kernel<<<grid1d(ctx, m->G * 32, 128, 16), 128, 0, st>>>(
-                m->group_rows, m->G, Kpad, KK, m->d_beta, m->hdp.aa, ctx->stirling, ctx->stirling_rows, ctx->seed,
-                m->sweep_index, (uint32_t)hh, reinterpret_cast<unsigned long long *>(m->d_tables), d_err);
+// births: the serial pass over the queue + parallel re-sampling of the rest (src/HDP.jl:320-331), until it is empty
+static int hdp_phase_births(bias_model *m) {
+    cudaStream_t st = m->ctx->stream;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)m->Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+    int32_t *list_cur = m->pending_base, *list_next = m->pending_base + std::max<int64_t>(1, m->N);
+    m->pending = list_cur;
+    BIAS_TRY(resolve_births(m, list_cur, list_next));
+    m->pending = m->pending_base;
+    return BIAS_OK;
+}
+
+// table counts M_jk from the Stirling table and the alpha0 auxiliaries of this rank's groups (src/HDP.jl:343-361, :133-147)
+static int hdp_phase_tables(bias_model *m, int hh) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int Kpad = m->Kpad, KK = m->hdp.KK;
+    int *d_err = reinterpret_cast<int *>(m->scratch + 4);
+    BIAS_TRY(ensure_stirling(ctx, (int32_t)std::min<int64_t>(m->max_group_len, 10000)));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->d_tables, 0, ((size_t)Kpad + 1) * 8, st));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (m->G > 0) {
+        hdp_tables_kernel<<<grid1d(ctx, m->G * 32, 128, 16), 128, 0, st>>>(
+            m->group_rows, m->G, Kpad, KK, m->d_beta, m->hdp.aa, ctx->stirling, ctx->stirling_rows, ctx->seed,
+            m->sweep_index, (uint32_t)hh, reinterpret_cast<unsigned long long *>(m->d_tables), d_err);
+        ctx->launches += 1;
+        if (m->hdp.sample_hyperparam) {
+            hdp_hyper_kernel<<<grid1d(ctx, m->G, 128, 4), 128, 0, st>>>(m->group_ptr, m->G, m->hdp.aa, ctx->seed,
+                                                                       m->sweep_index, (uint32_t)hh, m->d_hyper);
             ctx->launches += 1;
-            if (m->hdp.sample_hyperparam) {
-                hdp_hyper_kernel<<<grid1d(ctx, m->G, 128, 4), 128, 0, st>>>(m->group_ptr, m->G, m->hdp.aa, ctx->seed,
-                                                                           m->sweep_index, (uint32_t)hh, m->d_hyper);
-                ctx->launches += 1;
-            }
-            BIAS_CUDA_TRY(cudaGetLastError());
         }
-        double hyper[2] = {0.0, 0.0};
-        int err = 0;
-        BIAS_CUDA_TRY(cudaMemcpyAsync(tables.data(), m->d_tables, ((size_t)Kpad + 1) * 8, cudaMemcpyDeviceToHost, st));
-        BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
-        BIAS_CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
-        BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-        if (err == 1)
-            return fail(BIAS_ERANGE, "HDP: some n_jk exceeds the %d-row Stirling table (the reference throws BoundsError, src/HDP.jl:355)",
-                        ctx->stirling_rows);
-        // beta ~ Dirichlet([sum_j M_jk ..., gg])  (src/HDP.jl:362-364)
-        double tot = 0.0;
-        for (int k = 0; k <= KK; ++k) {
-            const double a = (k < KK) ? (double)tables[k] : m->hdp.gg;
-            double g = 0.0;
-            if (a > 0.0) {
-                std::gamma_distribution<double> gd(a, 1.0);
-                g = gd(m->host_rng);
-            }
-            m->h_beta[k] = g;
-            tot += g;
+        BIAS_CUDA_TRY(cudaGetLastError());
+    }
+    return BIAS_OK;
+}
+
+// beta ~ Dirichlet([sum_j M_jk ..., gg]) (src/HDP.jl:362-364), alpha0 and gamma (:124-159) from the (possibly
+// all-reduced) contents of d_tables / d_hyper; n_groups_total = number of groups over all ranks
+static int hdp_phase_draw(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int Kpad = m->Kpad, KK = m->hdp.KK;
+    int *d_err = reinterpret_cast<int *>(m->scratch + 4);
+    std::vector<unsigned long long> tables((size_t)Kpad + 1);
+    double hyper[2] = {0.0, 0.0};
+    int err = 0;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(tables.data(), m->d_tables, ((size_t)Kpad + 1) * 8, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (err == 1)
+        return fail(BIAS_ERANGE, "HDP: some n_jk exceeds the %d-row Stirling table (the reference throws BoundsError, src/HDP.jl:355)",
+                    ctx->stirling_rows);
+    double tot = 0.0;
+    for (int k = 0; k <= KK; ++k) {
+        const double a = (k < KK) ? (double)tables[k] : m->hdp.gg;
+        double g = 0.0;
+        if (a > 0.0) {
+            std::gamma_distribution<double> gd(a, 1.0);
+            g = gd(m->host_rng);
         }
-        for (int k = 0; k <= KK; ++k) m->h_beta[k] = tot > 0.0 ? m->h_beta[k] / tot : 1.0 / (KK + 1);
-        for (size_t k = (size_t)KK + 1; k < m->h_beta.size(); ++k) m->h_beta[k] = 0.0;
-        if (m->hdp.sample_hyperparam) {            // src/HDP.jl:124-159
-            const double mt = (double)tables[Kpad];
-            const double aa_shape = m->hdp.a1 + mt - hyper[1];
-            const double aa_rate = m->hdp.a2 - hyper[0];
-            if (aa_shape > 0.0 && aa_rate > 0.0) {
-                std::gamma_distribution<double> ga(aa_shape, 1.0);
-                m->hdp.aa = ga(m->host_rng) / aa_rate;
-            }
-            std::gamma_distribution<double> g1(m->hdp.gg + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
-            const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
-            const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
-            const double le = std::log(eta);
-            const double pi_eta = 1.0 / (1.0 + (mt * (m->hdp.g2 - le)) / (m->hdp.g1 + KK - 1.0));   // :152
-            std::uniform_real_distribution<double> ud(0.0, 1.0);
-            const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
-            if (shape > 0.0) {
-                std::gamma_distribution<double> gg(shape, 1.0);
-                m->hdp.gg = gg(m->host_rng) / (m->hdp.g2 - le);
-            }
+        m->h_beta[k] = g;
+        tot += g;
+    }
+    for (int k = 0; k <= KK; ++k) m->h_beta[k] = tot > 0.0 ? m->h_beta[k] / tot : 1.0 / (KK + 1);
+    for (size_t k = (size_t)KK + 1; k < m->h_beta.size(); ++k) m->h_beta[k] = 0.0;
+    if (m->hdp.sample_hyperparam) {            // src/HDP.jl:124-159
+        const double mt = (double)tables[Kpad];
+        const double aa_shape = m->hdp.a1 + mt - hyper[1];
+        const double aa_rate = m->hdp.a2 - hyper[0];
+        if (aa_shape > 0.0 && aa_rate > 0.0) {
+            std::gamma_distribution<double> ga(aa_shape, 1.0);
+            m->hdp.aa = ga(m->host_rng) / aa_rate;
+        }
+        std::gamma_distribution<double> g1(m->hdp.gg + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
+        const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
+        const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
+        const double le = std::log(eta);
+        const double pi_eta = 1.0 / (1.0 + (mt * (m->hdp.g2 - le)) / (m->hdp.g1 + KK - 1.0));   // :152
+        std::uniform_real_distribution<double> ud(0.0, 1.0);
+        const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
+        if (shape > 0.0) {
+            std::gamma_distribution<double> gg(shape, 1.0);
+            m->hdp.gg = gg(m->host_rng) / (m->hdp.g2 - le);
         }
     }
-    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
+    return BIAS_OK;
+}
+
+static int hdp_phase_end(bias_model *m) {
+    cudaStream_t st = m->ctx->stream;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)m->Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
     m->sweep_index += 1;
     m->stats_pending = true;
     return BIAS_OK;
+}
+
+int hdp_sweep(bias_model *m) {
+    BIAS_TRY(hdp_prune(m));                       // src/HDP.jl:248-264
+    BIAS_TRY(hdp_phase_pass(m));
+    BIAS_TRY(hdp_phase_births(m));
+    BIAS_TRY(hdp_prune(m));                       // components that died during the pass (src/HDP.jl:291-307)
+    for (int hh = 0; hh < m->hdp.n_internals; ++hh) {
+        BIAS_TRY(hdp_phase_tables(m, hh));
+        BIAS_TRY(hdp_phase_draw(m));
+    }
+    return hdp_phase_end(m);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -737,6 +767,67 @@ int bias_model_get_hdp(bias_model *m, bias_hdp_params *params, double *beta) {
         for (int k = 0; k < n; ++k) beta[k] = (k < (int)m->h_beta.size()) ? m->h_beta[k] : 0.0;
     }
     return BIAS_OK;
+}
+
+// ---- sharded HDP: the phases of one sweep, with the caller's exchanges between them (include/bias_cuda.h) ----
+static int check_hdp(bias_model *m) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (m->model != BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "not an HDP model");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    return BIAS_OK;
+}
+
+int bias_model_set_host_seed(bias_model *m, uint64_t seed) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    m->host_rng.seed(seed);
+    return BIAS_OK;
+}
+
+int bias_hdp_shard_pass(bias_model *m) {
+    BIAS_TRY(check_hdp(m));
+    return hdp_phase_pass(m);
+}
+
+int bias_hdp_shard_births(bias_model *m, int32_t *KK_out, double *beta_out) {
+    BIAS_TRY(check_hdp(m));
+    BIAS_TRY(hdp_phase_births(m));
+    if (KK_out) *KK_out = m->hdp.KK;
+    if (beta_out)
+        for (int k = 0; k <= m->hdp.Kmax; ++k) beta_out[k] = (k < (int)m->h_beta.size()) ? m->h_beta[k] : 0.0;
+    return BIAS_OK;
+}
+
+int bias_hdp_shard_adopt(bias_model *m, int32_t KK, const double *beta) {
+    BIAS_TRY(check_hdp(m));
+    if (!beta) return fail(BIAS_EINVAL, "null argument");
+    if (KK < m->hdp.KK || KK + 2 > m->hdp.Kmax) return fail(BIAS_ERANGE, "HDP shard: KK = %d outside [%d, Kmax - 2 = %d]", KK, m->hdp.KK, m->hdp.Kmax - 2);
+    m->hdp.KK = KK;
+    for (int k = 0; k < (int)m->h_beta.size(); ++k) m->h_beta[k] = (k <= KK) ? beta[k] : 0.0;
+    return BIAS_OK;
+}
+
+int bias_hdp_shard_prune(bias_model *m) {
+    BIAS_TRY(check_hdp(m));
+    return hdp_prune(m);
+}
+
+int bias_hdp_shard_tables(bias_model *m, int32_t internal, void **tables_dev, int64_t *n_tables, void **hyper_dev) {
+    BIAS_TRY(check_hdp(m));
+    BIAS_TRY(hdp_phase_tables(m, internal));
+    if (tables_dev) *tables_dev = m->d_tables;
+    if (n_tables) *n_tables = (int64_t)m->Kpad + 1;
+    if (hyper_dev) *hyper_dev = m->d_hyper;
+    return BIAS_OK;
+}
+
+int bias_hdp_shard_draw(bias_model *m) {
+    BIAS_TRY(check_hdp(m));
+    return hdp_phase_draw(m);
+}
+
+int bias_hdp_shard_end(bias_model *m) {
+    BIAS_TRY(check_hdp(m));
+    return hdp_phase_end(m);
 }
 
 int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out) {

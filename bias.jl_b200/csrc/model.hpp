@@ -72,6 +72,7 @@ struct bias_model {
     double *d_hyper = nullptr;      // [0] sum log w, [1] sum s
     int32_t *d_remap = nullptr;     // [Kpad] slot compaction map
     std::mt19937_64 host_rng;
+    int32_t *pending_base = nullptr; // start of the two-half pending queue buffer (pending may point at either half)
 
     // RCRP (epochs are the groups)
     std::vector<double> h_aa_t;     // [T] per-epoch concentration

@@ -200,6 +200,7 @@ class ResidentSampler:
     def __init__(self, ctx: Context, model, data: FlatData, zz_flat: np.ndarray, *, sample_hyperparam=True,
                  n_internals=10):
         self.ctx, self.model, self.data = ctx, model, data
+        self.n_internals = int(n_internals)
         self.spec = model.component.spec(data.datum)
         self.h = C.c_void_p()
         hp = _hdp_params(model, sample_hyperparam, n_internals) if isinstance(model, HDP) else None
@@ -317,6 +318,39 @@ class ResidentSampler:
         s, n = C.c_double(), C.c_int64()
         check(lib().bias_model_heldout_log_likelihood(self.h, ptr(hp), ptr(hw), C.byref(s), C.byref(n)))
         return s.value, n.value
+
+    # -- sharded HDP phases (see include/bias_cuda.h and sharding.ShardedHDP)
+    def set_host_seed(self, seed: int):
+        check(lib().bias_model_set_host_seed(self.h, C.c_uint64(seed & (2**64 - 1))))
+
+    def hdp_shard_pass(self):
+        check(lib().bias_hdp_shard_pass(self.h))
+
+    def hdp_shard_births(self):
+        """-> (KK, beta[Kmax+1]) after this rank's births"""
+        kk = C.c_int32()
+        beta = np.zeros(self.model.Kmax + 1)
+        check(lib().bias_hdp_shard_births(self.h, C.byref(kk), ptr(beta)))
+        return kk.value, beta
+
+    def hdp_shard_adopt(self, KK: int, beta: np.ndarray):
+        bb = _lib.as_f64(beta)
+        check(lib().bias_hdp_shard_adopt(self.h, int(KK), ptr(bb)))
+
+    def hdp_shard_prune(self):
+        check(lib().bias_hdp_shard_prune(self.h))
+
+    def hdp_shard_tables(self, internal: int):
+        """-> [(device_ptr, n, 'int64'), (device_ptr, 2, 'float64')]: this rank's table counts and alpha0 auxiliaries"""
+        pt, ph, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(lib().bias_hdp_shard_tables(self.h, internal, C.byref(pt), C.byref(n), C.byref(ph)))
+        return [(pt.value, n.value, "int64"), (ph.value, 2, "float64")]
+
+    def hdp_shard_draw(self):
+        check(lib().bias_hdp_shard_draw(self.h))
+
+    def hdp_shard_end(self):
+        check(lib().bias_hdp_shard_end(self.h))
 
     # -- multi-GPU exchange (AD-LDA)
     def delta_begin(self):

@@ -34,7 +34,7 @@ class _CudaView:
     """Zero-copy torch view of a raw device pointer (through __cuda_array_interface__)."""
 
     def __init__(self, ptr: int, n: int, dtype: str):
-        typestr = {"int32": "<i4", "float64": "<f8"}[dtype]
+        typestr = {"int32": "<i4", "float64": "<f8", "int64": "<i8"}[dtype]
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
@@ -96,3 +96,117 @@ class GpuShard:
 
     def delta_apply(self):
         self.rs.delta_apply()
+
+
+# ------------------------------------------------------------------ sharded HDP
+class DistComm:
+    """Collectives of one rank of a torch.distributed job (NCCL on GPUs)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.ranks = [self.rank]          # global rank of each local shard
+
+    def bcast_state(self, turn: int, states, device):
+        """states[i] = (KK, beta) of local shard i if it is rank `turn`, else None -> (KK, beta) of rank `turn`"""
+        import torch
+        mine = states[0]
+        if self.world == 1:
+            return mine
+        n = len(mine[1]) if mine is not None else 0
+        nn = torch.tensor([n], dtype=torch.int64, device=device)
+        self.dist.all_reduce(nn, op=self.dist.ReduceOp.MAX, group=self.group)
+        buf = torch.zeros(int(nn.item()) + 1, dtype=torch.float64, device=device)
+        if mine is not None:
+            buf[0] = float(mine[0])
+            buf[1:] = torch.from_numpy(mine[1]).to(device)
+        self.dist.broadcast(buf, src=turn, group=self.group)
+        h = buf.cpu().numpy()
+        return int(round(h[0])), h[1:].copy()
+
+    def allreduce(self, tensor_lists):
+        if self.world == 1:
+            return
+        for ts in tensor_lists:           # one list per local shard (here: exactly one)
+            for t in ts:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class LocalComm:
+    """All 'ranks' are samplers of this process (tests: several shards on one GPU); sums are done in place."""
+
+    def __init__(self, n_shards: int):
+        self.world, self.ranks = n_shards, list(range(n_shards))
+
+    def bcast_state(self, turn: int, states, device):
+        return states[turn]
+
+    def allreduce(self, tensor_lists):
+        for seg in range(len(tensor_lists[0])):
+            total = tensor_lists[0][seg].clone()
+            for ts in tensor_lists[1:]:
+                total += ts[seg]
+            for ts in tensor_lists:
+                ts[seg].copy_(total)
+
+
+class ShardedHDP:
+    """HDP direct-assignment sampler with the groups split over ranks.  Every rank keeps a full replica of
+    the component statistics, beta, alpha0 and gamma; per sweep the ranks sample their groups in parallel, take turns
+    giving birth to new components (all-reducing the deltas of the component statistics after every turn), and
+    all-reduce the per-component table totals of each internal iteration (the protocol is spelled out in include/bias_cuda.h).  `samplers` are this process's
+    ResidentSampler shards (one per process under torch.distributed; several with LocalComm)."""
+
+    def __init__(self, samplers, comm, device, host_seed: int = 0):
+        self.s, self.comm, self.device = list(samplers), comm, device
+        for rs in self.s:
+            rs.set_host_seed(host_seed)
+        if comm.world > 1:
+            # counts were built from the local groups only: merge them, then drop empty components consistently
+            for rs in self.s:
+                rs.delta_begin_zero()
+            self._exchange_deltas()
+            for rs in self.s:
+                rs.hdp_shard_prune()
+
+    def _tensors(self, packs):
+        return [[device_tensor(p, n, dt, self.device) for (p, n, dt) in pk] for pk in packs]
+
+    def _allreduce(self, packs):
+        """The library works on its contexts' streams, torch / NCCL on torch's current stream: order them explicitly
+        (the HDP sweep synchronises with the host at every phase anyway)."""
+        import torch
+        for rs in self.s:
+            rs.ctx.sync()
+        self.comm.allreduce(self._tensors(packs))
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def _exchange_deltas(self):
+        self._allreduce([rs.delta_pack() for rs in self.s])
+        for rs in self.s:
+            rs.delta_apply()
+
+    def sweep(self, n_sweeps: int = 1):
+        for _ in range(n_sweeps):
+            for rs in self.s:
+                rs.delta_begin()
+            for rs in self.s:
+                rs.hdp_shard_pass()
+            for turn in range(self.comm.world):
+                # rank `turn` gives birth against everything the ranks before it opened; the others adopt its KK / beta
+                states = [rs.hdp_shard_births() if r == turn else None for rs, r in zip(self.s, self.comm.ranks)]
+                KK, beta = self.comm.bcast_state(turn, states, self.device)
+                for rs, r in zip(self.s, self.comm.ranks):
+                    if r != turn:
+                        rs.hdp_shard_adopt(KK, beta[:KK + 1])
+                self._exchange_deltas()
+            for rs in self.s:
+                rs.hdp_shard_prune()
+            for hh in range(self.s[0].n_internals):
+                self._allreduce([rs.hdp_shard_tables(hh) for rs in self.s])
+                for rs in self.s:
+                    rs.hdp_shard_draw()
+            for rs in self.s:
+                rs.hdp_shard_end()

@@ -201,6 +201,29 @@ BIAS_API int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t
 BIAS_API int bias_model_heldout_log_likelihood(bias_model *m, const int64_t *heldout_ptr, const int32_t *heldout_word,
                       double *sum_log_p, int64_t *n_tokens);
 
+/* ---- sharded HDP (groups split over ranks) ---------------------------------- */
+/* One sweep of collapsed_gibbs_sampler!(::HDP) (src/HDP.jl:235-373) cut at the points where ranks must agree:
+ *   bias_model_delta_begin
+ *   bias_hdp_shard_pass      parallel assignment pass; items that draw the new-component slot are queued
+ *   for r = 0 .. world-1:    the ranks take turns giving birth, so that a rank sees the components the ranks before
+ *                            it opened in this sweep (two ranks meeting the same new atom do not both open one)
+ *       rank r:       bias_hdp_shard_births  -> its KK and beta (stick-breaking of src/HDP.jl:325-328)
+ *       other ranks:  [broadcast KK, beta from r]  bias_hdp_shard_adopt
+ *       all ranks:    bias_model_delta_pack / [all-reduce] / bias_model_delta_apply
+ *   bias_hdp_shard_prune     dead components (the same on every rank: counts are global now)
+ *   n_internals x { bias_hdp_shard_tables  [all-reduce tables (int64[n_tables]) and hyper (double[2])]  bias_hdp_shard_draw }
+ *   bias_hdp_shard_end
+ * beta, alpha0 and gamma are drawn on every rank from the same host RNG stream (bias_model_set_host_seed with one
+ * seed for all ranks), so replicas stay identical.  bias.jl_b200/sharding.py drives this protocol. */
+BIAS_API int bias_model_set_host_seed(bias_model *m, uint64_t seed);
+BIAS_API int bias_hdp_shard_pass(bias_model *m);
+BIAS_API int bias_hdp_shard_births(bias_model *m, int32_t *KK_out, double *beta_out /* [Kmax+1] */);
+BIAS_API int bias_hdp_shard_adopt(bias_model *m, int32_t KK, const double *beta /* [KK+1] */);
+BIAS_API int bias_hdp_shard_prune(bias_model *m);
+BIAS_API int bias_hdp_shard_tables(bias_model *m, int32_t internal, void **tables_dev, int64_t *n_tables, void **hyper_dev);
+BIAS_API int bias_hdp_shard_draw(bias_model *m);
+BIAS_API int bias_hdp_shard_end(bias_model *m);
+
 /* ---- multi-GPU exchange (AD-LDA: one allreduce of count deltas per sweep) --------------- */
 /* Snapshot the shared component statistics (n_wk, n_k / sumx, n) as the base of the next delta. */
 BIAS_API int bias_model_delta_begin(bias_model *m);

@@ -175,3 +175,101 @@ def test_kmax_exhaustion_is_an_error(ctx):
     with pytest.raises(b.BiasError) as e:
         b.collapsed_gibbs_sampler(hdp, [x], [np.zeros(len(x), dtype=np.int64)], 5, 0, 1, ctx=ctx)
     assert e.value.code == 5
+
+
+@pytest.mark.parametrize("n_shards", [2, 3])
+def test_sharded_hdp_on_one_gpu(ctx, n_shards):
+    """The N>1 HDP protocol (sharding.ShardedHDP) with the ranks played by several samplers on one device: replicas
+    of the component statistics, beta, alpha0, gamma and KK stay identical, counts equal the recomputation from the
+    gathered zz, and the atoms are recovered as well as by the single-GPU sampler."""
+    import torch
+    from bias_jl_b200.sharding import LocalComm, ShardedHDP, shard_csr
+    zz_true, n_atoms = b.data.gen_crf_data([80] * 36, 1.0, 0.5, seed=5)
+    rng = np.random.default_rng(6)
+    xx = [2.0 * (z + 1) + np.sqrt(0.001) * rng.standard_normal(len(z)) for z in zz_true]
+    allx = np.concatenate(xx)
+    ptr = np.concatenate([[0], np.cumsum([len(x) for x in xx])]).astype(np.int64)
+    hdp = b.HDP(b.Gaussian1DGaussian1D(float(allx.mean()), 10.0, 0.001), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=64)
+    ctxs, samplers = [], []
+    for r in range(n_shards):
+        lo, hi, i0, i1, lptr = shard_csr(ptr, r, n_shards)
+        data = b.FlatData.from_csr(b._lib.F64, i1 - i0, group_ptr=lptr, x=allx[i0:i1])
+        c = b.Context(0, seed=900 + r)
+        ctxs.append(c)
+        samplers.append(b.ResidentSampler(c, hdp, data, np.zeros(i1 - i0, dtype=np.int32), sample_hyperparam=True,
+                                          n_internals=5))
+    sh = ShardedHDP(samplers, LocalComm(n_shards), torch.device("cuda", 0), host_seed=31)
+    for sweep in range(25):
+        sh.sweep(1)
+        states = [rs.hdp_state() for rs in samplers]
+        KK = states[0][0].KK
+        z = np.concatenate([rs.get_zz() for rs in samplers])
+        assert ((z >= 0) & (z < KK)).all() and set(np.unique(z)) == set(range(KK))
+        for rs, (hp, beta) in zip(samplers, states):
+            assert hp.KK == KK and hp.gg == states[0][0].gg and hp.aa == states[0][0].aa
+            assert np.array_equal(beta, states[0][1]) and abs(beta.sum() - 1.0) < 1e-9
+            comp = rs.components()
+            assert np.array_equal(comp["nn"], np.bincount(z, minlength=KK))
+            for k in range(KK):
+                assert abs(comp["mu"][k] - allx[z == k].mean()) < 1e-9
+    used = len(np.unique(np.concatenate(zz_true)))
+    # the ranks take turns giving birth, so two ranks that meet the same new atom in one sweep do not both open a
+    # component for it: KK stays where the single-GPU sampler puts it
+    assert used - 1 <= KK <= used + 3, (KK, used)
+    zt = np.concatenate(zz_true)
+    homogeneity = sum(np.bincount(zt[z == c]).max() for c in np.unique(z)) / len(z)
+    assert homogeneity > 0.97, homogeneity
+    for rs in samplers:
+        rs.close()
+    for c in ctxs:
+        c.close()
+
+
+def test_sharded_hdp_multinomial_counts_stay_consistent(ctx):
+    import torch
+    from bias_jl_b200.sharding import LocalComm, ShardedHDP, shard_csr
+    V = 25
+    xx, _, _ = b.data.bars_lda_corpus(n_groups=40, n_tokens=60, seed=3)
+    words = np.concatenate(xx)
+    ptr = np.concatenate([[0], np.cumsum([len(x) for x in xx])]).astype(np.int64)
+    hdp = b.HDP(b.MultinomialDirichlet(V, 2.5), 2, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=48)
+    z0 = np.random.default_rng(1).integers(0, 2, len(words)).astype(np.int32)
+    samplers, ctxs = [], []
+    for r in range(2):
+        lo, hi, i0, i1, lptr = shard_csr(ptr, r, 2)
+        data = b.FlatData.from_csr(b._lib.INT, i1 - i0, group_ptr=lptr, word=words[i0:i1])
+        c = b.Context(0, seed=50 + r)
+        ctxs.append(c)
+        samplers.append(b.ResidentSampler(c, hdp, data, z0[i0:i1], sample_hyperparam=True, n_internals=3))
+    sh = ShardedHDP(samplers, LocalComm(2), torch.device("cuda", 0), host_seed=7)
+    sh.sweep(30)
+    KK = samplers[0].hdp_state()[0].KK
+    z = np.concatenate([rs.get_zz() for rs in samplers])
+    mi = np.zeros((KK, V), dtype=np.int64)
+    np.add.at(mi, (z, words), 1)
+    for rs in samplers:
+        comp = rs.components()
+        assert np.array_equal(comp["mi"], mi) and np.array_equal(comp["mm"], mi.sum(1))
+    assert 1 <= KK <= 46, KK
+    for rs in samplers:
+        rs.close()
+    for c in ctxs:
+        c.close()
+
+
+def test_sharded_hdp_over_nccl_two_processes():
+    """The same protocol with real ranks: two processes, two GPUs, NCCL (tools/hdp_sharded_check.py)."""
+    import os
+    import subprocess
+    import sys
+    if b.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HDP_GROUPS="4000")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "hdp_sharded_check.py")],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["replicas_consistent"] and line["homogeneity"] > 0.97 and 20 <= line["KK"] <= 25
