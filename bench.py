@@ -387,15 +387,24 @@ def ours(args):
     def e2e_download(i):
         return pipes[i][0].get_zz(out=zz_out_h[i].numpy())      # waits for the model's own stream only
 
+    verbose = bool(os.environ.get("BIAS_BENCH_VERBOSE")) and rank == 0
+
     def e2e_run(n_steps):
+        marks = [time.perf_counter()]
         e2e_upload(0)
         e2e_sweep(0)
         for s_ in range(n_steps):
             cur, nxt = s_ % 2, 1 - (s_ % 2)
             if s_ + 1 < n_steps:
                 e2e_upload(nxt)
+                marks.append(time.perf_counter())
                 e2e_sweep(nxt)
+                marks.append(time.perf_counter())
             e2e_download(cur)
+            marks.append(time.perf_counter())
+        if verbose:
+            print("e2e host marks (ms since start; per step: upload done, sweep enqueued, download done):",
+                  [round(1e3 * (m_ - marks[0]), 2) for m_ in marks], file=sys.stderr)
 
     e2e_run(2)                                   # warm both pipelines (first-touch of the pinned buffers, NCCL)
     barrier()

@@ -56,7 +56,6 @@ struct LdaFastParams {
     const int32_t *gate;        // nullable: the kernel runs only when *gate == gate_expect (16-bit / 32-bit hand-over)
     int32_t gate_expect;
     int32_t *nk_rep;            // half-warp kernels: [kNkRep][Kpad] replicas collecting this sweep's changes of n_k
-    int32_t exp_flags;          // experiments only (BIAS_LDA_EXP): 1 = skip the global atomics, 2 = weak (L1-cached) row loads
     int32_t pf_dist;            // lda_half.cuh: rows are pulled into L2 this many tokens ahead (0: off; at most 16)
 };
 

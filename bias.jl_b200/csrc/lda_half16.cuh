@@ -283,13 +283,8 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             int c_own_n = 0;
             if (i + 1 < nb_both) {
                 const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
-                if (p.exp_flags & 2) {
 #pragma unroll
-                    for (int j = 0; j < NC8; ++j) c[j] = reinterpret_cast<const uint4 *>(rown)[j * 16 + l16];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
-                }
+                for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
                 c_own_n = __ldcg(rown + kold_n);
             }
 
@@ -349,7 +344,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                         r_s[r_pos(knew)] = r_new;
                         R_s[knew >> 7] += r_new - r2;
                     }
-                    if (l16 >= 8 && l16 < 12 && !(p.exp_flags & 1)) {
+                    if (l16 >= 8 && l16 < 12) {
                         // lanes 8..11: n_wk16[kold]--, n_wk16[knew]++, n_k[kold]--, n_k[knew]++ (the int32 table is
                         // rewritten from the shadow after the sweep, shadow_fold_kernel)
                         const int which = l16 - 8, kk = (which & 1) ? knew : kold;

@@ -194,8 +194,6 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     {
         const char *pf = getenv("BIAS_LDA_PF");
         p.pf_dist = pf ? std::max(0, std::min(16, atoi(pf))) : 2;
-        const char *ex = getenv("BIAS_LDA_EXP");
-        p.exp_flags = ex ? atoi(ex) : 0;
     }
     p.nk_rep = m->nk_rep;
     const bool half_path = use_half_kernel(m) && !eval && m->nk_rep;

@@ -360,3 +360,64 @@ def test_counts_beyond_16_bits_fall_back_to_the_int32_rows(ctx):
     assert_draws_match(draw, odraw, oprob, u[idx], 1e-12)
     assert_draws_match(fd[idx], odraw, oprob, u[idx], 2e-5)
     rs.close()
+
+
+def test_production_kernel_conditionals_recovered_from_its_draws(ctx):
+    """Parity level (a) for the fp32 production kernel itself (the fp64 verification kernel is checked directly
+    above): with frozen counts the kernel's draw as a function of the uniform is a step function whose steps are the
+    CDF of its conditional.  Bisection on the uniform of every token at once recovers each token's CDF edges to
+    the resolution of a float uniform; the conditional built from them must match the oracle's within
+    1e-5 relative (+1e-6) in log-probability wherever the probability is resolvable (p > 1e-3)."""
+    K, V = 8, 30
+    rng = np.random.default_rng(12)
+    xx = [rng.integers(0, V, n).astype(np.int64) for n in rng.integers(20, 60, 40)]
+    rs, state, data, z0, words, _ = _setup(ctx, xx, K, V, 0.3, 0.2 * V, seed=6)
+    rs.sweep(3)                                   # a non-trivial state
+    z = rs.get_zz()
+    N = data.n_items
+    st = orc.LDAState(orc.Comps.md(K, V, 0.2 * V), orc.Data.words(words), data.group_ptr, z, 0.3)
+    oraw, oprob, _ = _oracle_conditionals(st, data, np.arange(N), np.full(N, 0.5))
+    edges = np.zeros((N, K - 1))
+    for e in range(K - 1):
+        lo, hi = np.zeros(N), np.ones(N)          # draw(lo) <= e < draw(hi)
+        for _ in range(26):
+            mid = 0.5 * (lo + hi)
+            d = rs.frozen_draws(mid)
+            up = d > e
+            hi = np.where(up, mid, hi)
+            lo = np.where(up, lo, mid)
+        edges[:, e] = 0.5 * (lo + hi)
+    cdf = np.concatenate([edges, np.ones((N, 1))], axis=1)
+    prob = np.diff(np.concatenate([np.zeros((N, 1)), cdf], axis=1), axis=1)
+    assert np.abs(cdf[:, :-1] - np.cumsum(oprob, 1)[:, :-1]).max() < 2e-6
+    ok = oprob > 1e-3
+    err = np.abs(np.log(prob[ok]) - np.log(oprob[ok]))
+    # the recovered edges carry the 6e-8 resolution of a 24-bit uniform: that alone is 1.2e-7 / p in log p
+    tol = 1e-5 * np.abs(np.log(oprob[ok])) + 1e-6 + 2.5e-7 / oprob[ok]
+    assert (err <= tol).all(), (err / tol).max()
+    rs.close()
+
+
+def test_production_kernel_cdf_at_k1024(ctx):
+    """The same recovery at K = 1024 (8 chunks of 128 topics, the headline shape) for a subset of CDF edges: every chunk
+    boundary (the chunk-selection scan) and a few edges inside chunks (the in-chunk scan and the 8-entry walk)."""
+    K, V = 1024, 300
+    rng = np.random.default_rng(13)
+    xx = [rng.integers(0, V, n).astype(np.int64) for n in rng.integers(40, 120, 16)]
+    rs, state, data, z0, words, _ = _setup(ctx, xx, K, V, 0.1, 0.1 * V, seed=7)
+    rs.sweep(2)
+    z = rs.get_zz()
+    N = data.n_items
+    st = orc.LDAState(orc.Comps.md(K, V, 0.1 * V), orc.Data.words(words), data.group_ptr, z, 0.1)
+    _, oprob, _ = _oracle_conditionals(st, data, np.arange(N), np.full(N, 0.5))
+    ocdf = np.cumsum(oprob, 1)
+    edges = sorted(set([128 * j - 1 for j in range(1, 8)] + [0, 5, 130, 519, 700, 1001, 1022]))
+    for e in edges:
+        lo, hi = np.zeros(N), np.ones(N)
+        for _ in range(25):
+            mid = 0.5 * (lo + hi)
+            up = rs.frozen_draws(mid) > e
+            hi = np.where(up, mid, hi)
+            lo = np.where(up, lo, mid)
+        assert np.abs(0.5 * (lo + hi) - ocdf[:, e]).max() < 3e-6, e
+    rs.close()
