@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbias_cuda.so")
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE, ESTATE = range(7)
 MD, G1G1 = 0, 1
 INT, SENT, F64 = 0, 1, 2
-MODEL_LDA, MODEL_BMM, MODEL_HDP, MODEL_RCRP = 0, 1, 2, 3
+MODEL_LDA, MODEL_BMM, MODEL_HDP, MODEL_RCRP, MODEL_CRF = 0, 1, 2, 3, 4
 
 # every symbol include/bias_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -31,6 +31,7 @@ SYMBOLS = [
     "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload", "bias_model_heldout_log_likelihood",
     "bias_model_set_host_seed", "bias_hdp_shard_pass", "bias_hdp_shard_births", "bias_hdp_shard_adopt", "bias_hdp_shard_prune",
     "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
+    "bias_crf_sweep_with_uniforms", "bias_crf_get_tables",
 ]
 
 
@@ -127,6 +128,8 @@ def lib():
     L.bias_hdp_shard_tables.argtypes = [vp, i32, pp, C.POINTER(i64), pp]
     L.bias_hdp_shard_draw.argtypes = [vp]
     L.bias_hdp_shard_end.argtypes = [vp]
+    L.bias_crf_sweep_with_uniforms.argtypes = [vp, vp]
+    L.bias_crf_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int

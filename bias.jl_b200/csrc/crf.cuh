@@ -1,0 +1,345 @@
+// crf.cuh — Chinese-restaurant-franchise sampler of the HDP (reference src/HDP.jl:402-709, CRF_gibbs_sampler!)
+// for Gaussian1DGaussian1D x Float64 (the combination the reference exercises, doc/examples/demo_CRF_*.jl).
+// Included by hdp.cu inside namespace bias (uses its PhiloxStream, hdp_hyper_kernel, grid1d, compaction kernels).
+//
+// The reference walks the restaurants one after the other; inside a restaurant every step depends on the one
+// before (tables open and close, indices shift).  Here ONE WARP owns a restaurant and performs exactly the
+// reference's serial steps for it, lanes sharing the work of each step (scores over tables / dishes, shifting the
+// table arrays, re-labelling the customers); restaurants run in parallel against the shared dish statistics
+// (sum x, n, tables per dish) with atomics — the same cross-group staleness as the other samplers.
+//   pass 1 (crf_tables_kernel)  :506-587  a table for every customer; a new table draws its dish
+//   pass 2 (crf_dishes_kernel)  :593-655  a dish for every table (all its customers move together)
+// Differences from the serial reference, both documented in DESIGN.md: a dish that loses its last table keeps its slot
+// (weight log 0 = never chosen) until the end of the iteration instead of being spliced out at once (:531-545,
+// :610-621 renumber every restaurant), and a new dish takes the next free slot with one atomic.  With a single
+// restaurant and supplied uniforms the kernels reproduce the serial sampler's iteration exactly (tests/test_gpu_crf.py).
+//
+// Layout: tables of group j live at [group_ptr[j], group_ptr[j] + n_tbls[j]) of njt / kjt (a group has at most as
+// many tables as customers); tji[i] is the table of customer i within its group; mm[k] = tables serving dish k.
+#pragma once
+
+struct CrfParams {
+    const int64_t *group_ptr;
+    int64_t G;
+    const double *x;
+    int32_t *z, *tji, *njt, *kjt, *n_tbls, *mm;
+    int32_t *n_items;           // customers per dish (component statistics, shared with the other samplers)
+    double *sumx;
+    int32_t *d_KK;              // dish slots in use (grows by atomics during a pass)
+    int32_t Kmax;
+    double m0, v0, vv, aa, gg;
+    uint64_t seed;
+    uint32_t sweep;
+    const double *ext_uniforms; // nullable: [3N] = per item slot i: table draw, dish-of-a-new-table draw; per table slot: dish draw
+    int *lock;                  // births are decided one at a time (see crf_lock)
+    int *err;                   // 2: dish slots exhausted
+    unsigned long long *moved;
+    int32_t max_len;            // longest group (capacity of the per-warp staging buffers)
+};
+
+constexpr int kCrfWarps = 4;
+__host__ __device__ inline size_t crf_smem_bytes(int max_len, int Kmax) {
+    // per warp: scores double[max(max_len, Kmax) + 2] + staged values double[max_len]
+    const size_t n = (size_t)(max_len > Kmax ? max_len : Kmax) + 2;
+    return (size_t)kCrfWarps * (n + (size_t)max_len) * sizeof(double);
+}
+
+// first-appearance tables from z (src/HDP.jl:441-470): kjt[jj] = unique(zz[jj])
+__global__ void crf_init_kernel(CrfParams p) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.G) return;
+    const int64_t p0 = p.group_ptr[j], n = p.group_ptr[j + 1] - p0;
+    int nt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int kk = p.z[p0 + i];
+        int t = -1;
+        for (int q = 0; q < nt; ++q)
+            if (p.kjt[p0 + q] == kk) { t = q; break; }
+        if (t < 0) {
+            t = nt++;
+            p.kjt[p0 + t] = kk;
+            p.njt[p0 + t] = 0;
+            atomicAdd(p.mm + kk, 1);
+        }
+        p.tji[p0 + i] = t;
+        p.njt[p0 + t] += 1;
+    }
+    p.n_tbls[j] = nt;
+}
+
+__device__ __forceinline__ double crf_draw_uniform(const CrfParams &p, int64_t idx, int which) {
+    if (p.ext_uniforms) return p.ext_uniforms[3 * idx + which];
+    PhiloxStream rs(p.seed, (uint32_t)idx, (uint32_t)((uint64_t)idx >> 32), p.sweep * 8u + 5u + (uint32_t)which);
+    return rs.u01();
+}
+
+// max over the warp of the scores a lane wrote, then the draw (same arithmetic as the generic kernel)
+__device__ __forceinline__ int crf_draw(double *sc, int n_out, double u, int lane) {
+    double lmax = -INFINITY;
+    for (int k = lane; k < n_out; k += 32) lmax = fmax(lmax, sc[k]);
+    lmax = warp_max(lmax);
+    __syncwarp();
+    return draw_parallel(sc, n_out, lmax, u, lane);
+}
+
+// Restaurants that meet a new atom at the same moment would each open a dish for it (hundreds of duplicates in the
+// first iteration).  A warp whose draw says "new dish" therefore takes a global lock, scores the menu again — it now
+// holds whatever the previous lock holders opened — and opens a dish only if the draw (same uniform) still says so.
+// With one restaurant this is the serial sampler step for step.
+__device__ __forceinline__ void crf_lock(const CrfParams &p, int lane) {
+    if (lane == 0)
+        while (atomicCAS(p.lock, 0, 1) != 0) __nanosleep(200);
+    __syncwarp();
+    __threadfence();
+}
+__device__ __forceinline__ void crf_unlock(const CrfParams &p, int lane) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(p.lock, 0);
+}
+
+// a new dish: the next free slot (one atomic); -1 when the slots are exhausted
+__device__ __forceinline__ int crf_new_dish(const CrfParams &p, int lane) {
+    int k = 0;
+    if (lane == 0) {
+        k = atomicAdd(p.d_KK, 1);
+        if (k + 2 > p.Kmax) {
+            atomicSub(p.d_KK, 1);
+            *p.err = 2;
+            k = -1;
+        }
+    }
+    return __shfl_sync(kFull, k, 0);
+}
+
+// ---- pass 1: a table for every customer (src/HDP.jl:506-587) ----
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_sc = (size_t)(p.max_len > p.Kmax ? p.max_len : p.Kmax) + 2;
+    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n_sc + p.max_len);
+    const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
+    unsigned long long moved = 0;
+    for (int64_t j = (int64_t)blockIdx.x * kCrfWarps + warp; j < p.G; j += n_warps) {
+        const int64_t p0 = p.group_ptr[j];
+        const int n = (int)(p.group_ptr[j + 1] - p0);
+        int32_t *njt = p.njt + p0, *kjt = p.kjt + p0, *tji = p.tji + p0;
+        int nt = p.n_tbls[j];
+        for (int ii = 0; ii < n; ++ii) {
+            const int64_t i = p0 + ii;
+            const double x = p.x[i];
+            int kk = p.z[i], tbl = tji[ii];
+            // remove the customer (:511-515)
+            int left = 0;
+            if (lane == 0) {
+                atomicAdd(p.n_items + kk, -1);
+                atomicAdd(p.sumx + kk, -x);
+                left = njt[tbl] - 1;
+                njt[tbl] = left;
+            }
+            left = __shfl_sync(kFull, left, 0);
+            if (left == 0) {
+                // the table empties: it is removed and the tables after it move down (:517-529); the dish keeps its
+                // slot even if this was its last table
+                if (lane == 0) atomicAdd(p.mm + kk, -1);
+                for (int b = tbl; b < nt - 1; b += 32) {
+                    const int q = b + lane;
+                    int a0 = 0, a1 = 0;
+                    if (q < nt - 1) { a0 = kjt[q + 1]; a1 = njt[q + 1]; }
+                    __syncwarp();
+                    if (q < nt - 1) { kjt[q] = a0; njt[q] = a1; }
+                    __syncwarp();
+                }
+                nt -= 1;
+                for (int q = lane; q < n; q += 32)
+                    if (tji[q] > tbl) tji[q] -= 1;
+            }
+            __threadfence();
+            __syncwarp();
+            // scores of the tables and of a new one (:549-555)
+            for (int t = lane; t < nt; t += 32) {
+                const int kt = kjt[t];
+                const double cn = (double)__ldcg(p.n_items + kt), sx = __ldcg(p.sumx + kt);
+                sc[t] = log((double)njt[t]) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+            }
+            if (lane == 0) sc[nt] = log(p.aa) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
+            __syncwarp();
+            tbl = crf_draw(sc, nt + 1, crf_draw_uniform(p, i, 0), lane);
+            if (tbl == nt) {
+                // a new table draws its dish from the menu (:559-581)
+                const int KK = __ldcg(p.d_KK);
+                for (int k = lane; k < KK; k += 32) {
+                    const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
+                    sc[k] = log((double)__ldcg(p.mm + k)) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+                }
+                if (lane == 0) sc[KK] = log(p.gg) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
+                __syncwarp();
+                const double u_dish = crf_draw_uniform(p, i, 1);
+                int knew = crf_draw(sc, KK + 1, u_dish, lane);
+                const bool locked = knew == KK;
+                if (locked) {
+                    crf_lock(p, lane);
+                    const int KK2 = __ldcg(p.d_KK);
+                    for (int k = lane; k < KK2; k += 32) {
+                        const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
+                        sc[k] = log((double)__ldcg(p.mm + k)) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+                    }
+                    if (lane == 0) sc[KK2] = log(p.gg) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
+                    __syncwarp();
+                    knew = crf_draw(sc, KK2 + 1, u_dish, lane);
+                    if (knew == KK2) {
+                        knew = crf_new_dish(p, lane);
+                        if (knew < 0) knew = KK2 - 1;
+                    }
+                }
+                if (lane == 0) {
+                    kjt[tbl] = knew;
+                    njt[tbl] = 0;
+                    atomicAdd(p.mm + knew, 1);
+                }
+                nt += 1;
+                __syncwarp();
+                if (locked) {
+                    // seat the customer before the lock is released: the next lock holder must see a dish somebody eats
+                    if (lane == 0) {
+                        tji[ii] = tbl;
+                        njt[tbl] = 1;
+                        atomicAdd(p.n_items + knew, 1);
+                        atomicAdd(p.sumx + knew, x);
+                        if (knew != kk) { p.z[i] = knew; moved += 1; }
+                    }
+                    crf_unlock(p, lane);
+                    continue;
+                }
+            }
+            const int kn = kjt[tbl];
+            if (lane == 0) {
+                tji[ii] = tbl;
+                njt[tbl] += 1;
+                atomicAdd(p.n_items + kn, 1);
+                atomicAdd(p.sumx + kn, x);
+                if (kn != kk) { p.z[i] = kn; moved += 1; }
+            }
+            __threadfence();
+            __syncwarp();
+        }
+        if (lane == 0) p.n_tbls[j] = nt;
+    }
+    if (lane == 0 && moved) atomicAdd(p.moved, moved);
+}
+
+// ---- pass 2: a dish for every table (src/HDP.jl:593-655) ----
+__global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_sc = (size_t)(p.max_len > p.Kmax ? p.max_len : p.Kmax) + 2;
+    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n_sc + p.max_len);
+    double *xs = sc + n_sc;                       // the values of the table's customers
+    const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
+    unsigned long long moved = 0;
+    for (int64_t j = (int64_t)blockIdx.x * kCrfWarps + warp; j < p.G; j += n_warps) {
+        const int64_t p0 = p.group_ptr[j];
+        const int n = (int)(p.group_ptr[j + 1] - p0);
+        int32_t *kjt = p.kjt + p0;
+        const int32_t *tji = p.tji + p0;
+        const int nt = p.n_tbls[j];
+        for (int tbl = 0; tbl < nt; ++tbl) {
+            const int kk = kjt[tbl];
+            // the table's customers, in index order (tidx = find(x -> x==tbl, tji[jj]), :602)
+            int nti = 0;
+            double sum = 0.0;
+            for (int b = 0; b < n; b += 32) {
+                const int q = b + lane;
+                const bool mine = q < n && tji[q] == tbl;
+                const unsigned bal = __ballot_sync(kFull, mine);
+                if (mine) {
+                    const double xv = p.x[p0 + q];
+                    xs[nti + __popc(bal & ((1u << lane) - 1u))] = xv;
+                    sum += xv;
+                }
+                nti += __popc(bal);
+            }
+            sum = warp_sum(sum);
+            // the table leaves its dish (:599, :626-628)
+            if (lane == 0) {
+                atomicAdd(p.mm + kk, -1);
+                atomicAdd(p.n_items + kk, -nti);
+                atomicAdd(p.sumx + kk, -sum);
+            }
+            __threadfence();
+            __syncwarp();
+            // score of every dish for the whole table: the sum of the customers' individual predictives (:633-643)
+            const int KK = __ldcg(p.d_KK);
+            for (int k = lane; k <= KK; k += 32) {
+                double cn = 0.0, sx = 0.0, s;
+                if (k < KK) {
+                    cn = (double)__ldcg(p.n_items + k);
+                    sx = __ldcg(p.sumx + k);
+                    s = log((double)__ldcg(p.mm + k));
+                } else {
+                    s = log(p.gg);
+                }
+                for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+                sc[k] = s;
+            }
+            __syncwarp();
+            const double u_dish = crf_draw_uniform(p, p0 + tbl, 2);
+            int knew = crf_draw(sc, KK + 1, u_dish, lane);
+            const bool locked = knew == KK;
+            if (locked) {
+                crf_lock(p, lane);
+                const int KK2 = __ldcg(p.d_KK);
+                for (int k = lane; k <= KK2; k += 32) {
+                    double cn = 0.0, sx = 0.0, s_;
+                    if (k < KK2) {
+                        cn = (double)__ldcg(p.n_items + k);
+                        sx = __ldcg(p.sumx + k);
+                        s_ = log((double)__ldcg(p.mm + k));
+                    } else {
+                        s_ = log(p.gg);
+                    }
+                    for (int q = 0; q < nti; ++q) s_ += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+                    sc[k] = s_;
+                }
+                __syncwarp();
+                knew = crf_draw(sc, KK2 + 1, u_dish, lane);
+                if (knew == KK2) {
+                    knew = crf_new_dish(p, lane);
+                    if (knew < 0) knew = kk;
+                }
+            }
+            if (lane == 0) {
+                kjt[tbl] = knew;
+                atomicAdd(p.mm + knew, 1);
+                atomicAdd(p.n_items + knew, nti);
+                atomicAdd(p.sumx + knew, sum);
+                if (knew != kk) moved += (unsigned long long)nti;
+            }
+            if (locked) crf_unlock(p, lane);
+            if (knew != kk)
+                for (int q = lane; q < n; q += 32)
+                    if (tji[q] == tbl) p.z[p0 + q] = knew;
+            __threadfence();
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && moved) atomicAdd(p.moved, moved);
+}
+
+// diagnostic of src/HDP.jl:669-673: sum of logpredictive(components[zz], xx) with every customer seated
+__global__ void crf_diag_kernel(CrfParams p, int64_t N, double *out) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = p.z[i];
+        acc += g1g1_logpred((double)p.n_items[k], p.sumx[k], p.x[i], p.m0, p.v0, p.vv);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+__global__ void crf_sum_tables_kernel(const int32_t *n_tbls, int64_t G, unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G; j += (int64_t)gridDim.x * blockDim.x) acc += (unsigned)n_tbls[j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}

@@ -563,6 +563,28 @@ static int hdp_phase_tables(bias_model *m, int hh) {
     return BIAS_OK;
 }
 
+// alpha0 (Teh et al. eq. 50 with the device-side auxiliaries sum log w_j, sum s_j) and gamma (Escobar-West), src/HDP.jl:124-159
+static void hdp_host_hyper(bias_model *m, double mt, double sum_logw, double sum_s) {
+    const int KK = m->hdp.KK;
+    const double aa_shape = m->hdp.a1 + mt - sum_s;
+    const double aa_rate = m->hdp.a2 - sum_logw;
+    if (aa_shape > 0.0 && aa_rate > 0.0) {
+        std::gamma_distribution<double> ga(aa_shape, 1.0);
+        m->hdp.aa = ga(m->host_rng) / aa_rate;
+    }
+    std::gamma_distribution<double> g1(m->hdp.gg + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
+    const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
+    const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
+    const double le = std::log(eta);
+    const double pi_eta = 1.0 / (1.0 + (mt * (m->hdp.g2 - le)) / (m->hdp.g1 + KK - 1.0));   // :152
+    std::uniform_real_distribution<double> ud(0.0, 1.0);
+    const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
+    if (shape > 0.0) {
+        std::gamma_distribution<double> gg(shape, 1.0);
+        m->hdp.gg = gg(m->host_rng) / (m->hdp.g2 - le);
+    }
+}
+
 // beta ~ Dirichlet([sum_j M_jk ..., gg]) (src/HDP.jl:362-364), alpha0 and gamma (:124-159) from the (possibly
 // all-reduced) contents of d_tables / d_hyper; n_groups_total = number of groups over all ranks
 static int hdp_phase_draw(bias_model *m) {
@@ -593,26 +615,7 @@ static int hdp_phase_draw(bias_model *m) {
     }
     for (int k = 0; k <= KK; ++k) m->h_beta[k] = tot > 0.0 ? m->h_beta[k] / tot : 1.0 / (KK + 1);
     for (size_t k = (size_t)KK + 1; k < m->h_beta.size(); ++k) m->h_beta[k] = 0.0;
-    if (m->hdp.sample_hyperparam) {            // src/HDP.jl:124-159
-        const double mt = (double)tables[Kpad];
-        const double aa_shape = m->hdp.a1 + mt - hyper[1];
-        const double aa_rate = m->hdp.a2 - hyper[0];
-        if (aa_shape > 0.0 && aa_rate > 0.0) {
-            std::gamma_distribution<double> ga(aa_shape, 1.0);
-            m->hdp.aa = ga(m->host_rng) / aa_rate;
-        }
-        std::gamma_distribution<double> g1(m->hdp.gg + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
-        const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
-        const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
-        const double le = std::log(eta);
-        const double pi_eta = 1.0 / (1.0 + (mt * (m->hdp.g2 - le)) / (m->hdp.g1 + KK - 1.0));   // :152
-        std::uniform_real_distribution<double> ud(0.0, 1.0);
-        const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
-        if (shape > 0.0) {
-            std::gamma_distribution<double> gg(shape, 1.0);
-            m->hdp.gg = gg(m->host_rng) / (m->hdp.g2 - le);
-        }
-    }
+    if (m->hdp.sample_hyperparam) hdp_host_hyper(m, (double)tables[Kpad], hyper[0], hyper[1]);
     return BIAS_OK;
 }
 
@@ -635,6 +638,156 @@ int hdp_sweep(bias_model *m) {
         BIAS_TRY(hdp_phase_draw(m));
     }
     return hdp_phase_end(m);
+}
+
+// ---------------------------------------------------------------------------------------
+// CRF (reference src/HDP.jl:402-709): tables and dishes
+// ---------------------------------------------------------------------------------------
+#include "crf.cuh"
+
+static CrfParams crf_params(bias_model *m, const double *ext_uniforms) {
+    CrfParams p{};
+    p.group_ptr = m->group_ptr;
+    p.G = m->G;
+    p.x = m->x;
+    p.z = m->z;
+    p.tji = m->crf_tji;
+    p.njt = m->crf_njt;
+    p.kjt = m->crf_kjt;
+    p.n_tbls = m->crf_n_tbls;
+    p.mm = m->crf_mm;
+    p.n_items = m->n_items;
+    p.sumx = m->sumx;
+    p.d_KK = m->d_KK;
+    p.Kmax = m->hdp.Kmax;
+    p.m0 = m->conj.m0;
+    p.v0 = m->conj.v0;
+    p.vv = m->conj.vv;
+    p.aa = m->hdp.aa;
+    p.gg = m->hdp.gg;
+    p.seed = m->ctx->seed;
+    p.sweep = m->sweep_index;
+    p.ext_uniforms = ext_uniforms;
+    p.lock = reinterpret_cast<int *>(m->scratch + 7);
+    p.err = reinterpret_cast<int *>(m->scratch + 4);
+    p.moved = m->scratch + 1;
+    p.max_len = (int32_t)m->max_group_len;
+    return p;
+}
+
+int crf_create(bias_model *m) {
+    cudaStream_t st = m->ctx->stream;
+    if (m->conj.kind != BIAS_G1G1)
+        return fail(BIAS_EINVAL, "the CRF sampler covers Gaussian1DGaussian1D x Float64 (the combination the reference exercises)");
+    if (crf_smem_bytes((int)m->max_group_len, m->hdp.Kmax) > 200 * 1024)
+        return fail(BIAS_ERANGE, "CRF: groups of %lld items with Kmax = %d do not fit the per-warp staging buffers",
+                    (long long)m->max_group_len, m->hdp.Kmax);
+    const size_t n = (size_t)std::max<int64_t>(1, m->N), g = (size_t)std::max<int64_t>(1, m->G);
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_tji, n * 4));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_njt, n * 4));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_kjt, n * 4));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_n_tbls, g * 4));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_mm, (size_t)m->Kpad * 4));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_tji, 0, n * 4, st));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_njt, 0, n * 4, st));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_kjt, 0, n * 4, st));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_n_tbls, 0, g * 4, st));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_mm, 0, (size_t)m->Kpad * 4, st));
+    if (m->G > 0) {
+        crf_init_kernel<<<(unsigned)((m->G + 127) / 128), 128, 0, st>>>(crf_params(m, nullptr));
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+    }
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BIAS_OK;
+}
+
+int crf_destroy(bias_model *m) {
+    for (void *p : {(void *)m->crf_tji, (void *)m->crf_njt, (void *)m->crf_kjt, (void *)m->crf_n_tbls, (void *)m->crf_mm})
+        if (p) cudaFree(p);
+    m->crf_tji = m->crf_njt = m->crf_kjt = m->crf_n_tbls = m->crf_mm = nullptr;
+    return BIAS_OK;
+}
+
+// dishes that lost their last table leave the menu (src/HDP.jl:531-545, :610-621, applied once per iteration)
+static int crf_prune(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int KK = m->hdp.KK, Kpad = m->Kpad;
+    std::vector<int32_t> ni(Kpad), mmv(Kpad);
+    BIAS_CUDA_TRY(cudaMemcpyAsync(ni.data(), m->n_items, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(mmv.data(), m->crf_mm, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    int alive = 0;
+    std::vector<int32_t> n_mm(Kpad, 0);
+    for (int k = 0; k < KK; ++k)
+        if (ni[k] > 0) n_mm[alive++] = mmv[k];
+    if (alive == KK || alive == 0) return BIAS_OK;
+    BIAS_TRY(hdp_prune(m));                      // compacts n_items / sumx / z (same alive order) and leaves d_remap on the device
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->crf_mm, n_mm.data(), (size_t)Kpad * 4, cudaMemcpyHostToDevice, st));
+    if (m->N > 0) {
+        remap_z_kernel<<<grid1d(ctx, m->N, 256), 256, 0, st>>>(m->crf_kjt, m->N, m->d_remap);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));    // n_mm must outlive the copy
+    return BIAS_OK;
+}
+
+int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
+    if (m->G > 0) {
+        const CrfParams p = crf_params(m, ext_uniforms_dev);
+        const size_t smem = crf_smem_bytes(p.max_len, p.Kmax);
+        static size_t smem_set = 0;
+        if (smem > 48 * 1024 && smem > smem_set) {
+            BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m->G + kCrfWarps - 1) / kCrfWarps, (int64_t)ctx->num_sms * 8));
+        crf_tables_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
+        crf_dishes_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    int32_t kk = 0;
+    int err = 0;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&kk, m->d_KK, 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&err, reinterpret_cast<int *>(m->scratch + 4), 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->hdp.KK = kk;
+    if (err == 2)
+        return fail(BIAS_ERANGE, "CRF: Kmax = %d dish slots exhausted (KK = %d); construct the model with a larger Kmax", m->hdp.Kmax, kk);
+    BIAS_TRY(crf_prune(m));
+    if (m->hdp.sample_hyperparam && m->G > 0) {     // src/HDP.jl:658-667 -> :124-164
+        unsigned long long *d_m = m->scratch + 5;
+        crf_sum_tables_kernel<<<grid1d(ctx, m->G, 256, 4), 256, 0, st>>>(m->crf_n_tbls, m->G, d_m);
+        ctx->launches += 1;
+        unsigned long long mt = 0;
+        BIAS_CUDA_TRY(cudaMemcpyAsync(&mt, d_m, 8, cudaMemcpyDeviceToHost, st));
+        for (int hh = 0; hh < m->hdp.n_internals; ++hh) {
+            double hyper[2] = {0.0, 0.0};
+            BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
+            hdp_hyper_kernel<<<grid1d(ctx, m->G, 128, 4), 128, 0, st>>>(m->group_ptr, m->G, m->hdp.aa, ctx->seed, m->sweep_index,
+                                                                       (uint32_t)hh, m->d_hyper);
+            ctx->launches += 1;
+            BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
+            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+            hdp_host_hyper(m, (double)mt, hyper[0], hyper[1]);
+        }
+    }
+    if (m->N > 0) {
+        crf_diag_kernel<<<grid1d(ctx, m->N, 256, 4), 256, 0, st>>>(crf_params(m, nullptr), m->N, reinterpret_cast<double *>(m->scratch));
+        BIAS_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    return BIAS_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -760,7 +913,7 @@ extern "C" {
 
 int bias_model_get_hdp(bias_model *m, bias_hdp_params *params, double *beta) {
     if (!m) return fail(BIAS_EINVAL, "null model");
-    if (m->model != BIAS_MODEL_HDP) return fail(BIAS_EINVAL, "not an HDP model");
+    if (m->model != BIAS_MODEL_HDP && m->model != BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "not an HDP model");
     if (params) *params = m->hdp;
     if (beta) {
         const int n = m->hdp.Kmax + 1;
@@ -828,6 +981,34 @@ int bias_hdp_shard_draw(bias_model *m) {
 int bias_hdp_shard_end(bias_model *m) {
     BIAS_TRY(check_hdp(m));
     return hdp_phase_end(m);
+}
+
+int bias_crf_sweep_with_uniforms(bias_model *m, const double *uniforms) {
+    if (!m || !uniforms) return fail(BIAS_EINVAL, "null argument");
+    if (m->model != BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "not a CRF model");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    double *d_u = nullptr;
+    const size_t n = (size_t)std::max<int64_t>(1, m->N) * 3;
+    BIAS_CUDA_TRY(cudaMalloc((void **)&d_u, n * 8));
+    cudaError_t e = cudaMemcpyAsync(d_u, uniforms, (size_t)m->N * 3 * 8, cudaMemcpyHostToDevice, m->ctx->stream);
+    int rc = (e == cudaSuccess) ? crf_sweep(m, d_u) : fail(BIAS_ECUDA, "%s", cudaGetErrorString(e));
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(d_u);
+    return rc;
+}
+
+int bias_crf_get_tables(bias_model *m, int32_t *tji, int32_t *njt, int32_t *kjt, int32_t *n_tbls, int32_t *mm) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (m->model != BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "not a CRF model");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    if (tji) BIAS_CUDA_TRY(cudaMemcpyAsync(tji, m->crf_tji, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st));
+    if (njt) BIAS_CUDA_TRY(cudaMemcpyAsync(njt, m->crf_njt, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st));
+    if (kjt) BIAS_CUDA_TRY(cudaMemcpyAsync(kjt, m->crf_kjt, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st));
+    if (n_tbls) BIAS_CUDA_TRY(cudaMemcpyAsync(n_tbls, m->crf_n_tbls, (size_t)m->G * 4, cudaMemcpyDeviceToHost, st));
+    if (mm) BIAS_CUDA_TRY(cudaMemcpyAsync(mm, m->crf_mm, (size_t)m->hdp.KK * 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BIAS_OK;
 }
 
 int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out) {

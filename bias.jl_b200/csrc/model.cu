@@ -17,7 +17,9 @@ namespace bias {
 
 static thread_local std::string g_err;
 
-bool is_dynamic_K(const bias_model *m) { return m->model == BIAS_MODEL_HDP || m->model == BIAS_MODEL_RCRP; }
+bool is_dynamic_K(const bias_model *m) {
+    return m->model == BIAS_MODEL_HDP || m->model == BIAS_MODEL_RCRP || m->model == BIAS_MODEL_CRF;
+}
 
 void set_error(const char *fmt, ...) {
     char buf[1024];
@@ -520,6 +522,7 @@ int bias_model_destroy(bias_model *m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     hdp_destroy(m);
+    crf_destroy(m);
     void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
                     m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
                     m->delta_f64, m->scratch, m->d_aa_t, m->n_wk16, m->word_freq, m->wide_flag, m->nk_rep};
@@ -535,11 +538,11 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
                       int32_t K, double alpha, const bias_hdp_params *hdp, bias_model **out) {
     if (!ctx || !out) return fail(BIAS_EINVAL, "null argument");
     *out = nullptr;
-    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_RCRP) return fail(BIAS_EINVAL, "unknown model %d", model);
-    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP) {
+    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "unknown model %d", model);
+    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF) {
         if (!hdp) return fail(BIAS_EINVAL, "HDP / RCRP parameters are required");
         if (hdp->KK < 1 || hdp->Kmax < hdp->KK + 2) return fail(BIAS_EINVAL, "HDP: need 1 <= KK and Kmax >= KK + 2");
-        if (model == BIAS_MODEL_HDP && (!(hdp->gg > 0.0) || !(hdp->aa > 0.0))) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
+        if (model != BIAS_MODEL_RCRP && (!(hdp->gg > 0.0) || !(hdp->aa > 0.0))) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
         if (hdp->Kmax > 4096) return fail(BIAS_EINVAL, "HDP: Kmax is limited to 4096 component slots");
         if (hdp->n_internals < 0) return fail(BIAS_EINVAL, "HDP: n_internals < 0");
         K = hdp->KK;
@@ -559,7 +562,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     m->alpha = alpha;
     m->V = (conj->kind == BIAS_MD) ? conj->dd : 0;
     for (int64_t j = 0; j < m->G; ++j) m->max_group_len = std::max(m->max_group_len, group_ptr[j + 1] - group_ptr[j]);
-    const int32_t Kcap = (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP) ? hdp->Kmax : K;
+    const int32_t Kcap = (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF) ? hdp->Kmax : K;
     // pad K to 128 * 2^j (the fast kernel's chunk tree); the generic kernels only need the stride
     int32_t kp = 128;
     while (kp < Kcap) kp *= 2;
@@ -629,9 +632,10 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     M_CUDA(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
     M_CUDA(cudaMallocHost((void **)&m->h_scratch, 8 * sizeof(unsigned long long)));
     if (model != BIAS_MODEL_BMM) m->h_group_ptr.assign(group_ptr, group_ptr + m->G + 1);
-    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP) M_TRY(hdp_create(m, hdp));
+    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF) M_TRY(hdp_create(m, hdp));
     M_TRY(validate_on_device(m, K));
     M_TRY(rebuild_counts(m));
+    if (model == BIAS_MODEL_CRF) M_TRY(crf_create(m));
     // the uploads came from caller-owned pageable memory: finish them before returning
     M_CUDA(cudaStreamSynchronize(st));
 #undef M_TRY
@@ -697,6 +701,10 @@ int bias_model_set_zz(bias_model *m, const int32_t *zz) {
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
     BIAS_TRY(validate_on_device(m, Kcur));
     BIAS_TRY(rebuild_counts(m));
+    if (m->model == BIAS_MODEL_CRF) {            // the seating is rebuilt from the new assignments (src/HDP.jl:441-470)
+        crf_destroy(m);
+        BIAS_TRY(crf_create(m));
+    }
     BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
     return BIAS_OK;
 }
@@ -713,6 +721,7 @@ static int one_sweep(bias_model *m) {
     cudaStream_t st = m->ctx->stream;
     if (m->model == BIAS_MODEL_HDP) return hdp_sweep(m);
     if (m->model == BIAS_MODEL_RCRP) return rcrp_sweep(m);
+    if (m->model == BIAS_MODEL_CRF) return crf_sweep(m, nullptr);
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st));
     if (m->fast) {
         BIAS_TRY(launch_lda_fast(m, nullptr, 0, nullptr));

@@ -74,6 +74,9 @@ struct bias_model {
     std::mt19937_64 host_rng;
     int32_t *pending_base = nullptr; // start of the two-half pending queue buffer (pending may point at either half)
 
+    // CRF (tables and dishes of the Chinese restaurant franchise, csrc/crf.cuh)
+    int32_t *crf_tji = nullptr, *crf_njt = nullptr, *crf_kjt = nullptr, *crf_n_tbls = nullptr, *crf_mm = nullptr;
+
     // RCRP (epochs are the groups)
     std::vector<double> h_aa_t;     // [T] per-epoch concentration
     double *d_aa_t = nullptr;
@@ -86,6 +89,9 @@ int ensure_stirling(bias_ctx *ctx, int32_t rows);
 int hdp_create(bias_model *m, const bias_hdp_params *hp);
 int hdp_sweep(bias_model *m);
 int hdp_destroy(bias_model *m);
+int crf_create(bias_model *m);
+int crf_sweep(bias_model *m, const double *ext_uniforms_dev);
+int crf_destroy(bias_model *m);
 int rcrp_create(bias_model *m, const bias_rcrp_params *rp, const double *aa);
 int rcrp_sweep(bias_model *m);
 bool is_dynamic_K(const bias_model *m);

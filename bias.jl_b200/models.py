@@ -7,6 +7,7 @@
   collapsed_gibbs_sampler(model, xx, zz, n_burnins, n_lags, n_samples, ...)
                                       src/LDA.jl:67-148, src/BMM.jl:46-130, src/HDP.jl:166-399
   posterior(model, xx, zz)            src/LDA.jl:151-167, src/BMM.jl:134-151
+  CRF_gibbs_sampler(hdp, xx, zz, n_burnins, n_lags, n_samples, ...)   src/HDP.jl:402-709
   RCRP(c, KK, aa, TT, a1, a2)         src/RCRP.jl:18-28
   RCRP_gibbs_sampler(rcrp, xx, zz, n_burnins, n_lags, n_samples, ...)   src/RCRP.jl:77-416
   posterior(rcrp, xx, KK_dict, KK)    src/RCRP.jl:418-453
@@ -198,7 +199,7 @@ class ResidentSampler:
     """bias_model: xx, zz and the component statistics live in HBM between sweeps."""
 
     def __init__(self, ctx: Context, model, data: FlatData, zz_flat: np.ndarray, *, sample_hyperparam=True,
-                 n_internals=10):
+                 n_internals=10, crf: bool = False):
         self.ctx, self.model, self.data = ctx, model, data
         self.n_internals = int(n_internals)
         self.spec = model.component.spec(data.datum)
@@ -214,7 +215,10 @@ class ResidentSampler:
             check(lib().bias_rcrp_create(ctx.h, C.byref(self.spec), C.byref(data.c), data.n_groups,
                                          ptr(data.group_ptr), ptr(self.zz), C.byref(rp), ptr(aa), C.byref(self.h)))
             return
-        check(lib().bias_model_create(ctx.h, model.model_id, C.byref(self.spec), C.byref(data.c), data.n_groups,
+        self.crf = bool(crf)
+        if crf and not isinstance(model, HDP):
+            raise TypeError("the CRF sampler is a sampler of the HDP (src/HDP.jl:402)")
+        check(lib().bias_model_create(ctx.h, _lib.MODEL_CRF if crf else model.model_id, C.byref(self.spec), C.byref(data.c), data.n_groups,
                                       ptr(data.group_ptr), ptr(self.zz), model.KK, model.aa,
                                       C.byref(hp) if hp is not None else None, C.byref(self.h)))
 
@@ -276,6 +280,21 @@ class ResidentSampler:
         beta = np.zeros(self.model.Kmax + 1)
         check(lib().bias_model_get_hdp(self.h, C.byref(hp), ptr(beta)))
         return hp, beta[:hp.KK + 1].copy()
+
+    # -- CRF seating (src/HDP.jl:420-425)
+    def crf_tables(self):
+        """-> dict(tji, njt, kjt, n_tbls, mm): njt / kjt hold the tables of group j at group_ptr[j] .. + n_tbls[j]"""
+        N, G, KK = self.data.n_items, self.data.n_groups, self.current_KK()
+        out = {"tji": np.zeros(N, np.int32), "njt": np.zeros(N, np.int32), "kjt": np.zeros(N, np.int32),
+               "n_tbls": np.zeros(G, np.int32), "mm": np.zeros(KK, np.int32)}
+        check(lib().bias_crf_get_tables(self.h, ptr(out["tji"]), ptr(out["njt"]), ptr(out["kjt"]), ptr(out["n_tbls"]),
+                                        ptr(out["mm"])))
+        return out
+
+    def crf_sweep_with_uniforms(self, uniforms):
+        u = _lib.as_f64(uniforms)
+        assert u.size == 3 * self.data.n_items
+        check(lib().bias_crf_sweep_with_uniforms(self.h, ptr(u)))
 
     def rcrp_state(self):
         rp = _lib.RcrpParams()
@@ -511,6 +530,55 @@ def RCRP_gibbs_sampler(rcrp: RCRP, xx, zz, n_burnins: int, n_lags: int, n_sample
         _scatter_zz(rs.get_zz(), zz, True, data.group_ptr)
         rp, aa = rs.rcrp_state()
         rcrp.KK, rcrp.aa = int(rp.KK), aa
+    finally:
+        rs.close()
+    return KK_list, KK_dict
+
+
+def CRF_gibbs_sampler(hdp: HDP, xx, zz, n_burnins: int, n_lags: int, n_samples: int, sample_hyperparam: bool = True,
+                      n_internals: int = 10, store_every: int = 100, filename: str | None = None,
+                      KK_list: Sequence[int] = (), KK_dict: dict | None = None, ctx: Context | None = None,
+                      verbose: bool = False):
+    """CRF_gibbs_sampler!(hdp, xx, zz, n_burnins, n_lags, n_samples, sample_hyperparam, n_internals, store_every,
+    filename, KK_list, KK_dict) -> (KK_list, KK_dict)   (src/HDP.jl:402-709): the HDP sampled through the Chinese
+    restaurant franchise (a table for every customer, a dish for every table).  zz, hdp.KK, hdp.gg and hdp.aa are
+    updated in place."""
+    ctx = ctx or default_context()
+    data = FlatData(hdp.component, xx, True)
+    n_iterations = n_burnins + n_samples * (n_lags + 1)
+    n_old = len(KK_list)
+    KK_list = list(KK_list) + [0] * n_samples
+    KK_dict = {} if (KK_dict is None or n_old == 0) else KK_dict
+    try:
+        rs = ResidentSampler(ctx, hdp, data, _flat_zz(zz, True), sample_hyperparam=sample_hyperparam,
+                             n_internals=n_internals, crf=True)
+    except _lib.BiasError as e:
+        if e.code == _lib.EINVAL:
+            raise ValueError(str(e)) from None
+        raise
+    try:
+        if n_samples > 0:
+            KK_list[0] = hdp.KK                                         # :468
+        for iteration in range(1, n_iterations + 1):
+            rs.sweep(1)
+            if verbose:
+                s = rs.stats()
+                burn = "Burning... " if iteration < n_burnins else ""
+                print(f"{burn}iteration: {iteration}, KK={s.KK}, gg={s.gg:.2f}, aa={s.aa:.2f}, likelihood={s.log_likelihood:.2f}")
+            if (iteration - n_burnins) % (n_lags + 1) == 0 and iteration > n_burnins:
+                i = n_old + (iteration - n_burnins) // (n_lags + 1)
+                hp, _ = rs.hdp_state()
+                _scatter_zz(rs.get_zz(), zz, True, data.group_ptr)
+                KK_list[i - 1] = hp.KK
+                KK_dict[hp.KK] = [np.array(g, dtype=np.int64) for g in zz]
+                if filename is not None and i % store_every == 0:
+                    _store(filename, i, zz=np.concatenate(zz), KK_list=np.asarray(KK_list), iteration=iteration)
+        _scatter_zz(rs.get_zz(), zz, True, data.group_ptr)
+        hp, _ = rs.hdp_state()
+        hdp.KK, hdp.gg, hdp.aa = hp.KK, hp.gg, hp.aa
+        if n_samples > 0:                                               # :697-701
+            KK_list[n_old + n_samples - 1] = hp.KK
+            KK_dict[hp.KK] = [np.array(g, dtype=np.int64) for g in zz]
     finally:
         rs.close()
     return KK_list, KK_dict

@@ -138,6 +138,7 @@ BIAS_API int bias_rcrp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias
 #define BIAS_MODEL_BMM 1
 #define BIAS_MODEL_HDP 2
 #define BIAS_MODEL_RCRP 3
+#define BIAS_MODEL_CRF 4   /* HDP sampled by CRF_gibbs_sampler! (src/HDP.jl:402-709): bias_model_create with hdp params */
 /* Uploads xx and zz and runs the initialisation pass (src/LDA.jl:91-98, src/BMM.jl:70-75,
  * src/HDP.jl:217-228).  For BMM pass n_groups = 0, group_ptr = NULL; hdp = NULL unless model is HDP. */
 BIAS_API int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, const bias_data *data,
@@ -200,6 +201,13 @@ BIAS_API int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t
  * training counts.  Held-out perplexity = exp(-sum / n_tokens) (north_star level (c)). */
 BIAS_API int bias_model_heldout_log_likelihood(bias_model *m, const int64_t *heldout_ptr, const int32_t *heldout_word,
                       double *sum_log_p, int64_t *n_tokens);
+
+/* ---- CRF (model BIAS_MODEL_CRF) --------------------------------------------------------- */
+/* One iteration with caller-supplied uniforms (verification): per item slot i [3i] table draw, [3i+1] dish of a new table; per table slot [3(group_ptr[j]+t)+2] dish draw. */
+BIAS_API int bias_crf_sweep_with_uniforms(bias_model *m, const double *uniforms /* [3 * n_items] */);
+/* The seating: tji[n_items] table of each customer within its group, njt / kjt [n_items] customers and dish per table
+ * (tables of group j at group_ptr[j] ...), n_tbls[n_groups], mm[KK] tables per dish.  Any pointer may be NULL. */
+BIAS_API int bias_crf_get_tables(bias_model *m, int32_t *tji, int32_t *njt, int32_t *kjt, int32_t *n_tbls, int32_t *mm);
 
 /* ---- sharded HDP (groups split over ranks) ---------------------------------- */
 /* One sweep of collapsed_gibbs_sampler!(::HDP) (src/HDP.jl:235-373) cut at the points where ranks must agree:

@@ -887,3 +887,160 @@ int64_t orc_rcrp_conditional(const orc_rcrp *h, orc_comps *c, const orc_data *d,
     if (c->kind == ORC_G1G1) c->mu[zi] = mu_saved;
     return k;
 }
+
+/* ======================================================================
+ * src/HDP.jl:402-709 — CRF_gibbs_sampler! (Chinese restaurant franchise: tables and dishes)
+ * ====================================================================== */
+void orc_crf_init(const orc_hdp *h, orc_crf *f, orc_comps *c, const orc_data *d, const int64_t *z)
+{                                                   /* :441-470 */
+    for (int64_t k = 0; k < h->Kmax; ++k) f->mm[k] = 0;
+    for (int64_t j = 0; j < f->G; ++j) {
+        int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0, nt = 0;
+        for (int64_t i = 0; i < n; ++i) {            /* kjt[jj] = unique(zz[jj]): first-appearance order */
+            int64_t kk = z[p0 + i], t = -1;
+            for (int64_t q = 0; q < nt; ++q) if (f->kjt[p0 + q] == kk) { t = q; break; }
+            if (t < 0) { t = nt++; f->kjt[p0 + t] = kk; f->njt[p0 + t] = 0; }
+            orc_additem(c, kk, d, p0 + i);
+            f->tji[p0 + i] = t;
+            f->njt[p0 + t] += 1;
+        }
+        f->n_tbls[j] = nt;
+        for (int64_t q = 0; q < nt; ++q) f->mm[f->kjt[p0 + q]] += 1;
+    }
+}
+
+/* a dish nobody serves any more leaves the menu (:531-545, :610-621): everything above it moves down by one */
+static void crf_delete_dish(orc_hdp *h, orc_crf *f, orc_comps *c, int64_t *z, int64_t kk)
+{
+    int64_t KK = h->KK, N = f->ptr[f->G];
+    for (int64_t i = 0; i < N; ++i) if (z[i] > kk) z[i] -= 1;
+    for (int64_t j = 0; j < f->G; ++j)
+        for (int64_t q = 0; q < f->n_tbls[j]; ++q) if (f->kjt[f->ptr[j] + q] > kk) f->kjt[f->ptr[j] + q] -= 1;
+    for (int64_t k = kk; k < KK - 1; ++k) { orc_comps_move(c, k, k + 1); f->mm[k] = f->mm[k + 1]; }
+    orc_comps_reset(c, KK - 1);
+    f->mm[KK - 1] = 0;
+    h->KK -= 1;
+}
+
+/* Conditional of the table of item i of group j with the item removed from its table (:548-556); the table is
+ * NOT deleted when the removal empties it (its entry is log(0) = -Inf).  raw/prob have n_tbls[j] + 1 entries. */
+int64_t orc_crf_table_conditional(const orc_hdp *h, const orc_crf *f, orc_comps *c, const orc_data *d, int64_t j,
+                                  int64_t i, int64_t *z, double r, double *raw, double *prob)
+{
+    int64_t p0 = f->ptr[j], nt = f->n_tbls[j], kk = z[i], t0 = f->tji[i];
+    double mu_saved = (c->kind == ORC_G1G1) ? c->mu[kk] : 0.0;
+    orc_delitem(c, kk, d, i);
+    for (int64_t t = 0; t < nt; ++t) {
+        int64_t n = f->njt[p0 + t] - (t == t0 ? 1 : 0);
+        raw[t] = log((double)n) + orc_logpredictive(c, f->kjt[p0 + t], d, i);
+    }
+    raw[nt] = log(h->aa) + orc_logpredictive(c, c->K - 1, d, i);
+    memcpy(prob, raw, (size_t)(nt + 1) * sizeof(double));
+    orc_lognormalize(prob, nt + 1);
+    int64_t t = orc_sample(prob, nt + 1, r);
+    orc_additem(c, kk, d, i);
+    if (c->kind == ORC_G1G1) c->mu[kk] = mu_saved;
+    return t;
+}
+
+double orc_crf_sweep(orc_hdp *h, orc_crf *f, orc_comps *c, const orc_data *d, int64_t *z, orc_rng *g,
+                     const double *uniforms, int defer_deaths, int sample_hyper, int n_internals)
+{
+    int64_t S = h->Kmax, G = f->G;
+    int64_t maxn = 1;
+    for (int64_t j = 0; j < G; ++j) if (f->ptr[j + 1] - f->ptr[j] > maxn) maxn = f->ptr[j + 1] - f->ptr[j];
+    double *pp = (double *)malloc((size_t)((S > maxn ? S : maxn) + 2) * sizeof(double));
+    int64_t *tidx = (int64_t *)malloc((size_t)maxn * sizeof(int64_t));
+#define CRF_U(idx, which) (uniforms ? uniforms[3 * (idx) + (which)] : orc_rand(g))
+    /* 1. resampling tables for customers (:506-587) */
+    for (int64_t j = 0; j < G; ++j) {
+        int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0;
+        for (int64_t ii = 0; ii < n; ++ii) {
+            int64_t i = p0 + ii, kk = z[i], tbl = f->tji[i];
+            orc_delitem(c, kk, d, i);
+            f->njt[p0 + tbl] -= 1;
+            if (f->njt[p0 + tbl] == 0) {                        /* the table empties: remove it (:517-546) */
+                int64_t nt = f->n_tbls[j];
+                f->mm[kk] -= 1;
+                for (int64_t q = tbl; q < nt - 1; ++q) { f->kjt[p0 + q] = f->kjt[p0 + q + 1]; f->njt[p0 + q] = f->njt[p0 + q + 1]; }
+                f->n_tbls[j] = nt - 1;
+                for (int64_t q = 0; q < n; ++q) if (f->tji[p0 + q] > tbl) f->tji[p0 + q] -= 1;
+                if (f->mm[kk] == 0 && !defer_deaths) crf_delete_dish(h, f, c, z, kk);
+            }
+            int64_t nt = f->n_tbls[j];
+            for (int64_t t = 0; t < nt; ++t)
+                pp[t] = log((double)f->njt[p0 + t]) + orc_logpredictive(c, f->kjt[p0 + t], d, i);      /* :551-554 */
+            pp[nt] = log(h->aa) + orc_logpredictive(c, c->K - 1, d, i);                                /* :555 */
+            orc_lognormalize(pp, nt + 1);
+            tbl = orc_sample(pp, nt + 1, CRF_U(i, 0));
+            if (tbl == nt) {                                    /* a new table: draw its dish (:559-581) */
+                f->n_tbls[j] = nt + 1;
+                f->njt[p0 + tbl] = 0;
+                for (int64_t k = 0; k < h->KK; ++k) pp[k] = log((double)f->mm[k]) + orc_logpredictive(c, k, d, i);
+                pp[h->KK] = log(h->gg) + orc_logpredictive(c, c->K - 1, d, i);
+                orc_lognormalize(pp, h->KK + 1);
+                kk = orc_sample(pp, h->KK + 1, CRF_U(i, 1));
+                if (kk == h->KK) {
+                    if (h->KK + 1 >= S) { free(pp); free(tidx); return NAN; }
+                    orc_comps_reset(c, h->KK);
+                    f->mm[h->KK] = 0;
+                    h->KK += 1;
+                }
+                f->kjt[p0 + tbl] = kk;
+                f->mm[kk] += 1;
+            }
+            kk = f->kjt[p0 + tbl];
+            f->tji[i] = tbl;
+            f->njt[p0 + tbl] += 1;
+            orc_additem(c, kk, d, i);
+            z[i] = kk;
+        }
+    }
+    /* 2. resampling dishes (:593-655) */
+    for (int64_t j = 0; j < G; ++j) {
+        int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0;
+        for (int64_t tbl = 0; tbl < f->n_tbls[j]; ++tbl) {
+            int64_t kk = f->kjt[p0 + tbl], nti = 0;
+            f->mm[kk] -= 1;
+            for (int64_t q = 0; q < n; ++q) if (f->tji[p0 + q] == tbl) tidx[nti++] = p0 + q;
+            if (f->mm[kk] == 0 && !defer_deaths) {
+                crf_delete_dish(h, f, c, z, kk);                /* the component is dropped with its items (:608-621) */
+            } else {
+                for (int64_t q = 0; q < nti; ++q) orc_delitem(c, kk, d, tidx[q]);                     /* :626-628 */
+            }
+            for (int64_t k = 0; k < h->KK; ++k) {               /* :633-639 */
+                pp[k] = log((double)f->mm[k]);
+                for (int64_t q = 0; q < nti; ++q) pp[k] += orc_logpredictive(c, k, d, tidx[q]);
+            }
+            pp[h->KK] = 0.0;
+            pp[h->KK] += log(h->gg);                            /* :640-643 */
+            for (int64_t q = 0; q < nti; ++q) pp[h->KK] += orc_logpredictive(c, c->K - 1, d, tidx[q]);
+            orc_lognormalize(pp, h->KK + 1);
+            kk = orc_sample(pp, h->KK + 1, CRF_U(p0 + tbl, 2));
+            if (kk == h->KK) {
+                if (h->KK + 1 >= S) { free(pp); free(tidx); return NAN; }
+                orc_comps_reset(c, h->KK);
+                f->mm[h->KK] = 0;
+                h->KK += 1;
+            }
+            f->kjt[p0 + tbl] = kk;
+            for (int64_t q = 0; q < nti; ++q) { orc_additem(c, kk, d, tidx[q]); z[tidx[q]] = kk; }
+            f->mm[kk] += 1;
+        }
+    }
+#undef CRF_U
+    if (defer_deaths) {                             /* dishes that lost their last table leave the menu now */
+        for (int64_t k = h->KK - 1; k >= 0; --k) if (f->mm[k] == 0) crf_delete_dish(h, f, c, z, k);
+    }
+    if (sample_hyper) {                             /* :658-667 */
+        int64_t m = 0;
+        for (int64_t j = 0; j < G; ++j) m += f->n_tbls[j];
+        for (int it = 0; it < n_internals; ++it) orc_hdp_sample_hyperparam(h, G, f->ptr, m, g);
+    }
+    double ll = 0.0;                                /* :669-673 */
+    int64_t N = f->ptr[G];
+    for (int64_t i = 0; i < N; ++i) ll += orc_logpredictive(c, z[i], d, i);
+    free(pp);
+    free(tidx);
+    return ll;
+}

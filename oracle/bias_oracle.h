@@ -153,6 +153,26 @@ double orc_rcrp_sweep(orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_
 int64_t orc_rcrp_conditional(const orc_rcrp *h, orc_comps *c, const orc_data *d, const int64_t *ptr, int64_t t,
                              int64_t i, int64_t zi, int64_t *nn, double r, double *raw, double *prob);
 
+/* ---- src/HDP.jl:402-709 CRF_gibbs_sampler! (Chinese restaurant franchise) -----------------------
+ * Tables live in CSR arrays with the items' offsets (a group has at most as many tables as items):
+ * tji[N] table of each item (0-based within its group), njt[N] customers per table, kjt[N] dish per table,
+ * n_tbls[G], mm[Kmax] tables per dish. */
+typedef struct {
+    int64_t G;
+    const int64_t *ptr;
+    int64_t *tji, *njt, *kjt, *n_tbls, *mm;
+} orc_crf;
+void orc_crf_init(const orc_hdp *h, orc_crf *f, orc_comps *c, const orc_data *d, const int64_t *z);     /* :441-470 */
+/* One iteration (:506-667): tables for customers, dishes for tables, hyper-parameters.  uniforms (nullable) holds three
+ * numbers per item slot: [3i] table draw and [3i+1] dish-of-a-new-table draw of item i, [3(ptr[j]+t)+2] dish draw of
+ * table t of group j.  defer_deaths = 0 is the reference (a dish that loses its last table is removed at once and
+ * everything above it renumbered); 1 keeps the slot (its weight is log 0) until the end of the iteration — the order
+ * the GPU engine uses.  Returns the log_likelihood diagnostic (:669-673), NaN on capacity. */
+double orc_crf_sweep(orc_hdp *h, orc_crf *f, orc_comps *c, const orc_data *d, int64_t *z, orc_rng *g,
+                     const double *uniforms, int defer_deaths, int sample_hyper, int n_internals);
+int64_t orc_crf_table_conditional(const orc_hdp *h, const orc_crf *f, orc_comps *c, const orc_data *d, int64_t j,
+                                  int64_t i, int64_t *z, double r, double *raw, double *prob);
+
 /* Normalised log unsigned Stirling numbers of the first kind, rows n = 1..nmax, packed:
  * entry (n, m), 1 <= m <= n, at index n*(n-1)/2 + (m-1); each row shifted so its maximum is 0.
  * Regenerates the missing src/StirlingNums_10K.mat (snumbersNormalizedSparse, src/HDP.jl:207-209). */

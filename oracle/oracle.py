@@ -59,6 +59,11 @@ class _Rcrp(C.Structure):
                 ("a1", C.c_double), ("a2", C.c_double)]
 
 
+class _Crf(C.Structure):
+    _fields_ = [("G", C.c_int64), ("ptr", C.c_void_p), ("tji", C.c_void_p), ("njt", C.c_void_p), ("kjt", C.c_void_p),
+                ("n_tbls", C.c_void_p), ("mm", C.c_void_p)]
+
+
 class _Rng(C.Structure):
     _fields_ = [("s", C.c_uint64 * 4)]
 
@@ -131,6 +136,12 @@ def lib():
         L.orc_rcrp_sweep.argtypes = [rcp, cp, dpp, vp, vp, vp, rp, vp, i32, i32, i32]
         L.orc_rcrp_conditional.restype = i64
         L.orc_rcrp_conditional.argtypes = [rcp, cp, dpp, vp, i64, i64, i64, vp, f64, vp, vp]
+        fp = C.POINTER(_Crf)
+        L.orc_crf_init.argtypes = [hp, fp, cp, dpp, vp]
+        L.orc_crf_sweep.restype = f64
+        L.orc_crf_sweep.argtypes = [hp, fp, cp, dpp, vp, rp, vp, i32, i32, i32]
+        L.orc_crf_table_conditional.restype = i64
+        L.orc_crf_table_conditional.argtypes = [hp, fp, cp, dpp, i64, i64, vp, f64, vp, vp]
         _lib = L
     return _lib
 
@@ -419,3 +430,39 @@ class RCRPState:
         k = lib().orc_rcrp_conditional(C.byref(self.h), self.c.ref(), self.d.ref(), _p(self.ptr), t, i, int(self.z[i]),
                                        _p(self.nn), float(r), _p(raw), _p(prob))
         return int(k), raw, prob
+
+
+# ------------------------------------------------------------------ HDP.jl CRF_gibbs_sampler!
+class CRFState:
+    """Chinese-restaurant-franchise state (src/HDP.jl:402-470). comps.K == Kmax; the last slot stays empty (prototype)."""
+
+    def __init__(self, comps: Comps, data: Data, ptr, z, KK, gg, g1, g2, aa, a1, a2):
+        self.c, self.d = comps, data
+        self.ptr = _i64(ptr)
+        self.G = self.ptr.size - 1
+        N = int(self.ptr[-1])
+        self.z = _i64(z).copy()
+        self.Kmax = comps.K
+        self.beta = np.zeros(self.Kmax + 1)
+        self.h = _Hdp(KK, self.Kmax, gg, g1, g2, aa, a1, a2, _p(self.beta))
+        self.tji, self.njt, self.kjt = (np.zeros(max(N, 1), dtype=np.int64) for _ in range(3))
+        self.n_tbls = np.zeros(max(self.G, 1), dtype=np.int64)
+        self.mm = np.zeros(self.Kmax, dtype=np.int64)
+        self.f = _Crf(self.G, _p(self.ptr), _p(self.tji), _p(self.njt), _p(self.kjt), _p(self.n_tbls), _p(self.mm))
+        lib().orc_crf_init(C.byref(self.h), C.byref(self.f), comps.ref(), data.ref(), _p(self.z))
+
+    @property
+    def KK(self):
+        return int(self.h.KK)
+
+    def sweep(self, rng: Rng, uniforms=None, defer_deaths=False, sample_hyper=False, n_internals=10) -> float:
+        u = None if uniforms is None else _f64(uniforms)
+        return lib().orc_crf_sweep(C.byref(self.h), C.byref(self.f), self.c.ref(), self.d.ref(), _p(self.z), rng.ref(),
+                                   _p(u), int(defer_deaths), int(sample_hyper), int(n_internals))
+
+    def table_conditional(self, j, i, r):
+        n = int(self.n_tbls[j]) + 1
+        raw, prob = np.zeros(n), np.zeros(n)
+        t = lib().orc_crf_table_conditional(C.byref(self.h), C.byref(self.f), self.c.ref(), self.d.ref(), j, i,
+                                            _p(self.z), float(r), _p(raw), _p(prob))
+        return int(t), raw, prob

@@ -109,6 +109,42 @@ def c4(ctx, n_groups):
             "KK": int(s.KK), "cpu_items_per_s": ng * 100 / tc, "cpu_sample": f"first {ng} groups, 4th sweep of the serial sampler"}
 
 
+def c4_crf(ctx, n_groups):
+    """The same HDP data through the Chinese-restaurant-franchise sampler (CRF_gibbs_sampler!, src/HDP.jl:402-709)."""
+    rng = np.random.default_rng(123)
+    n_atoms = 20
+    ks = rng.integers(0, n_atoms, (n_groups, 4))
+    zt = np.take_along_axis(ks, rng.integers(0, 4, (n_groups, 100)), axis=1)
+    allx = (2.0 * (zt + 1) + np.sqrt(0.001) * rng.standard_normal(zt.shape)).reshape(-1)
+    hdp = b.HDP(b.Gaussian1DGaussian1D(float(allx.mean()), 10.0, 0.001), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=256)
+    ptr = np.arange(n_groups + 1, dtype=np.int64) * 100
+    data = b.FlatData.from_csr(b._lib.F64, len(allx), group_ptr=ptr, x=allx)
+    rs = b.ResidentSampler(ctx, hdp, data, np.zeros(len(allx), dtype=np.int32), sample_hyperparam=True, n_internals=10, crf=True)
+    ctx.sync()
+    t0 = time.perf_counter()
+    rs.sweep(3)
+    ctx.sync()
+    t_first = (time.perf_counter() - t0) / 3
+    t = timed_sweeps(rs, 5, warm=2)
+    KK = rs.stats().KK
+    z = rs.get_zz()
+    rs.close()
+    homog = sum(np.bincount(zt.reshape(-1)[z == c]).max() for c in range(KK)) / len(z)
+    ng = min(n_groups, 40)
+    st = orc.CRFState(orc.Comps.g1g1(256, float(allx.mean()), 10.0, 0.001), orc.Data.reals(allx[:ng * 100]), ptr[:ng + 1],
+                      np.zeros(ng * 100, dtype=np.int64), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
+    r = orc.Rng(1)
+    for _ in range(3):
+        st.sweep(r, sample_hyper=True)
+    t0 = time.perf_counter()
+    st.sweep(r, sample_hyper=True)
+    tc = time.perf_counter() - t0
+    return {"config": f"C4 (CRF sampler) HDP x Gaussian {n_groups} groups x 100 points", "items": len(allx),
+            "gpu_ms_per_sweep": 1e3 * t, "gpu_ms_per_sweep_first3": 1e3 * t_first, "gpu_items_per_s": len(allx) / t,
+            "KK": int(KK), "homogeneity": homog, "cpu_items_per_s": ng * 100 / tc,
+            "cpu_sample": f"first {ng} groups, 4th iteration of the serial sampler"}
+
+
 def c5(ctx, n_epochs, n_per):
     _, zz_true, _ = b.data.gen_rcrp_data([n_per] * n_epochs, 0.5, seed=123)
     rng = np.random.default_rng(5)
@@ -147,7 +183,7 @@ def main():
     args = ap.parse_args()
     ctx = b.Context(0, seed=123)
     for fn in (lambda: c1(ctx), lambda: c2(ctx, args.sentences), lambda: c4(ctx, args.hdp_groups),
-               lambda: c5(ctx, 100, 500)):
+               lambda: c4_crf(ctx, args.hdp_groups), lambda: c5(ctx, 100, 500)):
         print(json.dumps(fn()), flush=True)
     ctx.close()
 
