@@ -145,6 +145,8 @@ static int launch_lda_half16_t(bias_model *m, const LdaFastParams &p) {
 static bool use_half16_kernel(const bias_model *m) {
     const char *force = getenv("BIAS_LDA_KERNEL");
     if (force && (force[0] == 't' || force[0] == 'r' || force[0] == 'h')) return false;
+    // small corpora are launch-bound: the shadow's two extra passes per sweep cost more than the narrower rows save
+    if (m->N < 2000000 && !(force && force[0] == 'u')) return false;
     return m->n_wk16 && m->Kpad <= 1024 && m->max_group_len <= 65535;
 }
 

@@ -190,6 +190,43 @@ function hdp!(hdp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
     KK_list, KK_dict, betas, gammas, alphas
 end
 
+# ---- CRF_gibbs_sampler!(hdp::HDP, xx, zz, ...)  src/HDP.jl:402-709
+# Resident model created with BIAS_MODEL_CRF (= 4): one bias_model_sweep per iteration.
+function crf!(hdp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
+              sample_hyperparam::Bool=true, n_internals::Int=10; Kmax::Int=256, seed=0)
+    items = vcat(xx...)
+    d, keep, datum = flat_data(items)
+    c = conj_spec(hdp.component, datum)
+    ptr = flat_ptr(zz)
+    z = flat_zz(zz)
+    hp = HdpParams(hdp.KK, Kmax, hdp.gg, hdp.g1, hdp.g2, hdp.aa, hdp.a1, hdp.a2, sample_hyperparam, n_internals)
+    m = Ptr{Void}[C_NULL]
+    check(ccall((:bias_model_create, LIB), Cint,
+                (Ptr{Void}, Int32, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Int32, Float64, Ptr{HdpParams}, Ptr{Ptr{Void}}),
+                context(seed), 4, [c], [d], length(zz), ptr, z, hdp.KK, hdp.aa, pointer_from_objref(hp), m))
+    KK_list = zeros(Int, n_samples); KK_dict = Dict{Int, Vector{Vector{Int}}}()
+    beta = zeros(Float64, Kmax + 1)
+    try
+        for iteration = 1:(n_burnins + n_samples * (n_lags + 1))
+            check(ccall((:bias_model_sweep, LIB), Cint, (Ptr{Void}, Int32), m[1], 1))
+            if (iteration - n_burnins) % (n_lags + 1) == 0 && iteration > n_burnins
+                check(ccall((:bias_model_get_zz, LIB), Cint, (Ptr{Void}, Ptr{Int32}), m[1], z))
+                check(ccall((:bias_model_get_hdp, LIB), Cint, (Ptr{Void}, Ptr{HdpParams}, Ptr{Float64}), m[1], pointer_from_objref(hp), beta))
+                scatter!(zz, z)
+                s = div(iteration - n_burnins, n_lags + 1)
+                KK_list[s] = hp.KK; KK_dict[hp.KK] = deepcopy(zz)
+            end
+        end
+        check(ccall((:bias_model_get_zz, LIB), Cint, (Ptr{Void}, Ptr{Int32}), m[1], z))
+        check(ccall((:bias_model_get_hdp, LIB), Cint, (Ptr{Void}, Ptr{HdpParams}, Ptr{Float64}), m[1], pointer_from_objref(hp), beta))
+        scatter!(zz, z)
+        hdp.KK, hdp.gg, hdp.aa = hp.KK, hp.gg, hp.aa
+    finally
+        ccall((:bias_model_destroy, LIB), Cint, (Ptr{Void},), m[1])
+    end
+    KK_list, KK_dict
+end
+
 # ---- RCRP_gibbs_sampler!(rcrp::RCRP, xx, zz, ...)  src/RCRP.jl:77-416
 # Resident model: upload once, one bias_model_sweep per iteration, zz read back at every kept sample.
 function rcrp!(rcrp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
