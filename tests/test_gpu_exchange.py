@@ -94,3 +94,20 @@ def test_two_bmm_gaussian_shards_on_one_gpu(ctx):
             if comp["nn"][k]:
                 assert abs(comp["mu"][k] - x[z == k].mean()) < 1e-9
         rs.close()
+
+
+def test_sharded_lda_over_nccl_two_processes():
+    """The real N>1 path: two processes, two GPUs, NCCL all-reduce of the count deltas (tools/lda_sharded_check.py)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if b.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(root, "tools", "lda_sharded_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["replicas_equal_recount"] and line["loglik_improved"]
