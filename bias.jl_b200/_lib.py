@@ -31,7 +31,7 @@ SYMBOLS = [
     "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload", "bias_model_heldout_log_likelihood",
     "bias_model_set_host_seed", "bias_hdp_shard_pass", "bias_hdp_shard_births", "bias_hdp_shard_adopt", "bias_hdp_shard_prune",
     "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
-    "bias_crf_sweep_with_uniforms", "bias_crf_get_tables",
+    "bias_crf_sweep_with_uniforms", "bias_crf_get_tables", "bias_model_delta_pack16", "bias_model_delta_apply16",
 ]
 
 
@@ -130,6 +130,8 @@ def lib():
     L.bias_hdp_shard_end.argtypes = [vp]
     L.bias_crf_sweep_with_uniforms.argtypes = [vp, vp]
     L.bias_crf_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.bias_model_delta_pack16.argtypes = [vp, i32, pp, C.POINTER(i64), pp, C.POINTER(i64)]
+    L.bias_model_delta_apply16.argtypes = [vp]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int

@@ -991,7 +991,7 @@ int bias_model_heldout_log_likelihood(bias_model *m, const int64_t *heldout_ptr,
 static int ensure_exchange(bias_model *m) {
     if (!m->base_i32) {
         BIAS_TRY(dev_alloc(&m->base_i32, (size_t)m->n_i32));
-        BIAS_TRY(dev_alloc(&m->delta_i32, (size_t)m->n_i32));
+        BIAS_TRY(dev_alloc(&m->delta_i32, (size_t)m->n_i32 + 4));      // + the overflow flag of the 16-bit exchange
         if (m->n_f64) {
             BIAS_TRY(dev_alloc(&m->base_f64, (size_t)m->n_f64));
             BIAS_TRY(dev_alloc(&m->delta_f64, (size_t)m->n_f64));
@@ -1037,6 +1037,52 @@ int bias_model_delta_pack(bias_model *m, void **delta_i32_dev, int64_t *n_i32, v
     *n_i32 = m->n_i32;
     if (delta_f64_dev) *delta_f64_dev = m->delta_f64;
     if (n_f64) *n_f64 = m->n_f64;
+    return BIAS_OK;
+}
+
+// 16-bit exchange of the word-topic part (LDA x MD x Int): the int16 deltas live in the first half of the delta buffer,
+// the n_k / n_items deltas (int32) and the overflow flag behind the word-topic region
+int bias_model_delta_pack16(bias_model *m, int32_t world, void **d16_dev, int64_t *n16, void **small_dev, int64_t *n_small) {
+    if (!m || !d16_dev || !n16 || !small_dev || !n_small) return fail(BIAS_EINVAL, "null argument");
+    if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
+    if (m->conj.kind != BIAS_MD || m->n_f64 != 0 || world < 1) return fail(BIAS_EINVAL, "the 16-bit exchange covers MultinomialDirichlet count tables");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    const int64_t n_wk_elems = m->V * (int64_t)m->Kpad, n_small_i = m->n_i32 - n_wk_elems;
+    int32_t *small = m->delta_i32 + n_wk_elems, *flag = m->delta_i32 + m->n_i32;
+    BIAS_CUDA_TRY(cudaMemsetAsync(flag, 0, 4 * sizeof(int32_t), st));
+    if (n_wk_elems > 0) {
+        delta_pack16_kernel<<<grid_for(m->ctx, n_wk_elems / 8, 256), 256, 0, st>>>(m->i32_block, m->base_i32,
+            reinterpret_cast<int16_t *>(m->delta_i32), n_wk_elems / 8, 32767 / world, flag);
+        m->ctx->launches += 1;
+    }
+    delta_pack_i32_kernel<<<grid_for(m->ctx, n_small_i / 4, 256), 256, 0, st>>>(m->i32_block + n_wk_elems, m->base_i32 + n_wk_elems,
+                                                                               small, n_small_i / 4);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
+    *d16_dev = m->delta_i32;
+    *n16 = n_wk_elems;
+    *small_dev = small;
+    *n_small = n_small_i + 4;
+    return BIAS_OK;
+}
+
+int bias_model_delta_apply16(bias_model *m) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    const int64_t n_wk_elems = m->V * (int64_t)m->Kpad, n_small_i = m->n_i32 - n_wk_elems;
+    if (n_wk_elems > 0) {
+        delta_apply16_kernel<<<grid_for(m->ctx, n_wk_elems / 8, 256), 256, 0, st>>>(m->i32_block, m->base_i32,
+            reinterpret_cast<const int16_t *>(m->delta_i32), n_wk_elems / 8, m->delta_i32 + m->n_i32);
+        m->ctx->launches += 1;
+    }
+    delta_apply_i32_kernel<<<grid_for(m->ctx, n_small_i / 4, 256), 256, 0, st>>>(m->i32_block + n_wk_elems, m->base_i32 + n_wk_elems,
+                                                                                m->delta_i32 + n_wk_elems, n_small_i / 4,
+                                                                                m->delta_i32 + m->n_i32);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += 1;
     return BIAS_OK;
 }
 

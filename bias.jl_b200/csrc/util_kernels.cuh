@@ -134,12 +134,54 @@ __global__ void delta_pack_i32_kernel(const int32_t *live, const int32_t *base, 
         reinterpret_cast<int4 *>(delta)[i] = make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
     }
 }
-__global__ void delta_apply_i32_kernel(int32_t *live, int32_t *base, const int32_t *delta, int64_t n4) {
+__global__ void delta_apply_i32_kernel(int32_t *live, int32_t *base, const int32_t *delta, int64_t n4,
+                                       const int32_t *skip_if_set = nullptr) {
+    if (skip_if_set && *skip_if_set != 0) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const int4 b = reinterpret_cast<const int4 *>(base)[i], d = reinterpret_cast<const int4 *>(delta)[i];
         const int4 v = make_int4(b.x + d.x, b.y + d.y, b.z + d.z, b.w + d.w);
         reinterpret_cast<int4 *>(live)[i] = v;
         reinterpret_cast<int4 *>(base)[i] = v;
+    }
+}
+// 16-bit exchange of the word-topic deltas: 8 cells per thread; *flag is raised when a delta could overflow int16 once
+// `world` of them are summed (the caller then repeats the exchange in 32 bits).  NCCL has no int16 sum, so two deltas
+// travel in one int32 as d1 * 65536 + d0 (arithmetic, not bitwise): the int32 sum over ranks is D1 * 65536 + D0, and
+// with |D0| < 2^15 both come back exactly (D0 = sign-extended low half, D1 = (X - D0) >> 16).
+__global__ void delta_pack16_kernel(const int32_t *live, const int32_t *base, int16_t *d16, int64_t n8, int limit, int32_t *flag) {
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 a0 = reinterpret_cast<const int4 *>(live)[2 * i], a1 = reinterpret_cast<const int4 *>(live)[2 * i + 1];
+        const int4 b0 = reinterpret_cast<const int4 *>(base)[2 * i], b1 = reinterpret_cast<const int4 *>(base)[2 * i + 1];
+        const int d[8] = {a0.x - b0.x, a0.y - b0.y, a0.z - b0.z, a0.w - b0.w, a1.x - b1.x, a1.y - b1.y, a1.z - b1.z, a1.w - b1.w};
+        unsigned o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            bad |= (abs(d[2 * e]) > limit) | (abs(d[2 * e + 1]) > limit);
+            o[e] = (unsigned)(d[2 * e + 1] * 65536 + d[2 * e]);
+        }
+        reinterpret_cast<uint4 *>(d16)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+__global__ void delta_apply16_kernel(int32_t *live, int32_t *base, const int16_t *d16, int64_t n8, const int32_t *flag) {
+    if (*flag != 0) return;         // some rank's delta did not fit: nothing is applied, the deltas stay pending
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 x = reinterpret_cast<const uint4 *>(d16)[i];
+        const int4 b0 = reinterpret_cast<const int4 *>(base)[2 * i], b1 = reinterpret_cast<const int4 *>(base)[2 * i + 1];
+        const int xs[4] = {(int)x.x, (int)x.y, (int)x.z, (int)x.w};
+        int lo[4], hi[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            lo[e] = (int)(int16_t)(xs[e] & 0xffff);
+            hi[e] = (xs[e] - lo[e]) >> 16;
+        }
+        const int4 v0 = make_int4(b0.x + lo[0], b0.y + hi[0], b0.z + lo[1], b0.w + hi[1]);
+        const int4 v1 = make_int4(b1.x + lo[2], b1.y + hi[2], b1.z + lo[3], b1.w + hi[3]);
+        reinterpret_cast<int4 *>(live)[2 * i] = v0;
+        reinterpret_cast<int4 *>(live)[2 * i + 1] = v1;
+        reinterpret_cast<int4 *>(base)[2 * i] = v0;
+        reinterpret_cast<int4 *>(base)[2 * i + 1] = v1;
     }
 }
 __global__ void delta_pack_f64_kernel(const double *live, const double *base, double *delta, int64_t n) {

@@ -390,6 +390,19 @@ class ResidentSampler:
     def delta_apply(self):
         check(lib().bias_model_delta_apply(self.h))
 
+    def delta_pack16(self, world: int):
+        """-> [(ptr, n, 'int32'), (ptr, n, 'int32')] or None when the model has no 16-bit exchange (not MD counts).
+        The first buffer holds two 16-bit word-topic deltas per int32 (d1 * 65536 + d0: NCCL has no int16 sum, an
+        int32 sum of this encoding is exact while the summed deltas fit 16 bits)."""
+        if self.spec.kind != _lib.MD:
+            return None
+        p16, ps, n16, ns = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        check(lib().bias_model_delta_pack16(self.h, int(world), C.byref(p16), C.byref(n16), C.byref(ps), C.byref(ns)))
+        return [(p16.value, n16.value // 2, "int32"), (ps.value, ns.value, "int32")]
+
+    def delta_apply16(self):
+        check(lib().bias_model_delta_apply16(self.h))
+
     def close(self):
         if self.h:
             lib().bias_model_destroy(self.h)

@@ -34,7 +34,7 @@ class _CudaView:
     """Zero-copy torch view of a raw device pointer (through __cuda_array_interface__)."""
 
     def __init__(self, ptr: int, n: int, dtype: str):
-        typestr = {"int32": "<i4", "float64": "<f8", "int64": "<i8"}[dtype]
+        typestr = {"int32": "<i4", "float64": "<f8", "int64": "<i8", "int16": "<i2"}[dtype]
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
@@ -55,15 +55,39 @@ class ShardedSampler:
         import torch.distributed as dist
         self.shard, self.group, self.dist = shard, group, dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._flag_host, self._flag_event = None, None
         self.merge_local_counts()
 
     def merge_local_counts(self):
         """After (re)building the counts from the local shard only: sum them into the global replica."""
         if self.world > 1:
             self.shard.delta_begin_zero()
-            self._exchange()
+            self._exchange(force32=True)        # whole counts, not deltas: they do not fit 16 bits in general
 
-    def _exchange(self):
+    def _exchange(self, force32: bool = False):
+        # Word-topic deltas travel in 16 bits when the shard offers it (half the all-reduce bytes).  The overflow flag
+        # rides in the small int32 buffer; apply16 checks it on the device and applies nothing when it is set, so the
+        # host never has to wait for it: it reads the flag of exchange s when it starts exchange s+1 (a pinned-memory
+        # copy finished long before), and if it was set makes that one a 32-bit exchange — the skipped deltas are still
+        # in live - base and simply ride along, one sweep late.
+        pack16 = getattr(self.shard, "delta_tensors16", None)
+        use16 = pack16 is not None and not force32
+        if use16 and self._flag_event is not None:
+            self._flag_event.synchronize()      # recorded one sweep ago: returns at once
+            use16 = int(self._flag_host[0]) == 0
+            self._flag_event = None
+        ts = pack16(self.world) if use16 else None
+        if ts is not None:
+            import torch
+            for t in ts:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.shard.delta_apply16()
+            if self._flag_host is None:
+                self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._flag_host.copy_(ts[1][-4:-3], non_blocking=True)
+            self._flag_event = torch.cuda.Event()
+            self._flag_event.record()
+            return
         for t in self.shard.delta_tensors():
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         self.shard.delta_apply()
@@ -96,6 +120,15 @@ class GpuShard:
 
     def delta_apply(self):
         self.rs.delta_apply()
+
+    def delta_tensors16(self, world):
+        packs = self.rs.delta_pack16(world)
+        if packs is None or packs[0][1] == 0:
+            return None
+        return [device_tensor(p, n, dt, self.device) for (p, n, dt) in packs]
+
+    def delta_apply16(self):
+        self.rs.delta_apply16()
 
 
 # ------------------------------------------------------------------ sharded HDP

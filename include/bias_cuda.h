@@ -245,6 +245,15 @@ BIAS_API int bias_model_delta_pack(bias_model *m, void **delta_i32_dev, int64_t 
                           void **delta_f64_dev, int64_t *n_f64);
 /* live = base + (all-reduced) delta. */
 BIAS_API int bias_model_delta_apply(bias_model *m);
+/* The same exchange with the word-topic deltas in 16 bits (half the all-reduce bytes; LDA x MD x Int).  pack16 writes
+ * 16-bit deltas, two per int32 as d1 * 65536 + d0 (NCCL has no int16 sum; all-reduce the buffer as n16 / 2 int32 —
+ * exact while the summed deltas fit 16 bits), and a small int32 buffer (n_k / n_items deltas followed by 4 ints whose first is
+ * an overflow flag: non-zero after the SUM all-reduce means some |delta| * world exceeded int16 on some rank).
+ * All-reduce both buffers, then apply16: it checks the flag ON THE DEVICE and applies nothing when it is set — the
+ * deltas stay pending (base is not advanced) and ride along with the next exchange, which the caller makes a 32-bit
+ * one (bias_model_delta_pack / apply) once it has seen the flag; no host synchronisation is needed in between. */
+BIAS_API int bias_model_delta_pack16(bias_model *m, int32_t world, void **d16_dev, int64_t *n16, void **small_dev, int64_t *n_small);
+BIAS_API int bias_model_delta_apply16(bias_model *m);
 
 /* ---- instrumentation ------------------------------------------------------------------ */
 /* Device time of the most recent bias_model_sweep call's sweep kernels, measured with CUDA

@@ -111,3 +111,68 @@ def test_sharded_lda_over_nccl_two_processes():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["replicas_equal_recount"] and line["loglik_improved"]
+
+
+def test_16_bit_exchange_of_word_topic_deltas(ctx):
+    """bias_model_delta_pack16 / apply16: int16 deltas for n_wk, int32 for n_k / n_items, overflow flag raised when a
+    delta times the number of ranks would not fit; both shards end up with the recount from the gathered zz."""
+    K, V = 10, 25
+    xx, _, _ = b.data.bars_lda_corpus(n_groups=50, n_tokens=40, seed=4)
+    words = np.concatenate(xx)
+    ptr = np.concatenate([[0], np.cumsum([len(x) for x in xx])]).astype(np.int64)
+    z0 = np.random.default_rng(2).integers(0, K, len(words)).astype(np.int32)
+    lda = b.LDA(b.MultinomialDirichlet(V, 2.5), K, 0.1)
+    dev = torch.device("cuda", 0)
+    samplers = []
+    for r in range(2):
+        lo, hi, i0, i1, lptr = shard_csr(ptr, r, 2)
+        data = b.FlatData.from_csr(b._lib.INT, i1 - i0, group_ptr=lptr, word=words[i0:i1])
+        samplers.append(b.ResidentSampler(ctx, lda, data, z0[i0:i1]))
+
+    def exchange16(world):
+        packs = [rs.delta_pack16(world) for rs in samplers]
+        ctx.sync()
+        tens = [[device_tensor(*seg, dev) for seg in p] for p in packs]
+        for seg in range(2):
+            total = tens[0][seg].clone()
+            total += tens[1][seg]
+            for t in tens:
+                t[seg].copy_(total)
+        torch.cuda.synchronize()
+        return int(tens[0][1][-4].item())
+
+    for rs in samplers:
+        rs.delta_begin_zero()
+    assert exchange16(2) == 0                    # the initial merge: counts of a 2000-token corpus fit easily
+    for rs in samplers:
+        rs.delta_apply16()
+    mi0 = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi0, (z0, words), 1)
+    for rs in samplers:
+        assert np.array_equal(rs.components()["mi"], mi0)
+    for _ in range(3):
+        for rs in samplers:
+            rs.sweep(1)
+        assert exchange16(2) == 0
+        for rs in samplers:
+            rs.delta_apply16()
+    z = np.concatenate([rs.get_zz() for rs in samplers])
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, words), 1)
+    for rs in samplers:
+        comp = rs.components()
+        assert np.array_equal(comp["mi"], mi) and np.array_equal(comp["mm"], mi.sum(1))
+    # a "world" so large that any non-zero delta could overflow raises the flag; nothing is applied, and the 32-bit
+    # exchange that follows gives the right tables
+    for rs in samplers:
+        rs.sweep(1)
+    assert exchange16(40000) != 0
+    for rs in samplers:
+        rs.delta_apply16()                       # gated on the device: the raised flag makes this a no-op
+    _exchange(samplers)
+    z = np.concatenate([rs.get_zz() for rs in samplers])
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, words), 1)
+    for rs in samplers:
+        assert np.array_equal(rs.components()["mi"], mi)
+        rs.close()
