@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbias_cuda.so")
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE, ESTATE = range(7)
 MD, G1G1 = 0, 1
 INT, SENT, F64 = 0, 1, 2
-MODEL_LDA, MODEL_BMM, MODEL_HDP, MODEL_RCRP, MODEL_CRF = 0, 1, 2, 3, 4
+MODEL_LDA, MODEL_BMM, MODEL_HDP, MODEL_RCRP, MODEL_CRF, MODEL_RCRF = 0, 1, 2, 3, 4, 5
 
 # every symbol include/bias_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -32,6 +32,7 @@ SYMBOLS = [
     "bias_model_set_host_seed", "bias_hdp_shard_pass", "bias_hdp_shard_births", "bias_hdp_shard_adopt", "bias_hdp_shard_prune",
     "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
     "bias_crf_sweep_with_uniforms", "bias_crf_get_tables", "bias_model_delta_pack16", "bias_model_delta_apply16",
+    "bias_rcrf_create", "bias_model_get_rcrf",
 ]
 
 
@@ -65,6 +66,11 @@ class HdpParams(C.Structure):
 class RcrpParams(C.Structure):
     _fields_ = [("KK", C.c_int32), ("Kmax", C.c_int32), ("a1", C.c_double), ("a2", C.c_double),
                 ("sample_hyperparam", C.c_int32), ("n_internals", C.c_int32)]
+
+
+class RcrfParams(C.Structure):
+    _fields_ = [("KK", C.c_int32), ("Kmax", C.c_int32), ("g1", C.c_double), ("g2", C.c_double), ("a1", C.c_double),
+                ("a2", C.c_double), ("sample_hyperparam", C.c_int32), ("n_internals", C.c_int32), ("join_tables", C.c_int32)]
 
 
 _lib = None
@@ -132,6 +138,8 @@ def lib():
     L.bias_crf_get_tables.argtypes = [vp, vp, vp, vp, vp, vp]
     L.bias_model_delta_pack16.argtypes = [vp, i32, pp, C.POINTER(i64), pp, C.POINTER(i64)]
     L.bias_model_delta_apply16.argtypes = [vp]
+    L.bias_rcrf_create.argtypes = [vp, cj, dt, i64, vp, i64, vp, vp, C.POINTER(RcrfParams), vp, vp, pp]
+    L.bias_model_get_rcrf.argtypes = [vp, C.POINTER(i32), vp, vp]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int

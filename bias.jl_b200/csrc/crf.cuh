@@ -35,6 +35,11 @@ struct CrfParams {
     int *err;                   // 2: dish slots exhausted
     unsigned long long *moved;
     int32_t max_len;            // longest group (capacity of the per-warp staging buffers)
+    // RCRF (src/RCRF.jl): the launch covers the restaurants [g0, g1) of epoch t; mm is [T][Kpad] and the dish prior
+    // couples epochs t-1, t, t+1.  Plain CRF: rcrf = 0, T = 1, t = 0, g0 = 0, g1 = G.
+    int32_t rcrf, T, t, Kpad;
+    int64_t g0, g1;
+    int32_t *tmp;               // [N] scratch of the table-joining pass
 };
 
 constexpr int kCrfWarps = 4;
@@ -46,8 +51,8 @@ __host__ __device__ inline size_t crf_smem_bytes(int max_len, int Kmax) {
 
 // first-appearance tables from z (src/HDP.jl:441-470): kjt[jj] = unique(zz[jj])
 __global__ void crf_init_kernel(CrfParams p) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= p.G) return;
+    const int64_t j = p.g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.g1) return;
     const int64_t p0 = p.group_ptr[j], n = p.group_ptr[j + 1] - p0;
     int nt = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -59,7 +64,7 @@ __global__ void crf_init_kernel(CrfParams p) {
             t = nt++;
             p.kjt[p0 + t] = kk;
             p.njt[p0 + t] = 0;
-            atomicAdd(p.mm + kk, 1);
+            atomicAdd(p.mm + (size_t)p.t * p.Kpad + kk, 1);
         }
         p.tji[p0 + i] = t;
         p.njt[p0 + t] += 1;
@@ -98,6 +103,45 @@ __device__ __forceinline__ void crf_unlock(const CrfParams &p, int lane) {
     if (lane == 0) atomicExch(p.lock, 0);
 }
 
+// ---- the prior weight of a dish for a new table / a table that re-draws its dish ----
+// CRF: log(mm[k]) (src/HDP.jl:566, :634).  RCRF, epoch t (src/RCRF.jl:303-327, :534-556, :762-768): dishes served in
+// epochs t-1..t are eligible with weight log(mm[t-1,k] + mm[t,k]) plus a look-ahead factor over the tables of epoch
+// t+1.  The reference evaluates that factor as sum(L1) - L2 with L1[k] = sum_{i < mm[t+1,k]} log(i + mm[t,k] + gg/K')
+// and the candidate's entry replaced by sum_i log(i + mm[t,k] + 1 + aa/K') (gg in one, aa in the other: reproduced);
+// everything but the candidate's own two sums is common to all outcomes, and the sums are lgamma differences.
+struct CrfLook {
+    double a, g;        // aa[t] / K', gg[t] / K'
+    bool on;            // epoch t has a successor
+};
+__device__ __forceinline__ CrfLook crf_look(const CrfParams &p, int KK, int lane) {
+    CrfLook L{0.0, 0.0, false};
+    if (!p.rcrf || p.t >= p.T - 1) return L;
+    const int32_t *mt = p.mm + (size_t)p.t * p.Kpad;
+    int alive = 0;
+    for (int k = lane; k < KK; k += 32) alive += (__ldcg(mt + k) + __ldcg(mt + p.Kpad + k)) > 0 ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) alive += __shfl_xor_sync(kFull, alive, o);
+    L.a = p.aa / (double)(alive + 1);
+    L.g = p.gg / (double)(alive + 1);
+    L.on = true;
+    return L;
+}
+__device__ __forceinline__ double crf_dish_prior(const CrfParams &p, const CrfLook &L, int k) {
+    const int32_t *mt = p.mm + (size_t)p.t * p.Kpad;
+    if (!p.rcrf) return log((double)__ldcg(mt + k));
+    const int m = __ldcg(mt + k);
+    const int cnt = m + (p.t > 0 ? __ldcg(mt - p.Kpad + k) : 0);
+    if (cnt <= 0) return -INFINITY;
+    double v = log((double)cnt);
+    if (L.on) {
+        const int nx = __ldcg(mt + p.Kpad + k);
+        if (nx > 0) {
+            const double dm = (double)m, dn = (double)nx;
+            v += (lgamma(dm + 1.0 + L.a + dn) - lgamma(dm + 1.0 + L.a)) - (lgamma(dm + L.g + dn) - lgamma(dm + L.g));
+        }
+    }
+    return v;
+}
+
 // a new dish: the next free slot (one atomic); -1 when the slots are exhausted
 __device__ __forceinline__ int crf_new_dish(const CrfParams &p, int lane) {
     int k = 0;
@@ -120,7 +164,8 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
     double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n_sc + p.max_len);
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
     unsigned long long moved = 0;
-    for (int64_t j = (int64_t)blockIdx.x * kCrfWarps + warp; j < p.G; j += n_warps) {
+    int32_t *const mm_t = p.mm + (size_t)p.t * p.Kpad;
+    for (int64_t j = p.g0 + (int64_t)blockIdx.x * kCrfWarps + warp; j < p.g1; j += n_warps) {
         const int64_t p0 = p.group_ptr[j];
         const int n = (int)(p.group_ptr[j + 1] - p0);
         int32_t *njt = p.njt + p0, *kjt = p.kjt + p0, *tji = p.tji + p0;
@@ -141,7 +186,8 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
             if (left == 0) {
                 // the table empties: it is removed and the tables after it move down (:517-529); the dish keeps its
                 // slot even if this was its last table
-                if (lane == 0) atomicAdd(p.mm + kk, -1);
+                if (lane == 0) atomicAdd(mm_t + kjt[tbl], -1);
+                __syncwarp();
                 for (int b = tbl; b < nt - 1; b += 32) {
                     const int q = b + lane;
                     int a0 = 0, a1 = 0;
@@ -168,9 +214,10 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
             if (tbl == nt) {
                 // a new table draws its dish from the menu (:559-581)
                 const int KK = __ldcg(p.d_KK);
+                const CrfLook L = crf_look(p, KK, lane);
                 for (int k = lane; k < KK; k += 32) {
                     const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
-                    sc[k] = log((double)__ldcg(p.mm + k)) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+                    sc[k] = crf_dish_prior(p, L, k) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
                 }
                 if (lane == 0) sc[KK] = log(p.gg) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
                 __syncwarp();
@@ -180,9 +227,10 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                 if (locked) {
                     crf_lock(p, lane);
                     const int KK2 = __ldcg(p.d_KK);
+                    const CrfLook L2 = crf_look(p, KK2, lane);
                     for (int k = lane; k < KK2; k += 32) {
                         const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
-                        sc[k] = log((double)__ldcg(p.mm + k)) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+                        sc[k] = crf_dish_prior(p, L2, k) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
                     }
                     if (lane == 0) sc[KK2] = log(p.gg) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
                     __syncwarp();
@@ -195,7 +243,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                 if (lane == 0) {
                     kjt[tbl] = knew;
                     njt[tbl] = 0;
-                    atomicAdd(p.mm + knew, 1);
+                    atomicAdd(mm_t + knew, 1);
                 }
                 nt += 1;
                 __syncwarp();
@@ -237,7 +285,8 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
     double *xs = sc + n_sc;                       // the values of the table's customers
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
     unsigned long long moved = 0;
-    for (int64_t j = (int64_t)blockIdx.x * kCrfWarps + warp; j < p.G; j += n_warps) {
+    int32_t *const mm_t = p.mm + (size_t)p.t * p.Kpad;
+    for (int64_t j = p.g0 + (int64_t)blockIdx.x * kCrfWarps + warp; j < p.g1; j += n_warps) {
         const int64_t p0 = p.group_ptr[j];
         const int n = (int)(p.group_ptr[j + 1] - p0);
         int32_t *kjt = p.kjt + p0;
@@ -262,7 +311,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
             sum = warp_sum(sum);
             // the table leaves its dish (:599, :626-628)
             if (lane == 0) {
-                atomicAdd(p.mm + kk, -1);
+                atomicAdd(mm_t + kk, -1);
                 atomicAdd(p.n_items + kk, -nti);
                 atomicAdd(p.sumx + kk, -sum);
             }
@@ -270,16 +319,18 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
             __syncwarp();
             // score of every dish for the whole table: the sum of the customers' individual predictives (:633-643)
             const int KK = __ldcg(p.d_KK);
+            const CrfLook L = crf_look(p, KK, lane);
             for (int k = lane; k <= KK; k += 32) {
                 double cn = 0.0, sx = 0.0, s;
                 if (k < KK) {
                     cn = (double)__ldcg(p.n_items + k);
                     sx = __ldcg(p.sumx + k);
-                    s = log((double)__ldcg(p.mm + k));
+                    s = crf_dish_prior(p, L, k);
                 } else {
                     s = log(p.gg);
                 }
-                for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+                if (s != -INFINITY)
+                    for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
                 sc[k] = s;
             }
             __syncwarp();
@@ -289,16 +340,18 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
             if (locked) {
                 crf_lock(p, lane);
                 const int KK2 = __ldcg(p.d_KK);
+                const CrfLook L2 = crf_look(p, KK2, lane);
                 for (int k = lane; k <= KK2; k += 32) {
                     double cn = 0.0, sx = 0.0, s_;
                     if (k < KK2) {
                         cn = (double)__ldcg(p.n_items + k);
                         sx = __ldcg(p.sumx + k);
-                        s_ = log((double)__ldcg(p.mm + k));
+                        s_ = crf_dish_prior(p, L2, k);
                     } else {
                         s_ = log(p.gg);
                     }
-                    for (int q = 0; q < nti; ++q) s_ += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+                    if (s_ != -INFINITY)
+                        for (int q = 0; q < nti; ++q) s_ += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
                     sc[k] = s_;
                 }
                 __syncwarp();
@@ -310,7 +363,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
             }
             if (lane == 0) {
                 kjt[tbl] = knew;
-                atomicAdd(p.mm + knew, 1);
+                atomicAdd(mm_t + knew, 1);
                 atomicAdd(p.n_items + knew, nti);
                 atomicAdd(p.sumx + knew, sum);
                 if (knew != kk) moved += (unsigned long long)nti;
@@ -324,6 +377,36 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
         }
     }
     if (lane == 0 && moved) atomicAdd(p.moved, moved);
+}
+
+// RCRF join_tables (src/RCRF.jl:351-377): the tables of a restaurant that serve the same dish become one table
+// (first-appearance order of the dishes).  One thread per restaurant; the compaction is done in place.
+__global__ void crf_join_kernel(CrfParams p) {
+    const int64_t j = p.g0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.g1) return;
+    const int64_t p0 = p.group_ptr[j];
+    const int n = (int)(p.group_ptr[j + 1] - p0), nt = p.n_tbls[j];
+    int32_t *kjt = p.kjt + p0, *njt = p.njt + p0, *tji = p.tji + p0, *map = p.tmp + p0;
+    int nu = 0;
+    for (int q = 0; q < nt; ++q) {
+        const int k = kjt[q], cnt = njt[q];
+        int u = -1;
+        for (int r = 0; r < nu; ++r)
+            if (kjt[r] == k) { u = r; break; }
+        if (u < 0) {
+            u = nu++;
+            kjt[u] = k;
+            njt[u] = cnt;
+        } else {
+            njt[u] += cnt;
+            atomicAdd(p.mm + (size_t)p.t * p.Kpad + k, -1);
+        }
+        map[q] = u;
+    }
+    if (nu != nt) {
+        for (int q = 0; q < n; ++q) tji[q] = map[tji[q]];
+        p.n_tbls[j] = nu;
+    }
 }
 
 // diagnostic of src/HDP.jl:669-673: sum of logpredictive(components[zz], xx) with every customer seated

@@ -564,15 +564,19 @@ static int hdp_phase_tables(bias_model *m, int hh) {
 }
 
 // alpha0 (Teh et al. eq. 50 with the device-side auxiliaries sum log w_j, sum s_j) and gamma (Escobar-West), src/HDP.jl:124-159
+static void hdp_host_hyper_on(bias_model *m, double mt, double sum_logw, double sum_s, int KK, double &aa_io, double &gg_io);
 static void hdp_host_hyper(bias_model *m, double mt, double sum_logw, double sum_s) {
-    const int KK = m->hdp.KK;
+    hdp_host_hyper_on(m, mt, sum_logw, sum_s, m->hdp.KK, m->hdp.aa, m->hdp.gg);
+}
+// the same update on any (aa, gg) pair: the HDP's, or one epoch's of the RCRF (src/RCRF.jl:80-118 with KK = dishes of the epoch)
+static void hdp_host_hyper_on(bias_model *m, double mt, double sum_logw, double sum_s, int KK, double &aa_io, double &gg_io) {
     const double aa_shape = m->hdp.a1 + mt - sum_s;
     const double aa_rate = m->hdp.a2 - sum_logw;
     if (aa_shape > 0.0 && aa_rate > 0.0) {
         std::gamma_distribution<double> ga(aa_shape, 1.0);
-        m->hdp.aa = ga(m->host_rng) / aa_rate;
+        aa_io = ga(m->host_rng) / aa_rate;
     }
-    std::gamma_distribution<double> g1(m->hdp.gg + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
+    std::gamma_distribution<double> g1(gg_io + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
     const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
     const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
     const double le = std::log(eta);
@@ -581,7 +585,7 @@ static void hdp_host_hyper(bias_model *m, double mt, double sum_logw, double sum
     const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
     if (shape > 0.0) {
         std::gamma_distribution<double> gg(shape, 1.0);
-        m->hdp.gg = gg(m->host_rng) / (m->hdp.g2 - le);
+        gg_io = gg(m->host_rng) / (m->hdp.g2 - le);
     }
 }
 
@@ -672,6 +676,26 @@ static CrfParams crf_params(bias_model *m, const double *ext_uniforms) {
     p.err = reinterpret_cast<int *>(m->scratch + 4);
     p.moved = m->scratch + 1;
     p.max_len = (int32_t)m->max_group_len;
+    p.rcrf = 0;
+    p.T = 1;
+    p.t = 0;
+    p.Kpad = m->Kpad;
+    p.g0 = 0;
+    p.g1 = m->G;
+    p.tmp = m->crf_tmp;
+    return p;
+}
+
+// the launch parameters of epoch t of an RCRF model
+static CrfParams rcrf_params(bias_model *m, int t, const double *ext_uniforms) {
+    CrfParams p = crf_params(m, ext_uniforms);
+    p.rcrf = 1;
+    p.T = (int32_t)m->h_epoch_gptr.size() - 1;
+    p.t = t;
+    p.g0 = m->h_epoch_gptr[t];
+    p.g1 = m->h_epoch_gptr[t + 1];
+    p.aa = m->h_aa_t[t];
+    p.gg = m->h_gg_t[t];
     return p;
 }
 
@@ -687,50 +711,54 @@ int crf_create(bias_model *m) {
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_njt, n * 4));
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_kjt, n * 4));
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_n_tbls, g * 4));
-    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_mm, (size_t)m->Kpad * 4));
+    const size_t T = (m->model == BIAS_MODEL_RCRF) ? m->h_epoch_gptr.size() - 1 : 1;
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_mm, T * (size_t)m->Kpad * 4));
+    BIAS_CUDA_TRY(cudaMalloc((void **)&m->crf_tmp, n * 4));
     BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_tji, 0, n * 4, st));
     BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_njt, 0, n * 4, st));
     BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_kjt, 0, n * 4, st));
     BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_n_tbls, 0, g * 4, st));
-    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_mm, 0, (size_t)m->Kpad * 4, st));
-    if (m->G > 0) {
-        crf_init_kernel<<<(unsigned)((m->G + 127) / 128), 128, 0, st>>>(crf_params(m, nullptr));
-        BIAS_CUDA_TRY(cudaGetLastError());
-        m->ctx->launches += 1;
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->crf_mm, 0, T * (size_t)m->Kpad * 4, st));
+    for (size_t t = 0; t < T; ++t) {
+        const CrfParams p = (m->model == BIAS_MODEL_RCRF) ? rcrf_params(m, (int)t, nullptr) : crf_params(m, nullptr);
+        if (p.g1 > p.g0) {
+            crf_init_kernel<<<(unsigned)((p.g1 - p.g0 + 127) / 128), 128, 0, st>>>(p);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+        }
     }
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
     return BIAS_OK;
 }
 
 int crf_destroy(bias_model *m) {
-    for (void *p : {(void *)m->crf_tji, (void *)m->crf_njt, (void *)m->crf_kjt, (void *)m->crf_n_tbls, (void *)m->crf_mm})
+    for (void *p : {(void *)m->crf_tji, (void *)m->crf_njt, (void *)m->crf_kjt, (void *)m->crf_n_tbls, (void *)m->crf_mm, (void *)m->crf_tmp})
         if (p) cudaFree(p);
-    m->crf_tji = m->crf_njt = m->crf_kjt = m->crf_n_tbls = m->crf_mm = nullptr;
+    m->crf_tji = m->crf_njt = m->crf_kjt = m->crf_n_tbls = m->crf_mm = m->crf_tmp = nullptr;
     return BIAS_OK;
 }
 
-// dishes that lost their last table leave the menu (src/HDP.jl:531-545, :610-621, applied once per iteration)
+// dishes that lost their last table leave the menu (src/HDP.jl:531-545, :610-621; src/RCRF.jl:271-284), applied once per
+// iteration: a dish without tables has no customers, so the test is n_items == 0
 static int crf_prune(bias_model *m) {
     bias_ctx *ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     const int KK = m->hdp.KK, Kpad = m->Kpad;
-    std::vector<int32_t> ni(Kpad), mmv(Kpad);
+    std::vector<int32_t> ni(Kpad);
     BIAS_CUDA_TRY(cudaMemcpyAsync(ni.data(), m->n_items, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
-    BIAS_CUDA_TRY(cudaMemcpyAsync(mmv.data(), m->crf_mm, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
     int alive = 0;
-    std::vector<int32_t> n_mm(Kpad, 0);
-    for (int k = 0; k < KK; ++k)
-        if (ni[k] > 0) n_mm[alive++] = mmv[k];
+    for (int k = 0; k < KK; ++k) alive += ni[k] > 0;
     if (alive == KK || alive == 0) return BIAS_OK;
-    BIAS_TRY(hdp_prune(m));                      // compacts n_items / sumx / z (same alive order) and leaves d_remap on the device
-    BIAS_CUDA_TRY(cudaMemcpyAsync(m->crf_mm, n_mm.data(), (size_t)Kpad * 4, cudaMemcpyHostToDevice, st));
+    BIAS_TRY(hdp_prune(m));                      // compacts n_items / sumx / z (alive order) and leaves d_remap on the device
+    const int64_t T = (m->model == BIAS_MODEL_RCRF) ? (int64_t)m->h_epoch_gptr.size() - 1 : 1;
+    compact_columns_kernel<<<grid1d(ctx, T * 128, 128), 128, (size_t)KK * 4, st>>>(m->crf_mm, T, Kpad, KK, m->d_remap);
+    ctx->launches += 1;
     if (m->N > 0) {
         remap_z_kernel<<<grid1d(ctx, m->N, 256), 256, 0, st>>>(m->crf_kjt, m->N, m->d_remap);
-        BIAS_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
-    BIAS_CUDA_TRY(cudaStreamSynchronize(st));    // n_mm must outlive the copy
+    BIAS_CUDA_TRY(cudaGetLastError());
     return BIAS_OK;
 }
 
@@ -785,6 +813,84 @@ int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
         BIAS_CUDA_TRY(cudaGetLastError());
         ctx->launches += 1;
     }
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    return BIAS_OK;
+}
+
+// RCRF (reference src/RCRF.jl:122-938): per epoch the CRF's two passes over that epoch's restaurants with the dish
+// prior coupled to the neighbouring epochs' menus, same-dish tables joined in between, the epoch's hyper-parameters after
+int rcrf_create(bias_model *m, int64_t n_epochs, const int64_t *epoch_ptr, const double *gg, const double *aa, int join_tables) {
+    m->h_epoch_gptr.assign(epoch_ptr, epoch_ptr + n_epochs + 1);
+    m->h_gg_t.assign(gg, gg + n_epochs);
+    m->h_aa_t.assign(aa, aa + n_epochs);
+    m->crf_join = join_tables ? 1 : 0;
+    return crf_create(m);
+}
+
+int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
+    bias_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int T = (int)m->h_epoch_gptr.size() - 1, Kpad = m->Kpad;
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
+    const size_t smem = crf_smem_bytes((int)m->max_group_len, m->hdp.Kmax);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    std::vector<int32_t> mm_row(Kpad);
+    for (int t = 0; t < T; ++t) {
+        const CrfParams p = rcrf_params(m, t, ext_uniforms_dev);
+        const int64_t Gt = p.g1 - p.g0;
+        if (Gt <= 0) continue;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Gt + kCrfWarps - 1) / kCrfWarps, (int64_t)ctx->num_sms * 8));
+        crf_tables_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
+        if (m->crf_join) crf_join_kernel<<<(unsigned)((Gt + 127) / 128), 128, 0, st>>>(p);
+        crf_dishes_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        ctx->launches += m->crf_join ? 3 : 2;
+        if (m->hdp.sample_hyperparam) {             // src/RCRF.jl:464-468 -> :80-118
+            unsigned long long *d_m = m->scratch + 5;
+            unsigned long long mt = 0;
+            BIAS_CUDA_TRY(cudaMemsetAsync(d_m, 0, 8, st));
+            crf_sum_tables_kernel<<<grid1d(ctx, Gt, 256, 4), 256, 0, st>>>(m->crf_n_tbls + p.g0, Gt, d_m);
+            ctx->launches += 1;
+            BIAS_CUDA_TRY(cudaMemcpyAsync(&mt, d_m, 8, cudaMemcpyDeviceToHost, st));
+            BIAS_CUDA_TRY(cudaMemcpyAsync(mm_row.data(), m->crf_mm + (size_t)t * Kpad, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
+            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+            int KK_t = 0;
+            for (int k = 0; k < Kpad; ++k) KK_t += mm_row[k] != 0;
+            for (int hh = 0; hh < m->hdp.n_internals; ++hh) {
+                double hyper[2] = {0.0, 0.0};
+                BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
+                hdp_hyper_kernel<<<grid1d(ctx, Gt, 128, 4), 128, 0, st>>>(m->group_ptr + p.g0, Gt, m->h_aa_t[t], ctx->seed,
+                                                                          m->sweep_index * 1024u + (uint32_t)t, (uint32_t)hh, m->d_hyper);
+                ctx->launches += 1;
+                BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
+                BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+                hdp_host_hyper_on(m, (double)mt, hyper[0], hyper[1], KK_t, m->h_aa_t[t], m->h_gg_t[t]);
+            }
+        }
+    }
+    int32_t kk = 0;
+    int err = 0;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&kk, m->d_KK, 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&err, reinterpret_cast<int *>(m->scratch + 4), 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->hdp.KK = kk;
+    if (err == 2)
+        return fail(BIAS_ERANGE, "RCRF: Kmax = %d dish slots exhausted (KK = %d); construct the model with a larger Kmax", m->hdp.Kmax, kk);
+    BIAS_TRY(crf_prune(m));
+    if (m->N > 0) {
+        crf_diag_kernel<<<grid1d(ctx, m->N, 256, 4), 256, 0, st>>>(crf_params(m, nullptr), m->N, reinterpret_cast<double *>(m->scratch));
+        BIAS_CUDA_TRY(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    m->hdp.aa = m->h_aa_t[0];
+    m->hdp.gg = m->h_gg_t[0];
     m->sweep_index += 1;
     m->stats_pending = true;
     return BIAS_OK;
@@ -913,7 +1019,7 @@ extern "C" {
 
 int bias_model_get_hdp(bias_model *m, bias_hdp_params *params, double *beta) {
     if (!m) return fail(BIAS_EINVAL, "null model");
-    if (m->model != BIAS_MODEL_HDP && m->model != BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "not an HDP model");
+    if (m->model != BIAS_MODEL_HDP && m->model != BIAS_MODEL_CRF && m->model != BIAS_MODEL_RCRF) return fail(BIAS_EINVAL, "not an HDP model");
     if (params) *params = m->hdp;
     if (beta) {
         const int n = m->hdp.Kmax + 1;
@@ -985,13 +1091,14 @@ int bias_hdp_shard_end(bias_model *m) {
 
 int bias_crf_sweep_with_uniforms(bias_model *m, const double *uniforms) {
     if (!m || !uniforms) return fail(BIAS_EINVAL, "null argument");
-    if (m->model != BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "not a CRF model");
+    if (m->model != BIAS_MODEL_CRF && m->model != BIAS_MODEL_RCRF) return fail(BIAS_EINVAL, "not a CRF / RCRF model");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     double *d_u = nullptr;
     const size_t n = (size_t)std::max<int64_t>(1, m->N) * 3;
     BIAS_CUDA_TRY(cudaMalloc((void **)&d_u, n * 8));
     cudaError_t e = cudaMemcpyAsync(d_u, uniforms, (size_t)m->N * 3 * 8, cudaMemcpyHostToDevice, m->ctx->stream);
-    int rc = (e == cudaSuccess) ? crf_sweep(m, d_u) : fail(BIAS_ECUDA, "%s", cudaGetErrorString(e));
+    int rc = (e != cudaSuccess) ? fail(BIAS_ECUDA, "%s", cudaGetErrorString(e))
+                                : (m->model == BIAS_MODEL_RCRF ? rcrf_sweep(m, d_u) : crf_sweep(m, d_u));
     cudaStreamSynchronize(m->ctx->stream);
     cudaFree(d_u);
     return rc;
@@ -999,15 +1106,28 @@ int bias_crf_sweep_with_uniforms(bias_model *m, const double *uniforms) {
 
 int bias_crf_get_tables(bias_model *m, int32_t *tji, int32_t *njt, int32_t *kjt, int32_t *n_tbls, int32_t *mm) {
     if (!m) return fail(BIAS_EINVAL, "null model");
-    if (m->model != BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "not a CRF model");
+    if (m->model != BIAS_MODEL_CRF && m->model != BIAS_MODEL_RCRF) return fail(BIAS_EINVAL, "not a CRF / RCRF model");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
     if (tji) BIAS_CUDA_TRY(cudaMemcpyAsync(tji, m->crf_tji, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st));
     if (njt) BIAS_CUDA_TRY(cudaMemcpyAsync(njt, m->crf_njt, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st));
     if (kjt) BIAS_CUDA_TRY(cudaMemcpyAsync(kjt, m->crf_kjt, (size_t)m->N * 4, cudaMemcpyDeviceToHost, st));
     if (n_tbls) BIAS_CUDA_TRY(cudaMemcpyAsync(n_tbls, m->crf_n_tbls, (size_t)m->G * 4, cudaMemcpyDeviceToHost, st));
-    if (mm) BIAS_CUDA_TRY(cudaMemcpyAsync(mm, m->crf_mm, (size_t)m->hdp.KK * 4, cudaMemcpyDeviceToHost, st));
+    if (mm) {       // [T][KK] row-major (T = 1 for the CRF)
+        const int64_t T = (m->model == BIAS_MODEL_RCRF) ? (int64_t)m->h_epoch_gptr.size() - 1 : 1;
+        BIAS_CUDA_TRY(cudaMemcpy2DAsync(mm, (size_t)m->hdp.KK * 4, m->crf_mm, (size_t)m->Kpad * 4, (size_t)m->hdp.KK * 4, (size_t)T,
+                                        cudaMemcpyDeviceToHost, st));
+    }
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BIAS_OK;
+}
+
+int bias_model_get_rcrf(bias_model *m, int32_t *KK, double *gg, double *aa) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (m->model != BIAS_MODEL_RCRF) return fail(BIAS_EINVAL, "not an RCRF model");
+    if (KK) *KK = m->hdp.KK;
+    if (gg) std::copy(m->h_gg_t.begin(), m->h_gg_t.end(), gg);
+    if (aa) std::copy(m->h_aa_t.begin(), m->h_aa_t.end(), aa);
     return BIAS_OK;
 }
 

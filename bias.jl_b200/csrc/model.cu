@@ -18,7 +18,7 @@ namespace bias {
 static thread_local std::string g_err;
 
 bool is_dynamic_K(const bias_model *m) {
-    return m->model == BIAS_MODEL_HDP || m->model == BIAS_MODEL_RCRP || m->model == BIAS_MODEL_CRF;
+    return m->model == BIAS_MODEL_HDP || m->model == BIAS_MODEL_RCRP || m->model == BIAS_MODEL_CRF || m->model == BIAS_MODEL_RCRF;
 }
 
 void set_error(const char *fmt, ...) {
@@ -540,8 +540,9 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
                       int32_t K, double alpha, const bias_hdp_params *hdp, bias_model **out) {
     if (!ctx || !out) return fail(BIAS_EINVAL, "null argument");
     *out = nullptr;
-    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_CRF) return fail(BIAS_EINVAL, "unknown model %d", model);
-    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF) {
+    if (model < BIAS_MODEL_LDA || model > BIAS_MODEL_RCRF) return fail(BIAS_EINVAL, "unknown model %d", model);
+    const bool dynamic = model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF || model == BIAS_MODEL_RCRF;
+    if (dynamic) {
         if (!hdp) return fail(BIAS_EINVAL, "HDP / RCRP parameters are required");
         if (hdp->KK < 1 || hdp->Kmax < hdp->KK + 2) return fail(BIAS_EINVAL, "HDP: need 1 <= KK and Kmax >= KK + 2");
         if (model != BIAS_MODEL_RCRP && (!(hdp->gg > 0.0) || !(hdp->aa > 0.0))) return fail(BIAS_EINVAL, "HDP: gg and aa must be > 0");
@@ -564,7 +565,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     m->alpha = alpha;
     m->V = (conj->kind == BIAS_MD) ? conj->dd : 0;
     for (int64_t j = 0; j < m->G; ++j) m->max_group_len = std::max(m->max_group_len, group_ptr[j + 1] - group_ptr[j]);
-    const int32_t Kcap = (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF) ? hdp->Kmax : K;
+    const int32_t Kcap = dynamic ? hdp->Kmax : K;
     // pad K to 128 * 2^j (the fast kernel's chunk tree); the generic kernels only need the stride
     int32_t kp = 128;
     while (kp < Kcap) kp *= 2;
@@ -634,7 +635,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     M_CUDA(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
     M_CUDA(cudaMallocHost((void **)&m->h_scratch, 8 * sizeof(unsigned long long)));
     if (model != BIAS_MODEL_BMM) m->h_group_ptr.assign(group_ptr, group_ptr + m->G + 1);
-    if (model == BIAS_MODEL_HDP || model == BIAS_MODEL_RCRP || model == BIAS_MODEL_CRF) M_TRY(hdp_create(m, hdp));
+    if (dynamic) M_TRY(hdp_create(m, hdp));
     M_TRY(validate_on_device(m, K));
     M_TRY(rebuild_counts(m));
     if (model == BIAS_MODEL_CRF) M_TRY(crf_create(m));
@@ -703,7 +704,7 @@ int bias_model_set_zz(bias_model *m, const int32_t *zz) {
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
     BIAS_TRY(validate_on_device(m, Kcur));
     BIAS_TRY(rebuild_counts(m));
-    if (m->model == BIAS_MODEL_CRF) {            // the seating is rebuilt from the new assignments (src/HDP.jl:441-470)
+    if (m->model == BIAS_MODEL_CRF || m->model == BIAS_MODEL_RCRF) {   // the seating is rebuilt from the new assignments (src/HDP.jl:441-470)
         crf_destroy(m);
         BIAS_TRY(crf_create(m));
     }
@@ -724,6 +725,7 @@ static int one_sweep(bias_model *m) {
     if (m->model == BIAS_MODEL_HDP) return hdp_sweep(m);
     if (m->model == BIAS_MODEL_RCRP) return rcrp_sweep(m);
     if (m->model == BIAS_MODEL_CRF) return crf_sweep(m, nullptr);
+    if (m->model == BIAS_MODEL_RCRF) return rcrf_sweep(m, nullptr);
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st));
     if (m->fast) {
         BIAS_TRY(launch_lda_fast(m, nullptr, 0, nullptr));
@@ -1133,6 +1135,36 @@ static int run_model(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, c
     if (rc == BIAS_OK) rc = bias_model_get_zz(m, zz);
     if (rc == BIAS_OK && hp) rc = bias_model_get_hdp(m, hp, beta_out);
     bias_model_destroy(m);
+    return rc;
+}
+
+int bias_rcrf_create(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int64_t n_groups,
+                     const int64_t *group_ptr, int64_t n_epochs, const int64_t *epoch_ptr, const int32_t *zz,
+                     const bias_rcrf_params *params, const double *gg, const double *aa, bias_model **out) {
+    if (!params || !gg || !aa || !epoch_ptr || !out) return fail(BIAS_EINVAL, "null argument");
+    if (n_epochs < 2) return fail(BIAS_EINVAL, "RCRF needs at least two epochs (src/RCRF.jl has first, middle and last epoch blocks)");
+    if (epoch_ptr[0] != 0 || epoch_ptr[n_epochs] != n_groups) return fail(BIAS_EINVAL, "epoch_ptr must start at 0 and end at n_groups");
+    for (int64_t t = 0; t < n_epochs; ++t) {
+        if (epoch_ptr[t + 1] < epoch_ptr[t]) return fail(BIAS_EINVAL, "epoch_ptr must be non-decreasing");
+        if (!(aa[t] > 0.0) || !(gg[t] > 0.0)) return fail(BIAS_EINVAL, "RCRF: aa[%lld] and gg[%lld] must be > 0", (long long)t, (long long)t);
+    }
+    bias_hdp_params hp{};
+    hp.KK = params->KK;
+    hp.Kmax = params->Kmax;
+    hp.gg = gg[0];
+    hp.g1 = params->g1;
+    hp.g2 = params->g2;
+    hp.aa = aa[0];
+    hp.a1 = params->a1;
+    hp.a2 = params->a2;
+    hp.sample_hyperparam = params->sample_hyperparam;
+    hp.n_internals = params->n_internals;
+    BIAS_TRY(bias_model_create(ctx, BIAS_MODEL_RCRF, conj, data, n_groups, group_ptr, zz, params->KK, aa[0], &hp, out));
+    int rc = rcrf_create(*out, n_epochs, epoch_ptr, gg, aa, params->join_tables);
+    if (rc != BIAS_OK) {
+        bias_model_destroy(*out);
+        *out = nullptr;
+    }
     return rc;
 }
 

@@ -76,6 +76,11 @@ struct bias_model {
 
     // CRF (tables and dishes of the Chinese restaurant franchise, csrc/crf.cuh)
     int32_t *crf_tji = nullptr, *crf_njt = nullptr, *crf_kjt = nullptr, *crf_n_tbls = nullptr, *crf_mm = nullptr;
+    int32_t *crf_tmp = nullptr;             // [N] scratch of the table-joining pass
+    // RCRF: restaurants of all epochs are the groups; first restaurant of each epoch, per-epoch gg (aa in h_aa_t)
+    std::vector<int64_t> h_epoch_gptr;
+    std::vector<double> h_gg_t;
+    int32_t crf_join = 1;
 
     // RCRP (epochs are the groups)
     std::vector<double> h_aa_t;     // [T] per-epoch concentration
@@ -92,6 +97,8 @@ int hdp_destroy(bias_model *m);
 int crf_create(bias_model *m);
 int crf_sweep(bias_model *m, const double *ext_uniforms_dev);
 int crf_destroy(bias_model *m);
+int rcrf_create(bias_model *m, int64_t n_epochs, const int64_t *epoch_ptr, const double *gg, const double *aa, int join_tables);
+int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev);
 int rcrp_create(bias_model *m, const bias_rcrp_params *rp, const double *aa);
 int rcrp_sweep(bias_model *m);
 bool is_dynamic_K(const bias_model *m);

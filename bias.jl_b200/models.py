@@ -9,6 +9,7 @@
   posterior(model, xx, zz)            src/LDA.jl:151-167, src/BMM.jl:134-151
   CRF_gibbs_sampler(hdp, xx, zz, n_burnins, n_lags, n_samples, ...)   src/HDP.jl:402-709
   RCRP(c, KK, aa, TT, a1, a2)         src/RCRP.jl:18-28
+  RCRF(c, KK, gg, g1, g2, aa, a1, a2, TT), RCRF_gibbs_sampler(rcrf, xx, zz, ...)   src/RCRF.jl:16-37, 122-938
   RCRP_gibbs_sampler(rcrp, xx, zz, n_burnins, n_lags, n_samples, ...)   src/RCRP.jl:77-416
   posterior(rcrp, xx, KK_dict, KK)    src/RCRP.jl:418-453
 
@@ -86,6 +87,25 @@ class RCRP:
 
     def __repr__(self):
         return (f"Recurrent Chinese Restaurant Process with {self.KK} "
+                f"{type(self.component).__name__} components")
+
+
+class RCRF:
+    """Recurrent Chinese restaurant franchise over TT epochs (src/RCRF.jl:16-37).  gg and aa hold one concentration per
+    epoch; KK, gg and aa are updated in place by the sampler.  Kmax is the engine's dish-slot capacity."""
+    model_id = _lib.MODEL_RCRF
+
+    def __init__(self, component, KK: int, gg, g1: float, g2: float, aa, a1: float, a2: float, TT: int | None = None,
+                 Kmax: int = 256):
+        self.component, self.KK = component, int(KK)
+        if (np.isscalar(gg) or np.isscalar(aa)) and TT is None:
+            raise ValueError("RCRF(c, KK, gg, g1, g2, aa, a1, a2, TT): TT is required when gg / aa are scalars")
+        self.gg = np.full(int(TT), float(gg)) if np.isscalar(gg) else np.array(gg, dtype=np.float64)
+        self.aa = np.full(int(TT), float(aa)) if np.isscalar(aa) else np.array(aa, dtype=np.float64)
+        self.g1, self.g2, self.a1, self.a2, self.Kmax = float(g1), float(g2), float(a1), float(a2), int(Kmax)
+
+    def __repr__(self):
+        return (f"Recurrent Chinese Restaurant Franchise Mixture Model with {self.KK} "
                 f"{type(self.component).__name__} components")
 
 
@@ -199,13 +219,24 @@ class ResidentSampler:
     """bias_model: xx, zz and the component statistics live in HBM between sweeps."""
 
     def __init__(self, ctx: Context, model, data: FlatData, zz_flat: np.ndarray, *, sample_hyperparam=True,
-                 n_internals=10, crf: bool = False):
+                 n_internals=10, crf: bool = False, epoch_ptr=None, join_tables: bool = True):
         self.ctx, self.model, self.data = ctx, model, data
         self.n_internals = int(n_internals)
         self.spec = model.component.spec(data.datum)
         self.h = C.c_void_p()
         hp = _hdp_params(model, sample_hyperparam, n_internals) if isinstance(model, HDP) else None
         self.zz = _lib.as_i32(zz_flat)
+        if isinstance(model, RCRF):
+            self.epoch_ptr = _lib.as_i64(epoch_ptr)
+            rp = _lib.RcrfParams(model.KK, model.Kmax, model.g1, model.g2, model.a1, model.a2, int(bool(sample_hyperparam)),
+                                 int(n_internals), int(bool(join_tables)))
+            gg, aa = _lib.as_f64(model.gg), _lib.as_f64(model.aa)
+            if len(gg) != len(self.epoch_ptr) - 1 or len(aa) != len(gg):
+                raise ValueError(f"RCRF: gg / aa have {len(gg)} / {len(aa)} entries for {len(self.epoch_ptr) - 1} epochs")
+            check(lib().bias_rcrf_create(ctx.h, C.byref(self.spec), C.byref(data.c), data.n_groups, ptr(data.group_ptr),
+                                         len(gg), ptr(self.epoch_ptr), ptr(self.zz), C.byref(rp), ptr(gg), ptr(aa),
+                                         C.byref(self.h)))
+            return
         if isinstance(model, RCRP):
             rp = _lib.RcrpParams(model.KK, model.Kmax, model.a1, model.a2, int(bool(sample_hyperparam)),
                                  int(n_internals))
@@ -285,11 +316,19 @@ class ResidentSampler:
     def crf_tables(self):
         """-> dict(tji, njt, kjt, n_tbls, mm): njt / kjt hold the tables of group j at group_ptr[j] .. + n_tbls[j]"""
         N, G, KK = self.data.n_items, self.data.n_groups, self.current_KK()
+        mm_shape = (len(self.epoch_ptr) - 1, KK) if isinstance(self.model, RCRF) else (KK,)
         out = {"tji": np.zeros(N, np.int32), "njt": np.zeros(N, np.int32), "kjt": np.zeros(N, np.int32),
-               "n_tbls": np.zeros(G, np.int32), "mm": np.zeros(KK, np.int32)}
+               "n_tbls": np.zeros(G, np.int32), "mm": np.zeros(mm_shape, np.int32)}
         check(lib().bias_crf_get_tables(self.h, ptr(out["tji"]), ptr(out["njt"]), ptr(out["kjt"]), ptr(out["n_tbls"]),
                                         ptr(out["mm"])))
         return out
+
+    def rcrf_state(self):
+        """-> (KK, gg[TT], aa[TT])"""
+        TT = len(self.epoch_ptr) - 1
+        kk, gg, aa = C.c_int32(), np.zeros(TT), np.zeros(TT)
+        check(lib().bias_model_get_rcrf(self.h, C.byref(kk), ptr(gg), ptr(aa)))
+        return kk.value, gg, aa
 
     def crf_sweep_with_uniforms(self, uniforms):
         u = _lib.as_f64(uniforms)
@@ -308,7 +347,7 @@ class ResidentSampler:
     # -- verification
     def conditionals(self, item_idx, uniforms):
         idx, u = _lib.as_i64(item_idx), _lib.as_f64(uniforms)
-        n_out = self.current_KK() + (1 if isinstance(self.model, (HDP, RCRP)) else 0)
+        n_out = self.current_KK() + (1 if isinstance(self.model, (HDP, RCRP, RCRF)) else 0)
         raw, prob = np.zeros((len(idx), n_out)), np.zeros((len(idx), n_out))
         draw = np.zeros(len(idx), dtype=np.int32)
         check(lib().bias_model_conditionals(self.h, len(idx), ptr(idx), ptr(u), ptr(raw), ptr(prob), ptr(draw)))
@@ -592,6 +631,68 @@ def CRF_gibbs_sampler(hdp: HDP, xx, zz, n_burnins: int, n_lags: int, n_samples: 
         if n_samples > 0:                                               # :697-701
             KK_list[n_old + n_samples - 1] = hp.KK
             KK_dict[hp.KK] = [np.array(g, dtype=np.int64) for g in zz]
+    finally:
+        rs.close()
+    return KK_list, KK_dict
+
+
+def _flatten_epochs(xx3):
+    """xx::Vector{Vector{Vector{T}}} (epochs of restaurants of customers) -> (list of restaurants, epoch_ptr)"""
+    groups = [g for ep in xx3 for g in ep]
+    eptr = np.concatenate([[0], np.cumsum([len(ep) for ep in xx3])]).astype(np.int64)
+    return groups, eptr
+
+
+def RCRF_gibbs_sampler(rcrf: RCRF, xx, zz, n_burnins: int, n_lags: int, n_samples: int, sample_hyperparam: bool = True,
+                       n_internals: int = 10, store_every: int = 100, filename: str | None = None, join_tables: bool = True,
+                       KK_list: Sequence[int] = (), KK_dict: dict | None = None, ctx: Context | None = None,
+                       verbose: bool = False):
+    """RCRF_gibbs_sampler!(rcrf, xx, zz, n_burnins, n_lags, n_samples, sample_hyperparam, n_internals, store_every,
+    filename, join_tables, KK_list, KK_dict) -> (KK_list, KK_dict)   (src/RCRF.jl:122-938).  xx / zz are lists over
+    epochs of lists over restaurants; zz, rcrf.KK, rcrf.gg and rcrf.aa are updated in place."""
+    ctx = ctx or default_context()
+    groups, eptr = _flatten_epochs(xx)
+    zgroups, _ = _flatten_epochs(zz)
+    data = FlatData(rcrf.component, groups, True)
+    n_iterations = n_burnins + n_samples * (n_lags + 1)
+    n_old = len(KK_list)
+    KK_list = list(KK_list) + [0] * n_samples
+    KK_dict = {} if (KK_dict is None or n_old == 0) else KK_dict
+    try:
+        rs = ResidentSampler(ctx, rcrf, data, _flat_zz(zgroups, True), sample_hyperparam=sample_hyperparam,
+                             n_internals=n_internals, epoch_ptr=eptr, join_tables=join_tables)
+    except _lib.BiasError as e:
+        if e.code == _lib.EINVAL:
+            raise ValueError(str(e)) from None
+        raise
+
+    def snapshot():
+        _scatter_zz(rs.get_zz(), zgroups, True, data.group_ptr)
+        it = iter(zgroups)
+        for ep in zz:
+            for j in range(len(ep)):
+                ep[j] = next(it)
+        return [[np.array(g, dtype=np.int64) for g in ep] for ep in zz]
+
+    try:
+        if n_samples > 0:
+            KK_list[0] = rcrf.KK
+        for iteration in range(1, n_iterations + 1):
+            if iteration > n_burnins:                                   # src/RCRF.jl:226-228
+                rs.set_sample_hyperparam(False)
+            rs.sweep(1)
+            if verbose:
+                s = rs.stats()
+                print(f"iteration: {iteration}, KK={s.KK}, likelihood={s.log_likelihood:.2f}")
+            if (iteration - n_burnins) % (n_lags + 1) == 0 and iteration > n_burnins:
+                i = n_old + (iteration - n_burnins) // (n_lags + 1)
+                KK = rs.current_KK()
+                KK_list[i - 1] = KK
+                KK_dict[KK] = snapshot()
+                if filename is not None and i % store_every == 0:
+                    _store(filename, i, zz=rs.get_zz(), KK_list=np.asarray(KK_list), iteration=iteration)
+        snapshot()
+        rcrf.KK, rcrf.gg, rcrf.aa = rs.rcrf_state()
     finally:
         rs.close()
     return KK_list, KK_dict

@@ -138,6 +138,7 @@ BIAS_API int bias_rcrp_run(bias_ctx *ctx, const bias_conjugate *conj, const bias
 #define BIAS_MODEL_BMM 1
 #define BIAS_MODEL_HDP 2
 #define BIAS_MODEL_RCRP 3
+#define BIAS_MODEL_RCRF 5  /* recurrent Chinese restaurant franchise (src/RCRF.jl): created with bias_rcrf_create */
 #define BIAS_MODEL_CRF 4   /* HDP sampled by CRF_gibbs_sampler! (src/HDP.jl:402-709): bias_model_create with hdp params */
 /* Uploads xx and zz and runs the initialisation pass (src/LDA.jl:91-98, src/BMM.jl:70-75,
  * src/HDP.jl:217-228).  For BMM pass n_groups = 0, group_ptr = NULL; hdp = NULL unless model is HDP. */
@@ -208,6 +209,25 @@ BIAS_API int bias_crf_sweep_with_uniforms(bias_model *m, const double *uniforms 
 /* The seating: tji[n_items] table of each customer within its group, njt / kjt [n_items] customers and dish per table
  * (tables of group j at group_ptr[j] ...), n_tbls[n_groups], mm[KK] tables per dish.  Any pointer may be NULL. */
 BIAS_API int bias_crf_get_tables(bias_model *m, int32_t *tji, int32_t *njt, int32_t *kjt, int32_t *n_tbls, int32_t *mm);
+
+/* ---- RCRF (src/RCRF.jl:122-938, Gaussian1DGaussian1D x Float64) -------------------------- */
+/* RCRF(c, KK, gg, g1, g2, aa, a1, a2, TT), src/RCRF.jl:16-37; gg and aa (one per epoch) travel as separate arrays. */
+typedef struct {
+    int32_t KK;
+    int32_t Kmax;             /* dish-slot capacity (engine parameter) */
+    double  g1, g2, a1, a2;
+    int32_t sample_hyperparam;
+    int32_t n_internals;
+    int32_t join_tables;      /* src/RCRF.jl:130 */
+} bias_rcrf_params;
+/* xx::Vector{Vector{Vector{T}}} arrives flattened: the restaurants of all epochs are the groups (group_ptr), epoch_ptr
+ * [n_epochs + 1] holds the first restaurant of each epoch.  One bias_model_sweep = one iteration of
+ * RCRF_gibbs_sampler! (:217-905): per epoch, tables for customers, joining of same-dish tables, dishes for tables, the
+ * epoch's hyper-parameters.  bias_crf_get_tables returns mm as [n_epochs][KK]. */
+BIAS_API int bias_rcrf_create(bias_ctx *ctx, const bias_conjugate *conj, const bias_data *data, int64_t n_groups,
+                     const int64_t *group_ptr, int64_t n_epochs, const int64_t *epoch_ptr, const int32_t *zz,
+                     const bias_rcrf_params *params, const double *gg, const double *aa, bias_model **out);
+BIAS_API int bias_model_get_rcrf(bias_model *m, int32_t *KK, double *gg /* [n_epochs] */, double *aa /* [n_epochs] */);
 
 /* ---- sharded HDP (groups split over ranks) ---------------------------------- */
 /* One sweep of collapsed_gibbs_sampler!(::HDP) (src/HDP.jl:235-373) cut at the points where ranks must agree:

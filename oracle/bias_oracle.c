@@ -1044,3 +1044,231 @@ double orc_crf_sweep(orc_hdp *h, orc_crf *f, orc_comps *c, const orc_data *d, in
     free(tidx);
     return ll;
 }
+
+/* ======================================================================
+ * src/RCRF.jl — recurrent Chinese restaurant franchise (RCRF_gibbs_sampler!, :122-938)
+ * Per epoch: the CRF's two passes with the dish prior coupled to the neighbouring epochs' menus.
+ * ====================================================================== */
+static int64_t rcrf_mm_colsum(const orc_rcrf *f, int64_t k)
+{
+    int64_t s = 0;
+    for (int64_t t = 0; t < f->TT; ++t) s += f->mm[t * f->Kmax + k];
+    return s;
+}
+
+void orc_rcrf_init(orc_rcrf *f, orc_comps *c, const orc_data *d, const int64_t *z)
+{                                                   /* :177-209 */
+    for (int64_t i = 0; i < f->TT * f->Kmax; ++i) f->mm[i] = 0;
+    for (int64_t t = 0; t < f->TT; ++t)
+        for (int64_t j = f->eptr[t]; j < f->eptr[t + 1]; ++j) {
+            int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0, nt = 0;
+            for (int64_t i = 0; i < n; ++i) {
+                int64_t kk = z[p0 + i], tb = -1;
+                for (int64_t q = 0; q < nt; ++q) if (f->kjt[p0 + q] == kk) { tb = q; break; }
+                if (tb < 0) { tb = nt++; f->kjt[p0 + tb] = kk; f->njt[p0 + tb] = 0; }
+                orc_additem(c, kk, d, p0 + i);
+                f->tji[p0 + i] = tb;
+                f->njt[p0 + tb] += 1;
+            }
+            f->n_tbls[j] = nt;
+            for (int64_t q = 0; q < nt; ++q) f->mm[t * f->Kmax + f->kjt[p0 + q]] += 1;
+        }
+}
+
+static void rcrf_delete_dish(orc_rcrf *f, orc_comps *c, int64_t *z, int64_t kk)
+{                                                   /* :271-284 and its copies */
+    int64_t KK = f->KK, S = f->Kmax, G = f->eptr[f->TT], N = f->ptr[G];
+    for (int64_t i = 0; i < N; ++i) if (z[i] > kk) z[i] -= 1;
+    for (int64_t j = 0; j < G; ++j)
+        for (int64_t q = 0; q < f->n_tbls[j]; ++q) if (f->kjt[f->ptr[j] + q] > kk) f->kjt[f->ptr[j] + q] -= 1;
+    for (int64_t k = kk; k < KK - 1; ++k) orc_comps_move(c, k, k + 1);
+    orc_comps_reset(c, KK - 1);
+    for (int64_t t = 0; t < f->TT; ++t) {
+        for (int64_t k = kk; k < KK - 1; ++k) f->mm[t * S + k] = f->mm[t * S + k + 1];
+        f->mm[t * S + KK - 1] = 0;
+    }
+    f->KK -= 1;
+}
+
+/* log prior weight of every dish for a table of epoch t, and of a new dish in pr[KK] (:303-327, :534-556, :762-768).
+ * Written as the reference writes it, with the O(n) sums; note the reference's L1 uses gg/K' in the base term and aa/K'
+ * in the "+1" term (:313 vs :321) — reproduced. */
+static void rcrf_dish_prior(const orc_rcrf *f, int64_t t, double *pr)
+{
+    int64_t S = f->Kmax, KK = f->KK, TT = f->TT;
+    const int64_t *mt = f->mm + t * S, *mp = (t > 0) ? f->mm + (t - 1) * S : NULL, *mn = (t < TT - 1) ? f->mm + (t + 1) * S : NULL;
+    for (int64_t k = 0; k <= KK; ++k) pr[k] = -INFINITY;
+    if (!mn) {                                      /* last epoch */
+        for (int64_t k = 0; k < KK; ++k) {
+            int64_t cnt = mt[k] + (mp ? mp[k] : 0);
+            if (cnt > 0) pr[k] = log((double)cnt);
+        }
+        pr[KK] = log(f->gg[t]);
+        return;
+    }
+    int64_t KK_curnex = 1, sum_t = 0, sum_n = 0;
+    for (int64_t k = 0; k < KK; ++k) { if (mt[k] + mn[k] > 0) KK_curnex += 1; sum_t += mt[k]; sum_n += mn[k]; }
+    double *L1 = (double *)calloc((size_t)(KK > 0 ? KK : 1), sizeof(double));
+    for (int64_t k = 0; k < KK; ++k)
+        if (mt[k] + mn[k] > 0) L1[k] = rcrp_logsum(mn[k], (double)mt[k] + f->gg[t] / (double)KK_curnex);
+    double L2 = rcrp_logsum(sum_n, (double)sum_t + f->gg[t]);
+    for (int64_t k = 0; k < KK; ++k) {
+        int64_t cnt = mt[k] + (mp ? mp[k] : 0);
+        if (cnt <= 0) continue;
+        double old = L1[k];
+        L1[k] = rcrp_logsum(mn[k], (double)mt[k] + 1.0 + f->aa[t] / (double)KK_curnex);
+        pr[k] = log((double)cnt) + orc_julia_sum(L1, KK) - L2;
+        L1[k] = old;
+    }
+    pr[KK] = log(f->gg[t]) + orc_julia_sum(L1, KK) - L2;
+    free(L1);
+}
+
+static void rcrf_sample_hyperparam(orc_rcrf *f, int64_t t, int64_t m, int64_t KK, int iters, orc_rng *g)
+{                                                   /* :80-118 */
+    int64_t j0 = f->eptr[t], j1 = f->eptr[t + 1], D = j1 - j0;
+    double *logw = (double *)malloc((size_t)(D > 0 ? D : 1) * sizeof(double));
+    for (int it = 0; it < iters; ++it) {
+        int64_t sum_s = 0;
+        for (int64_t j = j0; j < j1; ++j) logw[j - j0] = log(orc_rand_beta(g, f->aa[t] + 1.0, (double)(f->ptr[j + 1] - f->ptr[j])));
+        for (int64_t j = j0; j < j1; ++j) {
+            double p = (double)(f->ptr[j + 1] - f->ptr[j]) / f->aa[t];
+            p = p / (p + 1.0);
+            sum_s += (orc_rand(g) < p) ? 1 : 0;
+        }
+        double aa_shape = f->a1 + (double)m - (double)sum_s, aa_rate = f->a2 - orc_julia_sum(logw, D);
+        f->aa[t] = orc_rand_gamma(g, aa_shape) / aa_rate;
+        double eta = orc_rand_beta(g, f->gg[t] + 1.0, (double)m);
+        double pi_eta = 1.0 / (1.0 + ((double)m * (f->g2 - log(eta))) / (f->g1 + (double)KK - 1.0));
+        if (orc_rand(g) < pi_eta) f->gg[t] = orc_rand_gamma(g, f->g1 + (double)KK) / (f->g2 - log(eta));
+        else f->gg[t] = orc_rand_gamma(g, f->g1 + (double)KK - 1.0) / (f->g2 - log(eta));
+    }
+    free(logw);
+}
+
+double orc_rcrf_sweep(orc_rcrf *f, orc_comps *c, const orc_data *d, int64_t *z, orc_rng *g, const double *uniforms,
+                      int defer_deaths, int join_tables, int sample_hyper, int n_internals)
+{
+    int64_t S = f->Kmax, TT = f->TT, G = f->eptr[TT];
+    int64_t maxn = 1;
+    for (int64_t j = 0; j < G; ++j) if (f->ptr[j + 1] - f->ptr[j] > maxn) maxn = f->ptr[j + 1] - f->ptr[j];
+    double *pp = (double *)malloc((size_t)((S > maxn ? S : maxn) + 2) * sizeof(double));
+    double *pr = (double *)malloc((size_t)(S + 2) * sizeof(double));
+    int64_t *tidx = (int64_t *)malloc((size_t)maxn * sizeof(int64_t));
+    int64_t *tmp = (int64_t *)malloc((size_t)maxn * 3 * sizeof(int64_t));
+#define RCRF_U(idx, which) (uniforms ? uniforms[3 * (idx) + (which)] : orc_rand(g))
+#define RCRF_FAIL() do { free(pp); free(pr); free(tidx); free(tmp); return NAN; } while (0)
+    for (int64_t t = 0; t < TT; ++t) {
+        /* tables for customers (:238-349, :477-576, :705-792) */
+        for (int64_t j = f->eptr[t]; j < f->eptr[t + 1]; ++j) {
+            int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0;
+            for (int64_t ii = 0; ii < n; ++ii) {
+                int64_t i = p0 + ii, kk = z[i], tbl = f->tji[i];
+                orc_delitem(c, kk, d, i);
+                f->njt[p0 + tbl] -= 1;
+                if (f->njt[p0 + tbl] == 0) {
+                    int64_t nt = f->n_tbls[j];
+                    kk = f->kjt[p0 + tbl];
+                    for (int64_t q = tbl; q < nt - 1; ++q) { f->kjt[p0 + q] = f->kjt[p0 + q + 1]; f->njt[p0 + q] = f->njt[p0 + q + 1]; }
+                    f->n_tbls[j] = nt - 1;
+                    for (int64_t q = 0; q < n; ++q) if (f->tji[p0 + q] > tbl) f->tji[p0 + q] -= 1;
+                    f->mm[t * S + kk] -= 1;
+                    if (!defer_deaths && rcrf_mm_colsum(f, kk) == 0) rcrf_delete_dish(f, c, z, kk);
+                }
+                int64_t nt = f->n_tbls[j];
+                for (int64_t q = 0; q < nt; ++q)
+                    pp[q] = log((double)f->njt[p0 + q]) + orc_logpredictive(c, f->kjt[p0 + q], d, i);
+                pp[nt] = log(f->aa[t]) + orc_logpredictive(c, c->K - 1, d, i);
+                orc_lognormalize(pp, nt + 1);
+                tbl = orc_sample(pp, nt + 1, RCRF_U(i, 0));
+                if (tbl == nt) {
+                    f->n_tbls[j] = nt + 1;
+                    f->njt[p0 + tbl] = 0;
+                    rcrf_dish_prior(f, t, pr);
+                    for (int64_t k = 0; k < f->KK; ++k)
+                        pp[k] = (pr[k] == -INFINITY) ? -INFINITY : pr[k] + orc_logpredictive(c, k, d, i);
+                    pp[f->KK] = pr[f->KK] + orc_logpredictive(c, c->K - 1, d, i);
+                    orc_lognormalize(pp, f->KK + 1);
+                    kk = orc_sample(pp, f->KK + 1, RCRF_U(i, 1));
+                    if (kk == f->KK) {
+                        if (f->KK + 1 >= S) RCRF_FAIL();
+                        orc_comps_reset(c, f->KK);
+                        for (int64_t tt = 0; tt < TT; ++tt) f->mm[tt * S + f->KK] = 0;
+                        f->KK += 1;
+                    }
+                    f->kjt[p0 + tbl] = kk;
+                    f->mm[t * S + kk] += 1;
+                }
+                kk = f->kjt[p0 + tbl];
+                f->tji[i] = tbl;
+                f->njt[p0 + tbl] += 1;
+                orc_additem(c, kk, d, i);
+                z[i] = kk;
+            }
+        }
+        /* tables of a restaurant that serve the same dish are joined (:351-377) */
+        if (join_tables)
+            for (int64_t j = f->eptr[t]; j < f->eptr[t + 1]; ++j) {
+                int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0, nt = f->n_tbls[j], nu = 0;
+                int64_t *new_k = tmp, *new_n = tmp + maxn, *map = tmp + 2 * maxn;
+                for (int64_t q = 0; q < nt; ++q) {
+                    int64_t u = -1;
+                    for (int64_t r = 0; r < nu; ++r) if (new_k[r] == f->kjt[p0 + q]) { u = r; break; }
+                    if (u < 0) { u = nu++; new_k[u] = f->kjt[p0 + q]; new_n[u] = 0; }
+                    else f->mm[t * S + f->kjt[p0 + q]] -= 1;
+                    new_n[u] += f->njt[p0 + q];
+                    map[q] = u;
+                }
+                if (nu != nt) {
+                    for (int64_t q = 0; q < n; ++q) f->tji[p0 + q] = map[f->tji[p0 + q]];
+                    for (int64_t r = 0; r < nu; ++r) { f->kjt[p0 + r] = new_k[r]; f->njt[p0 + r] = new_n[r]; }
+                    f->n_tbls[j] = nu;
+                }
+            }
+        /* dishes for tables (:380-461, :606-688, :822-894).  Deviation, documented: when the table is the last one of its
+         * dish in this epoch but the dish lives on in other epochs the reference skips the delitem! of the table's
+         * customers (:395-416, the else belongs to the outer if) and they end up counted twice; here they are removed. */
+        for (int64_t j = f->eptr[t]; j < f->eptr[t + 1]; ++j) {
+            int64_t p0 = f->ptr[j], n = f->ptr[j + 1] - p0;
+            for (int64_t tbl = 0; tbl < f->n_tbls[j]; ++tbl) {
+                int64_t kk = f->kjt[p0 + tbl], nti = 0;
+                f->mm[t * S + kk] -= 1;
+                for (int64_t q = 0; q < n; ++q) if (f->tji[p0 + q] == tbl) tidx[nti++] = p0 + q;
+                for (int64_t q = 0; q < nti; ++q) orc_delitem(c, kk, d, tidx[q]);
+                if (!defer_deaths && rcrf_mm_colsum(f, kk) == 0) rcrf_delete_dish(f, c, z, kk);
+                rcrf_dish_prior(f, t, pr);
+                for (int64_t k = 0; k <= f->KK; ++k) {
+                    if (pr[k] == -INFINITY) { pp[k] = -INFINITY; continue; }
+                    pp[k] = pr[k];
+                    for (int64_t q = 0; q < nti; ++q) pp[k] += orc_logpredictive(c, k < f->KK ? k : c->K - 1, d, tidx[q]);
+                }
+                orc_lognormalize(pp, f->KK + 1);
+                kk = orc_sample(pp, f->KK + 1, RCRF_U(p0 + tbl, 2));
+                if (kk == f->KK) {
+                    if (f->KK + 1 >= S) RCRF_FAIL();
+                    orc_comps_reset(c, f->KK);
+                    for (int64_t tt = 0; tt < TT; ++tt) f->mm[tt * S + f->KK] = 0;
+                    f->KK += 1;
+                }
+                f->kjt[p0 + tbl] = kk;
+                for (int64_t q = 0; q < nti; ++q) { orc_additem(c, kk, d, tidx[q]); z[tidx[q]] = kk; }
+                f->mm[t * S + kk] += 1;
+            }
+        }
+        if (sample_hyper) {                         /* :464-468 */
+            int64_t KK_t = 0, m = 0;
+            for (int64_t k = 0; k < f->KK; ++k) if (f->mm[t * S + k] != 0) KK_t += 1;
+            for (int64_t j = f->eptr[t]; j < f->eptr[t + 1]; ++j) m += f->n_tbls[j];
+            rcrf_sample_hyperparam(f, t, m, KK_t, n_internals, g);
+        }
+    }
+#undef RCRF_U
+#undef RCRF_FAIL
+    if (defer_deaths)
+        for (int64_t k = f->KK - 1; k >= 0; --k) if (rcrf_mm_colsum(f, k) == 0) rcrf_delete_dish(f, c, z, k);
+    free(pp); free(pr); free(tidx); free(tmp);
+    double ll = 0.0;
+    int64_t N = f->ptr[G];
+    for (int64_t i = 0; i < N; ++i) ll += orc_logpredictive(c, z[i], d, i);
+    return ll;
+}

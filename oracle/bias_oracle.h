@@ -173,6 +173,22 @@ double orc_crf_sweep(orc_hdp *h, orc_crf *f, orc_comps *c, const orc_data *d, in
 int64_t orc_crf_table_conditional(const orc_hdp *h, const orc_crf *f, orc_comps *c, const orc_data *d, int64_t j,
                                   int64_t i, int64_t *z, double r, double *raw, double *prob);
 
+/* ---- src/RCRF.jl (recurrent Chinese restaurant franchise, :122-938) ------------------------------
+ * Restaurants of all epochs are flattened: eptr[TT+1] = first restaurant of each epoch, ptr[G+1] = first customer of
+ * each restaurant; tables in CSR arrays as for the CRF; mm[TT*Kmax] row-major tables per (epoch, dish). */
+typedef struct {
+    int64_t KK, Kmax, TT;
+    const int64_t *eptr, *ptr;
+    int64_t *tji, *njt, *kjt, *n_tbls, *mm;
+    double *gg, *aa;   /* [TT] */
+    double g1, g2, a1, a2;
+} orc_rcrf;
+void orc_rcrf_init(orc_rcrf *f, orc_comps *c, const orc_data *d, const int64_t *z);                       /* :177-209 */
+/* One iteration (:217-905): per epoch, tables for customers, joining of same-dish tables, dishes for tables, and the
+ * epoch's hyper-parameters.  uniforms / defer_deaths as for orc_crf_sweep.  NaN on capacity. */
+double orc_rcrf_sweep(orc_rcrf *f, orc_comps *c, const orc_data *d, int64_t *z, orc_rng *g, const double *uniforms,
+                      int defer_deaths, int join_tables, int sample_hyper, int n_internals);
+
 /* Normalised log unsigned Stirling numbers of the first kind, rows n = 1..nmax, packed:
  * entry (n, m), 1 <= m <= n, at index n*(n-1)/2 + (m-1); each row shifted so its maximum is 0.
  * Regenerates the missing src/StirlingNums_10K.mat (snumbersNormalizedSparse, src/HDP.jl:207-209). */

@@ -64,6 +64,13 @@ class _Crf(C.Structure):
                 ("n_tbls", C.c_void_p), ("mm", C.c_void_p)]
 
 
+class _Rcrf(C.Structure):
+    _fields_ = [("KK", C.c_int64), ("Kmax", C.c_int64), ("TT", C.c_int64), ("eptr", C.c_void_p), ("ptr", C.c_void_p),
+                ("tji", C.c_void_p), ("njt", C.c_void_p), ("kjt", C.c_void_p), ("n_tbls", C.c_void_p), ("mm", C.c_void_p),
+                ("gg", C.c_void_p), ("aa", C.c_void_p), ("g1", C.c_double), ("g2", C.c_double), ("a1", C.c_double),
+                ("a2", C.c_double)]
+
+
 class _Rng(C.Structure):
     _fields_ = [("s", C.c_uint64 * 4)]
 
@@ -142,6 +149,10 @@ def lib():
         L.orc_crf_sweep.argtypes = [hp, fp, cp, dpp, vp, rp, vp, i32, i32, i32]
         L.orc_crf_table_conditional.restype = i64
         L.orc_crf_table_conditional.argtypes = [hp, fp, cp, dpp, i64, i64, vp, f64, vp, vp]
+        rfp = C.POINTER(_Rcrf)
+        L.orc_rcrf_init.argtypes = [rfp, cp, dpp, vp]
+        L.orc_rcrf_sweep.restype = f64
+        L.orc_rcrf_sweep.argtypes = [rfp, cp, dpp, vp, rp, vp, i32, i32, i32, i32]
         _lib = L
     return _lib
 
@@ -466,3 +477,34 @@ class CRFState:
         t = lib().orc_crf_table_conditional(C.byref(self.h), C.byref(self.f), self.c.ref(), self.d.ref(), j, i,
                                             _p(self.z), float(r), _p(raw), _p(prob))
         return int(t), raw, prob
+
+
+# ------------------------------------------------------------------ RCRF.jl
+class RCRFState:
+    """Recurrent Chinese restaurant franchise (src/RCRF.jl:122-209).  eptr[TT+1]: first restaurant of each epoch;
+    ptr[G+1]: first customer of each restaurant.  comps.K == Kmax; the last slot stays empty (prototype)."""
+
+    def __init__(self, comps: Comps, data: Data, eptr, ptr, z, KK, gg, g1, g2, aa, a1, a2):
+        self.c, self.d = comps, data
+        self.eptr, self.ptr = _i64(eptr), _i64(ptr)
+        self.TT, self.G = self.eptr.size - 1, self.ptr.size - 1
+        N = int(self.ptr[-1])
+        self.z = _i64(z).copy()
+        self.Kmax = comps.K
+        self.gg = _f64(np.full(self.TT, gg) if np.isscalar(gg) else gg).copy()
+        self.aa = _f64(np.full(self.TT, aa) if np.isscalar(aa) else aa).copy()
+        self.tji, self.njt, self.kjt = (np.zeros(max(N, 1), dtype=np.int64) for _ in range(3))
+        self.n_tbls = np.zeros(max(self.G, 1), dtype=np.int64)
+        self.mm = np.zeros((self.TT, self.Kmax), dtype=np.int64)
+        self.f = _Rcrf(KK, self.Kmax, self.TT, _p(self.eptr), _p(self.ptr), _p(self.tji), _p(self.njt), _p(self.kjt),
+                       _p(self.n_tbls), _p(self.mm), _p(self.gg), _p(self.aa), g1, g2, a1, a2)
+        lib().orc_rcrf_init(C.byref(self.f), comps.ref(), data.ref(), _p(self.z))
+
+    @property
+    def KK(self):
+        return int(self.f.KK)
+
+    def sweep(self, rng: Rng, uniforms=None, defer_deaths=False, join_tables=True, sample_hyper=False, n_internals=10) -> float:
+        u = None if uniforms is None else _f64(uniforms)
+        return lib().orc_rcrf_sweep(C.byref(self.f), self.c.ref(), self.d.ref(), _p(self.z), rng.ref(), _p(u),
+                                    int(defer_deaths), int(join_tables), int(sample_hyper), int(n_internals))
