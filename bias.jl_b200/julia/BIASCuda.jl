@@ -59,6 +59,18 @@ type RcrpParams                # bias_rcrp_params (mutable: KK comes back update
     n_internals::Int32
 end
 
+immutable RcrfParams           # bias_rcrf_params
+    KK::Int32
+    Kmax::Int32
+    g1::Float64
+    g2::Float64
+    a1::Float64
+    a2::Float64
+    sample_hyperparam::Int32
+    n_internals::Int32
+    join_tables::Int32
+end
+
 type HdpParams                 # bias_hdp_params (mutable: KK, gg, aa come back updated)
     KK::Int32
     Kmax::Int32
@@ -262,6 +274,48 @@ function rcrp!(rcrp, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int,
         scatter!(zz, z)
         rcrp.KK = rp.KK
         rcrp.aa[:] = aa
+    finally
+        ccall((:bias_model_destroy, LIB), Cint, (Ptr{Void},), m[1])
+    end
+    KK_list, KK_dict
+end
+
+# ---- RCRF_gibbs_sampler!(rcrf::RCRF, xx, zz, ...)  src/RCRF.jl:122-938
+# xx::Vector{Vector{Vector{T}}} is flattened: the restaurants of all epochs are the groups, epoch_ptr their epochs.
+function rcrf!(rcrf, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int, sample_hyperparam::Bool=true,
+               n_internals::Int=10; join_tables::Bool=true, Kmax::Int=256, seed=0)
+    groups = vcat(xx...); zgroups = vcat(zz...)
+    epoch_ptr = Int64[0; cumsum([length(ep) for ep in xx])]
+    d, keep, datum = flat_data(vcat(groups...))
+    c = conj_spec(rcrf.component, datum)
+    ptr = flat_ptr(zgroups)
+    z = flat_zz(zgroups)
+    rp = RcrfParams(rcrf.KK, Kmax, rcrf.g1, rcrf.g2, rcrf.a1, rcrf.a2, sample_hyperparam, n_internals, join_tables)
+    gg = copy(rcrf.gg); aa = copy(rcrf.aa); KK = Int32[rcrf.KK]
+    m = Ptr{Void}[C_NULL]
+    check(ccall((:bias_rcrf_create, LIB), Cint,
+                (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{RcrfParams},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Void}}),
+                context(seed), [c], [d], length(zgroups), ptr, length(xx), epoch_ptr, z, [rp], gg, aa, m))
+    KK_list = zeros(Int, n_samples); KK_dict = Dict{Int, Vector{Vector{Vector{Int}}}}()
+    try
+        for iteration = 1:(n_burnins + n_samples * (n_lags + 1))
+            if iteration > n_burnins                                            # src/RCRF.jl:226-228
+                check(ccall((:bias_model_set_sample_hyperparam, LIB), Cint, (Ptr{Void}, Int32), m[1], 0))
+            end
+            check(ccall((:bias_model_sweep, LIB), Cint, (Ptr{Void}, Int32), m[1], 1))
+            if (iteration - n_burnins) % (n_lags + 1) == 0 && iteration > n_burnins
+                check(ccall((:bias_model_get_zz, LIB), Cint, (Ptr{Void}, Ptr{Int32}), m[1], z))
+                check(ccall((:bias_model_get_rcrf, LIB), Cint, (Ptr{Void}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}), m[1], KK, gg, aa))
+                scatter!(zgroups, z)            # zgroups aliases the inner vectors of zz
+                s = div(iteration - n_burnins, n_lags + 1)
+                KK_list[s] = KK[1]; KK_dict[Int(KK[1])] = deepcopy(zz)
+            end
+        end
+        check(ccall((:bias_model_get_zz, LIB), Cint, (Ptr{Void}, Ptr{Int32}), m[1], z))
+        check(ccall((:bias_model_get_rcrf, LIB), Cint, (Ptr{Void}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}), m[1], KK, gg, aa))
+        scatter!(zgroups, z)
+        rcrf.KK = KK[1]; rcrf.gg[:] = gg; rcrf.aa[:] = aa
     finally
         ccall((:bias_model_destroy, LIB), Cint, (Ptr{Void},), m[1])
     end

@@ -5,7 +5,8 @@ on one B200, with the serial oracle timed on a bounded sample next to each.
   C1  LDA bars K=10 V=25, 1k docs x 100 tokens
   C2  BMM x Sent, K=64, V=1024, 1M sentences x 64 tokens
   C4  HDP x Gaussian, groups of 100 points (size set by --hdp-groups)
-  C5  RCRP x Gaussian, 100 epochs x 500 points (gen_RCRP_data, demo_RCRP_Gaussian1DGaussian1D.jl)
+  C5  RCRP x Gaussian, 100 epochs x 500 points (gen_RCRP_data, demo_RCRP_Gaussian1DGaussian1D.jl);
+      RCRF x Gaussian, 100 epochs x 200 restaurants x 50 points
 Writes one JSON object per config to stdout."""
 import argparse
 import json
@@ -176,6 +177,41 @@ def c5(ctx, n_epochs, n_per):
             "cpu_sample": "full data, 4th sweep of the serial sampler (O(n_{t+1,k}) look-ahead loops as in the reference)"}
 
 
+def c5_rcrf(ctx, n_epochs, n_rest, n_per):
+    """Config 5, second half: the recurrent Chinese restaurant franchise (RCRF_gibbs_sampler!, src/RCRF.jl) on
+    streaming data: n_epochs epochs of n_rest restaurants, atoms drifting over the epochs."""
+    rng = np.random.default_rng(321)
+    G = n_epochs * n_rest
+    eptr = np.arange(n_epochs + 1, dtype=np.int64) * n_rest
+    ptr = np.arange(G + 1, dtype=np.int64) * n_per
+    epoch = np.repeat(np.arange(G) // n_rest, n_per)
+    atoms = (rng.integers(0, 4, G * n_per) + epoch // 5) % 24
+    x = 3.0 * (atoms + 1) + 0.05 * rng.standard_normal(len(atoms))
+    rcrf = b.RCRF(b.Gaussian1DGaussian1D(float(x.mean()), 100.0, 0.0025), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, n_epochs, Kmax=256)
+    data = b.FlatData.from_csr(b._lib.F64, len(x), group_ptr=ptr, x=x)
+    rs = b.ResidentSampler(ctx, rcrf, data, np.zeros(len(x), dtype=np.int32), sample_hyperparam=True, n_internals=10, epoch_ptr=eptr)
+    rs.sweep(8)
+    rs.set_sample_hyperparam(False)
+    t = timed_sweeps(rs, 8, warm=2)
+    KK = rs.stats().KK
+    z = rs.get_zz()
+    rs.close()
+    homog = sum(np.bincount(atoms[z == c]).max() for c in np.unique(z)) / len(z)
+    ne = min(n_epochs, 10)
+    n_s = int(ptr[eptr[ne]])
+    st = orc.RCRFState(orc.Comps.g1g1(256, float(x.mean()), 100.0, 0.0025), orc.Data.reals(x[:n_s]), eptr[:ne + 1], ptr[:eptr[ne] + 1],
+                       np.zeros(n_s, dtype=np.int64), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
+    r = orc.Rng(1)
+    for _ in range(3):
+        st.sweep(r, sample_hyper=True)
+    t0 = time.perf_counter()
+    st.sweep(r)
+    tc = time.perf_counter() - t0
+    return {"config": f"C5 RCRF x Gaussian {n_epochs} epochs x {n_rest} restaurants x {n_per} points", "items": len(x),
+            "gpu_ms_per_sweep": 1e3 * t, "gpu_items_per_s": len(x) / t, "KK": int(KK), "atoms": int(len(np.unique(atoms))),
+            "homogeneity": homog, "cpu_items_per_s": n_s / tc, "cpu_sample": f"first {ne} epochs, 4th iteration of the serial sampler"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sentences", type=int, default=1_000_000)
@@ -183,7 +219,7 @@ def main():
     args = ap.parse_args()
     ctx = b.Context(0, seed=123)
     for fn in (lambda: c1(ctx), lambda: c2(ctx, args.sentences), lambda: c4(ctx, args.hdp_groups),
-               lambda: c4_crf(ctx, args.hdp_groups), lambda: c5(ctx, 100, 500)):
+               lambda: c4_crf(ctx, args.hdp_groups), lambda: c5(ctx, 100, 500), lambda: c5_rcrf(ctx, 100, 200, 50)):
         print(json.dumps(fn()), flush=True)
     ctx.close()
 
