@@ -365,7 +365,110 @@ __device__ __forceinline__ double diag_after(const GenericParams &p, const Datum
     return warp_sum(part);
 }
 
-#ifdef BIAS_GENERIC_KERNEL_IMPL      // the kernel itself is emitted by model.cu only
+#ifdef BIAS_GENERIC_KERNEL_IMPL      // the kernels themselves are emitted by model.cu only
+// ---------------------------------------------------------------------------------------
+// Gaussian1DGaussian1D x Float64 with few components (n_out <= kItemMaxOut): ONE THREAD per item.
+// With K ~ 20 a warp per item leaves most lanes idle; here a thread evaluates its item's K (+1) scores itself.  The
+// component statistics (n, sum x) are the same addresses for every lane, so a warp's loads of them are single
+// broadcast transactions; the 32 items of a warp are consecutive, i.e. almost always of one group, so the prior row is
+// shared too.  Same arithmetic as the warp-per-item kernel (scores, max-shift, exp, left-to-right sum — the
+// reference's order, src/common.jl:42-52 — and the strict `cw < r` walk of :69-79), same uniforms, same updates.
+// LDA / BMM / HDP; the RCRP prior and the verification modes stay on the warp-per-item kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int kItemMaxOut = 64;
+constexpr int kItemThreads = 256;
+
+__global__ void __launch_bounds__(kItemThreads) gauss_item_sweep_kernel(const GenericParams p) {
+    const Philox philox(p.seed);
+    const bool is_hdp = p.model == BIAS_MODEL_HDP;
+    const int K = p.K, Kpad = p.Kpad, n_out = p.n_out;
+    double diag_acc = 0.0;
+    unsigned long long moved_acc = 0;
+    double sc[kItemMaxOut];
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < p.n_work; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = p.item_idx ? p.item_idx[q] : (p.work_idx32 ? (int64_t)p.work_idx32[q] : p.work_base + q);
+        const int zold = p.z[i];                      // -1: the item is currently unassigned (HDP pending)
+        int32_t *prow = p.prior_rows + (p.row_of ? (size_t)p.row_of[p.row_by_work ? q : i] * Kpad : 0);
+        const double x = p.x[i];
+        double lmax = -INFINITY;
+        for (int k = 0; k < n_out; ++k) {
+            const bool own = (k == zold), fresh = (k >= K);
+            double prior, n = 0.0, sx = 0.0;
+            if (is_hdp)
+                prior = fresh ? log(p.alpha * p.hdp_beta[K])
+                              : log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + p.alpha * p.hdp_beta[k]);
+            else
+                prior = log((double)(__ldcg(prow + k) - (own ? 1 : 0)) + p.alpha);
+            if (!fresh) {
+                n = (double)(__ldcg(p.n_items + k) - (own ? 1 : 0));
+                sx = __ldcg(p.sumx + k) - (own ? x : 0.0);
+            }
+            const double s = prior + g1g1_logpred(n, sx, x, p.m0, p.v0, p.vv);
+            sc[k] = s;
+            lmax = fmax(lmax, s);
+        }
+        const int64_t uidx = (p.item_idx || p.work_idx32) ? q : i;
+        double u;
+        if (p.ext_uniforms) {
+            u = p.ext_uniforms[uidx];
+        } else {
+            uint32_t o[4];
+            philox((uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep, p.rng_stream, o);
+            u = u01_double(o[0], o[1]);
+        }
+        double total = 0.0;
+        for (int k = 0; k < n_out; ++k) {
+            const double e = exp(sc[k] - lmax);
+            sc[k] = e;
+            total += e;
+        }
+        const double target = u * total;
+        int knew = n_out - 1;
+        double cw = 0.0;
+        for (int k = 0; k < n_out; ++k) {
+            cw += sc[k];
+            if (cw >= target) { knew = k; break; }
+        }
+        if (p.frozen) {
+            if (p.draw_out) p.draw_out[q] = knew;
+            continue;
+        }
+        const bool born = is_hdp && knew >= K;      // deferred to the serial birth pass
+        const int kdst = born ? -1 : knew;
+        if (kdst != zold) {
+            if (zold >= 0) {
+                atomicAdd(p.sumx + zold, -x);
+                atomicAdd(p.n_items + zold, -1);
+                if (!p.prior_is_items) atomicAdd(prow + zold, -1);
+            }
+            if (kdst >= 0) {
+                atomicAdd(p.sumx + kdst, x);
+                atomicAdd(p.n_items + kdst, 1);
+                if (!p.prior_is_items) atomicAdd(prow + kdst, 1);
+            }
+            p.z[i] = kdst;
+            if (!born) moved_acc += 1;
+        }
+        if (born) {
+            const unsigned slot = atomicAdd(p.pending_count, 1u);
+            p.pending_list[slot] = (int32_t)i;
+        } else if (p.diag_sum) {
+            diag_acc += g1g1_loglik((double)__ldcg(p.n_items + knew), __ldcg(p.sumx + knew), x, p.m0, p.v0, p.vv);
+        }
+    }
+    if (!p.frozen) {
+        if (p.diag_sum) {
+            diag_acc = warp_sum(diag_acc);
+            if ((threadIdx.x & 31) == 0) atomicAdd(p.diag_sum, diag_acc);
+        }
+        if (p.moved) {
+            for (int o = 16; o > 0; o >>= 1) moved_acc += __shfl_xor_sync(kFull, moved_acc, o);
+            if ((threadIdx.x & 31) == 0 && moved_acc) atomicAdd(p.moved, moved_acc);
+        }
+    }
+}
+
+
 template <int KIND, int DATUM>
 __global__ void __launch_bounds__(kGenThreads, (KIND == BIAS_G1G1 || DATUM == BIAS_INT) ? 8 : 4)
 generic_sweep_kernel(const GenericParams p) {

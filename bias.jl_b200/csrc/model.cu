@@ -336,6 +336,16 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
     p.pending_list = m->pending;
     p.pending_count = reinterpret_cast<unsigned int *>(m->scratch + 3);
 
+    if (p.kind == BIAS_G1G1 && p.n_out <= kItemMaxOut && !faithful && !raw_out && !prob_out && m->model != BIAS_MODEL_RCRP &&
+        !getenv("BIAS_NO_ITEM_KERNEL")) {
+        // few Gaussian components: one thread per item (generic.cuh: gauss_item_sweep_kernel)
+        const int64_t blocks = (p.n_work + kItemThreads - 1) / kItemThreads;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)m->ctx->num_sms * 8));
+        gauss_item_sweep_kernel<<<grid, kItemThreads, 0, m->ctx->stream>>>(p);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+        return BIAS_OK;
+    }
     if (p.kind == BIAS_G1G1) return launch_generic_t<BIAS_G1G1, BIAS_F64>(m, p);
     if (p.datum == BIAS_INT) return launch_generic_t<BIAS_MD, BIAS_INT>(m, p);
     return launch_generic_t<BIAS_MD, BIAS_SENT>(m, p);

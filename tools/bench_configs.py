@@ -216,10 +216,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sentences", type=int, default=1_000_000)
     ap.add_argument("--hdp-groups", type=int, default=100_000)
+    ap.add_argument("--only", default="", help="comma-separated subset of c1,c2,c4,c4crf,c5,c5rcrf")
     args = ap.parse_args()
     ctx = b.Context(0, seed=123)
-    for fn in (lambda: c1(ctx), lambda: c2(ctx, args.sentences), lambda: c4(ctx, args.hdp_groups),
-               lambda: c4_crf(ctx, args.hdp_groups), lambda: c5(ctx, 100, 500), lambda: c5_rcrf(ctx, 100, 200, 50)):
+    runs = {"c1": lambda: c1(ctx), "c2": lambda: c2(ctx, args.sentences), "c4": lambda: c4(ctx, args.hdp_groups),
+            "c4crf": lambda: c4_crf(ctx, args.hdp_groups), "c5": lambda: c5(ctx, 100, 500),
+            "c5rcrf": lambda: c5_rcrf(ctx, 100, 200, 50)}
+    for name, fn in runs.items():
+        if args.only and name not in args.only.split(","):
+            continue
         print(json.dumps(fn()), flush=True)
     ctx.close()
 
