@@ -50,7 +50,8 @@ def _oracle_conditionals(state, data, idx, u):
     return raw, prob, draw
 
 
-@pytest.mark.parametrize("K,V,D,L", [(10, 25, 100, 50), (64, 400, 40, 80), (1024, 3000, 24, 96), (1500, 500, 8, 40)])
+@pytest.mark.parametrize("K,V,D,L", [(10, 25, 100, 50), (64, 400, 40, 80), (200, 300, 20, 70), (300, 150, 16, 90), (700, 90, 12, 60),
+                                     (1024, 3000, 24, 96), (1500, 500, 8, 40)])
 def test_conditionals_and_draws_match_oracle(ctx, K, V, D, L):
     if V == 25:
         xx, _, _ = b.data.bars_lda_corpus(n_groups=D, n_tokens=L, seed=5)
@@ -120,7 +121,7 @@ def test_argument_errors(ctx):
         b.collapsed_gibbs_sampler(b.LDA(b.MultinomialDirichlet(5, 1.0), 3, 0.0), xx, [np.array([0, 1, 2])], 1, 0, 1, ctx=ctx)
 
 
-@pytest.mark.parametrize("K,V", [(10, 25), (1024, 2000)])
+@pytest.mark.parametrize("K,V", [(10, 25), (200, 120), (300, 80), (1024, 2000)])
 def test_sweeps_conserve_counts_exactly(ctx, K, V):
     if V == 25:
         xx, _, _ = b.data.bars_lda_corpus(n_groups=300, n_tokens=100, seed=1)
