@@ -1,5 +1,6 @@
-// crf.cuh — Chinese-restaurant-franchise sampler of the HDP (reference src/HDP.jl:402-709, CRF_gibbs_sampler!)
-// for Gaussian1DGaussian1D x Float64 (the combination the reference exercises, doc/examples/demo_CRF_*.jl).
+// crf.cuh — Chinese-restaurant-franchise samplers (reference src/HDP.jl:402-709 CRF_gibbs_sampler!, src/RCRF.jl
+// RCRF_gibbs_sampler!) for the three item kinds of the reference's demos: Float64 x Gaussian1DGaussian1D
+// (demo_CRF_*, demo_RCRF_Gaussian1DGaussian1D.jl), word ids and Sent x MultinomialDirichlet (demo_RCRF_Multinomial*.jl).
 // Included by hdp.cu inside namespace bias (uses its PhiloxStream, hdp_hyper_kernel, grid1d, compaction kernels).
 //
 // The reference walks the restaurants one after the other; inside a restaurant every step depends on the one
@@ -25,6 +26,13 @@ struct CrfParams {
     int32_t *z, *tji, *njt, *kjt, *n_tbls, *mm;
     int32_t *n_items;           // customers per dish (component statistics, shared with the other samplers)
     double *sumx;
+    // MultinomialDirichlet items
+    const int32_t *word;
+    const int64_t *sent_ptr;
+    const int32_t *sent_word, *sent_count;
+    int32_t *n_wk, *n_k;
+    double beta;
+    int64_t V;
     int32_t *d_KK;              // dish slots in use (grows by atomics during a pass)
     int32_t Kmax;
     double m0, v0, vv, aa, gg;
@@ -87,6 +95,49 @@ __device__ __forceinline__ int crf_draw(double *sc, int n_out, double u, int lan
     return draw_parallel(sc, n_out, lmax, u, lane);
 }
 
+// ---- the conjugate, by item kind -------------------------------------------------------------------------
+// logpredictive(components[k], item) (src/conjugates.jl:92-103, :180, :181-198); k < 0: the empty prototype
+template <int DATUM>
+__device__ __forceinline__ double crf_logpred(const CrfParams &p, int k, int64_t idx) {
+    if (DATUM == BIAS_F64) {
+        const double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
+        return g1g1_logpred(cn, sx, p.x[idx], p.m0, p.v0, p.vv);
+    } else if (DATUM == BIAS_INT) {
+        const double nw = k < 0 ? 0.0 : (double)__ldcg(p.n_wk + (size_t)p.word[idx] * p.Kpad + k);
+        const double nk = k < 0 ? 0.0 : (double)__ldcg(p.n_k + k);
+        return log((p.beta + nw) / (p.beta * (double)p.V + nk));
+    } else {
+        const double nk = k < 0 ? 0.0 : (double)__ldcg(p.n_k + k), bv = p.beta * (double)p.V;
+        double m = 0.0, acc = 0.0, coef = 0.0;
+        for (int64_t t = p.sent_ptr[idx]; t < p.sent_ptr[idx + 1]; ++t) {
+            const double ct = (double)p.sent_count[t];
+            const double nw = k < 0 ? 0.0 : (double)__ldcg(p.n_wk + (size_t)p.sent_word[t] * p.Kpad + k);
+            acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
+            coef -= lgamma(ct + 1.0);
+            m += ct;
+        }
+        return (lgamma(m + 1.0) + coef) + lgamma(bv + nk) - lgamma(bv + nk + m) + acc;       // src/conjugates.jl:193-195
+    }
+}
+// additem! (sign = +1) / delitem! (sign = -1) of one item on dish k; executed by ONE lane
+template <int DATUM>
+__device__ __forceinline__ void crf_item_move(const CrfParams &p, int k, int64_t idx, int sign) {
+    if (DATUM == BIAS_F64) {
+        atomicAdd(p.sumx + k, (double)sign * p.x[idx]);
+    } else if (DATUM == BIAS_INT) {
+        atomicAdd(p.n_wk + (size_t)p.word[idx] * p.Kpad + k, sign);
+        atomicAdd(p.n_k + k, sign);
+    } else {
+        int m = 0;
+        for (int64_t t = p.sent_ptr[idx]; t < p.sent_ptr[idx + 1]; ++t) {
+            atomicAdd(p.n_wk + (size_t)p.sent_word[t] * p.Kpad + k, sign * p.sent_count[t]);
+            m += p.sent_count[t];
+        }
+        atomicAdd(p.n_k + k, sign * m);
+    }
+    atomicAdd(p.n_items + k, sign);
+}
+
 // Restaurants that meet a new atom at the same moment would each open a dish for it (hundreds of duplicates in the
 // first iteration).  A warp whose draw says "new dish" therefore takes a global lock, scores the menu again — it now
 // holds whatever the previous lock holders opened — and opens a dish only if the draw (same uniform) still says so.
@@ -142,6 +193,14 @@ __device__ __forceinline__ double crf_dish_prior(const CrfParams &p, const CrfLo
     return v;
 }
 
+// The number of dishes, read by ONE lane and broadcast: other warps open dishes concurrently, and lanes that read
+// different values would run the scoring loops and the draw's warp collectives with different trip counts.
+__device__ __forceinline__ int crf_read_KK(const CrfParams &p, int lane) {
+    int KK = 0;
+    if (lane == 0) KK = __ldcg(p.d_KK);
+    return __shfl_sync(kFull, KK, 0);
+}
+
 // a new dish: the next free slot (one atomic); -1 when the slots are exhausted
 __device__ __forceinline__ int crf_new_dish(const CrfParams &p, int lane) {
     int k = 0;
@@ -157,6 +216,7 @@ __device__ __forceinline__ int crf_new_dish(const CrfParams &p, int lane) {
 }
 
 // ---- pass 1: a table for every customer (src/HDP.jl:506-587) ----
+template <int DATUM>
 __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,13 +232,11 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
         int nt = p.n_tbls[j];
         for (int ii = 0; ii < n; ++ii) {
             const int64_t i = p0 + ii;
-            const double x = p.x[i];
             int kk = p.z[i], tbl = tji[ii];
             // remove the customer (:511-515)
             int left = 0;
             if (lane == 0) {
-                atomicAdd(p.n_items + kk, -1);
-                atomicAdd(p.sumx + kk, -x);
+                crf_item_move<DATUM>(p, kk, i, -1);
                 left = njt[tbl] - 1;
                 njt[tbl] = left;
             }
@@ -203,36 +261,32 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
             __threadfence();
             __syncwarp();
             // scores of the tables and of a new one (:549-555)
-            for (int t = lane; t < nt; t += 32) {
-                const int kt = kjt[t];
-                const double cn = (double)__ldcg(p.n_items + kt), sx = __ldcg(p.sumx + kt);
-                sc[t] = log((double)njt[t]) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
-            }
-            if (lane == 0) sc[nt] = log(p.aa) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
+            for (int t = lane; t < nt; t += 32) sc[t] = log((double)njt[t]) + crf_logpred<DATUM>(p, kjt[t], i);
+            if (lane == 0) sc[nt] = log(p.aa) + crf_logpred<DATUM>(p, -1, i);
             __syncwarp();
             tbl = crf_draw(sc, nt + 1, crf_draw_uniform(p, i, 0), lane);
             if (tbl == nt) {
                 // a new table draws its dish from the menu (:559-581)
-                const int KK = __ldcg(p.d_KK);
+                const int KK = crf_read_KK(p, lane);
                 const CrfLook L = crf_look(p, KK, lane);
                 for (int k = lane; k < KK; k += 32) {
-                    const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
-                    sc[k] = crf_dish_prior(p, L, k) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+                    const double pr = crf_dish_prior(p, L, k);
+                    sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i);
                 }
-                if (lane == 0) sc[KK] = log(p.gg) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
+                if (lane == 0) sc[KK] = log(p.gg) + crf_logpred<DATUM>(p, -1, i);
                 __syncwarp();
                 const double u_dish = crf_draw_uniform(p, i, 1);
                 int knew = crf_draw(sc, KK + 1, u_dish, lane);
                 const bool locked = knew == KK;
                 if (locked) {
                     crf_lock(p, lane);
-                    const int KK2 = __ldcg(p.d_KK);
+                    const int KK2 = crf_read_KK(p, lane);
                     const CrfLook L2 = crf_look(p, KK2, lane);
                     for (int k = lane; k < KK2; k += 32) {
-                        const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
-                        sc[k] = crf_dish_prior(p, L2, k) + g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
+                        const double pr = crf_dish_prior(p, L2, k);
+                        sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i);
                     }
-                    if (lane == 0) sc[KK2] = log(p.gg) + g1g1_logpred(0.0, 0.0, x, p.m0, p.v0, p.vv);
+                    if (lane == 0) sc[KK2] = log(p.gg) + crf_logpred<DATUM>(p, -1, i);
                     __syncwarp();
                     knew = crf_draw(sc, KK2 + 1, u_dish, lane);
                     if (knew == KK2) {
@@ -252,8 +306,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                     if (lane == 0) {
                         tji[ii] = tbl;
                         njt[tbl] = 1;
-                        atomicAdd(p.n_items + knew, 1);
-                        atomicAdd(p.sumx + knew, x);
+                        crf_item_move<DATUM>(p, knew, i, 1);
                         if (knew != kk) { p.z[i] = knew; moved += 1; }
                     }
                     crf_unlock(p, lane);
@@ -264,8 +317,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
             if (lane == 0) {
                 tji[ii] = tbl;
                 njt[tbl] += 1;
-                atomicAdd(p.n_items + kn, 1);
-                atomicAdd(p.sumx + kn, x);
+                crf_item_move<DATUM>(p, kn, i, 1);
                 if (kn != kk) { p.z[i] = kn; moved += 1; }
             }
             __threadfence();
@@ -277,12 +329,27 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
 }
 
 // ---- pass 2: a dish for every table (src/HDP.jl:593-655) ----
+// score of dish k (k < 0: a new dish) for a whole table: the sum of its customers' individual predictives (:633-643)
+template <int DATUM>
+__device__ __forceinline__ double crf_table_score(const CrfParams &p, int k, const double *xs, const int32_t *ids, int64_t p0, int nti) {
+    double s = 0.0;
+    if (DATUM == BIAS_F64) {
+        const double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
+        for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+    } else {
+        for (int q = 0; q < nti; ++q) s += crf_logpred<DATUM>(p, k, p0 + ids[q]);
+    }
+    return s;
+}
+
+template <int DATUM>
 __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t n_sc = (size_t)(p.max_len > p.Kmax ? p.max_len : p.Kmax) + 2;
     double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n_sc + p.max_len);
-    double *xs = sc + n_sc;                       // the values of the table's customers
+    double *xs = sc + n_sc;                                   // Float64 items: the values of the table's customers
+    int32_t *ids = reinterpret_cast<int32_t *>(xs);           // other items: their positions in the restaurant
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
     unsigned long long moved = 0;
     int32_t *const mm_t = p.mm + (size_t)p.t * p.Kpad;
@@ -302,35 +369,36 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
                 const bool mine = q < n && tji[q] == tbl;
                 const unsigned bal = __ballot_sync(kFull, mine);
                 if (mine) {
-                    const double xv = p.x[p0 + q];
-                    xs[nti + __popc(bal & ((1u << lane) - 1u))] = xv;
-                    sum += xv;
+                    const int slot = nti + __popc(bal & ((1u << lane) - 1u));
+                    if (DATUM == BIAS_F64) {
+                        const double xv = p.x[p0 + q];
+                        xs[slot] = xv;
+                        sum += xv;
+                    } else {
+                        ids[slot] = q;
+                    }
                 }
                 nti += __popc(bal);
             }
-            sum = warp_sum(sum);
+            __syncwarp();
             // the table leaves its dish (:599, :626-628)
-            if (lane == 0) {
-                atomicAdd(mm_t + kk, -1);
-                atomicAdd(p.n_items + kk, -nti);
-                atomicAdd(p.sumx + kk, -sum);
+            if (DATUM == BIAS_F64) {
+                sum = warp_sum(sum);
+                if (lane == 0) {
+                    atomicAdd(p.n_items + kk, -nti);
+                    atomicAdd(p.sumx + kk, -sum);
+                }
+            } else {
+                for (int q = lane; q < nti; q += 32) crf_item_move<DATUM>(p, kk, p0 + ids[q], -1);
             }
+            if (lane == 0) atomicAdd(mm_t + kk, -1);
             __threadfence();
             __syncwarp();
-            // score of every dish for the whole table: the sum of the customers' individual predictives (:633-643)
-            const int KK = __ldcg(p.d_KK);
+            const int KK = crf_read_KK(p, lane);
             const CrfLook L = crf_look(p, KK, lane);
             for (int k = lane; k <= KK; k += 32) {
-                double cn = 0.0, sx = 0.0, s;
-                if (k < KK) {
-                    cn = (double)__ldcg(p.n_items + k);
-                    sx = __ldcg(p.sumx + k);
-                    s = crf_dish_prior(p, L, k);
-                } else {
-                    s = log(p.gg);
-                }
-                if (s != -INFINITY)
-                    for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+                double s = (k < KK) ? crf_dish_prior(p, L, k) : log(p.gg);
+                if (s != -INFINITY) s += crf_table_score<DATUM>(p, k < KK ? k : -1, xs, ids, p0, nti);
                 sc[k] = s;
             }
             __syncwarp();
@@ -339,19 +407,11 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
             const bool locked = knew == KK;
             if (locked) {
                 crf_lock(p, lane);
-                const int KK2 = __ldcg(p.d_KK);
+                const int KK2 = crf_read_KK(p, lane);
                 const CrfLook L2 = crf_look(p, KK2, lane);
                 for (int k = lane; k <= KK2; k += 32) {
-                    double cn = 0.0, sx = 0.0, s_;
-                    if (k < KK2) {
-                        cn = (double)__ldcg(p.n_items + k);
-                        sx = __ldcg(p.sumx + k);
-                        s_ = crf_dish_prior(p, L2, k);
-                    } else {
-                        s_ = log(p.gg);
-                    }
-                    if (s_ != -INFINITY)
-                        for (int q = 0; q < nti; ++q) s_ += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+                    double s_ = (k < KK2) ? crf_dish_prior(p, L2, k) : log(p.gg);
+                    if (s_ != -INFINITY) s_ += crf_table_score<DATUM>(p, k < KK2 ? k : -1, xs, ids, p0, nti);
                     sc[k] = s_;
                 }
                 __syncwarp();
@@ -361,11 +421,17 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
                     if (knew < 0) knew = kk;
                 }
             }
+            if (DATUM == BIAS_F64) {
+                if (lane == 0) {
+                    atomicAdd(p.n_items + knew, nti);
+                    atomicAdd(p.sumx + knew, sum);
+                }
+            } else {
+                for (int q = lane; q < nti; q += 32) crf_item_move<DATUM>(p, knew, p0 + ids[q], 1);
+            }
             if (lane == 0) {
                 kjt[tbl] = knew;
                 atomicAdd(mm_t + knew, 1);
-                atomicAdd(p.n_items + knew, nti);
-                atomicAdd(p.sumx + knew, sum);
                 if (knew != kk) moved += (unsigned long long)nti;
             }
             if (locked) crf_unlock(p, lane);
@@ -410,12 +476,11 @@ __global__ void crf_join_kernel(CrfParams p) {
 }
 
 // diagnostic of src/HDP.jl:669-673: sum of logpredictive(components[zz], xx) with every customer seated
+template <int DATUM>
 __global__ void crf_diag_kernel(CrfParams p, int64_t N, double *out) {
     double acc = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = p.z[i];
-        acc += g1g1_logpred((double)p.n_items[k], p.sumx[k], p.x[i], p.m0, p.v0, p.vv);
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        acc += crf_logpred<DATUM>(p, p.z[i], i);
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }

@@ -662,6 +662,14 @@ static CrfParams crf_params(bias_model *m, const double *ext_uniforms) {
     p.mm = m->crf_mm;
     p.n_items = m->n_items;
     p.sumx = m->sumx;
+    p.word = m->word;
+    p.sent_ptr = m->sent_ptr;
+    p.sent_word = m->sent_word;
+    p.sent_count = m->sent_count;
+    p.n_wk = m->n_wk;
+    p.n_k = m->n_k;
+    p.beta = m->conj.aa;
+    p.V = m->V;
     p.d_KK = m->d_KK;
     p.Kmax = m->hdp.Kmax;
     p.m0 = m->conj.m0;
@@ -699,10 +707,55 @@ static CrfParams rcrf_params(bias_model *m, int t, const double *ext_uniforms) {
     return p;
 }
 
+// the two passes (and the diagnostic) for the model's item kind
+static int crf_launch_passes(bias_model *m, const CrfParams &p, int grid, size_t smem, bool join) {
+    cudaStream_t st = m->ctx->stream;
+    const int64_t Gt = p.g1 - p.g0;
+#define CRF_PASSES(D)                                                                          \
+    do {                                                                                       \
+        crf_tables_kernel<D><<<grid, kCrfWarps * 32, smem, st>>>(p);                            \
+        if (join) crf_join_kernel<<<(unsigned)((Gt + 127) / 128), 128, 0, st>>>(p);             \
+        crf_dishes_kernel<D><<<grid, kCrfWarps * 32, smem, st>>>(p);                            \
+    } while (0)
+    if (m->conj.kind == BIAS_G1G1) CRF_PASSES(BIAS_F64);
+    else if (m->conj.datum == BIAS_INT) CRF_PASSES(BIAS_INT);
+    else CRF_PASSES(BIAS_SENT);
+#undef CRF_PASSES
+    BIAS_CUDA_TRY(cudaGetLastError());
+    m->ctx->launches += join ? 3 : 2;
+    return BIAS_OK;
+}
+
+static int crf_set_smem(size_t smem) {
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel<BIAS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel<BIAS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel<BIAS_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel<BIAS_INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel<BIAS_SENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel<BIAS_SENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    return BIAS_OK;
+}
+
+static int crf_launch_diag(bias_model *m) {
+    bias_ctx *ctx = m->ctx;
+    if (m->N <= 0) return BIAS_OK;
+    const CrfParams p = crf_params(m, nullptr);
+    double *out = reinterpret_cast<double *>(m->scratch);
+    const int grid = grid1d(ctx, m->N, 256, 4);
+    if (m->conj.kind == BIAS_G1G1) crf_diag_kernel<BIAS_F64><<<grid, 256, 0, ctx->stream>>>(p, m->N, out);
+    else if (m->conj.datum == BIAS_INT) crf_diag_kernel<BIAS_INT><<<grid, 256, 0, ctx->stream>>>(p, m->N, out);
+    else crf_diag_kernel<BIAS_SENT><<<grid, 256, 0, ctx->stream>>>(p, m->N, out);
+    BIAS_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 1;
+    return BIAS_OK;
+}
+
 int crf_create(bias_model *m) {
     cudaStream_t st = m->ctx->stream;
-    if (m->conj.kind != BIAS_G1G1)
-        return fail(BIAS_EINVAL, "the CRF sampler covers Gaussian1DGaussian1D x Float64 (the combination the reference exercises)");
     if (crf_smem_bytes((int)m->max_group_len, m->hdp.Kmax) > 200 * 1024)
         return fail(BIAS_ERANGE, "CRF: groups of %lld items with Kmax = %d do not fit the per-warp staging buffers",
                     (long long)m->max_group_len, m->hdp.Kmax);
@@ -770,17 +823,9 @@ int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     if (m->G > 0) {
         const CrfParams p = crf_params(m, ext_uniforms_dev);
         const size_t smem = crf_smem_bytes(p.max_len, p.Kmax);
-        static size_t smem_set = 0;
-        if (smem > 48 * 1024 && smem > smem_set) {
-            BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            smem_set = smem;
-        }
+        BIAS_TRY(crf_set_smem(smem));
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m->G + kCrfWarps - 1) / kCrfWarps, (int64_t)ctx->num_sms * 8));
-        crf_tables_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
-        crf_dishes_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
-        BIAS_CUDA_TRY(cudaGetLastError());
-        ctx->launches += 2;
+        BIAS_TRY(crf_launch_passes(m, p, grid, smem, false));
     }
     int32_t kk = 0;
     int err = 0;
@@ -808,11 +853,7 @@ int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
             hdp_host_hyper(m, (double)mt, hyper[0], hyper[1]);
         }
     }
-    if (m->N > 0) {
-        crf_diag_kernel<<<grid1d(ctx, m->N, 256, 4), 256, 0, st>>>(crf_params(m, nullptr), m->N, reinterpret_cast<double *>(m->scratch));
-        BIAS_CUDA_TRY(cudaGetLastError());
-        ctx->launches += 1;
-    }
+    BIAS_TRY(crf_launch_diag(m));
     m->sweep_index += 1;
     m->stats_pending = true;
     return BIAS_OK;
@@ -835,23 +876,14 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
     const size_t smem = crf_smem_bytes((int)m->max_group_len, m->hdp.Kmax);
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    BIAS_TRY(crf_set_smem(smem));
     std::vector<int32_t> mm_row(Kpad);
     for (int t = 0; t < T; ++t) {
         const CrfParams p = rcrf_params(m, t, ext_uniforms_dev);
         const int64_t Gt = p.g1 - p.g0;
         if (Gt <= 0) continue;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Gt + kCrfWarps - 1) / kCrfWarps, (int64_t)ctx->num_sms * 8));
-        crf_tables_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
-        if (m->crf_join) crf_join_kernel<<<(unsigned)((Gt + 127) / 128), 128, 0, st>>>(p);
-        crf_dishes_kernel<<<grid, kCrfWarps * 32, smem, st>>>(p);
-        BIAS_CUDA_TRY(cudaGetLastError());
-        ctx->launches += m->crf_join ? 3 : 2;
+        BIAS_TRY(crf_launch_passes(m, p, grid, smem, m->crf_join != 0));
         if (m->hdp.sample_hyperparam) {             // src/RCRF.jl:464-468 -> :80-118
             unsigned long long *d_m = m->scratch + 5;
             unsigned long long mt = 0;
@@ -884,11 +916,7 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     if (err == 2)
         return fail(BIAS_ERANGE, "RCRF: Kmax = %d dish slots exhausted (KK = %d); construct the model with a larger Kmax", m->hdp.Kmax, kk);
     BIAS_TRY(crf_prune(m));
-    if (m->N > 0) {
-        crf_diag_kernel<<<grid1d(ctx, m->N, 256, 4), 256, 0, st>>>(crf_params(m, nullptr), m->N, reinterpret_cast<double *>(m->scratch));
-        BIAS_CUDA_TRY(cudaGetLastError());
-        ctx->launches += 1;
-    }
+    BIAS_TRY(crf_launch_diag(m));
     m->hdp.aa = m->h_aa_t[0];
     m->hdp.gg = m->h_gg_t[0];
     m->sweep_index += 1;

@@ -108,10 +108,75 @@ def test_crf_gibbs_sampler_entry_point(ctx):
     assert abs(hdp.KK - st.KK) <= 3, (hdp.KK, st.KK)
 
 
+def _md_case(kind, seed, lens, V=25):
+    rng = np.random.default_rng(seed)
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N = int(ptr[-1])
+    if kind == "int":
+        topics = b.data.gen_bars(6, V, 0.0)
+        zt = rng.integers(0, 6, N)
+        w = np.array([rng.choice(V, p=topics[k]) for k in zt])
+        return b.MultinomialDirichlet(V, 2.5), orc.Data.words(w), lambda K: orc.Comps.md(K, V, 2.5), ptr, \
+            b.FlatData.from_csr(b._lib.INT, N, group_ptr=ptr, word=w), N
+    sents, _, _ = b.data.bars_bmm_sentences(N, 10, 6, V, seed)
+    sp = np.concatenate([[0], np.cumsum([len(s_) for s_ in sents])]).astype(np.int64)
+    sw, sc = np.concatenate([s_.w for s_ in sents]), np.concatenate([s_.c for s_ in sents])
+    return b.MultinomialDirichlet(V, 2.5), orc.Data.sents(sp, sw, sc), lambda K: orc.Comps.md(K, V, 2.5), ptr, \
+        b.FlatData.from_csr(b._lib.SENT, N, group_ptr=ptr, sent_ptr=sp, sent_word=sw, sent_count=sc), N
+
+
+@pytest.mark.parametrize("kind", ["int", "sent"])
+def test_single_restaurant_iteration_is_reproduced_exactly_for_multinomial_items(ctx, kind):
+    """The same exact-reproduction check for word-id and Sent items (MultinomialDirichlet): a table's score for a dish is
+    the sum of its customers' individual predictives, counts move with the whole table."""
+    comp, odata, ocomp, ptr, data, N = _md_case(kind, 4, [70])
+    KK, Kmax = 3, 40
+    rng = np.random.default_rng(9)
+    z0 = rng.integers(0, KK, N).astype(np.int32)
+    hdp = b.HDP(comp, KK, 1.3, 0.1, 0.1, 0.9, 0.1, 0.1, Kmax=Kmax)
+    rs = b.ResidentSampler(ctx, hdp, data, z0, sample_hyperparam=False, crf=True)
+    st = orc.CRFState(ocomp(Kmax), odata, ptr, z0, KK, 1.3, 0.1, 0.1, 0.9, 0.1, 0.1)
+    r = orc.Rng(1)
+    for sweep in range(5):
+        u = rng.random(3 * N)
+        st.sweep(r, uniforms=u, defer_deaths=True)
+        rs.crf_sweep_with_uniforms(u)
+        t = rs.crf_tables()
+        nt = int(st.n_tbls[0])
+        assert rs.current_KK() == st.KK and np.array_equal(rs.get_zz(), st.z), sweep
+        assert t["n_tbls"][0] == nt and np.array_equal(t["tji"], st.tji[:N]) and np.array_equal(t["kjt"][:nt], st.kjt[:nt])
+        assert np.array_equal(t["mm"], st.mm[:st.KK])
+        comp_g = rs.components()
+        assert np.array_equal(comp_g["mi"], st.c.mi[:st.KK]) and np.array_equal(comp_g["mm"], st.c.mm[:st.KK])
+    rs.close()
+
+
+@pytest.mark.parametrize("kind", ["int", "sent"])
+def test_many_restaurants_with_multinomial_items_keep_the_seating_consistent(ctx, kind):
+    lens = np.random.default_rng(1).integers(15, 40, 60)
+    comp, odata, ocomp, ptr, data, N = _md_case(kind, 6, lens)
+    hdp = b.HDP(comp, 2, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=64)
+    rs = b.ResidentSampler(ctx, hdp, data, np.random.default_rng(2).integers(0, 2, N).astype(np.int32), sample_hyperparam=True,
+                           n_internals=3, crf=True)
+    for sweep in range(8):
+        rs.sweep(1)
+        hp, _ = rs.hdp_state()
+        z = rs.get_zz()
+        t = rs.crf_tables()
+        comp_g = rs.components()
+        check_crf_invariants(z, ptr, t["tji"], t["njt"], t["kjt"], t["n_tbls"], t["mm"], hp.KK, comp_g["nn"])
+    V = comp.dd
+    mi = np.zeros((hp.KK, V), dtype=np.int64)
+    if kind == "int":
+        np.add.at(mi, (z, np.asarray(odata.w)), 1)
+    else:
+        item = np.repeat(np.arange(N), np.diff(odata.sptr))
+        np.add.at(mi, (z[item], odata.sw), odata.sc)
+    assert np.array_equal(comp_g["mi"], mi)
+    rs.close()
+
+
 def test_crf_argument_errors(ctx):
-    lda_like = b.HDP(b.MultinomialDirichlet(5, 1.0), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
-    with pytest.raises(ValueError):
-        b.CRF_gibbs_sampler(lda_like, [np.array([0, 1, 2])], [np.zeros(3, dtype=np.int64)], 1, 0, 1, ctx=ctx)
     rng = np.random.default_rng(0)
     x = [np.concatenate([10.0 * k + 0.01 * rng.standard_normal(20) for k in range(6)])]
     hdp = b.HDP(b.Gaussian1DGaussian1D(25.0, 100.0, 0.001), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=3)

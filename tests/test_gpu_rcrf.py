@@ -64,6 +64,34 @@ def test_one_restaurant_per_epoch_is_reproduced_exactly(ctx, join):
     rs.close()
 
 
+@pytest.mark.parametrize("kind", ["int", "sent"])
+def test_one_restaurant_per_epoch_is_reproduced_exactly_for_multinomial_items(ctx, kind):
+    """demo_RCRF_MultinomialDirichlet(.jl / _sparse.jl): word-id and Sent items."""
+    from test_gpu_crf import _md_case
+    TT = 4
+    lens = [40, 55, 35, 50]
+    comp, odata, ocomp, ptr, data, N = _md_case(kind, 8, lens)
+    eptr = np.arange(TT + 1, dtype=np.int64)
+    KK, Kmax = 3, 40
+    rng = np.random.default_rng(3)
+    z0 = rng.integers(0, KK, N).astype(np.int32)
+    gg, aa = 0.7 + rng.random(TT), 0.6 + rng.random(TT)
+    rcrf = b.RCRF(comp, KK, gg, 0.1, 0.1, aa, 0.1, 0.1, Kmax=Kmax)
+    rs = b.ResidentSampler(ctx, rcrf, data, z0, sample_hyperparam=False, epoch_ptr=eptr)
+    st = orc.RCRFState(ocomp(Kmax), odata, eptr, ptr, z0, KK, gg, 0.1, 0.1, aa, 0.1, 0.1)
+    r = orc.Rng(1)
+    for sweep in range(5):
+        u = rng.random(3 * N)
+        st.sweep(r, uniforms=u, defer_deaths=True)
+        rs.crf_sweep_with_uniforms(u)
+        t = rs.crf_tables()
+        assert rs.current_KK() == st.KK and np.array_equal(rs.get_zz(), st.z), sweep
+        assert np.array_equal(t["n_tbls"], st.n_tbls[:TT]) and np.array_equal(t["tji"], st.tji[:N])
+        assert np.array_equal(t["mm"], st.mm[:, :st.KK])
+        assert np.array_equal(rs.components()["mi"], st.c.mi[:st.KK])
+    rs.close()
+
+
 def test_many_restaurants_keep_every_epoch_consistent(ctx):
     TT, G_per = 6, 40
     x, eptr, ptr, atoms, rng = _data(5, TT, G_per, 15, 50)
