@@ -210,7 +210,7 @@ BIAS_API int bias_crf_sweep_with_uniforms(bias_model *m, const double *uniforms 
  * (tables of group j at group_ptr[j] ...), n_tbls[n_groups], mm[KK] tables per dish.  Any pointer may be NULL. */
 BIAS_API int bias_crf_get_tables(bias_model *m, int32_t *tji, int32_t *njt, int32_t *kjt, int32_t *n_tbls, int32_t *mm);
 
-/* ---- RCRF (src/RCRF.jl:122-938, Gaussian1DGaussian1D x Float64) -------------------------- */
+/* ---- RCRF (src/RCRF.jl:122-938; Float64, word-id and Sent items) -------------------------- */
 /* RCRF(c, KK, gg, g1, g2, aa, a1, a2, TT), src/RCRF.jl:16-37; gg and aa (one per epoch) travel as separate arrays. */
 typedef struct {
     int32_t KK;
