@@ -79,6 +79,13 @@ enum : uint32_t { kStreamItemDraw = 1, kStreamTable = 2, kStreamHyper = 3, kStre
 #ifdef __CUDACC__
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// x / y as one MUFU.RCP and one FMUL (no denormal rescaling: the callers' divisors are >= alpha or >= V beta)
+__device__ __forceinline__ float fast_div(float x, float y) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+    return x * r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);

@@ -245,8 +245,8 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             const int jo = kold >> 7;
             const int cn = cnt_s[kold];
             const float r_old = r_s[r_pos(kold)];
-            const float inv = __fdividef(r_old, (float)cn + alpha);            // 1/(n_k + V beta)
-            const float inv_rm = __fdividef(inv, 1.f - inv);                   // 1/(n_k - 1 + V beta)
+            const float inv = fast_div(r_old, (float)cn + alpha);            // 1/(n_k + V beta)
+            const float inv_rm = fast_div(inv, 1.f - inv);                   // 1/(n_k - 1 + V beta)
             const float r_rm = ((float)(cn - 1) + alpha) * inv_rm;
 
             // ---- pass 1: chunk sums of n_wk * r (beta * sum r is added per chunk) ----
@@ -328,8 +328,8 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 // ---- additem!: the document's row changes only when the topic does ----
                 const int cn2 = cnt_s[knew];
                 const float r2 = r_s[r_pos(knew)];
-                const float inv2 = __fdividef(r2, (float)cn2 + alpha);
-                float inv_new = __fdividef(inv2, 1.f + inv2);                      // 1/(n_k + 1 + V beta)
+                const float inv2 = fast_div(r2, (float)cn2 + alpha);
+                float inv_new = fast_div(inv2, 1.f + inv2);                      // 1/(n_k + 1 + V beta)
                 const float r_new = ((float)(cn2 + 1) + alpha) * inv_new;
                 if (knew == kold) inv_new = inv;
                 __syncwarp();
