@@ -172,7 +172,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline_run(n_docs: int, n_sweeps: int, warm: int = 0):
+def cpu_baseline_run(n_docs: int, n_sweeps: int, warm: int = 0, diag_mode: int = 0):
     """The reference's serial sampler (oracle/bias_oracle.c, a port of src/LDA.jl:113-133) on the
     first n_docs documents of the workload at full K and V, sampling-only (the O(V) monitoring
     diagnostic of src/conjugates.jl:205 is skipped, which favours the reference)."""
@@ -186,7 +186,7 @@ def cpu_baseline_run(n_docs: int, n_sweeps: int, warm: int = 0):
     for s in range(warm + n_sweeps):
         u = rng.random(len(words))
         t0 = time.perf_counter()
-        state.sweep(u, diag_mode=0)
+        state.sweep(u, diag_mode=diag_mode)
         if s >= warm:
             times.append(time.perf_counter() - t0)
     return len(words), times
@@ -440,6 +440,11 @@ def ours(args):
         cpu = {"value": n_tok / times[0], "unit": "tokens/s", "cores": 1, "kind": "port",
                "sample": f"first {args.ref_docs} documents ({n_tok} tokens) of the same workload, one sweep of the "
                          f"serial Float64 sampler (oracle port of src/LDA.jl:113-133), sampling only"}
+        # the reference as it runs: every token also evaluates the O(V) monitoring diagnostic of src/conjugates.jl:205
+        f_docs = max(1, args.ref_docs // 50)
+        f_tok, f_times = cpu_baseline_run(f_docs, 1, 0, diag_mode=2)
+        cpu["faithful_value"] = f_tok / f_times[0]
+        cpu["faithful_sample"] = f"first {f_docs} documents ({f_tok} tokens), same sweep with the per-token O(V) diagnostic"
     if rank == 0:
         line = {
             "metric": "lda_gibbs_token_samples_per_sec_K1024", "value": value, "unit": "tokens/s",

@@ -726,8 +726,9 @@ static int crf_launch_passes(bias_model *m, const CrfParams &p, int grid, size_t
     return BIAS_OK;
 }
 
-static int crf_set_smem(size_t smem) {
-    static size_t smem_set = 0;
+static int crf_set_smem(bias_model *m, size_t smem) {
+    static size_t smem_cache[kMaxDevices] = {};          // function attributes are per device
+    size_t &smem_set = smem_cache[m->ctx->device % kMaxDevices];
     if (smem > 48 * 1024 && smem > smem_set) {
         BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_tables_kernel<BIAS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BIAS_CUDA_TRY(cudaFuncSetAttribute(crf_dishes_kernel<BIAS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -823,7 +824,7 @@ int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     if (m->G > 0) {
         const CrfParams p = crf_params(m, ext_uniforms_dev);
         const size_t smem = crf_smem_bytes(p.max_len, p.Kmax);
-        BIAS_TRY(crf_set_smem(smem));
+        BIAS_TRY(crf_set_smem(m, smem));
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((m->G + kCrfWarps - 1) / kCrfWarps, (int64_t)ctx->num_sms * 8));
         BIAS_TRY(crf_launch_passes(m, p, grid, smem, false));
     }
@@ -876,7 +877,7 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 8 * sizeof(unsigned long long), st));
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
     const size_t smem = crf_smem_bytes((int)m->max_group_len, m->hdp.Kmax);
-    BIAS_TRY(crf_set_smem(smem));
+    BIAS_TRY(crf_set_smem(m, smem));
     std::vector<int32_t> mm_row(Kpad);
     for (int t = 0; t < T; ++t) {
         const CrfParams p = rcrf_params(m, t, ext_uniforms_dev);

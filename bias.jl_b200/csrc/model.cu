@@ -58,7 +58,8 @@ static int grid_for(bias_ctx *ctx, int64_t n, int threads, int per_sm = 8) {
 // ---------------------------------------------------------------------------------------
 template <int NCH>
 static int launch_lda_fast_t(bias_model *m, const LdaFastParams &p) {
-    static int ctas_per_sm = 0;
+    static int ctas_cache[kMaxDevices] = {};          // function attributes are per device
+    int &ctas_per_sm = ctas_cache[m->ctx->device % kMaxDevices];
     const size_t smem = lda_fast_smem_bytes(NCH);
     const int threads = lda_fast_warps(NCH) * 32;
     if (ctas_per_sm == 0) {
@@ -79,7 +80,8 @@ static int launch_lda_fast_t(bias_model *m, const LdaFastParams &p) {
 
 template <int NCH>
 static int launch_lda_tma_t(bias_model *m, const LdaFastParams &p) {
-    static bool configured = false;
+    static bool conf_cache[kMaxDevices] = {};
+    bool &configured = conf_cache[m->ctx->device % kMaxDevices];
     const size_t smem = lda_tma_smem_bytes(NCH);
     if (!configured) {
         BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_tma_kernel<NCH>,
@@ -96,7 +98,8 @@ static int launch_lda_tma_t(bias_model *m, const LdaFastParams &p) {
 
 template <int NCK, int WARPS = kHalfWarps>
 static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
-    static int ctas_per_sm = 0;
+    static int ctas_cache[kMaxDevices] = {};          // function attributes are per device
+    int &ctas_per_sm = ctas_cache[m->ctx->device % kMaxDevices];
     const size_t smem = lda_half_smem_bytes(NCK, WARPS);
     const int threads = WARPS * 32;
     if (ctas_per_sm == 0) {
@@ -121,7 +124,8 @@ static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
 
 template <int NC8, int WARPS = kH16Warps, int CTAS = 3>
 static int launch_lda_half16_t(bias_model *m, const LdaFastParams &p) {
-    static int ctas_per_sm = 0;
+    static int ctas_cache[kMaxDevices] = {};          // function attributes are per device
+    int &ctas_per_sm = ctas_cache[m->ctx->device % kMaxDevices];
     const size_t smem = lda_half16_smem_bytes(NC8, WARPS);
     const int threads = WARPS * 32;
     if (ctas_per_sm == 0) {
@@ -266,8 +270,10 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
 template <int KIND, int DATUM>
 static int launch_generic_t(bias_model *m, const GenericParams &p) {
     const size_t smem = generic_smem_bytes(p.n_out);
-    static size_t smem_set = 0;
-    static int ctas_per_sm = 0;
+    static size_t smem_cache[kMaxDevices] = {};
+    size_t &smem_set = smem_cache[m->ctx->device % kMaxDevices];
+    static int ctas_cache[kMaxDevices] = {};          // function attributes are per device
+    int &ctas_per_sm = ctas_cache[m->ctx->device % kMaxDevices];
     if (smem > 48 * 1024 && smem > smem_set) {
         BIAS_CUDA_TRY(cudaFuncSetAttribute(generic_sweep_kernel<KIND, DATUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;

@@ -4,6 +4,8 @@
 #include <random>
 #include "common.cuh"
 
+constexpr int kMaxDevices = 64;     // size of the per-device caches of launch configurations
+
 struct bias_ctx {
     int device = 0;
     uint64_t seed = 0;
