@@ -1,6 +1,7 @@
 """Size-independent properties at BASELINE.json's full configuration sizes (the oracle cannot run these in
 reasonable time): exact integer conservation of every count table against a recomputation from the returned
-assignments, on 100 M tokens (C3), 1 M sentences (C2) and 10 M points (C4)."""
+assignments, on 100 M tokens (C3), 1 M sentences (C2), 10 M points (C4, both HDP samplers) and the 100-epoch RCRP /
+RCRF workloads (C5), plus the seating invariants of the franchise samplers."""
 import numpy as np
 import pytest
 
@@ -93,5 +94,102 @@ def test_c4_hdp_10m_points_counts_conserved(ctx):
     assert n_atoms <= hp.KK <= n_atoms + 6
     # every inferred component is pure in the generating atoms
     homog = sum(np.bincount(zt.reshape(-1)[z == c]).max() for c in range(hp.KK)) / len(z)
+    assert homog > 0.99
+    rs.close()
+
+
+def _seating_is_consistent(z, ptr, tji, njt, kjt, n_tbls, KK):
+    """The franchise invariants of tests/test_oracle_crf.py::check_crf_invariants, vectorised: every customer sits at
+    an existing table of its restaurant and eats that table's dish, njt counts the customers of each table, no
+    table is empty.  Returns the number of tables per (restaurant, dish slot) as flat (group, dish) arrays."""
+    n_items, lens = len(z), np.diff(ptr)
+    group = np.repeat(np.arange(len(lens)), lens)
+    assert ((z >= 0) & (z < KK)).all() and (tji >= 0).all() and (tji < n_tbls[group]).all()
+    assert ((n_tbls == 0) == (lens == 0)).all()
+    slot = ptr[group] + tji                                       # the table's position in njt / kjt
+    assert np.array_equal(kjt[slot], z)
+    live = (np.arange(n_items) - ptr[group]) < n_tbls[group]      # table slots in use
+    seated = np.bincount(slot, minlength=n_items)
+    assert np.array_equal(seated[live], njt[live]) and (seated[~live] == 0).all() and (njt[live] > 0).all()
+    return group[live], kjt[live]
+
+
+def test_c4_crf_10m_points_seating_consistent(ctx):
+    """Config 4 through the Chinese-restaurant-franchise sampler (CRF_gibbs_sampler!, src/HDP.jl:402-709)."""
+    rng = np.random.default_rng(123)
+    n_groups, n_per, n_atoms = 100_000, 100, 20
+    ks = rng.integers(0, n_atoms, (n_groups, 4))
+    zt = np.take_along_axis(ks, rng.integers(0, 4, (n_groups, n_per)), axis=1)
+    x = (2.0 * (zt + 1) + np.sqrt(0.001) * rng.standard_normal(zt.shape)).reshape(-1)
+    hdp = b.HDP(b.Gaussian1DGaussian1D(float(x.mean()), 10.0, 0.001), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=256)
+    ptr = np.arange(n_groups + 1, dtype=np.int64) * n_per
+    data = b.FlatData.from_csr(b._lib.F64, len(x), group_ptr=ptr, x=x)
+    rs = b.ResidentSampler(ctx, hdp, data, np.zeros(len(x), dtype=np.int32), sample_hyperparam=True, n_internals=5, crf=True)
+    rs.sweep(6)
+    hp, _ = rs.hdp_state()
+    z, t, comp = rs.get_zz(), rs.crf_tables(), rs.components()
+    _, dish = _seating_is_consistent(z, ptr, t["tji"], t["njt"], t["kjt"], t["n_tbls"], hp.KK)
+    assert np.array_equal(t["mm"], np.bincount(dish, minlength=hp.KK)) and (t["mm"] > 0).all()
+    assert np.array_equal(comp["nn"], np.bincount(z, minlength=hp.KK))
+    assert np.allclose(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=hp.KK), rtol=1e-9)
+    assert n_atoms <= hp.KK <= n_atoms + 12
+    homog = sum(np.bincount(zt.reshape(-1)[z == c]).max() for c in range(hp.KK)) / len(z)
+    assert homog > 0.99
+    rs.close()
+
+
+def test_c5_rcrp_100_epochs_counts_conserved(ctx):
+    """Config 5, gen_RCRP_data(fill(500, 100), 0.5) (src/generate_data.jl:57): per-epoch cluster sizes, component
+    statistics and the chain rule (a cluster that skipped an epoch does not come back, src/RCRP.jl:309-331)."""
+    n_epochs, n_per = 100, 500
+    _, zz_true, _ = b.data.gen_rcrp_data([n_per] * n_epochs, 0.5, seed=123)
+    rng = np.random.default_rng(5)
+    xx = [10.0 * (z + 1) + 0.1 * rng.standard_normal(len(z)) for z in zz_true]
+    x = np.concatenate(xx)
+    rcrp = b.RCRP(b.Gaussian1DGaussian1D(float(xx[0].mean()), 2.0, 0.01), 1, 1.0, n_epochs, 1.0, 1.0, Kmax=256)
+    rs = b.ResidentSampler(ctx, rcrp, b.FlatData(rcrp.component, xx, True), np.zeros(len(x), dtype=np.int32),
+                           sample_hyperparam=True, n_internals=10)
+    rs.sweep(12)
+    KK = rs.current_KK()
+    z, comp = rs.get_zz(), rs.components()
+    _, aa = rs.rcrp_state()
+    assert set(np.unique(z)) == set(range(KK)) and (aa > 0).all() and len(aa) == n_epochs
+    assert np.array_equal(comp["nn"], np.bincount(z, minlength=KK))
+    assert np.allclose(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=KK), rtol=1e-9)
+    per_epoch = np.stack([np.bincount(z[t * n_per:(t + 1) * n_per], minlength=KK) for t in range(n_epochs)])
+    for k in range(KK):                     # the epochs a cluster lives in are contiguous
+        on = np.flatnonzero(per_epoch[:, k] > 0)
+        assert len(on) == on[-1] - on[0] + 1, k
+    zt = np.concatenate(zz_true)
+    homog = sum(np.bincount(zt[z == c]).max() for c in range(KK)) / len(z)
+    assert homog > 0.97
+    rs.close()
+
+
+def test_c5_rcrf_100_epochs_seating_consistent(ctx):
+    """Config 5, the franchise over epochs (RCRF_gibbs_sampler!, src/RCRF.jl:122-938): 100 epochs x 200 restaurants x
+    50 points; the seating invariants per restaurant, the tables per (epoch, dish), the component statistics."""
+    n_epochs, n_rest, n_per = 100, 200, 50
+    rng = np.random.default_rng(321)
+    G = n_epochs * n_rest
+    eptr = np.arange(n_epochs + 1, dtype=np.int64) * n_rest
+    ptr = np.arange(G + 1, dtype=np.int64) * n_per
+    epoch = np.repeat(np.arange(G) // n_rest, n_per)
+    atoms = (rng.integers(0, 4, G * n_per) + epoch // 5) % 24
+    x = 3.0 * (atoms + 1) + 0.05 * rng.standard_normal(len(atoms))
+    rcrf = b.RCRF(b.Gaussian1DGaussian1D(float(x.mean()), 100.0, 0.0025), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, n_epochs, Kmax=256)
+    data = b.FlatData.from_csr(b._lib.F64, len(x), group_ptr=ptr, x=x)
+    rs = b.ResidentSampler(ctx, rcrf, data, np.zeros(len(x), dtype=np.int32), sample_hyperparam=True, n_internals=5, epoch_ptr=eptr)
+    rs.sweep(8)
+    KK, gg, aa = rs.rcrf_state()
+    z, t, comp = rs.get_zz(), rs.crf_tables(), rs.components()
+    grp, dish = _seating_is_consistent(z, ptr, t["tji"], t["njt"], t["kjt"], t["n_tbls"], KK)
+    mm = np.zeros((n_epochs, KK), dtype=np.int64)
+    np.add.at(mm, (grp // n_rest, dish), 1)
+    assert np.array_equal(np.asarray(t["mm"]).reshape(n_epochs, -1)[:, :KK], mm) and (mm.sum(0) > 0).all()
+    assert (gg > 0).all() and (aa > 0).all()
+    assert np.array_equal(comp["nn"], np.bincount(z, minlength=KK))
+    assert np.allclose(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=KK), rtol=1e-9)
+    homog = sum(np.bincount(atoms[z == c]).max() for c in range(KK)) / len(z)
     assert homog > 0.99
     rs.close()
