@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbias_cuda.so")
+# BIAS_CUDA_LIB: another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("BIAS_CUDA_LIB") or os.path.join(_HERE, "csrc", "libbias_cuda.so")
 
 OK, EINVAL, ENODEV, ECUDA, ENOMEM, ERANGE, ESTATE = range(7)
 MD, G1G1 = 0, 1

@@ -20,7 +20,14 @@
 
 namespace bias {
 
-constexpr int kH16Warps = 6;        // warps per CTA = 12 documents per CTA, 3 CTAs per SM
+#ifndef BIAS_H16_WARPS
+#define BIAS_H16_WARPS 6
+#endif
+#ifndef BIAS_H16_CTAS
+#define BIAS_H16_CTAS 3
+#endif
+constexpr int kH16Warps = BIAS_H16_WARPS;        // warps per CTA = 12 documents per CTA, 3 CTAs per SM
+constexpr int kH16Ctas = BIAS_H16_CTAS;
 
 __host__ __device__ inline size_t lda_half16_doc_bytes(int nc8) { return (size_t)nc8 * 128 * 6 + 64; }
 __host__ __device__ inline size_t lda_half16_smem_bytes(int nc8, int warps = kH16Warps) { return (size_t)warps * 2 * lda_half16_doc_bytes(nc8); }
@@ -106,19 +113,22 @@ __device__ __forceinline__ uint4 pick_chunk16(const uint4 (&c)[N], int j) {
     return r;
 }
 
+__device__ __forceinline__ float cvt_lo(unsigned x) { return (float)(x & 0xffffu); }
+__device__ __forceinline__ float cvt_hi(unsigned x) { return (float)(x >> 16); }
+
 __device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float4 b) {
-    float s = (float)(x.x & 0xffffu) * a.x;
-    s = fmaf((float)(x.x >> 16), a.y, s);
-    s = fmaf((float)(x.y & 0xffffu), a.z, s);
-    s = fmaf((float)(x.y >> 16), a.w, s);
-    float t = (float)(x.z & 0xffffu) * b.x;
-    t = fmaf((float)(x.z >> 16), b.y, t);
-    t = fmaf((float)(x.w & 0xffffu), b.z, t);
-    t = fmaf((float)(x.w >> 16), b.w, t);
+    float s = cvt_lo(x.x) * a.x;
+    s = fmaf(cvt_hi(x.x), a.y, s);
+    s = fmaf(cvt_lo(x.y), a.z, s);
+    s = fmaf(cvt_hi(x.y), a.w, s);
+    float t = cvt_lo(x.z) * b.x;
+    t = fmaf(cvt_hi(x.z), b.y, t);
+    t = fmaf(cvt_lo(x.w), b.z, t);
+    t = fmaf(cvt_hi(x.w), b.w, t);
     return s + t;
 }
 
-template <int NC8, int WARPS = kH16Warps, int CTAS = 3>
+template <int NC8, int WARPS = kH16Warps, int CTAS = kH16Ctas>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
 lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
     constexpr int LOG_NC = (NC8 == 1) ? 0 : (NC8 == 2) ? 1 : (NC8 == 4) ? 2 : 3;
