@@ -183,3 +183,36 @@ def test_crf_argument_errors(ctx):
     with pytest.raises(b.BiasError) as e:
         b.CRF_gibbs_sampler(hdp, x, [np.zeros(120, dtype=np.int64)], 4, 0, 1, ctx=ctx)
     assert e.value.code == 5
+
+
+@pytest.mark.parametrize("kind", ["f64", "int", "sent"])
+def test_empty_and_single_customer_restaurants(ctx, kind):
+    """Ragged input as the reference accepts it (xx[jj] may be empty): restaurants without customers have no tables,
+    a single customer always has exactly one, and the seating of the others is unaffected."""
+    lens = [0, 1, 35, 0, 2, 17, 0, 1, 0]
+    if kind == "f64":
+        x, ptr, _, _ = _data(8, lens)
+        N = len(x)
+        comp = b.Gaussian1DGaussian1D(float(x.mean()), 10.0, 0.0025)
+        data = b.FlatData.from_csr(b._lib.F64, N, group_ptr=ptr, x=x)
+    else:
+        comp, _, _, ptr, data, N = _md_case(kind, 8, lens)
+    hdp = b.HDP(comp, 2, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=48)
+    rs = b.ResidentSampler(ctx, hdp, data, np.random.default_rng(3).integers(0, 2, N).astype(np.int32), sample_hyperparam=True,
+                           n_internals=2, crf=True)
+    for _ in range(5):
+        rs.sweep(1)
+        hp, _ = rs.hdp_state()
+        t = rs.crf_tables()
+        check_crf_invariants(rs.get_zz(), ptr, t["tji"], t["njt"], t["kjt"], t["n_tbls"], t["mm"], hp.KK, rs.components()["nn"])
+        assert list(t["n_tbls"][[0, 1, 3, 6, 7, 8]]) == [0, 1, 0, 0, 1, 0]
+    rs.close()
+
+
+def test_crf_without_items(ctx):
+    hdp = b.HDP(b.Gaussian1DGaussian1D(0.0, 10.0, 0.0025), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, Kmax=8)
+    data = b.FlatData.from_csr(b._lib.F64, 0, group_ptr=np.zeros(3, dtype=np.int64), x=np.zeros(0))
+    rs = b.ResidentSampler(ctx, hdp, data, np.zeros(0, dtype=np.int32), sample_hyperparam=False, crf=True)
+    rs.sweep(2)
+    assert len(rs.get_zz()) == 0 and list(rs.crf_tables()["n_tbls"]) == [0, 0]
+    rs.close()

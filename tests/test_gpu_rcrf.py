@@ -147,3 +147,28 @@ def test_rcrf_argument_errors(ctx):
     with pytest.raises(ValueError):        # a single epoch
         b.RCRF_gibbs_sampler(b.RCRF(b.Gaussian1DGaussian1D(0.0, 1.0, 1.0), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, 1),
                              [[x]], [[np.zeros(6, dtype=np.int64)]], 1, 0, 1, ctx=ctx)
+
+
+def test_epochs_without_restaurants_and_empty_restaurants(ctx):
+    """Ragged epochs (xx[tt] may be empty, and so may xx[tt][jj]): the epoch loop skips what is not there and the
+    franchise invariants hold for the rest."""
+    rng = np.random.default_rng(11)
+    eptr = np.array([0, 3, 3, 7, 8, 8], dtype=np.int64)                 # epochs 1 and 4 have no restaurants
+    lens = [20, 0, 1, 0, 25, 30, 2, 12]
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N, TT = int(ptr[-1]), len(eptr) - 1
+    atoms = rng.integers(0, 4, N)
+    x = 3.0 * (atoms + 1) + 0.05 * rng.standard_normal(N)
+    rcrf = b.RCRF(b.Gaussian1DGaussian1D(float(x.mean()), 10.0, 0.0025), 2, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1, TT, Kmax=48)
+    data = b.FlatData.from_csr(b._lib.F64, N, group_ptr=ptr, x=x)
+    rs = b.ResidentSampler(ctx, rcrf, data, rng.integers(0, 2, N).astype(np.int32), sample_hyperparam=True, n_internals=2,
+                           epoch_ptr=eptr)
+    for _ in range(6):
+        rs.sweep(1)
+        KK, gg, aa = rs.rcrf_state()
+        t = rs.crf_tables()
+        check_rcrf_invariants(rs.get_zz(), eptr, ptr, t["tji"], t["njt"], t["kjt"], t["n_tbls"], t["mm"], KK,
+                              rs.components()["nn"])
+        assert (gg > 0).all() and (aa > 0).all() and np.isfinite(gg).all() and np.isfinite(aa).all()
+        assert not t["mm"][1].any() and not t["mm"][4].any()
+    rs.close()
