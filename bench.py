@@ -55,7 +55,7 @@ def sweep_kernel_name():
         return "lda_md_int_sweep_tma_kernel<8>"
     if force.startswith("h"):
         return "lda_md_int_sweep_half_kernel<16, 8>"
-    return "lda_md_int_sweep_half16_kernel<8, 6, 3>"
+    return "lda_md_int_sweep_half16_kernel<8, 6, 3, true>"
 
 
 def peaks():

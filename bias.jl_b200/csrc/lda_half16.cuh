@@ -16,6 +16,7 @@
 // Chunks are 128 topics wide (16 lanes x 8 uint16 = one LDG.128 per lane); r is stored in shared memory with
 // the two float4 halves of a lane's 8 topics de-interleaved, so that both LDS.128 of a chunk are conflict-free.
 #pragma once
+#include <type_traits>
 #include "lda_half.cuh"
 
 namespace bias {
@@ -28,9 +29,18 @@ namespace bias {
 #endif
 constexpr int kH16Warps = BIAS_H16_WARPS;        // warps per CTA = 12 documents per CTA, 3 CTAs per SM
 constexpr int kH16Ctas = BIAS_H16_CTAS;
+#ifndef BIAS_H16_WARPS8
+#define BIAS_H16_WARPS8 6
+#endif
+constexpr int kH16Warps8 = BIAS_H16_WARPS8;      // warps per CTA when the document counts are bytes (CNT8): the same
+                                                 // 36 documents per SM in 186 KB, which leaves 32 KB of L1 (7 x 3 spills)
 
-__host__ __device__ inline size_t lda_half16_doc_bytes(int nc8) { return (size_t)nc8 * 128 * 6 + 64; }
-__host__ __device__ inline size_t lda_half16_smem_bytes(int nc8, int warps = kH16Warps) { return (size_t)warps * 2 * lda_half16_doc_bytes(nc8); }
+// per document: r (fp32) + the document's topic counts (uint16, or uint8 when no document has more than 255 tokens)
+// + the per-chunk sums of r
+__host__ __device__ inline size_t lda_half16_doc_bytes(int nc8, bool cnt8 = false) { return (size_t)nc8 * 128 * (cnt8 ? 5 : 6) + 64; }
+__host__ __device__ inline size_t lda_half16_smem_bytes(int nc8, int warps = kH16Warps, bool cnt8 = false) {
+    return (size_t)warps * 2 * lda_half16_doc_bytes(nc8, cnt8);
+}
 
 #ifdef __CUDACC__
 
@@ -128,9 +138,11 @@ __device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float
     return s + t;
 }
 
-template <int NC8, int WARPS = kH16Warps, int CTAS = kH16Ctas>
+template <int NC8, int WARPS = kH16Warps, int CTAS = kH16Ctas, bool CNT8 = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
 lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
+    using cnt_t = typename std::conditional<CNT8, uint8_t, uint16_t>::type;
+    constexpr int CB = (int)sizeof(cnt_t);
     constexpr int LOG_NC = (NC8 == 1) ? 0 : (NC8 == 2) ? 1 : (NC8 == 4) ? 2 : 3;
     constexpr int GSHIFT = 4 - LOG_NC;      // l16 >> GSHIFT = chunk held by the lane after the transposing reduction
     constexpr int KPAD = NC8 * 128;
@@ -139,10 +151,10 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-    unsigned char *hbase = smem_raw + (size_t)(warp * 2 + half) * lda_half16_doc_bytes(NC8);
+    unsigned char *hbase = smem_raw + (size_t)(warp * 2 + half) * lda_half16_doc_bytes(NC8, CNT8);
     float *r_s = reinterpret_cast<float *>(hbase);                                  // permuted, see r_pos
-    uint16_t *cnt_s = reinterpret_cast<uint16_t *>(hbase + (size_t)KPAD * 4);
-    float *R_s = reinterpret_cast<float *>(hbase + (size_t)KPAD * 6);
+    cnt_t *cnt_s = reinterpret_cast<cnt_t *>(hbase + (size_t)KPAD * 4);
+    float *R_s = reinterpret_cast<float *>(hbase + (size_t)KPAD * (4 + CB));
     const float4 *r4 = reinterpret_cast<const float4 *>(r_s);
 
     int32_t *const my_nk = p.nk_rep + (blockIdx.x % kNkRep) * KPAD;
@@ -176,12 +188,13 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
         }
         if (__any_sync(kFull, fetched)) {
             if (fetched)
-                for (int q = l16; q < KPAD / 8; q += 16) reinterpret_cast<uint4 *>(cnt_s)[q] = make_uint4(0, 0, 0, 0);
+                for (int q = l16; q < KPAD * CB / 16; q += 16) reinterpret_cast<uint4 *>(cnt_s)[q] = make_uint4(0, 0, 0, 0);
             __syncwarp();
             if (fetched)
                 for (int64_t t = t_cur + l16; t < t_end; t += 16) {
                     const int k = p.z[t];
-                    atomicAdd(reinterpret_cast<unsigned *>(cnt_s) + (k >> 1), 1u << ((k & 1) * 16));
+                    if (CNT8) atomicAdd(reinterpret_cast<unsigned *>(cnt_s) + (k >> 2), 1u << ((k & 3) * 8));
+                    else atomicAdd(reinterpret_cast<unsigned *>(cnt_s) + (k >> 1), 1u << ((k & 1) * 16));
                 }
             __syncwarp();
 #pragma unroll
@@ -196,16 +209,28 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                     na.x += da.x; na.y += da.y; na.z += da.z; na.w += da.w;
                     nb4.x += db.x; nb4.y += db.y; nb4.z += db.z; nb4.w += db.w;
                 }
-                const uint4 cc = reinterpret_cast<const uint4 *>(cnt_s)[j * 16 + l16];
+                float cf[8];             // the document's counts of topics k0 .. k0 + 7
+                if (CNT8) {
+                    const uint2 cc = reinterpret_cast<const uint2 *>(cnt_s)[j * 16 + l16];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        cf[e] = (float)((cc.x >> (8 * e)) & 0xffu);
+                        cf[4 + e] = (float)((cc.y >> (8 * e)) & 0xffu);
+                    }
+                } else {
+                    const uint4 cc = reinterpret_cast<const uint4 *>(cnt_s)[j * 16 + l16];
+                    cf[0] = (float)(cc.x & 0xffffu); cf[1] = (float)(cc.x >> 16); cf[2] = (float)(cc.y & 0xffffu); cf[3] = (float)(cc.y >> 16);
+                    cf[4] = (float)(cc.z & 0xffffu); cf[5] = (float)(cc.z >> 16); cf[6] = (float)(cc.w & 0xffffu); cf[7] = (float)(cc.w >> 16);
+                }
                 float4 ra, rb;
-                ra.x = (k0 + 0 < p.K) ? __fdividef((float)(cc.x & 0xffffu) + alpha, (float)na.x + vbeta) : 0.f;
-                ra.y = (k0 + 1 < p.K) ? __fdividef((float)(cc.x >> 16) + alpha, (float)na.y + vbeta) : 0.f;
-                ra.z = (k0 + 2 < p.K) ? __fdividef((float)(cc.y & 0xffffu) + alpha, (float)na.z + vbeta) : 0.f;
-                ra.w = (k0 + 3 < p.K) ? __fdividef((float)(cc.y >> 16) + alpha, (float)na.w + vbeta) : 0.f;
-                rb.x = (k0 + 4 < p.K) ? __fdividef((float)(cc.z & 0xffffu) + alpha, (float)nb4.x + vbeta) : 0.f;
-                rb.y = (k0 + 5 < p.K) ? __fdividef((float)(cc.z >> 16) + alpha, (float)nb4.y + vbeta) : 0.f;
-                rb.z = (k0 + 6 < p.K) ? __fdividef((float)(cc.w & 0xffffu) + alpha, (float)nb4.z + vbeta) : 0.f;
-                rb.w = (k0 + 7 < p.K) ? __fdividef((float)(cc.w >> 16) + alpha, (float)nb4.w + vbeta) : 0.f;
+                ra.x = (k0 + 0 < p.K) ? __fdividef(cf[0] + alpha, (float)na.x + vbeta) : 0.f;
+                ra.y = (k0 + 1 < p.K) ? __fdividef(cf[1] + alpha, (float)na.y + vbeta) : 0.f;
+                ra.z = (k0 + 2 < p.K) ? __fdividef(cf[2] + alpha, (float)na.z + vbeta) : 0.f;
+                ra.w = (k0 + 3 < p.K) ? __fdividef(cf[3] + alpha, (float)na.w + vbeta) : 0.f;
+                rb.x = (k0 + 4 < p.K) ? __fdividef(cf[4] + alpha, (float)nb4.x + vbeta) : 0.f;
+                rb.y = (k0 + 5 < p.K) ? __fdividef(cf[5] + alpha, (float)nb4.y + vbeta) : 0.f;
+                rb.z = (k0 + 6 < p.K) ? __fdividef(cf[6] + alpha, (float)nb4.z + vbeta) : 0.f;
+                rb.w = (k0 + 7 < p.K) ? __fdividef(cf[7] + alpha, (float)nb4.w + vbeta) : 0.f;
                 const float s = half_sum(((ra.x + ra.y) + (ra.z + ra.w)) + ((rb.x + rb.y) + (rb.z + rb.w)));
                 if (fetched) {
                     reinterpret_cast<float4 *>(r_s)[j * 32 + l16] = ra;
@@ -347,10 +372,10 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                     // the document's row: lane 0; the global counts: ONE fire-and-forget RED instruction with six active
                     // lanes (a single lane issuing six atomics back to back sits on the token's critical path)
                     if (l16 == 0) {
-                        cnt_s[kold] = (uint16_t)(cn - 1);
+                        cnt_s[kold] = (cnt_t)(cn - 1);
                         r_s[r_pos(kold)] = r_rm;
                         R_s[jo] += r_rm - r_old;
-                        cnt_s[knew] = (uint16_t)(cn2 + 1);
+                        cnt_s[knew] = (cnt_t)(cn2 + 1);
                         r_s[r_pos(knew)] = r_new;
                         R_s[knew >> 7] += r_new - r2;
                     }

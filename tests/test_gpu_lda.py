@@ -14,13 +14,15 @@ from helpers import assert_conditionals_close, assert_draws_match, lda_token_log
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["u16", "half", "reg"], autouse=True)
+@pytest.fixture(params=["u16", "u16w", "half", "reg"], autouse=True)
 def sweep_kernel(request, monkeypatch):
     """Every test runs once per LDA sweep kernel (csrc/model.cu reads BIAS_LDA_KERNEL at each launch): the 16-bit
-    shadow-row kernel (the default above 2 M tokens), the int32-row half-warp kernel behind it, and the
-    one-document-per-warp kernel that serves K > 1024 and very long documents."""
-    monkeypatch.setenv("BIAS_LDA_KERNEL", request.param)
-    return request.param
+    shadow-row kernel (the default above 2 M tokens) with byte-wide document counts (documents of at most 255 tokens)
+    and with 16-bit ones ("u16w"), the int32-row half-warp kernel behind it, and the one-document-per-warp kernel
+    that serves K > 1024 and very long documents."""
+    monkeypatch.setenv("BIAS_LDA_KERNEL", request.param[:3])
+    monkeypatch.setenv("BIAS_LDA_CNT8", "0" if request.param == "u16w" else "1")
+    return request.param[:3]
 
 
 @pytest.fixture(scope="module")
@@ -108,6 +110,27 @@ def test_edge_cases_empty_and_ragged_documents(ctx):
     r0 = b.ResidentSampler(ctx, lda, d0, np.zeros(0, dtype=np.int32))
     r0.sweep(1)
     r0.close()
+
+
+def test_documents_longer_than_255_tokens(ctx):
+    """Documents above 255 tokens make the 16-bit kernel keep its per-document counts in uint16 (the byte-wide variant
+    serves corpora whose longest document has at most 255 tokens): draws against the oracle and count conservation
+    with one topic holding more than 255 tokens of a document."""
+    rng = np.random.default_rng(12)
+    V, K = 40, 5
+    xx = [rng.integers(0, V, n).astype(np.int64) for n in [700, 3, 256, 255, 1200]]
+    rs, state, data, z0, words, rng = _setup(ctx, xx, K, V, 0.3, 2.0, seed=6)
+    u = rng.random(data.n_items)
+    idx = np.arange(data.n_items)
+    _, oprob, odraw = _oracle_conditionals(state, data, idx, u)
+    assert_draws_match(rs.frozen_draws(u), odraw, oprob, u, 2e-5)
+    rs.sweep(4)
+    z = rs.get_zz()
+    comp = rs.components()
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, words), 1)
+    assert np.array_equal(comp["mi"], mi)
+    rs.close()
 
 
 def test_argument_errors(ctx):

@@ -3,5 +3,5 @@
 for so in "" bias.jl_b200/csrc/_exp/libbias_*.so; do
   name=${so:-default}
   BIAS_CUDA_LIB=$so timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 | \
-    python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['ms_per_step'],2), d['roofline']['kernel'], d['sweep_stats']['n_moved_last'])"
+    python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['ms_per_step'],2), d['sweep_stats']['n_moved_last'])"
 done
