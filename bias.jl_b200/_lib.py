@@ -29,7 +29,7 @@ SYMBOLS = [
     "bias_model_last_stats", "bias_model_get_components", "bias_model_get_group_counts", "bias_model_get_hdp",
     "bias_model_conditionals", "bias_model_frozen_draws", "bias_hdp_table_conditionals", "bias_stirling_rows",
     "bias_model_log_likelihood", "bias_model_delta_begin", "bias_model_delta_begin_zero", "bias_model_delta_pack", "bias_model_delta_apply", "bias_model_last_sweep_ms",
-    "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload", "bias_model_heldout_log_likelihood",
+    "bias_rcrp_run", "bias_rcrp_create", "bias_model_get_rcrp", "bias_model_set_sample_hyperparam", "bias_model_reload", "bias_model_reload_u16", "bias_model_get_zz_u16", "bias_model_heldout_log_likelihood",
     "bias_model_set_host_seed", "bias_hdp_shard_pass", "bias_hdp_shard_births", "bias_hdp_shard_adopt", "bias_hdp_shard_prune",
     "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
     "bias_crf_sweep_with_uniforms", "bias_crf_get_tables", "bias_model_delta_pack16", "bias_model_delta_apply16",
@@ -126,6 +126,8 @@ def lib():
     L.bias_model_get_rcrp.argtypes = [vp, rp, vp]
     L.bias_model_set_sample_hyperparam.argtypes = [vp, i32]
     L.bias_model_reload.argtypes = [vp, dt, i64, vp, vp]
+    L.bias_model_reload_u16.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.bias_model_get_zz_u16.argtypes = [vp, vp]
     L.bias_model_heldout_log_likelihood.argtypes = [vp, vp, vp, C.POINTER(f64), C.POINTER(i64)]
     L.bias_model_set_host_seed.argtypes = [vp, C.c_uint64]
     L.bias_hdp_shard_pass.argtypes = [vp]

@@ -553,7 +553,7 @@ int bias_model_destroy(bias_model *m) {
     crf_destroy(m);
     void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
                     m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
-                    m->delta_f64, m->scratch, m->d_aa_t, m->n_wk16, m->word_freq, m->wide_flag, m->nk_rep};
+                    m->delta_f64, m->scratch, m->d_aa_t, m->n_wk16, m->word_freq, m->wide_flag, m->nk_rep, m->stage16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
@@ -702,6 +702,7 @@ int bias_model_reload(bias_model *m, const bias_data *data, int64_t n_groups, co
         BIAS_CUDA_TRY(cudaMemcpyAsync(m->sent_count, data->sent_count, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    m->mirror16_valid = false;
     if (m->model != BIAS_MODEL_BMM) {
         m->max_group_len = 1;
         for (int64_t j = 0; j < G; ++j) m->max_group_len = std::max(m->max_group_len, group_ptr[j + 1] - group_ptr[j]);
@@ -723,11 +724,94 @@ int bias_model_reload(bias_model *m, const bias_data *data, int64_t n_groups, co
     return BIAS_OK;
 }
 
+// ---- 16-bit host formats (LDA x word ids): half the PCIe bytes of reload / get_zz ----
+static int64_t stage16_stride(const bias_model *m) { return (std::max<int64_t>(8, m->N_cap) + 7) / 8 * 8; }
+
+// the uint16 mirror of z (third part of stage16): written at the end of every sweep call once the 16-bit formats
+// are in use, so that get_zz_u16 is a plain copy-engine transfer that does not wait for SM time behind another
+// stream's sweep
+static int mirror16_update(bias_model *m) {
+    if (m->N > 0) {
+        narrow_u16_kernel<<<grid_for(m->ctx, m->N / 8 + 1, 256), 256, 0, m->ctx->stream>>>(m->z, m->N, m->stage16 + 2 * stage16_stride(m));
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+    }
+    m->mirror16_valid = true;
+    return BIAS_OK;
+}
+
+static int stage16_ready(bias_model *m) {
+    if (m->model != BIAS_MODEL_LDA || m->conj.kind != BIAS_MD || m->conj.datum != BIAS_INT)
+        return fail(BIAS_EINVAL, "the 16-bit host formats are defined for LDA x MultinomialDirichlet x word ids");
+    if (m->V > 65536 || m->K > 65536)
+        return fail(BIAS_ERANGE, "the 16-bit host formats need dd <= 65536 and KK <= 65536 (dd = %lld, KK = %d)", (long long)m->V, m->K);
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    if (!m->stage16) BIAS_CUDA_TRY(cudaMalloc((void **)&m->stage16, (size_t)stage16_stride(m) * 3 * sizeof(uint16_t)));
+    return BIAS_OK;
+}
+
+int bias_model_reload_u16(bias_model *m, int64_t n_items, const uint16_t *word, int64_t n_groups, const int64_t *group_ptr,
+                          const uint16_t *zz) {
+    if (!m || !word || !zz || !group_ptr) return fail(BIAS_EINVAL, "null argument");
+    BIAS_TRY(stage16_ready(m));
+    const int64_t G = n_groups;
+    if (n_items < 0 || G < 0) return fail(BIAS_EINVAL, "negative item or group count");
+    if (group_ptr[0] != 0 || group_ptr[G] != n_items) return fail(BIAS_EINVAL, "group_ptr must start at 0 and end at n_items");
+    int64_t max_len = 1;
+    for (int64_t j = 0; j < G; ++j) {
+        if (group_ptr[j + 1] < group_ptr[j]) return fail(BIAS_EINVAL, "group_ptr must be non-decreasing");
+        max_len = std::max(max_len, group_ptr[j + 1] - group_ptr[j]);
+    }
+    if (n_items > m->N_cap || G > m->G_cap)
+        return fail(BIAS_ERANGE, "reload: %lld items / %lld groups exceed the capacity the model was created with (%lld / %lld)",
+                    (long long)n_items, (long long)G, (long long)m->N_cap, (long long)m->G_cap);
+    cudaStream_t st = m->ctx->stream;
+    m->N = n_items;
+    m->G = G;
+    m->nnz = 0;
+    uint16_t *w16 = m->stage16, *z16 = m->stage16 + stage16_stride(m);
+    m->mirror16_valid = false;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(w16, word, (size_t)n_items * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(z16, zz, (size_t)n_items * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    if (n_items > 0) {
+        widen_u16_kernel<<<grid_for(m->ctx, n_items / 8 + 1, 256), 256, 0, st>>>(w16, n_items, m->word);
+        widen_u16_kernel<<<grid_for(m->ctx, n_items / 8 + 1, 256), 256, 0, st>>>(z16, n_items, m->z);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 2;
+    }
+    m->max_group_len = max_len;
+    m->h_group_ptr.assign(group_ptr, group_ptr + G + 1);
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->group_ptr, group_ptr, ((size_t)G + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (m->group_of && m->N > 0) {
+        group_of_kernel<<<grid_for(m->ctx, m->N, 256), 256, 0, st>>>(m->group_ptr, m->G, m->N, m->group_of);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+    }
+    BIAS_TRY(validate_on_device(m, m->K));
+    BIAS_TRY(rebuild_counts(m));
+    m->sweep_index = 0;
+    m->stats_pending = false;
+    m->timing_valid = false;
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));     // the uploads came from caller-owned memory
+    return BIAS_OK;
+}
+
+int bias_model_get_zz_u16(bias_model *m, uint16_t *zz) {
+    if (!m || !zz) return fail(BIAS_EINVAL, "null argument");
+    BIAS_TRY(stage16_ready(m));
+    cudaStream_t st = m->ctx->stream;
+    if (!m->mirror16_valid) BIAS_TRY(mirror16_update(m));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(zz, m->stage16 + 2 * stage16_stride(m), (size_t)m->N * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    return BIAS_OK;
+}
+
 int bias_model_set_zz(bias_model *m, const int32_t *zz) {
     if (!m || !zz) return fail(BIAS_EINVAL, "null argument");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     const int32_t Kcur = is_dynamic_K(m) ? m->hdp.KK : m->K;
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->z, zz, (size_t)m->N * sizeof(int32_t), cudaMemcpyHostToDevice, m->ctx->stream));
+    m->mirror16_valid = false;
     BIAS_TRY(validate_on_device(m, Kcur));
     BIAS_TRY(rebuild_counts(m));
     if (m->model == BIAS_MODEL_CRF || m->model == BIAS_MODEL_RCRF) {   // the seating is rebuilt from the new assignments (src/HDP.jl:441-470)
@@ -774,6 +858,8 @@ int bias_model_sweep(bias_model *m, int32_t n_sweeps) {
     BIAS_CUDA_TRY(cudaEventRecord(m->ctx->ev_a, m->ctx->stream));
     for (int32_t s = 0; s < n_sweeps; ++s) BIAS_TRY(one_sweep(m));
     BIAS_CUDA_TRY(cudaEventRecord(m->ctx->ev_b, m->ctx->stream));
+    m->mirror16_valid = false;
+    if (m->stage16 && n_sweeps > 0) BIAS_TRY(mirror16_update(m));     // 16-bit formats in use: see mirror16_update
     m->last_launches = (int32_t)(m->ctx->launches - l0);
     m->timing_valid = true;
     return BIAS_OK;

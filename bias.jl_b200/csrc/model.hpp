@@ -50,6 +50,9 @@ struct bias_model {
     int32_t *word_freq = nullptr;   // [V] occurrences of each word in the local shard
     int32_t *nk_rep = nullptr;      // [kNkRep][Kpad] replicas collecting a sweep's changes of n_k (half-warp kernels)
     int32_t *wide_flag = nullptr;   // [1] set by shadow_build_kernel when a count may leave 16 bits this sweep
+    uint16_t *stage16 = nullptr;    // [3][N_cap rounded up to 8]: uint16 word ids and assignments as uploaded by reload_u16, and the
+                                    // uint16 mirror of z that every sweep call leaves behind for get_zz_u16; allocated on first use
+    bool mirror16_valid = false;    // the mirror holds the current z
 
     // multi-GPU exchange buffers (allocated on first use)
     int32_t *base_i32 = nullptr, *delta_i32 = nullptr;

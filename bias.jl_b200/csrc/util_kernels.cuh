@@ -27,6 +27,30 @@ __global__ void validate_kernel(const int32_t *z, int64_t N, int K, const int32_
     if (bad) atomicOr(flag, bad);
 }
 
+// 16-bit host formats of the streaming path: word ids / assignments travel as uint16 and are widened (narrowed) here
+__global__ void widen_u16_kernel(const uint16_t *src, int64_t n, int32_t *dst) {
+    const int64_t n8 = n / 8, stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t q = t0; q < n8; q += stride) {
+        const uint4 x = reinterpret_cast<const uint4 *>(src)[q];
+        reinterpret_cast<int4 *>(dst)[2 * q] = make_int4((int)(x.x & 0xffffu), (int)(x.x >> 16), (int)(x.y & 0xffffu), (int)(x.y >> 16));
+        reinterpret_cast<int4 *>(dst)[2 * q + 1] = make_int4((int)(x.z & 0xffffu), (int)(x.z >> 16), (int)(x.w & 0xffffu), (int)(x.w >> 16));
+    }
+    for (int64_t i = n8 * 8 + t0; i < n; i += stride) dst[i] = (int32_t)src[i];
+}
+__global__ void narrow_u16_kernel(const int32_t *src, int64_t n, uint16_t *dst) {
+    const int64_t n8 = n / 8, stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t q = t0; q < n8; q += stride) {
+        const int4 a = reinterpret_cast<const int4 *>(src)[2 * q], b = reinterpret_cast<const int4 *>(src)[2 * q + 1];
+        uint4 o;
+        o.x = (unsigned)(a.x & 0xffff) | ((unsigned)a.y << 16);
+        o.y = (unsigned)(a.z & 0xffff) | ((unsigned)a.w << 16);
+        o.z = (unsigned)(b.x & 0xffff) | ((unsigned)b.y << 16);
+        o.w = (unsigned)(b.z & 0xffff) | ((unsigned)b.w << 16);
+        reinterpret_cast<uint4 *>(dst)[q] = o;
+    }
+    for (int64_t i = n8 * 8 + t0; i < n; i += stride) dst[i] = (uint16_t)src[i];
+}
+
 // item -> group id by binary search in the CSR offsets
 __global__ void group_of_kernel(const int64_t *ptr, int64_t G, int64_t N, int32_t *group_of) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {

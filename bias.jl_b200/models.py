@@ -215,6 +215,13 @@ def default_context(seed: int = 0) -> Context:
 
 
 # ------------------------------------------------------------------ resident sampler state
+class _BatchShape:
+    """What ResidentSampler needs to know about a batch it did not receive as FlatData (reload_u16)."""
+
+    def __init__(self, n_items: int, n_groups: int, group_ptr: np.ndarray):
+        self.n_items, self.n_groups, self.group_ptr = n_items, n_groups, group_ptr
+
+
 class ResidentSampler:
     """bias_model: xx, zz and the component statistics live in HBM between sweeps."""
 
@@ -258,6 +265,19 @@ class ResidentSampler:
         self.data = data
         self.zz = _lib.as_i32(zz_flat)
         check(lib().bias_model_reload(self.h, C.byref(data.c), data.n_groups, ptr(data.group_ptr), ptr(self.zz)))
+
+    def reload_u16(self, words16: np.ndarray, group_ptr: np.ndarray, zz16: np.ndarray):
+        """reload() with word ids and assignments as uint16 host arrays (LDA x word ids, dd and KK <= 65536): half
+        the bytes over PCIe.  Afterwards `self.data` only records the shape of the batch (the library owns its copy)."""
+        w, z, gp = np.ascontiguousarray(words16), np.ascontiguousarray(zz16), _lib.as_i64(group_ptr)
+        assert w.dtype == np.uint16 and z.dtype == np.uint16 and w.size == z.size
+        check(lib().bias_model_reload_u16(self.h, w.size, ptr(w), gp.size - 1, ptr(gp), ptr(z)))
+        self.data = _BatchShape(int(w.size), int(gp.size - 1), gp)
+
+    def get_zz_u16(self, out: np.ndarray) -> np.ndarray:
+        assert out.dtype == np.uint16 and out.flags.c_contiguous
+        check(lib().bias_model_get_zz_u16(self.h, ptr(out)))
+        return out
 
     # -- sweeps
     def sweep(self, n: int = 1):

@@ -158,6 +158,12 @@ BIAS_API int bias_model_set_sample_hyperparam(bias_model *m, int32_t on);
  * two contexts so that one batch uploads while the other is swept. */
 BIAS_API int bias_model_reload(bias_model *m, const bias_data *data, int64_t n_groups, const int64_t *group_ptr,
                       const int32_t *zz);
+/* 16-bit host formats of the same two calls for LDA x word ids (dd <= 65536, KK <= 65536): word ids and assignments
+ * cross PCIe as uint16 and are widened / narrowed on the device — half the bytes per step of a streaming caller
+ * (the reference's own arrays are Int64, src/LDA.jl:67-72: the shim converts either way). */
+BIAS_API int bias_model_reload_u16(bias_model *m, int64_t n_items, const uint16_t *word, int64_t n_groups,
+                          const int64_t *group_ptr, const uint16_t *zz);
+BIAS_API int bias_model_get_zz_u16(bias_model *m, uint16_t *zz);
 BIAS_API int bias_model_destroy(bias_model *m);
 /* n_sweeps asynchronous sweeps on the context stream (one iteration of the loop at src/LDA.jl:103). */
 BIAS_API int bias_model_sweep(bias_model *m, int32_t n_sweeps);

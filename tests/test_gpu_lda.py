@@ -280,6 +280,56 @@ def test_reload_refeeds_a_resident_model(ctx):
     rs.close()
 
 
+def test_reload_and_readback_in_16_bit_host_formats(ctx):
+    """bias_model_reload_u16 / bias_model_get_zz_u16: word ids and assignments as uint16 host arrays give the same
+    model state, draws and sweeps as the int32 calls; out-of-range input and unsupported models are rejected."""
+    K, V = 12, 40
+    rng = np.random.default_rng(6)
+    mk = lambda lens: [rng.integers(0, V, n).astype(np.int64) for n in lens]
+    xx1, xx2 = mk([50, 0, 70, 33, 11]), mk([20, 64, 0, 9])
+    lda = b.LDA(b.MultinomialDirichlet(V, 4.0), K, 0.3)
+    d1, d2 = b.FlatData(lda.component, xx1, True), b.FlatData(lda.component, xx2, True)
+    z2 = rng.integers(0, K, d2.n_items).astype(np.int32)
+    w2 = np.concatenate(xx2)
+    a = b.ResidentSampler(ctx, lda, d1, rng.integers(0, K, d1.n_items).astype(np.int32))
+    c = b.ResidentSampler(ctx, lda, d1, rng.integers(0, K, d1.n_items).astype(np.int32))
+    a.reload(d2, z2)
+    c.reload_u16(w2.astype(np.uint16), d2.group_ptr, z2.astype(np.uint16))
+    out16 = np.empty(d2.n_items, dtype=np.uint16)
+    assert np.array_equal(c.get_zz_u16(out16), z2) and np.array_equal(a.get_zz(), z2) and np.array_equal(c.get_zz(), z2)
+    ca, cc = a.components(), c.components()
+    assert np.array_equal(ca["mi"], cc["mi"]) and np.array_equal(ca["mm"], cc["mm"])
+    u = rng.random(d2.n_items)
+    assert np.array_equal(a.frozen_draws(u), c.frozen_draws(u))
+    c.sweep(3)
+    zc = c.get_zz()
+    assert np.array_equal(c.get_zz_u16(out16), zc) and not np.array_equal(zc, z2)     # the mirror follows the sweeps
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (zc, w2), 1)
+    assert np.array_equal(c.components()["mi"], mi)
+    with pytest.raises(b.BiasError):             # zz out of range
+        c.reload_u16(w2.astype(np.uint16), d2.group_ptr, np.full(d2.n_items, K, dtype=np.uint16))
+    with pytest.raises(b.BiasError) as e:        # larger than the capacity of the model
+        big = np.zeros(d1.n_items + 8, dtype=np.uint16)
+        c.reload_u16(big, np.array([0, len(big)]), big)
+    assert e.value.code == 5
+    a.close()
+    c.close()
+    wide = b.LDA(b.MultinomialDirichlet(70000, 4.0), K, 0.3)
+    dw = b.FlatData(wide.component, [np.array([0, 69999, 5])], True)
+    r = b.ResidentSampler(ctx, wide, dw, np.zeros(3, dtype=np.int32))
+    with pytest.raises(b.BiasError) as e:
+        r.get_zz_u16(np.empty(3, dtype=np.uint16))
+    assert e.value.code == 5
+    r.close()
+    bmm = b.BMM(b.Gaussian1DGaussian1D(0.0, 1.0, 1.0), 3, 1.0)
+    db = b.FlatData(bmm.component, np.array([0.1, 0.2, 0.3]), False)
+    r = b.ResidentSampler(ctx, bmm, db, np.zeros(3, dtype=np.int32))
+    with pytest.raises(b.BiasError):
+        r.get_zz_u16(np.empty(3, dtype=np.uint16))
+    r.close()
+
+
 def _heldout_case(seed, D=300, L=100, L_held=25, K=16, V=300):
     ptr, words = b.data.dirichlet_lda_corpus(D, L + L_held, K, V, beta_conc=0.05, alpha_conc=0.2, seed=seed)
     docs = [words[ptr[j]:ptr[j + 1]].astype(np.int64) for j in range(D)]
