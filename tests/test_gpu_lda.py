@@ -359,7 +359,8 @@ def test_heldout_log_likelihood_matches_numpy(ctx):
 def test_heldout_perplexity_converges_to_the_serial_samplers(ctx):
     """north_star level (c): held-out perplexity after a fixed number of sweeps within 1% of the serial reference
     sampler's.  Single chains differ by ~3% from seed to seed, so the comparison is between the means of several
-    chains (1% + the standard error of the two means), and every GPU chain must sit inside the serial spread."""
+    chains (1% + the standard error of the two means), and every GPU chain must sit inside the serial spread widened
+    by 5% (the test runs once per sweep kernel, 20 GPU chains in all against 5 serial ones)."""
     from helpers import lda_heldout_loglik
     train, held, K, V = _heldout_case(4)
     alpha, aa = 0.2, 0.05 * V
@@ -386,7 +387,7 @@ def test_heldout_perplexity_converges_to_the_serial_samplers(ctx):
     m_ref, m_gpu = np.mean(ppl_refs), np.mean(ppl_gpu)
     se = np.sqrt(np.var(ppl_refs, ddof=1) / n_chains + np.var(ppl_gpu, ddof=1) / n_chains)
     assert abs(m_gpu - m_ref) <= 0.01 * m_ref + 2 * se, (ppl_gpu, ppl_refs)
-    assert min(ppl_refs) * 0.97 <= min(ppl_gpu) and max(ppl_gpu) <= max(ppl_refs) * 1.03, (ppl_gpu, ppl_refs)
+    assert min(ppl_refs) * 0.95 <= min(ppl_gpu) and max(ppl_gpu) <= max(ppl_refs) * 1.05, (ppl_gpu, ppl_refs)
 
 
 def test_counts_beyond_16_bits_fall_back_to_the_int32_rows(ctx):
