@@ -464,8 +464,8 @@ def ours(args):
                          "traffic": traffic, "peak_source": peak_src, "kernel": sweep_kernel_name(),
                          "kernel_ms": kern_ms, "alg_bytes_per_token": B_ALG, "tokens_per_launch": tokens_per_launch,
                          "note": "frac > 1: the metric's algorithmic bytes assume int32 rows streamed from HBM; the kernel reads "
-                                 "uint16 shadow rows that mostly stay in L2 (traffic = ncu DRAM bytes). ncu (profiles/r01c_*): "
-                                 "DRAM 14 %, L2 23 %, issue slots 66 %, LSU pipe 70 % of peak - the sweep is SM-bound now; "
+                                 "uint16 shadow rows that mostly stay in L2 (traffic = ncu DRAM bytes). ncu (profiles/r01g_*): "
+                                 "DRAM 15 %, L2 24 %, issue slots 68 %, LSU data pipe 70 % of peak - the sweep is SM-bound now; "
                                  "kernel_ms spans the sweep's launches (shadow build / sweep kernel / fold, the sweep kernel "
                                  "is > 99 % of it)"},
             "cpu_baseline": cpu,
