@@ -28,7 +28,7 @@ __global__ void validate_kernel(const int32_t *z, int64_t N, int K, const int32_
 }
 
 // 16-bit host formats of the streaming path: word ids / assignments travel as uint16 and are widened (narrowed) here
-__global__ void widen_u16_kernel(const uint16_t *src, int64_t n, int32_t *dst) {
+__global__ void __launch_bounds__(256, 6) widen_u16_kernel(const uint16_t *src, int64_t n, int32_t *dst) {
     const int64_t n8 = n / 8, stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t q = t0; q < n8; q += stride) {
         const uint4 x = reinterpret_cast<const uint4 *>(src)[q];
@@ -37,7 +37,7 @@ __global__ void widen_u16_kernel(const uint16_t *src, int64_t n, int32_t *dst) {
     }
     for (int64_t i = n8 * 8 + t0; i < n; i += stride) dst[i] = (int32_t)src[i];
 }
-__global__ void narrow_u16_kernel(const int32_t *src, int64_t n, uint16_t *dst) {
+__global__ void __launch_bounds__(256, 6) narrow_u16_kernel(const int32_t *src, int64_t n, uint16_t *dst) {
     const int64_t n8 = n / 8, stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t q = t0; q < n8; q += stride) {
         const int4 a = reinterpret_cast<const int4 *>(src)[2 * q], b = reinterpret_cast<const int4 *>(src)[2 * q + 1];
