@@ -80,3 +80,19 @@ def test_crf_table_conditional_is_a_distribution_and_leaves_state_untouched():
         cdf = np.cumsum(prob)
         assert cdf[t] >= 0.37 and (t == 0 or cdf[t - 1] < 0.37)
     assert all(np.array_equal(a, b_) for a, b_ in zip(snap, (st.z, st.njt, st.c.mu, st.c.nn)))
+
+
+def test_crf_with_empty_and_single_customer_restaurants():
+    """xx[jj] may be empty in the reference (the loops over 1:length(xx[jj]) simply do not run): no tables there."""
+    rng = np.random.default_rng(1)
+    lens = [0, 1, 35, 0, 2, 17, 0, 1, 0]
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N = int(ptr[-1])
+    x = 3.0 * (rng.integers(0, 4, N) + 1) + 0.05 * rng.standard_normal(N)
+    st = orc.CRFState(orc.Comps.g1g1(48, float(x.mean()), 10.0, 0.0025), orc.Data.reals(x), ptr, rng.integers(0, 2, N), 2,
+                      1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
+    r = orc.Rng(3)
+    for _ in range(5):
+        assert not np.isnan(st.sweep(r, sample_hyper=True))
+        check_crf_invariants(st.z, ptr, st.tji, st.njt, st.kjt, st.n_tbls, st.mm, st.KK, st.c.nn)
+        assert list(st.n_tbls[[0, 1, 3, 6, 7, 8]]) == [0, 1, 0, 0, 1, 0]

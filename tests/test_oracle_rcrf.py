@@ -62,3 +62,19 @@ def test_rcrf_recovers_drifting_atoms():
         assert not np.isnan(st.sweep(r))
     homog = sum(np.bincount(atoms[st.z == c]).max() for c in np.unique(st.z)) / len(x)
     assert homog > 0.98 and len(np.unique(atoms)) <= st.KK <= len(np.unique(atoms)) + 4
+
+
+def test_rcrf_with_empty_epochs_and_restaurants():
+    rng = np.random.default_rng(2)
+    eptr = np.array([0, 3, 3, 7, 8, 8], dtype=np.int64)                 # epochs 1 and 4 have no restaurants
+    lens = [20, 0, 1, 0, 25, 30, 2, 12]
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N = int(ptr[-1])
+    x = 3.0 * (rng.integers(0, 4, N) + 1) + 0.05 * rng.standard_normal(N)
+    st = orc.RCRFState(orc.Comps.g1g1(48, float(x.mean()), 10.0, 0.0025), orc.Data.reals(x), eptr, ptr, rng.integers(0, 2, N),
+                       2, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
+    r = orc.Rng(3)
+    for _ in range(5):
+        assert not np.isnan(st.sweep(r, sample_hyper=True, n_internals=2))
+        check_rcrf_invariants(st.z, eptr, ptr, st.tji, st.njt, st.kjt, st.n_tbls, st.mm, st.KK, st.c.nn)
+        assert (st.gg > 0).all() and (st.aa > 0).all() and not st.mm[1].any() and not st.mm[4].any()
