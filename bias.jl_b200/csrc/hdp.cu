@@ -983,7 +983,12 @@ int rcrp_sweep(bias_model *m) {
     std::vector<int32_t> rows((size_t)TT * Kpad);
     for (int64_t t = 0; t < TT; ++t) {
         const int64_t i0 = m->h_group_ptr[t], i1 = m->h_group_ptr[t + 1];
-        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)TT * 8, cudaMemcpyHostToDevice, st));
+        // aa changes between epochs only while the hyper-parameters are resampled
+        if (t == 0 || m->hdp.sample_hyperparam)
+            BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)TT * 8, cudaMemcpyHostToDevice, st));
+        const bool middle = (t > 0 && t < TT - 1);
+        const bool need_rows = middle || m->hdp.sample_hyperparam;
+        bool have_rows = false;
         if (i1 > i0) {
             m->pending = list_cur;
             m->work_base = i0;
@@ -991,10 +996,15 @@ int rcrp_sweep(bias_model *m) {
                                     nullptr, nullptr, kStreamItemDraw);
             m->work_base = 0;
             BIAS_TRY(rc);
-            BIAS_TRY(resolve_births(m, list_cur, list_next));
+            // one round trip for the common case of an epoch without births: the queue length and the table together
+            unsigned int n_pending = 0;
+            BIAS_CUDA_TRY(cudaMemcpyAsync(&n_pending, reinterpret_cast<unsigned int *>(m->scratch + 3), 4, cudaMemcpyDeviceToHost, st));
+            if (need_rows) BIAS_CUDA_TRY(cudaMemcpyAsync(rows.data(), m->group_rows, rows.size() * 4, cudaMemcpyDeviceToHost, st));
+            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+            if (n_pending > 0) BIAS_TRY(resolve_births(m, list_cur, list_next));
+            else have_rows = need_rows;
         }
-        const bool middle = (t > 0 && t < TT - 1);
-        if (middle || m->hdp.sample_hyperparam) {
+        if (need_rows && !have_rows) {
             BIAS_CUDA_TRY(cudaMemcpyAsync(rows.data(), m->group_rows, rows.size() * 4, cudaMemcpyDeviceToHost, st));
             BIAS_CUDA_TRY(cudaStreamSynchronize(st));
         }

@@ -514,8 +514,19 @@ int bias_ctx_create(int device, uint64_t seed, void *stream, bias_ctx **out) {
     return BIAS_OK;
 }
 
+static void ctx_release(bias_ctx *ctx);
+
 int bias_ctx_destroy(bias_ctx *ctx) {
     if (!ctx) return BIAS_OK;
+    if (ctx->live_models > 0) {          // models still launch on this stream: the last bias_model_destroy releases it
+        ctx->closed = true;
+        return BIAS_OK;
+    }
+    ctx_release(ctx);
+    return BIAS_OK;
+}
+
+static void ctx_release(bias_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stirling) cudaFree(ctx->stirling);
@@ -523,7 +534,6 @@ int bias_ctx_destroy(bias_ctx *ctx) {
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
-    return BIAS_OK;
 }
 
 int bias_ctx_sync(bias_ctx *ctx) {
@@ -557,7 +567,9 @@ int bias_model_destroy(bias_model *m) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
+    bias_ctx *ctx = m->ctx;
     delete m;
+    if (--ctx->live_models == 0 && ctx->closed) ctx_release(ctx);
     return BIAS_OK;
 }
 
@@ -583,6 +595,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     bias_model *m = new (std::nothrow) bias_model();
     if (!m) return fail(BIAS_ENOMEM, "out of host memory");
     m->ctx = ctx;
+    ctx->live_models += 1;
     m->model = model;
     m->conj = *conj;
     m->N = data->n_items;
@@ -599,7 +612,7 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
     const char *force_generic = getenv("BIAS_FORCE_GENERIC");
     m->fast = (model == BIAS_MODEL_LDA && conj->kind == BIAS_MD && conj->datum == BIAS_INT && kp <= 4096 &&
                !(force_generic && force_generic[0] == '1'));
-    if (m->N >= (int64_t)1 << 31) { delete m; return fail(BIAS_EINVAL, "more than 2^31-1 items per device"); }
+    if (m->N >= (int64_t)1 << 31) { bias_model_destroy(m); return fail(BIAS_EINVAL, "more than 2^31-1 items per device"); }
 
     cudaStream_t st = ctx->stream;
     int rc = BIAS_OK;

@@ -17,6 +17,9 @@ struct bias_ctx {
     double *stirling = nullptr;
     int32_t stirling_rows = 0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // models created on this context; a context destroyed while models are alive is released by the last of them
+    int32_t live_models = 0;
+    bool closed = false;
 };
 
 struct bias_model {

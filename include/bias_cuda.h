@@ -102,6 +102,7 @@ BIAS_API const char *bias_last_error(void);
 BIAS_API int  bias_device_count(int *n_out);
 /* stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
 BIAS_API int  bias_ctx_create(int device, uint64_t seed, void *stream, bias_ctx **out);
+/* A context destroyed while models created on it are alive is released when the last of them is destroyed. */
 BIAS_API int  bias_ctx_destroy(bias_ctx *ctx);
 BIAS_API int  bias_ctx_sync(bias_ctx *ctx);
 BIAS_API int  bias_ctx_num_sms(bias_ctx *ctx, int *n_out);

@@ -18,6 +18,14 @@ def ctx():
     c.close()
 
 
+def _sums_agree(got, want):
+    """Component sums of a Gaussian model are Float64 atomics that every item passed through: a component that held
+    5e5 points (sum ~1e7) and shrank to five keeps the rounding of what passed through it, so the tolerance is
+    relative to the largest sum, not to each component's own (the reference's running mean drifts the same way,
+    src/conjugates.jl:62, :71)."""
+    return np.allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+
+
 def test_c3_lda_100m_tokens_counts_conserved(ctx):
     import torch
     K, V, D, L = 1024, 50_000, 500_000, 200
@@ -90,7 +98,7 @@ def test_c4_hdp_10m_points_counts_conserved(ctx):
     comp = rs.components()
     assert np.array_equal(comp["nn"], np.bincount(z, minlength=hp.KK))
     sums = np.bincount(z, weights=x, minlength=hp.KK)
-    assert np.allclose(comp["mu"] * comp["nn"], sums, rtol=1e-9)
+    assert _sums_agree(comp["mu"] * comp["nn"], sums)
     assert n_atoms <= hp.KK <= n_atoms + 6
     # every inferred component is pure in the generating atoms
     homog = sum(np.bincount(zt.reshape(-1)[z == c]).max() for c in range(hp.KK)) / len(z)
@@ -131,7 +139,7 @@ def test_c4_crf_10m_points_seating_consistent(ctx):
     _, dish = _seating_is_consistent(z, ptr, t["tji"], t["njt"], t["kjt"], t["n_tbls"], hp.KK)
     assert np.array_equal(t["mm"], np.bincount(dish, minlength=hp.KK)) and (t["mm"] > 0).all()
     assert np.array_equal(comp["nn"], np.bincount(z, minlength=hp.KK))
-    assert np.allclose(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=hp.KK), rtol=1e-9)
+    assert _sums_agree(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=hp.KK))
     assert n_atoms <= hp.KK <= n_atoms + 12
     homog = sum(np.bincount(zt.reshape(-1)[z == c]).max() for c in range(hp.KK)) / len(z)
     assert homog > 0.99
@@ -155,7 +163,7 @@ def test_c5_rcrp_100_epochs_counts_conserved(ctx):
     _, aa = rs.rcrp_state()
     assert set(np.unique(z)) == set(range(KK)) and (aa > 0).all() and len(aa) == n_epochs
     assert np.array_equal(comp["nn"], np.bincount(z, minlength=KK))
-    assert np.allclose(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=KK), rtol=1e-9)
+    assert _sums_agree(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=KK))
     per_epoch = np.stack([np.bincount(z[t * n_per:(t + 1) * n_per], minlength=KK) for t in range(n_epochs)])
     for k in range(KK):                     # the epochs a cluster lives in are contiguous
         on = np.flatnonzero(per_epoch[:, k] > 0)
@@ -189,7 +197,7 @@ def test_c5_rcrf_100_epochs_seating_consistent(ctx):
     assert np.array_equal(np.asarray(t["mm"]).reshape(n_epochs, -1)[:, :KK], mm) and (mm.sum(0) > 0).all()
     assert (gg > 0).all() and (aa > 0).all()
     assert np.array_equal(comp["nn"], np.bincount(z, minlength=KK))
-    assert np.allclose(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=KK), rtol=1e-9)
+    assert _sums_agree(comp["mu"] * comp["nn"], np.bincount(z, weights=x, minlength=KK))
     homog = sum(np.bincount(atoms[z == c]).max() for c in range(KK)) / len(z)
     assert homog > 0.99
     rs.close()

@@ -481,3 +481,26 @@ def test_production_kernel_cdf_at_k1024(ctx):
             lo = np.where(up, lo, mid)
         assert np.abs(0.5 * (lo + hi) - ocdf[:, e]).max() < 3e-6, e
     rs.close()
+
+
+def test_context_closed_before_its_models():
+    """bias_ctx_destroy with models still alive defers the release to the last bias_model_destroy (a failing caller
+    that unwinds in the wrong order must not leave a dangling stream behind)."""
+    rng = np.random.default_rng(3)
+    xx = [rng.integers(0, 20, 30).astype(np.int64) for _ in range(4)]
+    lda = b.LDA(b.MultinomialDirichlet(20, 2.0), 5, 0.3)
+    data = b.FlatData(lda.component, xx, True)
+    c = b.Context(0, seed=5)
+    r1 = b.ResidentSampler(c, lda, data, rng.integers(0, 5, data.n_items).astype(np.int32))
+    r2 = b.ResidentSampler(c, lda, data, rng.integers(0, 5, data.n_items).astype(np.int32))
+    c.close()
+    r1.sweep(2)                      # the stream is still there
+    assert len(r1.get_zz()) == data.n_items
+    r1.close()
+    r2.sweep(1)
+    r2.close()                       # releases the context
+    c2 = b.Context(0, seed=6)
+    r3 = b.ResidentSampler(c2, lda, data, rng.integers(0, 5, data.n_items).astype(np.int32))
+    r3.sweep(1)
+    r3.close()
+    c2.close()
