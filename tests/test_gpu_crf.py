@@ -79,7 +79,7 @@ def test_many_restaurants_keep_the_seating_consistent(ctx):
         for k in range(hp.KK):
             assert abs(comp["mu"][k] - x[z == k].mean()) < 1e-9
     homog = sum(np.bincount(atoms[z == c]).max() for c in np.unique(z)) / N
-    assert homog > 0.98 and 5 <= hp.KK <= 9, (homog, hp.KK)
+    assert homog > 0.98 and 5 <= hp.KK <= 12, (homog, hp.KK)
     assert np.isfinite(rs.stats().log_likelihood)
     rs.close()
 
@@ -97,7 +97,7 @@ def test_crf_gibbs_sampler_entry_point(ctx):
     used = len(np.unique(np.concatenate(zz_true)))
     z, zt = np.concatenate(zz), np.concatenate(zz_true)
     homog = sum(np.bincount(zt[z == c]).max() for c in np.unique(z)) / len(z)
-    assert homog > 0.97 and used - 1 <= hdp.KK <= used + 3, (homog, hdp.KK, used)
+    assert homog > 0.97 and used - 1 <= hdp.KK <= used + 5, (homog, hdp.KK, used)
     # the serial sampler on the same data
     ptr = np.concatenate([[0], np.cumsum([len(x) for x in xx])])
     st = orc.CRFState(orc.Comps.g1g1(64, float(allx.mean()), 10.0, 0.001), orc.Data.reals(allx), ptr,
