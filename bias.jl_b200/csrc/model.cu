@@ -105,10 +105,6 @@ static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
     if (ctas_per_sm == 0) {
         BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half_kernel<NCK, WARPS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const char *co = getenv("BIAS_LDA_CARVEOUT");
-        if (co)
-            BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half_kernel<NCK, WARPS>,
-                                               cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co)));
         int occ = 0;
         BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half_kernel<NCK, WARPS>, threads, smem));
         if (occ < 1) return fail(BIAS_ECUDA, "LDA half-warp sweep kernel does not fit on an SM (K padded to %d)", NCK * 64);
@@ -209,10 +205,7 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.frozen = frozen;
     p.diag_sum = reinterpret_cast<double *>(m->scratch);
     p.moved = m->scratch + 1;
-    {
-        const char *pf = getenv("BIAS_LDA_PF");
-        p.pf_dist = pf ? std::max(0, std::min(16, atoi(pf))) : 2;
-    }
+    p.pf_dist = 2;            // rows prefetched into L2 ahead of the token loop (int32-row half-warp kernel)
     p.nk_rep = m->nk_rep;
     const bool half_path = use_half_kernel(m) && !eval && m->nk_rep;
     if (use_half16_kernel(m) && !eval && m->V > 0) {
