@@ -98,10 +98,10 @@ __device__ __forceinline__ int crf_draw(double *sc, int n_out, double u, int lan
 // ---- the conjugate, by item kind -------------------------------------------------------------------------
 // logpredictive(components[k], item) (src/conjugates.jl:92-103, :180, :181-198); k < 0: the empty prototype
 template <int DATUM>
-__device__ __forceinline__ double crf_logpred(const CrfParams &p, int k, int64_t idx) {
-    if (DATUM == BIAS_F64) {
+__device__ __forceinline__ double crf_logpred(const CrfParams &p, int k, int64_t idx, double x) {
+    if (DATUM == BIAS_F64) {         // x = p.x[idx], loaded once by the caller (a re-load after every fence goes to L2)
         const double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
-        return g1g1_logpred(cn, sx, p.x[idx], p.m0, p.v0, p.vv);
+        return g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
     } else if (DATUM == BIAS_INT) {
         const double nw = k < 0 ? 0.0 : (double)__ldcg(p.n_wk + (size_t)p.word[idx] * p.Kpad + k);
         const double nk = k < 0 ? 0.0 : (double)__ldcg(p.n_k + k);
@@ -121,9 +121,10 @@ __device__ __forceinline__ double crf_logpred(const CrfParams &p, int k, int64_t
 }
 // additem! (sign = +1) / delitem! (sign = -1) of one item on dish k; executed by ONE lane
 template <int DATUM>
-__device__ __forceinline__ void crf_item_move(const CrfParams &p, int k, int64_t idx, int sign) {
+__device__ __forceinline__ void crf_item_move(const CrfParams &p, int k, int64_t idx, int sign, double x) {
+    atomicAdd(p.n_items + k, sign);
     if (DATUM == BIAS_F64) {
-        atomicAdd(p.sumx + k, (double)sign * p.x[idx]);
+        atomicAdd(p.sumx + k, (double)sign * x);
     } else if (DATUM == BIAS_INT) {
         atomicAdd(p.n_wk + (size_t)p.word[idx] * p.Kpad + k, sign);
         atomicAdd(p.n_k + k, sign);
@@ -135,13 +136,18 @@ __device__ __forceinline__ void crf_item_move(const CrfParams &p, int k, int64_t
         }
         atomicAdd(p.n_k + k, sign * m);
     }
-    atomicAdd(p.n_items + k, sign);
 }
 
 // Restaurants that meet a new atom at the same moment would each open a dish for it (hundreds of duplicates in the
 // first iteration).  A warp whose draw says "new dish" therefore takes a global lock, scores the menu again — it now
 // holds whatever the previous lock holders opened — and opens a dish only if the draw (same uniform) still says so.
 // With one restaurant this is the serial sampler step for step.
+// Only births are serialised: while a lock holder scores the menu, other warps keep moving customers between existing
+// dishes with pairs of independent atomics (n, then the sum), so a scorer can catch a dish between the two — its mean
+// off by one item, which for a dish of a handful of items is far outside the predictive and makes the holder open
+// a duplicate.  A dish is therefore opened only if kCrfBirthLooks consecutive scorings (same uniform) all say
+// "new"; with one restaurant every look gives the same answer, so the serial trajectory is unchanged.
+constexpr int kCrfBirthLooks = 6;
 __device__ __forceinline__ void crf_lock(const CrfParams &p, int lane) {
     if (lane == 0)
         while (atomicCAS(p.lock, 0, 1) != 0) __nanosleep(200);
@@ -233,10 +239,11 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
         for (int ii = 0; ii < n; ++ii) {
             const int64_t i = p0 + ii;
             int kk = p.z[i], tbl = tji[ii];
+            const double x = (DATUM == BIAS_F64) ? p.x[i] : 0.0;
             // remove the customer (:511-515)
             int left = 0;
             if (lane == 0) {
-                crf_item_move<DATUM>(p, kk, i, -1);
+                crf_item_move<DATUM>(p, kk, i, -1, x);
                 left = njt[tbl] - 1;
                 njt[tbl] = left;
             }
@@ -261,8 +268,8 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
             __threadfence();
             __syncwarp();
             // scores of the tables and of a new one (:549-555)
-            for (int t = lane; t < nt; t += 32) sc[t] = log((double)njt[t]) + crf_logpred<DATUM>(p, kjt[t], i);
-            if (lane == 0) sc[nt] = log(p.aa) + crf_logpred<DATUM>(p, -1, i);
+            for (int t = lane; t < nt; t += 32) sc[t] = log((double)njt[t]) + crf_logpred<DATUM>(p, kjt[t], i, x);
+            if (lane == 0) sc[nt] = log(p.aa) + crf_logpred<DATUM>(p, -1, i, x);
             __syncwarp();
             tbl = crf_draw(sc, nt + 1, crf_draw_uniform(p, i, 0), lane);
             if (tbl == nt) {
@@ -271,9 +278,9 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                 const CrfLook L = crf_look(p, KK, lane);
                 for (int k = lane; k < KK; k += 32) {
                     const double pr = crf_dish_prior(p, L, k);
-                    sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i);
+                    sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i, x);
                 }
-                if (lane == 0) sc[KK] = log(p.gg) + crf_logpred<DATUM>(p, -1, i);
+                if (lane == 0) sc[KK] = log(p.gg) + crf_logpred<DATUM>(p, -1, i, x);
                 __syncwarp();
                 const double u_dish = crf_draw_uniform(p, i, 1);
                 int knew = crf_draw(sc, KK + 1, u_dish, lane);
@@ -281,14 +288,18 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                 if (locked) {
                     crf_lock(p, lane);
                     const int KK2 = crf_read_KK(p, lane);
-                    const CrfLook L2 = crf_look(p, KK2, lane);
-                    for (int k = lane; k < KK2; k += 32) {
-                        const double pr = crf_dish_prior(p, L2, k);
-                        sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i);
+                    knew = KK2;
+                    for (int look = 0; look < kCrfBirthLooks && knew == KK2; ++look) {      // see kCrfBirthLooks
+                        const CrfLook L2 = crf_look(p, KK2, lane);
+                        for (int k = lane; k < KK2; k += 32) {
+                            const double pr = crf_dish_prior(p, L2, k);
+                            sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i, x);
+                        }
+                        if (lane == 0) sc[KK2] = log(p.gg) + crf_logpred<DATUM>(p, -1, i, x);
+                        __syncwarp();
+                        knew = crf_draw(sc, KK2 + 1, u_dish, lane);
+                        __syncwarp();
                     }
-                    if (lane == 0) sc[KK2] = log(p.gg) + crf_logpred<DATUM>(p, -1, i);
-                    __syncwarp();
-                    knew = crf_draw(sc, KK2 + 1, u_dish, lane);
                     if (knew == KK2) {
                         knew = crf_new_dish(p, lane);
                         if (knew < 0) knew = KK2 - 1;
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                     if (lane == 0) {
                         tji[ii] = tbl;
                         njt[tbl] = 1;
-                        crf_item_move<DATUM>(p, knew, i, 1);
+                        crf_item_move<DATUM>(p, knew, i, 1, x);
                         if (knew != kk) { p.z[i] = knew; moved += 1; }
                     }
                     crf_unlock(p, lane);
@@ -317,7 +328,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
             if (lane == 0) {
                 tji[ii] = tbl;
                 njt[tbl] += 1;
-                crf_item_move<DATUM>(p, kn, i, 1);
+                crf_item_move<DATUM>(p, kn, i, 1, x);
                 if (kn != kk) { p.z[i] = kn; moved += 1; }
             }
             __threadfence();
@@ -337,7 +348,7 @@ __device__ __forceinline__ double crf_table_score(const CrfParams &p, int k, con
         const double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
         for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
     } else {
-        for (int q = 0; q < nti; ++q) s += crf_logpred<DATUM>(p, k, p0 + ids[q]);
+        for (int q = 0; q < nti; ++q) s += crf_logpred<DATUM>(p, k, p0 + ids[q], 0.0);
     }
     return s;
 }
@@ -381,7 +392,9 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
                 nti += __popc(bal);
             }
             __syncwarp();
-            // the table leaves its dish (:599, :626-628)
+            // the table leaves its dish (:599, :626-628); the table count goes first: a dish must not look alive (prior
+            // log(mm)) while its statistics are already gone
+            if (lane == 0) atomicAdd(mm_t + kk, -1);
             if (DATUM == BIAS_F64) {
                 sum = warp_sum(sum);
                 if (lane == 0) {
@@ -389,9 +402,8 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
                     atomicAdd(p.sumx + kk, -sum);
                 }
             } else {
-                for (int q = lane; q < nti; q += 32) crf_item_move<DATUM>(p, kk, p0 + ids[q], -1);
+                for (int q = lane; q < nti; q += 32) crf_item_move<DATUM>(p, kk, p0 + ids[q], -1, 0.0);
             }
-            if (lane == 0) atomicAdd(mm_t + kk, -1);
             __threadfence();
             __syncwarp();
             const int KK = crf_read_KK(p, lane);
@@ -408,18 +420,27 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
             if (locked) {
                 crf_lock(p, lane);
                 const int KK2 = crf_read_KK(p, lane);
-                const CrfLook L2 = crf_look(p, KK2, lane);
-                for (int k = lane; k <= KK2; k += 32) {
-                    double s_ = (k < KK2) ? crf_dish_prior(p, L2, k) : log(p.gg);
-                    if (s_ != -INFINITY) s_ += crf_table_score<DATUM>(p, k < KK2 ? k : -1, xs, ids, p0, nti);
-                    sc[k] = s_;
+                knew = KK2;
+                for (int look = 0; look < kCrfBirthLooks && knew == KK2; ++look) {          // see kCrfBirthLooks
+                    const CrfLook L2 = crf_look(p, KK2, lane);
+                    for (int k = lane; k <= KK2; k += 32) {
+                        double s_ = (k < KK2) ? crf_dish_prior(p, L2, k) : log(p.gg);
+                        if (s_ != -INFINITY) s_ += crf_table_score<DATUM>(p, k < KK2 ? k : -1, xs, ids, p0, nti);
+                        sc[k] = s_;
+                    }
+                    __syncwarp();
+                    knew = crf_draw(sc, KK2 + 1, u_dish, lane);
+                    __syncwarp();
                 }
-                __syncwarp();
-                knew = crf_draw(sc, KK2 + 1, u_dish, lane);
                 if (knew == KK2) {
                     knew = crf_new_dish(p, lane);
                     if (knew < 0) knew = kk;
                 }
+            }
+            if (lane == 0) {
+                kjt[tbl] = knew;
+                atomicAdd(mm_t + knew, 1);
+                if (knew != kk) moved += (unsigned long long)nti;
             }
             if (DATUM == BIAS_F64) {
                 if (lane == 0) {
@@ -427,12 +448,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
                     atomicAdd(p.sumx + knew, sum);
                 }
             } else {
-                for (int q = lane; q < nti; q += 32) crf_item_move<DATUM>(p, knew, p0 + ids[q], 1);
-            }
-            if (lane == 0) {
-                kjt[tbl] = knew;
-                atomicAdd(mm_t + knew, 1);
-                if (knew != kk) moved += (unsigned long long)nti;
+                for (int q = lane; q < nti; q += 32) crf_item_move<DATUM>(p, knew, p0 + ids[q], 1, 0.0);
             }
             if (locked) crf_unlock(p, lane);
             if (knew != kk)
@@ -480,7 +496,7 @@ template <int DATUM>
 __global__ void crf_diag_kernel(CrfParams p, int64_t N, double *out) {
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
-        acc += crf_logpred<DATUM>(p, p.z[i], i);
+        acc += crf_logpred<DATUM>(p, p.z[i], i, (DATUM == BIAS_F64) ? p.x[i] : 0.0);
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
