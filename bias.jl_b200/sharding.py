@@ -43,6 +43,13 @@ def device_tensor(ptr: int, n: int, dtype: str, device):
     return torch.as_tensor(_CudaView(ptr, n, dtype), device=device)
 
 
+class _Done:
+    """Stand-in for a recorded CUDA event when the shard lives in host memory."""
+
+    def synchronize(self):
+        pass
+
+
 class ShardedSampler:
     """Drives one rank's shard: delta_begin -> sweep -> delta_pack -> all_reduce -> delta_apply.
 
@@ -82,11 +89,15 @@ class ShardedSampler:
             for t in ts:
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
             self.shard.delta_apply16()
-            if self._flag_host is None:
-                self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            self._flag_host.copy_(ts[1][-4:-3], non_blocking=True)
-            self._flag_event = torch.cuda.Event()
-            self._flag_event.record()
+            if ts[1].is_cuda:
+                if self._flag_host is None:
+                    self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._flag_host.copy_(ts[1][-4:-3], non_blocking=True)
+                self._flag_event = torch.cuda.Event()
+                self._flag_event.record()
+            else:                                   # host shards (the CPU tests): the flag is there already
+                self._flag_host = ts[1][-4:-3].clone()
+                self._flag_event = _Done()
             return
         for t in self.shard.delta_tensors():
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)

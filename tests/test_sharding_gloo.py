@@ -1,6 +1,7 @@
 """The N>1 path on CPU: two gloo ranks drive ShardedSampler (the same class bench.py uses over NCCL)
-with an oracle-backed shard.  Checks the exchange protocol: replicas stay identical, integer counts
-are conserved exactly, and the merged state equals the counts recomputed from the gathered zz."""
+with an oracle-backed shard.  Checks the exchange protocol — the int32 one and the 16-bit one with its overflow flag
+and one-sweep-late fallback: replicas stay identical, integer counts are conserved exactly, and the merged state
+equals the counts recomputed from the gathered zz."""
 import os
 import socket
 import sys
@@ -47,6 +48,85 @@ class OracleShard:
         for d, a, b_ in zip(self.delta, self.live, self.base):
             a[...] = b_ + d
             b_[...] = a
+
+
+class OracleShard16(OracleShard):
+    """The same stand-in offering the 16-bit exchange of GpuShard: two word-topic deltas per int32 as d1 * 65536 + d0
+    (arithmetically, so that the all-reduced sums unpack as long as every summed delta fits 16 bits), the other deltas
+    and the overflow flag (fourth from the end) in a small int32 buffer; apply16 applies nothing when the flag is set."""
+
+    def __init__(self, *a, limit=32767, **kw):
+        super().__init__(*a, **kw)
+        self.limit = limit
+        self.n16 = 0                     # exchanges that went through in 16 bits
+        self.skipped = 0                 # 16-bit exchanges refused by the flag
+
+    def delta_tensors16(self, world):
+        d = (self.live[0] - self.base[0]).reshape(-1)
+        small = np.concatenate([(self.live[1] - self.base[1]).reshape(-1), (self.live[2] - self.base[2]).reshape(-1),
+                                np.zeros(4, dtype=np.int64)])
+        small[-4] = int(np.abs(d).max(initial=0) * world > self.limit)
+        self._packed = torch.from_numpy((d[1::2] * 65536 + d[0::2]).astype(np.int32))
+        self._small = torch.from_numpy(small.astype(np.int32))
+        return [self._packed, self._small]
+
+    def delta_apply16(self):
+        small = self._small.numpy().astype(np.int64)
+        if small[-4] != 0:
+            self.skipped += 1
+            return                       # the deltas stay in live - base and ride along with the next (32-bit) exchange
+        pk = self._packed.numpy().astype(np.int64)
+        d0 = (pk + 32768) % 65536 - 32768
+        d1 = (pk - d0) // 65536
+        d = np.empty(2 * len(pk), dtype=np.int64)
+        d[0::2], d[1::2] = d0, d1
+        n1 = self.live[1].size
+        sums = [d.reshape(self.live[0].shape), small[:n1].reshape(self.live[1].shape),
+                small[n1:-4].reshape(self.live[2].shape)]
+        for a, b_, sd in zip(self.live, self.base, sums):
+            a[...] = b_ + sd
+            b_[...] = a
+        self.n16 += 1
+
+
+def _worker16(rank, world, port, out_dir, limit):
+    """The 16-bit exchange under gloo: with a generous limit every exchange after the initial merge is a 16-bit one;
+    with a limit of 0 every 16-bit attempt is refused by the flag and the next exchange, a 32-bit one, carries the
+    skipped deltas.  Either way the replicas end up equal to the counts recomputed from the gathered zz."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bias_jl_b200 as b
+    from bias_jl_b200.sharding import ShardedSampler, shard_csr
+
+    K, V = 10, 26
+    xx, _, _ = b.data.bars_lda_corpus(n_groups=41, n_tokens=30, seed=3)
+    words = np.concatenate(xx)
+    ptr = np.concatenate([[0], np.cumsum([len(x) for x in xx])]).astype(np.int64)
+    z0 = np.random.default_rng(0).integers(0, K, len(words))
+    lo, hi, i0, i1, lptr = shard_csr(ptr, rank, world)
+    shard = OracleShard16(K, V, 2.6, 0.1, lptr, words[i0:i1], z0[i0:i1], seed=100 + rank, limit=limit)
+    sampler = ShardedSampler(shard)
+    n_sweeps = 6
+    sampler.sweep(n_sweeps)
+    if limit == 0:
+        # refused, then a 32-bit exchange, alternately; a trailing refused one leaves the last sweep's deltas pending
+        assert shard.n16 == 0 and shard.skipped == n_sweeps // 2
+        sampler._exchange(force32=True)
+    else:
+        assert shard.n16 == n_sweeps and shard.skipped == 0
+    zs = [None] * world
+    dist.all_gather_object(zs, (i0, i1, shard.state.z.copy()))
+    z = np.empty_like(z0)
+    for a, b_, seg in zs:
+        z[a:b_] = seg
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z, words), 1)
+    assert np.array_equal(shard.state.c.mi, mi), "replica != counts recomputed from the gathered zz"
+    assert np.array_equal(shard.state.c.mm, mi.sum(1)) and shard.state.c.mm.sum() == len(words)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def _worker(rank, world, port, out_dir):
@@ -116,3 +196,10 @@ def test_single_rank_needs_no_process_group():
     shard = OracleShard(10, 25, 2.5, 0.1, ptr, words, z0, seed=1)
     ShardedSampler(shard).sweep(2)
     assert shard.state.c.mm.sum() == 100
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("limit", [32767, 0])
+def test_two_rank_16_bit_exchange_over_gloo(tmp_path, limit):
+    world = 2
+    mp.spawn(_worker16, args=(world, _free_port(), str(tmp_path), limit), nprocs=world, join=True)
