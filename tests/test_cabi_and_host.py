@@ -3,6 +3,7 @@ without a GPU, and the host mirror of the reference API behaves like the referen
 against the oracle and the golden vectors)."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -120,3 +121,23 @@ def test_shard_bounds_cover_everything():
     ptr = np.array([0, 3, 3, 10, 12])
     lo, hi, i0, i1, lp = shard_csr(ptr, 1, 2)
     assert (lo, hi, i0, i1) == (2, 4, 3, 12) and lp.tolist() == [0, 7, 9]
+
+
+@pytest.mark.timeout(400)
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores only (the serial sampler, one instance per core) and prints one
+    JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=380, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "lda_gibbs_token_samples_per_sec_K1024" and d["unit"] == "tokens/s"
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["higher_is_better"] is True and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
