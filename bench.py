@@ -28,7 +28,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, V, D_TOTAL, L_DOC = 1024, int(os.environ.get("BIAS_BENCH_V", 50_000)), 500_000, 200   # BIAS_BENCH_V: experiments only
+K, V, D_TOTAL, L_DOC = 1024, 50_000, 500_000, 200
+CORPUS = "dirichlet"            # --corpus zipf: word frequencies ~ 1 / rank (hot words: int32 rows inside the same kernel)
 ALPHA, BETA = 0.1, 0.1          # aa_total = BETA * V
 PHI_CONC, THETA_CONC = 0.01, 0.1
 B_ALG = 4 * K + 12              # algorithmic bytes per token-sample
@@ -47,12 +48,10 @@ def emit(line: dict):
 
 
 def sweep_kernel_name():
-    """The kernel bias_model_sweep launches for this workload (csrc/model.cu: use_half_kernel / use_tma_kernel)."""
+    """The kernel bias_model_sweep launches for this workload (csrc/model.cu: use_half16_kernel / use_half_kernel)."""
     force = os.environ.get("BIAS_LDA_KERNEL", "")
     if force.startswith("r"):
         return "lda_md_int_sweep_kernel<8>"
-    if force.startswith("t"):
-        return "lda_md_int_sweep_tma_kernel<8>"
     if force.startswith("h"):
         return "lda_md_int_sweep_half_kernel<16, 8>"
     return "lda_md_int_sweep_half16_kernel<8, 6, 3, true>"
@@ -99,6 +98,25 @@ def gen_docs_torch(cdf_flat, d0, d1, device):
         u = torch.rand(topics.shape, device=device, dtype=torch.float64, generator=g)
         flat = torch.searchsorted(cdf_flat, topics.to(torch.float64) + u)
         words = (flat - topics * V).clamp_(0, V - 1).to(torch.int32)
+        a, b_ = max(d0, lo) - lo, min(d1, hi) - lo
+        out.append(words[a:b_].reshape(-1))
+    return torch.cat(out) if out else torch.zeros(0, dtype=torch.int32, device=device)
+
+
+def gen_docs_zipf_torch(d0, d1, device):
+    """--corpus zipf: word ids drawn independently with p(w) ~ 1 / (w + 1) (Zipf exponent 1.0), so that a handful of
+    words carry a large share of the tokens, as in natural-language corpora (at 100 M tokens over V = 50,000 about 130
+    words exceed 65,535 occurrences and hold ~48 % of the tokens)."""
+    import torch
+    p = 1.0 / torch.arange(1, V + 1, device=device, dtype=torch.float64)
+    cdf = torch.cumsum(p / p.sum(), 0)
+    out = []
+    for c in range(d0 // CHUNK_DOCS, (d1 + CHUNK_DOCS - 1) // CHUNK_DOCS):
+        lo, hi = c * CHUNK_DOCS, min((c + 1) * CHUNK_DOCS, D_TOTAL)
+        g = torch.Generator(device=device)
+        g.manual_seed(SEED * 1_000_003 + c)
+        u = torch.rand(((hi - lo), L_DOC), device=device, dtype=torch.float64, generator=g)
+        words = torch.searchsorted(cdf, u).clamp_(0, V - 1).to(torch.int32)
         a, b_ = max(d0, lo) - lo, min(d1, hi) - lo
         out.append(words[a:b_].reshape(-1))
     return torch.cat(out) if out else torch.zeros(0, dtype=torch.int32, device=device)
@@ -263,11 +281,67 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------ our arm
+def ncu_facts():
+    """Per-token figures of the dominant kernel from the committed ncu capture (profiles/lda_sweep_traffic.json)."""
+    tp = os.path.join(ROOT, "profiles", "lda_sweep_traffic.json")
+    try:
+        return json.load(open(tp))
+    except Exception:
+        return {}
+
+
+def make_corpus(dev, d0, d1):
+    import torch
+    if CORPUS == "zipf":
+        return gen_docs_zipf_torch(d0, d1, dev)
+    cdf = topic_cdf_torch(dev)
+    w = gen_docs_torch(cdf, d0, d1, dev)
+    del cdf
+    torch.cuda.empty_cache()
+    return w
+
+
+def hbm_regime_line(b, ctx, dev, steps, warmup):
+    """The same sweep at V = 200,000: the 16-bit rows are a 410 MB table that cannot live in the 126 MB L2, so every
+    token's row (2 K bytes) comes from HBM.  This is the regime the metric's roofline was written for; algorithmic
+    bytes per token-sample here are 2 K + 12 (16-bit row + word id + z read + z write)."""
+    import torch
+    global V
+    v_saved, V = V, 200_000
+    try:
+        n_docs = 250_000                          # 50 M tokens: rows are still touched ~250 times each per sweep
+        words = make_corpus(dev, 0, n_docs)
+        n = int(words.numel())
+        g = torch.Generator(device=dev)
+        g.manual_seed(SEED + 5)
+        z = torch.randint(0, K, (n,), device=dev, dtype=torch.int32, generator=g)
+        lda = b.LDA(b.MultinomialDirichlet(V, BETA * V), K, ALPHA)
+        data = b.FlatData.from_csr(b._lib.INT, n, group_ptr=np.arange(n_docs + 1, dtype=np.int64) * L_DOC, word=words.cpu().numpy())
+        rs = b.ResidentSampler(ctx, lda, data, z.cpu().numpy())
+        del words, z
+        for _ in range(warmup):
+            rs.sweep(1)
+        ms = []
+        for _ in range(steps):
+            rs.sweep(1)
+            ms.append(rs.last_sweep_ms()[0])
+        rs.close()
+        peak, _ = peaks()
+        k_ms = float(np.mean(ms))
+        b_alg = 2 * K + 12
+        achieved = b_alg * n / (k_ms * 1e-3) / 1e9
+        return {"workload": f"LDA K={K} V={V} {n} tokens (16-bit rows: {2 * K * V / 1e6:.0f} MB > L2)", "kernel_ms": k_ms,
+                "tokens_per_s": n / (k_ms * 1e-3), "alg_bytes_per_token": b_alg, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak}
+    finally:
+        V = v_saved
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
     import bias_jl_b200 as b
-    from bias_jl_b200.sharding import GpuShard, ShardedSampler, shard_bounds
+    from bias_jl_b200.sharding import attach_ranks, device_tensor, shard_bounds
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -278,14 +352,12 @@ def ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)      # plumbing: barriers, max over ranks, the IPC handles
 
     n_docs_total = args.docs
     d0, d1 = shard_bounds(n_docs_total, rank, world)
     t_gen = time.perf_counter()
-    cdf = topic_cdf_torch(dev)
-    words_dev = gen_docs_torch(cdf, d0, d1, dev)
-    del cdf
+    words_dev = make_corpus(dev, d0, d1)
     n_local = int(words_dev.numel())
     gz = torch.Generator(device=dev)
     gz.manual_seed(SEED + 17 + rank)
@@ -296,20 +368,24 @@ def ours(args):
     words_h.copy_(words_dev)
     z_h.copy_(z_dev)
     torch.cuda.synchronize()
-    del words_dev, z_dev
+    del z_dev
     torch.cuda.empty_cache()
     ptr = np.arange(d1 - d0 + 1, dtype=np.int64) * L_DOC
     gen_s = time.perf_counter() - t_gen
 
     stream = torch.cuda.Stream(device=dev)     # a real (non-null) stream: the library launches on it and the events time it
     torch.cuda.set_stream(stream)
-    ctx = b.Context(local, seed=SEED + rank, stream=stream.cuda_stream)
+    ctx = b.Context(local, seed=SEED, stream=stream.cuda_stream)
     lda = b.LDA(b.MultinomialDirichlet(V, BETA * V), K, ALPHA)
     data = b.FlatData.from_csr(b._lib.INT, n_local, group_ptr=ptr, word=words_h.numpy())
 
-    def make_sampler():
-        rs = b.ResidentSampler(ctx, lda, data, z_h.numpy())
-        return rs, ShardedSampler(GpuShard(rs, dev))
+    def make_sampler(c):
+        """A resident shard; with more than one rank its sweep call is collective: local sweep + the library's own count
+        exchange over NVLink peer memory (csrc/comm.cu) — no NCCL on the data path."""
+        rs_ = b.ResidentSampler(c, lda, data, z_h.numpy())
+        if world > 1:
+            attach_ranks(rs_, n_local)
+        return rs_
 
     def barrier():
         if world > 1:
@@ -324,24 +400,21 @@ def ours(args):
         return float(t.item())
 
     # ---- device-resident arm: inputs already in HBM when the timed region starts ----
-    rs, sh = make_sampler()
+    rs = make_sampler(ctx)
     for _ in range(args.warmup):
-        sh.sweep(1)
+        rs.sweep(1)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
     launches0 = ctx.launches
-    kernel_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
-        sh.sweep(1)
-        if args.kernel_timing:
-            kernel_ms.append(rs.last_sweep_ms()[0])      # waits for this step's kernel: off by default
+        rs.sweep(1)
     ev1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
@@ -349,47 +422,78 @@ def ours(args):
     launches = ctx.launches - launches0
     clock_rec = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     stats = rs.stats()
-    ll_sum, ll_n = rs.log_likelihood()           # training log-likelihood per token of the local shard (not timed)
+    narrow_current, n_hot, hot_cap = rs.narrow_info()
 
-    # dominant-kernel duration: the sweep kernel alone, CUDA events on the launching stream
+    # dominant-kernel duration: the sweep call alone (at N > 1 it includes the exchange), CUDA events on the launching stream
     barrier()
     k_ms = []
     for _ in range(min(3, args.steps)):
         rs.sweep(1)
         k_ms.append(rs.last_sweep_ms()[0])
     kern_ms = max_over_ranks(float(np.mean(k_ms)))
+
+    # ---- every replica against the recount from ALL ranks' assignments (not timed) ----
+    z_now = torch.from_numpy(rs.get_zz()).to(dev)
+    Kpad = 1024
+    recount = torch.bincount(words_dev.to(torch.int64) * Kpad + z_now.to(torch.int64), minlength=V * Kpad).to(torch.int32)
+    nk_ref = torch.bincount(z_now.to(torch.int64), minlength=Kpad).to(torch.int32)
+    if world > 1:
+        dist.all_reduce(recount)
+        dist.all_reduce(nk_ref)
+    digest = rs.replica_digest()
+    rs.delta_begin_zero()                     # zero base => the delta buffer is the live [n_wk | n_k | n_items]
+    (p32, n32, _), = rs.delta_pack()
+    live = device_tensor(p32, n32, "int32", dev)
+    ctx.sync()
+    ok = bool(torch.equal(live[:V * Kpad], recount)) and bool(torch.equal(live[V * Kpad:V * Kpad + Kpad], nk_ref))
+    chk = torch.tensor([1 if ok else 0, digest & 0x7fffffff, -(digest & 0x7fffffff)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(chk, op=dist.ReduceOp.MIN)
+    replica_check = "ok" if int(chk[0]) == 1 and int(chk[1]) == -int(chk[2]) else "FAILED"
+    del recount, live, z_now
+    ll_sum, ll_n = rs.log_likelihood()           # training log-likelihood per token of the local shard (not timed)
     rs.close()
+    del words_dev
+    torch.cuda.empty_cache()
 
     # ---- end-to-end arm: host buffers in, host assignments out, every step ----
     # Streaming use of the public API: two resident models on two contexts (streams) are re-fed in turn
-    # (ResidentSampler.reload: H2D of the step's words / zz / offsets from pinned host memory + the
-    # initialisation pass, no allocation), swept once, and read back (get_zz: D2H into pinned host memory).
+    # (ResidentSampler.reload_u16: H2D of the step's words / zz / offsets from pinned host memory + the
+    # initialisation pass, no allocation), swept once (at N > 1 the sweep call first merges the ranks' fresh local
+    # counts, then sweeps and exchanges), and read back (get_zz_u16: D2H into pinned host memory).
     # The upload of step s+1 and the download of step s run on the copy engines while step s / s+1 is swept.
     e2e_steps = max(1, args.e2e_steps)
     streams = [stream, torch.cuda.Stream(device=dev)]
-    ctxs = [ctx, b.Context(local, seed=SEED + 1000 + rank, stream=streams[1].cuda_stream)]
+    ctxs = [ctx, b.Context(local, seed=SEED + 1000, stream=streams[1].cuda_stream)]
     # K = 1024 and V = 50,000 fit 16 bits: the step's word ids and assignments go up, and the new assignments come
     # back, as uint16 (bias_model_reload_u16 / bias_model_get_zz_u16) - half the PCIe bytes of the int32 calls
-    words16_h = torch.from_numpy(words_h.numpy().astype(np.uint16)).pin_memory()
-    z16_h = torch.from_numpy(z_h.numpy().astype(np.uint16)).pin_memory()
-    zz_out_h = [torch.from_numpy(np.zeros(n_local, dtype=np.uint16)).pin_memory() for _ in range(2)]
+    use16 = V <= 65536
+    t_fl = time.perf_counter()
+    words16_np = words_h.numpy().astype(np.int64).astype(np.uint16 if use16 else np.int32)   # what the shim does: Int64 -> narrow, flat
+    flatten_ms = 1e3 * (time.perf_counter() - t_fl)
+    words16_h = torch.from_numpy(words16_np).pin_memory()
+    z16_h = torch.from_numpy(z_h.numpy().astype(words16_np.dtype)).pin_memory()
+    zz_out_h = [torch.from_numpy(np.zeros(n_local, dtype=words16_np.dtype)).pin_memory() for _ in range(2)]
     pipes = []
     for i in range(2):
         with torch.cuda.stream(streams[i]):
-            rs_i = b.ResidentSampler(ctxs[i], lda, data, z_h.numpy())
-            pipes.append((rs_i, ShardedSampler(GpuShard(rs_i, dev))))
+            pipes.append(make_sampler(ctxs[i]))
 
     def e2e_upload(i):
         with torch.cuda.stream(streams[i]):
-            pipes[i][0].reload_u16(words16_h.numpy(), ptr, z16_h.numpy())
-            pipes[i][1].merge_local_counts()
+            if use16:
+                pipes[i].reload_u16(words16_h.numpy(), ptr, z16_h.numpy())
+            else:
+                pipes[i].reload(b.FlatData.from_csr(b._lib.INT, n_local, group_ptr=ptr, word=words16_h.numpy()), z16_h.numpy())
 
     def e2e_sweep(i):
         with torch.cuda.stream(streams[i]):
-            pipes[i][1].sweep(1)
+            pipes[i].sweep(1)
 
     def e2e_download(i):
-        return pipes[i][0].get_zz_u16(zz_out_h[i].numpy())      # waits for the model's own stream only
+        if use16:
+            return pipes[i].get_zz_u16(zz_out_h[i].numpy())      # waits for the model's own stream only
+        return pipes[i].get_zz(zz_out_h[i].numpy())
 
     verbose = bool(os.environ.get("BIAS_BENCH_VERBOSE")) and rank == 0
 
@@ -410,17 +514,17 @@ def ours(args):
             print("e2e host marks (ms since start; per step: upload done, sweep enqueued, download done):",
                   [round(1e3 * (m_ - marks[0]), 2) for m_ in marks], file=sys.stderr)
 
-    e2e_run(2)                                   # warm both pipelines (first-touch of the pinned buffers, NCCL)
+    e2e_run(2)                                   # warm both pipelines (first-touch of the pinned buffers)
     barrier()
     t0 = time.perf_counter()
     e2e_run(e2e_steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    moved_e2e = int(pipes[(e2e_steps - 1) % 2][0].stats().n_moved)
+    moved_e2e = int(pipes[(e2e_steps - 1) % 2].stats().n_moved)
     assert moved_e2e > 0 and int(zz_out_h[(e2e_steps - 1) % 2].numpy().max()) < K
-    h2d = words16_h.numel() * 2 + z16_h.numel() * 2 + ptr.nbytes
-    d2h = zz_out_h[0].numel() * 2
-    for rs_i, _ in pipes:
+    h2d = words16_h.numel() * words16_h.element_size() + z16_h.numel() * z16_h.element_size() + ptr.nbytes
+    d2h = zz_out_h[0].numel() * zz_out_h[0].element_size()
+    for rs_i in pipes:
         rs_i.close()
     ctxs[1].close()
 
@@ -430,13 +534,13 @@ def ours(args):
     peak, peak_src = peaks()
     tokens_per_launch = n_local
     achieved = B_ALG * tokens_per_launch / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "lda_sweep_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_token") * tokens_per_launch   # ncu capture scaled to this launch
-        except Exception:
-            traffic = None
+    facts = ncu_facts()
+    traffic = facts.get("dram_bytes_per_token")
+    traffic = traffic * tokens_per_launch if traffic is not None else None    # ncu capture scaled to this launch
+    l2_bytes = 2 * K + 12 + 4          # what one token-sample pulls through L2: its 16-bit row, word id, z, hot-row index
+    hbm_regime = None
+    if rank == 0 and world == 1 and not args.no_hbm_regime and V == 50_000 and CORPUS == "dirichlet":
+        hbm_regime = hbm_regime_line(b, ctx, dev, 3, 3)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -450,31 +554,49 @@ def ours(args):
         cpu["faithful_value"] = f_tok / f_times[0]
         cpu["faithful_sample"] = f"first {f_docs} documents ({f_tok} tokens), same sweep with the per-token O(V) diagnostic"
     if rank == 0:
+        table_mb = 2 * K * V / 1e6
         line = {
             "metric": "lda_gibbs_token_samples_per_sec_K1024", "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"LDA collapsed Gibbs K={K} V={V} {n_total} tokens ({n_docs_total} docs x {L_DOC}), "
-                                   f"BASELINE config 3", "K": K, "V": V, "tokens": n_total, "docs": n_docs_total,
-                       "parallelism": f"documents sharded over {world} GPU(s), 1 all-reduce of count deltas per sweep",
-                       "l2": "inputs larger than L2 (n_wk 205 MB + tokens 800 MB per sweep vs 126 MB L2)",
+                                   f"BASELINE config 3" + ("" if CORPUS == "dirichlet" else f", corpus={CORPUS}"),
+                       "K": K, "V": V, "tokens": n_total, "docs": n_docs_total, "corpus": CORPUS,
+                       "parallelism": f"documents sharded over {world} GPU(s); per sweep one reduce-scatter + all-gather of the "
+                                      f"16-bit count tables by the library's own kernel over NVLink peer memory (no NCCL on the data path)",
+                       "l2": f"per sweep the kernel streams {n_total * 12 / world / 1e6:.0f} MB of token arrays (word, z read, z write) per GPU, "
+                             f"far larger than the 126 MB L2; the {table_mb:.0f} MB table of 16-bit count rows it gathers from is "
+                             + ("smaller than L2 and mostly stays resident between steps (the table is the state being updated, not an input; "
+                                "ncu sector hit rate in roofline.l2)" if table_mb < 126 else "larger than L2"),
                        "corpus_gen_s": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": sweep_kernel_name(),
                          "kernel_ms": kern_ms, "alg_bytes_per_token": B_ALG, "tokens_per_launch": tokens_per_launch,
-                         "note": "frac > 1: the metric's algorithmic bytes assume int32 rows streamed from HBM; the kernel reads "
-                                 "uint16 shadow rows that mostly stay in L2 (traffic = ncu DRAM bytes). ncu (profiles/r01g_*): "
-                                 "DRAM 15 %, L2 24 %, issue slots 68 %, LSU data pipe 70 % of peak - the sweep is SM-bound now; "
-                                 "kernel_ms spans the sweep's launches (shadow build / sweep kernel / fold, the sweep kernel "
-                                 "is > 99 % of it)"},
+                         "note": "achieved uses SURVEY 8(d)'s 4 K + 12 bytes (int32 row from HBM) for continuity; the kernel reads "
+                                 "2 K-byte 16-bit rows that mostly hit in L2, so frac > 1 says the metric's HBM bound no longer binds "
+                                 "at V = 50,000. What binds: l2 / issue below (from the committed ncu capture); the HBM-bound regime "
+                                 "is measured in hbm_regime (V = 200,000, rows cannot stay in L2). kernel_ms spans the sweep call's "
+                                 "launches (sweep kernel > 99 %; at N > 1 also the exchange).",
+                         "l2": {"bytes_per_token": l2_bytes, "achieved_gbs": l2_bytes * tokens_per_launch / (kern_ms * 1e-3) / 1e9,
+                                "sector_hit_rate_pct": facts.get("lts_sector_hit_rate_pct"), "throughput_pct": facts.get("lts_throughput_pct")},
+                         "issue": {"issue_slot_pct": facts.get("issue_slot_pct"), "inst_per_token": facts.get("inst_per_token"),
+                                   "capture": facts.get("capture")},
+                         "hbm_regime": hbm_regime},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
-                    "how": "2 resident models on 2 streams, re-fed in turn (reload_u16 = H2D of uint16 word ids / assignments + init pass, sweep, get_zz_u16 = D2H); "
-                           "wall clock over the steps, barrier + synchronize both sides, max over ranks"},
+                    "how": "2 resident models on 2 streams, re-fed in turn (reload_u16 = H2D of uint16 word ids / assignments + init pass, "
+                           "sweep [N > 1: merge of the fresh local counts + sweep + exchange], get_zz_u16 = D2H); "
+                           "wall clock over the steps, barrier + synchronize both sides, max over ranks",
+                    "shim_flatten_ms_per_call": flatten_ms,
+                    "shim_note": "the Julia arrays are Vector{Vector{Int64}}: flattening / narrowing this rank's tokens to the flat "
+                                 "16-bit host arrays fed above costs shim_flatten_ms_per_call on one host core, once per "
+                                 "collapsed_gibbs_sampler! call (hundreds of sweeps), not per sweep; it is outside the timed steps"},
             "gpu_launches": int(launches),
             "clocks": clock_rec,
+            "replica_check": replica_check,
+            "narrow_tables": {"current": bool(narrow_current), "hot_words": int(n_hot), "hot_rows_allocated": int(hot_cap)},
             "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood,
                             "train_loglik_per_token_rank0": ll_sum / max(1, ll_n), "sweeps_done": args.warmup + args.steps},
         }
@@ -482,9 +604,12 @@ def ours(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if replica_check != "ok":
+        raise SystemExit("replica check failed: a rank's count tables differ from the recount of all ranks' assignments")
 
 
 def main():
+    global V, CORPUS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -495,7 +620,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=16)
     ap.add_argument("--kernel-timing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-regime", action="store_true", help="skip the V = 200,000 measurement of roofline.hbm_regime")
+    ap.add_argument("--corpus", default="dirichlet", choices=["dirichlet", "zipf"])
+    ap.add_argument("--vocab", type=int, default=V, help="vocabulary size (default: BASELINE config 3's 50,000)")
     args = ap.parse_args()
+    V, CORPUS = args.vocab, args.corpus
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3) if os.environ.get("BIAS_BENCH_STRICT", "1") == "1" else args.warmup
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr

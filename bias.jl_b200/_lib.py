@@ -34,6 +34,8 @@ SYMBOLS = [
     "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
     "bias_crf_sweep_with_uniforms", "bias_crf_get_tables", "bias_model_delta_pack16", "bias_model_delta_apply16",
     "bias_rcrf_create", "bias_model_get_rcrf",
+    "bias_model_frozen_draws_dev", "bias_model_sweep_with_uniforms", "bias_lda_run_multi", "bias_group_create", "bias_group_sweep",
+    "bias_group_destroy", "bias_model_share_prepare", "bias_model_share_export", "bias_model_share_attach", "bias_model_replica_digest", "bias_model_narrow_info",
 ]
 
 
@@ -72,6 +74,11 @@ class RcrpParams(C.Structure):
 class RcrfParams(C.Structure):
     _fields_ = [("KK", C.c_int32), ("Kmax", C.c_int32), ("g1", C.c_double), ("g2", C.c_double), ("a1", C.c_double),
                 ("a2", C.c_double), ("sample_hyperparam", C.c_int32), ("n_internals", C.c_int32), ("join_tables", C.c_int32)]
+
+
+class ShareHandle(C.Structure):
+    _fields_ = [("ipc", C.c_ubyte * 64), ("bytes", C.c_int64), ("dd", C.c_int64), ("Kpad", C.c_int32),
+                ("hot_cap", C.c_int32), ("rank", C.c_int32), ("device", C.c_int32)]
 
 
 _lib = None
@@ -143,6 +150,17 @@ def lib():
     L.bias_model_delta_apply16.argtypes = [vp]
     L.bias_rcrf_create.argtypes = [vp, cj, dt, i64, vp, i64, vp, vp, C.POINTER(RcrfParams), vp, vp, pp]
     L.bias_model_get_rcrf.argtypes = [vp, C.POINTER(i32), vp, vp]
+    L.bias_model_frozen_draws_dev.argtypes = [vp, vp, vp]
+    L.bias_model_sweep_with_uniforms.argtypes = [vp, vp]
+    L.bias_lda_run_multi.argtypes = [vp, i32, C.c_uint64, cj, dt, i64, vp, vp, i32, f64, i32, st]
+    L.bias_group_create.argtypes = [vp, i32, pp]
+    L.bias_group_sweep.argtypes = [vp, i32]
+    L.bias_group_destroy.argtypes = [vp]
+    L.bias_model_share_prepare.argtypes = [vp, i32, i32, i64]
+    L.bias_model_share_export.argtypes = [vp, C.POINTER(ShareHandle)]
+    L.bias_model_share_attach.argtypes = [vp, C.POINTER(ShareHandle), i32]
+    L.bias_model_replica_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.bias_model_narrow_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     for name in SYMBOLS:
         if name != "bias_last_error":
             getattr(L, name).restype = C.c_int
@@ -172,6 +190,7 @@ class Context:
         self.h = C.c_void_p()
         check(lib().bias_ctx_create(device, C.c_uint64(seed & (2**64 - 1)), C.c_void_p(stream or 0), C.byref(self.h)))
         self.device = device
+        self.stream_handle = int(stream or 0)      # 0: the library created a private stream (stream 0 cannot be passed)
 
     def sync(self):
         check(lib().bias_ctx_sync(self.h))

@@ -52,9 +52,8 @@ struct LdaFastParams {
     unsigned long long *moved;  // tokens whose assignment changed
     const int64_t *eval_ptr;    // eval mode, nullable: CSR of held-out tokens per document (document completion)
     const int32_t *eval_word;   //   their word ids; theta_d still comes from the document's training tokens (z)
-    uint16_t *n_wk16;           // lda_half16.cuh: 16-bit shadow of n_wk, [V][Kpad]
-    const int32_t *gate;        // nullable: the kernel runs only when *gate == gate_expect (16-bit / 32-bit hand-over)
-    int32_t gate_expect;
+    uint16_t *n_wk16;           // lda_half16.cuh: the narrow tables, [V + 2 * hot_cap][Kpad]
+    const int32_t *word_hot;    // lda_half16.cuh: [V] hot-row index of each word or -1
     int32_t *nk_rep;            // half-warp kernels: [kNkRep][Kpad] replicas collecting this sweep's changes of n_k
     int32_t pf_dist;            // lda_half.cuh: rows are pulled into L2 this many tokens ahead (0: off; at most 16)
 };

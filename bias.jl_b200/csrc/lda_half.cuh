@@ -108,8 +108,6 @@ lda_md_int_sweep_half_kernel(const LdaFastParams p) {
     constexpr int GSHIFT = 4 - LOG_NCK;     // l16 >> GSHIFT = chunk held by the lane after the transposing reduction
     constexpr int KPAD = NCK * 64;
 
-    if (p.gate && *p.gate != p.gate_expect) return;     // the 16-bit kernel (lda_half16.cuh) took this sweep
-
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
     unsigned char *hbase = smem_raw + (size_t)(warp * 2 + half) * lda_half_doc_bytes(NCK);

@@ -1,23 +1,26 @@
-// lda_half16.cuh — LDA x MultinomialDirichlet x word-id sweep over a 16-bit shadow of the count table (sm_100a).
+// lda_half16.cuh — LDA x MultinomialDirichlet x word-id sweep over the narrow count tables (sm_100a): the headline kernel.
 //
 // Same sampler, mapping and arithmetic as lda_half.cuh (two documents per warp, reference src/LDA.jl:113-133);
-// what changes is where a token's row comes from.  The canonical table n_wk stays int32 [V][Kpad] (the generic
-// kernels, the exchange and the exports read it), and at the start of every sweep `shadow_build_kernel` copies
-// it into n_wk16 uint16 [V][Kpad].  The sweep reads the 2*Kpad-byte shadow rows — half the L2->SM bytes and half
-// the LSU wavefronts of the int32 rows, 32 instead of 64 registers per lane for the row, and a 102 MB table at
-// K = 1024, V = 50k that the 126 MB L2 can hold — applies every move to the shadow with RED atomics, and
-// `shadow_fold_kernel` rewrites the int32 table from the shadow when the sweep is over.
+// what changes is where a token's row comes from.  On this path the word-topic counts live in the NARROW TABLES:
+// uint16 [V][Kpad] rows for every word whose corpus frequency is at most 65,535 (no cell of such a row can leave 16 bits)
+// and int32 rows, appended to the same allocation, for the few HOT words above that (see classify_words_kernel).  The
+// tables are the canonical state while sweeps run: nothing is rebuilt or folded per sweep.  The int32 table n_wk
+// [V][Kpad] that the generic kernels, the verification entry points and the exports read is a VIEW that model.cu
+// refreshes on demand (narrow_fold_kernel) and converts back when somebody wrote to it (narrow_build_kernel).
 //
-// Exactness: the shadow is used only while no count can leave 16 bits during the sweep.  shadow_build_kernel
-// raises `wide` when max_k n_wk[w][k] + freq[w] > 65535 for any word (freq[w] = occurrences of w in this rank's
-// shard = the most a cell of the row can grow by within one sweep); the 16-bit kernel then exits at once and
-// the int32 kernel of lda_half.cuh, launched right behind it with the opposite gate, does the sweep.
+// A 16-bit row is 2*Kpad bytes — half the L2->SM bytes and half the LSU wavefronts of an int32 row, 32 instead of
+// 64 registers per lane, and a 102 MB table at K = 1024, V = 50k that the 126 MB L2 can hold.  A hot row is 4*Kpad
+// bytes; its first half is fetched one token ahead exactly like a 16-bit row (same address pattern), the second half
+// streams through 16 registers during the chunk pass and the selected chunk is read again for the in-chunk pass (hot
+// rows are few and stay in L2).  The two halves of a warp may take different routes through the loads and the
+// int->float conversions; every shuffle, ballot and shared-memory update is common code.
 //
 // Chunks are 128 topics wide (16 lanes x 8 uint16 = one LDG.128 per lane); r is stored in shared memory with
 // the two float4 halves of a lane's 8 topics de-interleaved, so that both LDS.128 of a chunk are conflict-free.
 #pragma once
 #include <type_traits>
 #include "lda_half.cuh"
+#include "narrow.cuh"
 
 namespace bias {
 
@@ -43,52 +46,6 @@ __host__ __device__ inline size_t lda_half16_smem_bytes(int nc8, int warps = kH1
 }
 
 #ifdef __CUDACC__
-
-// position of topic k's r inside the shared-memory vector (see the header comment)
-__device__ __forceinline__ int r_pos(int k) {
-    return (k & ~127) | (((k >> 2) & 1) << 6) | (((k >> 3) & 15) << 2) | (k & 3);
-}
-
-// One warp per word: int32 row -> uint16 row, and the sweep-wide overflow check.
-__global__ void shadow_build_kernel(const int32_t *n_wk, const int32_t *freq, int64_t V, int Kpad, uint16_t *n_wk16,
-                                    int32_t *wide) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int bad = 0;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < V; w += nw) {
-        const int4 *src = reinterpret_cast<const int4 *>(n_wk + (size_t)w * Kpad);
-        uint4 *dst = reinterpret_cast<uint4 *>(n_wk16 + (size_t)w * Kpad);
-        int mx = 0;
-        for (int q = lane; q < Kpad / 8; q += 32) {
-            const int4 a = __ldcg(src + 2 * q), b = __ldcg(src + 2 * q + 1);
-            mx = max(mx, max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w))));
-            uint4 o;
-            o.x = (unsigned)(a.x & 0xffff) | ((unsigned)a.y << 16);
-            o.y = (unsigned)(a.z & 0xffff) | ((unsigned)a.w << 16);
-            o.z = (unsigned)(b.x & 0xffff) | ((unsigned)b.y << 16);
-            o.w = (unsigned)(b.z & 0xffff) | ((unsigned)b.w << 16);
-            dst[q] = o;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(kFull, mx, o));
-        if ((int64_t)mx + (int64_t)freq[w] > 65535) bad = 1;
-    }
-    if (__any_sync(kFull, bad) && lane == 0) atomicOr(wide, 1);
-}
-
-// After a 16-bit sweep: the int32 table is rewritten from the shadow (runs only when the 16-bit kernel did).
-__global__ void shadow_fold_kernel(const uint16_t *n_wk16, int64_t V, int Kpad, int32_t *n_wk, const int32_t *wide) {
-    if (*wide != 0) return;
-    const int64_t n8 = V * (int64_t)Kpad / 8;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 x = __ldcg(reinterpret_cast<const uint4 *>(n_wk16) + q);
-        int4 a, b;
-        a.x = (int)(x.x & 0xffffu); a.y = (int)(x.x >> 16); a.z = (int)(x.y & 0xffffu); a.w = (int)(x.y >> 16);
-        b.x = (int)(x.z & 0xffffu); b.y = (int)(x.z >> 16); b.z = (int)(x.w & 0xffffu); b.w = (int)(x.w >> 16);
-        reinterpret_cast<int4 *>(n_wk)[2 * q] = a;
-        reinterpret_cast<int4 *>(n_wk)[2 * q + 1] = b;
-    }
-}
 
 // freq[w] = occurrences of word w in the local shard (row sums of the freshly built local counts)
 __global__ void word_freq_kernel(const int32_t *n_wk, int64_t V, int Kpad, int32_t *freq) {
@@ -138,6 +95,19 @@ __device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float
     return s + t;
 }
 
+// the same eight products for a hot row: a = cells of topics +0..3, b = +4..7 (int32, stored in r_pos order)
+__device__ __forceinline__ float dot8i(const uint4 a, const uint4 b, const float4 ra, const float4 rb) {
+    float s = (float)(int)a.x * ra.x;
+    s = fmaf((float)(int)a.y, ra.y, s);
+    s = fmaf((float)(int)a.z, ra.z, s);
+    s = fmaf((float)(int)a.w, ra.w, s);
+    float t = (float)(int)b.x * rb.x;
+    t = fmaf((float)(int)b.y, rb.y, t);
+    t = fmaf((float)(int)b.z, rb.z, t);
+    t = fmaf((float)(int)b.w, rb.w, t);
+    return s + t;
+}
+
 template <int NC8, int WARPS = kH16Warps, int CTAS = kH16Ctas, bool CNT8 = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
 lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
@@ -146,8 +116,6 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
     constexpr int LOG_NC = (NC8 == 1) ? 0 : (NC8 == 2) ? 1 : (NC8 == 4) ? 2 : 3;
     constexpr int GSHIFT = 4 - LOG_NC;      // l16 >> GSHIFT = chunk held by the lane after the transposing reduction
     constexpr int KPAD = NC8 * 128;
-
-    if (*p.gate != p.gate_expect) return;   // a count may leave 16 bits this sweep: the int32 kernel runs instead
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
@@ -245,10 +213,13 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
         if (nb_both == 0) break;
 
         // ---- up to 16 tokens of each half's document ----
+        // my_w is the token's ROW in the narrow tables: the word id, or V + 2h for the h-th hot word
         int my_w = 0, my_z = 0;
         float my_u = 0.5f;
         if (l16 < nb) {
             my_w = p.word[t_cur + l16];
+            const int h = __ldg(p.word_hot + my_w);
+            if (h >= 0) my_w = p.V + 2 * h;
             my_z = p.z[t_cur + l16];
             const uint64_t tid = (uint64_t)(t_cur + l16);
             if (p.ext_uniforms) {
@@ -271,10 +242,13 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
 #pragma unroll
             for (int j = 0; j < NC8; ++j) c[j] = __ldcg(row + j * 16 + l16);
         }
-        int c_own = __ldcg(p.n_wk16 + (size_t)w * KPAD + kold);
+        int c_own = (w >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(p.n_wk16 + (size_t)w * KPAD) + r_pos(kold))
+                               : (int)__ldcg(p.n_wk16 + (size_t)w * KPAD + kold);
 
         for (int i = 0; i < nb_both; ++i) {
             const bool on = i < nb;
+            const bool hot = w >= p.V;         // uniform over the half; the two halves of the warp may differ
+            const uint4 *row_cur = reinterpret_cast<const uint4 *>(p.n_wk16 + (size_t)w * KPAD);
 
             // ---- delitem!, arithmetically: r[kold] with n_dk and n_k one lower; nothing is stored ----
             const int jo = kold >> 7;
@@ -286,8 +260,36 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
 
             // ---- pass 1: chunk sums of n_wk * r (beta * sum r is added per chunk) ----
             float acc[NC8];
+            if (!hot) {
 #pragma unroll
-            for (int j = 0; j < NC8; ++j) acc[j] = dot8(c[j], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
+                for (int j = 0; j < NC8; ++j) acc[j] = dot8(c[j], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
+            } else {
+                // c[] holds the first NC8 of the row's 2 * NC8 16-byte pieces (piece jj of lane l: topics
+                // (jj >> 1) * 128 + l * 8 + (jj & 1) * 4 .. + 3); the rest streams through d[]
+                constexpr int ND = NC8 < 4 ? NC8 : 4;
+                uint4 d[ND];
+#pragma unroll
+                for (int e = 0; e < ND; ++e) d[e] = __ldcg(row_cur + (NC8 + e) * 16 + l16);
+                if constexpr (NC8 == 1) {
+                    acc[0] = dot8i(c[0], d[0], r4[l16], r4[16 + l16]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC8 / 2; ++j) acc[j] = dot8i(c[2 * j], c[2 * j + 1], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
+                    if constexpr (NC8 == 8) {
+                        // chunks 6, 7 go through c[0..3], which the first half no longer needs
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) c[e] = __ldcg(row_cur + (12 + e) * 16 + l16);
+                        acc[4] = dot8i(d[0], d[1], r4[4 * 32 + l16], r4[4 * 32 + 16 + l16]);
+                        acc[5] = dot8i(d[2], d[3], r4[5 * 32 + l16], r4[5 * 32 + 16 + l16]);
+                        acc[6] = dot8i(c[0], c[1], r4[6 * 32 + l16], r4[6 * 32 + 16 + l16]);
+                        acc[7] = dot8i(c[2], c[3], r4[7 * 32 + l16], r4[7 * 32 + 16 + l16]);
+                    } else {
+#pragma unroll
+                        for (int j = NC8 / 2; j < NC8; ++j)
+                            acc[j] = dot8i(d[2 * j - NC8], d[2 * j - NC8 + 1], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
+                    }
+                }
+            }
             float T = transpose_reduce_half<NC8>(acc, l16);                    // lane l: chunk (l >> GSHIFT)
             const int myj = l16 >> GSHIFT;
             T = fmaf(beta, R_s[myj], T);
@@ -308,7 +310,11 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             const int src_lane = bal ? (__ffs(bal) - 1) : 15;
             const int jsel = src_lane >> GSHIFT;
             const float base = __shfl_sync(kFull, P - T, src_lane, 16);
-            const uint4 cs = pick_chunk16<NC8>(c, jsel);
+            uint4 cs = pick_chunk16<NC8>(c, jsel), cs2 = make_uint4(0, 0, 0, 0);
+            if (hot) {                   // the selected chunk of a hot row is read again (two pieces per lane)
+                cs = __ldcg(row_cur + (2 * jsel) * 16 + l16);
+                cs2 = __ldcg(row_cur + (2 * jsel + 1) * 16 + l16);
+            }
 
             // ---- the next token's operands and row: in flight during pass 2 and the update ----
             const int inext = (i + 1) & 15;
@@ -320,14 +326,20 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
 #pragma unroll
                 for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
-                c_own_n = __ldcg(rown + kold_n);
+                c_own_n = (w_n >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(rown) + r_pos(kold_n)) : (int)__ldcg(rown + kold_n);
             }
 
             // ---- pass 2: CDF inside the selected chunk (8 topics per lane) ----
             const float4 qa = r4[jsel * 32 + l16], qb = r4[jsel * 32 + 16 + l16];
             const int kb = jsel * 128 + l16 * 8;
-            float n[8] = {(float)(cs.x & 0xffffu), (float)(cs.x >> 16), (float)(cs.y & 0xffffu), (float)(cs.y >> 16),
-                          (float)(cs.z & 0xffffu), (float)(cs.z >> 16), (float)(cs.w & 0xffffu), (float)(cs.w >> 16)};
+            float n[8];
+            if (!hot) {
+                n[0] = (float)(cs.x & 0xffffu); n[1] = (float)(cs.x >> 16); n[2] = (float)(cs.y & 0xffffu); n[3] = (float)(cs.y >> 16);
+                n[4] = (float)(cs.z & 0xffffu); n[5] = (float)(cs.z >> 16); n[6] = (float)(cs.w & 0xffffu); n[7] = (float)(cs.w >> 16);
+            } else {
+                n[0] = (float)(int)cs.x; n[1] = (float)(int)cs.y; n[2] = (float)(int)cs.z; n[3] = (float)(int)cs.w;
+                n[4] = (float)(int)cs2.x; n[5] = (float)(int)cs2.y; n[6] = (float)(int)cs2.z; n[7] = (float)(int)cs2.w;
+            }
             float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
             const int eo = kold - kb;           // own token excluded (the clamp only matters for a count caught mid-update)
 #pragma unroll
@@ -380,14 +392,15 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                         R_s[knew >> 7] += r_new - r2;
                     }
                     if (l16 >= 8 && l16 < 12) {
-                        // lanes 8..11: n_wk16[kold]--, n_wk16[knew]++, n_k[kold]--, n_k[knew]++ (the int32 table is
-                        // rewritten from the shadow after the sweep, shadow_fold_kernel)
+                        // lanes 8..11: row[kold]--, row[knew]++, n_k[kold]--, n_k[knew]++ (a 16-bit cell is half of a 32-bit
+                        // word, a hot cell a whole one)
                         const int which = l16 - 8, kk = (which & 1) ? knew : kold;
                         unsigned *ptr;
                         unsigned val;
                         if (which < 2) {
-                            ptr = reinterpret_cast<unsigned *>(p.n_wk16 + (size_t)w * KPAD) + (kk >> 1);
-                            val = 1u << ((kk & 1) * 16);
+                            unsigned *rowu = reinterpret_cast<unsigned *>(p.n_wk16 + (size_t)w * KPAD);
+                            ptr = hot ? rowu + r_pos(kk) : rowu + (kk >> 1);
+                            val = hot ? 1u : 1u << ((kk & 1) * 16);
                         } else {
                             ptr = reinterpret_cast<unsigned *>(my_nk) + kk;
                             val = 1u;
@@ -397,7 +410,9 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                     if (l16 == 0) moved_acc += 1;
                 }
                 if (l16 == 0 && on) {
-                    if (nsel < 0.f) nsel = (float)__ldcg(p.n_wk16 + (size_t)w * KPAD + knew) - (knew == kold ? 1.f : 0.f);
+                    if (nsel < 0.f)
+                        nsel = (hot ? (float)__ldcg(reinterpret_cast<const int32_t *>(p.n_wk16 + (size_t)w * KPAD) + r_pos(knew))
+                                    : (float)__ldcg(p.n_wk16 + (size_t)w * KPAD + knew)) - (knew == kold ? 1.f : 0.f);
                     diag_acc += (nsel + 1.f + beta) * inv_new;
                 }
                 // the next token's row was read before this update: when it is the same word, read it again
@@ -408,7 +423,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                         const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
 #pragma unroll
                         for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
-                        c_own_n = __ldcg(rown + kold_n);
+                        c_own_n = hot ? __ldcg(reinterpret_cast<const int32_t *>(rown) + r_pos(kold_n)) : (int)__ldcg(rown + kold_n);
                     }
                 }
                 __syncwarp();

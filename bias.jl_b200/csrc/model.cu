@@ -6,7 +6,6 @@
 #include <new>
 #include "model.hpp"
 #include "lda_fast.cuh"
-#include "lda_tma.cuh"
 #include "lda_half.cuh"
 #include "lda_half16.cuh"
 #define BIAS_GENERIC_KERNEL_IMPL
@@ -78,24 +77,6 @@ static int launch_lda_fast_t(bias_model *m, const LdaFastParams &p) {
     return BIAS_OK;
 }
 
-template <int NCH>
-static int launch_lda_tma_t(bias_model *m, const LdaFastParams &p) {
-    static bool conf_cache[kMaxDevices] = {};
-    bool &configured = conf_cache[m->ctx->device % kMaxDevices];
-    const size_t smem = lda_tma_smem_bytes(NCH);
-    if (!configured) {
-        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_tma_kernel<NCH>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const int64_t want = (p.D + kTmaWarps - 1) / kTmaWarps;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms));
-    lda_md_int_sweep_tma_kernel<NCH><<<grid, kTmaWarps * 32, smem, m->ctx->stream>>>(p);
-    BIAS_CUDA_TRY(cudaGetLastError());
-    m->ctx->launches += 1;
-    return BIAS_OK;
-}
-
 template <int NCK, int WARPS = kHalfWarps>
 static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
     static int ctas_cache[kMaxDevices] = {};          // function attributes are per device
@@ -150,31 +131,19 @@ static int launch_lda_half16(bias_model *m, const LdaFastParams &p) {
     return launch_lda_half16_t<NC8, kH16Warps, kH16Ctas, false>(m, p);
 }
 
-// 16-bit shadow rows (lda_half16.cuh): the default whenever the half-warp kernel applies and the shadow table was
-// allocated; BIAS_LDA_KERNEL=half keeps the int32 rows
+// the narrow tables (lda_half16.cuh): the default whenever they were allocated (K <= 1024) and every document is shorter
+// than 65,536 tokens; BIAS_LDA_KERNEL=half / reg keep the sweeps on the int32 table
 static bool use_half16_kernel(const bias_model *m) {
     const char *force = getenv("BIAS_LDA_KERNEL");
-    if (force && (force[0] == 't' || force[0] == 'r' || force[0] == 'h')) return false;
-    // small corpora are launch-bound: the shadow's two extra passes per sweep cost more than the narrower rows save
-    if (m->N < 2000000 && !(force && force[0] == 'u')) return false;
+    if (force && (force[0] == 'r' || force[0] == 'h')) return false;
     return m->n_wk16 && m->Kpad <= 1024 && m->max_group_len <= 65535;
 }
 
 // two documents per warp (lda_half.cuh): the default for K <= 1024 and documents shorter than 65,536 tokens;
-// BIAS_LDA_KERNEL=reg selects the one-document-per-warp kernel, =tma the shared-memory staged one
+// BIAS_LDA_KERNEL=reg selects the one-document-per-warp kernel
 static bool use_half_kernel(const bias_model *m) {
     const char *force = getenv("BIAS_LDA_KERNEL");
-    if (force && (force[0] == 't' || force[0] == 'r')) return false;
-    return m->Kpad <= 1024 && m->max_group_len <= 65535;
-}
-
-// which LDA x MD x Int kernel: rows kept in registers (default: measured faster on B200, r01:
-// 57.0 ms vs 73.4 ms per 100M-token sweep — the sweep is bound by the LSU/shared-memory data pipe, and
-// staging rows in shared memory doubles their trips through it) or staged in shared memory by bulk
-// async copies (BIAS_LDA_KERNEL=tma; K <= 1024 and every document shorter than 65,536 tokens)
-static bool use_tma_kernel(const bias_model *m) {
-    const char *force = getenv("BIAS_LDA_KERNEL");
-    if (!(force && force[0] == 't')) return false;
+    if (force && force[0] == 'r') return false;
     return m->Kpad <= 1024 && m->max_group_len <= 65535;
 }
 
@@ -198,7 +167,7 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.beta = (float)m->conj.aa;
     p.vbeta = (float)(m->conj.aa * (double)m->V);
     p.doc_counter = m->scratch + 2;
-    p.seed = m->ctx->seed;
+    p.seed = m->ctx->seed ^ m->seed_mix;
     p.sweep = m->sweep_index;
     p.ext_uniforms = ext_uniforms;
     p.draws_out = draws_out;
@@ -208,38 +177,34 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     p.pf_dist = 2;            // rows prefetched into L2 ahead of the token loop (int32-row half-warp kernel)
     p.nk_rep = m->nk_rep;
     const bool half_path = use_half_kernel(m) && !eval && m->nk_rep;
-    if (use_half16_kernel(m) && !eval && m->V > 0) {
-        // refresh the 16-bit shadow; the 16-bit kernel runs unless a count may leave 16 bits during this sweep,
-        // in which case it exits at once and the int32 kernel behind it does the work
-        cudaStream_t st = m->ctx->stream;
-        BIAS_CUDA_TRY(cudaMemsetAsync(m->wide_flag, 0, sizeof(int32_t), st));
-        shadow_build_kernel<<<grid_for(m->ctx, m->V * 32, 256), 256, 0, st>>>(m->n_wk, m->word_freq, m->V, m->Kpad,
-                                                                             m->n_wk16, m->wide_flag);
-        BIAS_CUDA_TRY(cudaGetLastError());
-        m->ctx->launches += 1;
+    if (use_half16_kernel(m) && !eval && m->V > 0 && m->nk_rep) {
+        BIAS_TRY(ensure_narrow(m));
         p.n_wk16 = m->n_wk16;
-        p.gate = m->wide_flag;
-        p.gate_expect = 0;
+        p.word_hot = m->word_hot;
         switch (m->Kpad / 128) {
             case 1: BIAS_TRY(launch_lda_half16<1>(m, p)); break;
             case 2: BIAS_TRY(launch_lda_half16<2>(m, p)); break;
             case 4: BIAS_TRY(launch_lda_half16<4>(m, p)); break;
             case 8: BIAS_TRY(launch_lda_half16<8>(m, p)); break;
+            default: return fail(BIAS_EINVAL, "unsupported padded K %d for the 16-bit LDA kernel", m->Kpad);
         }
-        p.gate_expect = 1;
+        if (!frozen) {
+            fold_nk_kernel<<<(m->Kpad + 255) / 256, 256, 0, m->ctx->stream>>>(m->n_k, m->nk_rep, m->Kpad, kNkRep);
+            BIAS_CUDA_TRY(cudaGetLastError());
+            m->ctx->launches += 1;
+            m->wide_valid = false;          // the int32 view is refreshed when somebody asks for it (ensure_wide)
+        }
+        return BIAS_OK;
     }
+    BIAS_TRY(ensure_wide(m));
+    if (!frozen && !eval) m->narrow_valid = false;
     if (half_path) {
         switch (m->Kpad / 64) {
             case 2: BIAS_TRY(launch_lda_half_t<2>(m, p)); break;
             case 4: BIAS_TRY(launch_lda_half_t<4>(m, p)); break;
             case 8: BIAS_TRY(launch_lda_half_t<8>(m, p)); break;
-            default: BIAS_TRY(launch_lda_half_t<16>(m, p)); break;
-        }
-        if (!frozen && p.n_wk16) {
-            shadow_fold_kernel<<<grid_for(m->ctx, m->V * (int64_t)m->Kpad / 8, 256), 256, 0, m->ctx->stream>>>(
-                m->n_wk16, m->V, m->Kpad, m->n_wk, m->wide_flag);
-            BIAS_CUDA_TRY(cudaGetLastError());
-            m->ctx->launches += 1;
+            case 16: BIAS_TRY(launch_lda_half_t<16>(m, p)); break;
+            default: return fail(BIAS_EINVAL, "unsupported padded K %d for the half-warp LDA kernel", m->Kpad);
         }
         if (!frozen) {
             fold_nk_kernel<<<(m->Kpad + 255) / 256, 256, 0, m->ctx->stream>>>(m->n_k, m->nk_rep, m->Kpad, kNkRep);
@@ -247,14 +212,6 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
             m->ctx->launches += 1;
         }
         return BIAS_OK;
-    }
-    if (use_tma_kernel(m) && !eval) {
-        switch (m->Kpad / 128) {
-            case 1: return launch_lda_tma_t<1>(m, p);
-            case 2: return launch_lda_tma_t<2>(m, p);
-            case 4: return launch_lda_tma_t<4>(m, p);
-            case 8: return launch_lda_tma_t<8>(m, p);
-        }
     }
     switch (m->Kpad / 128) {
         case 1: return launch_lda_fast_t<1>(m, p);
@@ -297,6 +254,8 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
                    int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,
                    int row_by_work) {
     if (n_work <= 0) return BIAS_OK;
+    BIAS_TRY(ensure_wide(m));
+    if (!frozen) m->narrow_valid = false;
     GenericParams p{};
     p.model = m->model;
     p.kind = m->conj.kind;
@@ -331,7 +290,7 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
     p.vv = m->conj.vv;
     p.alpha = (m->model == BIAS_MODEL_HDP) ? m->hdp.aa : m->alpha;
     p.hdp_beta = m->d_beta;
-    p.seed = m->ctx->seed;
+    p.seed = m->ctx->seed ^ m->seed_mix;
     p.sweep = m->sweep_index;
     p.rng_stream = rng_stream;
     p.ext_uniforms = ext_uniforms;
@@ -361,10 +320,33 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
 }
 
 // ---------------------------------------------------------------------------------------
+// the two representations of the word-topic counts on the fast LDA path (lda_half16.cuh)
+// ---------------------------------------------------------------------------------------
+int ensure_wide(bias_model *m) {
+    if (m->wide_valid || !m->n_wk16) return BIAS_OK;
+    if (!m->narrow_valid) return fail(BIAS_ESTATE, "neither representation of the counts is current");
+    return narrow_fold(m);
+}
+
+int ensure_narrow(bias_model *m) {
+    if (m->narrow_valid) return BIAS_OK;
+    if (!m->n_wk16) return fail(BIAS_ESTATE, "the model has no narrow tables");
+    if (!m->wide_valid) return fail(BIAS_ESTATE, "neither representation of the counts is current");
+    if (!m->class_valid) {
+        BIAS_TRY(comm_global_word_freq(m));         // one GPU: the local frequencies; a sharded run sums them in its sweep call
+        BIAS_TRY(narrow_classify(m));
+    }
+    return narrow_build(m);
+}
+
+// ---------------------------------------------------------------------------------------
 // initialisation pass: additem! for every item
 // ---------------------------------------------------------------------------------------
 int rebuild_counts(bias_model *m) {
     cudaStream_t st = m->ctx->stream;
+    m->wide_valid = true;           // the pass below writes the int32 table
+    m->narrow_valid = false;
+    m->class_valid = false;
     BIAS_CUDA_TRY(cudaMemsetAsync(m->i32_block, 0, (size_t)m->n_i32 * sizeof(int32_t), st));
     if (m->n_f64) BIAS_CUDA_TRY(cudaMemsetAsync(m->f64_block, 0, (size_t)m->n_f64 * sizeof(double), st));
     if (m->word_freq) BIAS_CUDA_TRY(cudaMemsetAsync(m->word_freq, 0, (size_t)std::max<int64_t>(1, m->V) * sizeof(int32_t), st));
@@ -449,6 +431,27 @@ static int validate(const bias_conjugate *c, const bias_data *d, int64_t G, cons
     // the O(N) range checks on zz / word ids / Sent entries run on the device (validate_kernel)
     return BIAS_OK;
 }
+
+int model_local_sweep(bias_model *m) {
+    cudaStream_t st = m->ctx->stream;
+    if (m->model == BIAS_MODEL_HDP) return hdp_sweep(m);
+    if (m->model == BIAS_MODEL_RCRP) return rcrp_sweep(m);
+    if (m->model == BIAS_MODEL_CRF) return crf_sweep(m, nullptr);
+    if (m->model == BIAS_MODEL_RCRF) return rcrf_sweep(m, nullptr);
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st));
+    if (m->fast) {
+        BIAS_TRY(launch_lda_fast(m, nullptr, 0, nullptr));
+    } else {
+        int32_t *prior = (m->model == BIAS_MODEL_BMM) ? m->n_items : m->group_rows;
+        const int32_t *row_of = (m->model == BIAS_MODEL_BMM) ? nullptr : m->group_of;
+        BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, row_of, prior, nullptr, 0, 0, nullptr, nullptr, nullptr,
+                                kStreamItemDraw));
+    }
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    return BIAS_OK;
+}
+
 
 }  // namespace bias
 
@@ -556,9 +559,10 @@ int bias_model_destroy(bias_model *m) {
     crf_destroy(m);
     void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
                     m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
-                    m->delta_f64, m->scratch, m->d_aa_t, m->n_wk16, m->word_freq, m->wide_flag, m->nk_rep, m->stage16};
+                    m->delta_f64, m->scratch, m->d_aa_t, m->word_freq, m->word_freq_g, m->word_hot, m->hot_info, m->nk_rep, m->stage16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    narrow_free(m);
     if (m->h_scratch) cudaFreeHost(m->h_scratch);
     bias_ctx *ctx = m->ctx;
     delete m;
@@ -657,9 +661,11 @@ int bias_model_create(bias_ctx *ctx, int32_t model, const bias_conjugate *conj, 
         m->sumx = m->f64_block;
     }
     if (m->fast && m->Kpad <= 1024) {
-        M_TRY(dev_alloc(&m->n_wk16, (size_t)n_wk_elems));
+        M_TRY(narrow_alloc(m, narrow_hot_cap(m->V, m->N)));
         M_TRY(dev_alloc(&m->word_freq, (size_t)std::max<int64_t>(1, m->V)));
-        M_TRY(dev_alloc(&m->wide_flag, 4));
+        M_TRY(dev_alloc(&m->word_freq_g, (size_t)std::max<int64_t>(1, m->V)));
+        M_TRY(dev_alloc(&m->word_hot, (size_t)std::max<int64_t>(1, m->V)));
+        M_TRY(dev_alloc(&m->hot_info, 4));
         M_TRY(dev_alloc(&m->nk_rep, (size_t)kNkRep * m->Kpad));
         M_CUDA(cudaMemsetAsync(m->nk_rep, 0, (size_t)kNkRep * m->Kpad * sizeof(int32_t), st));
     }
@@ -722,7 +728,7 @@ int bias_model_reload(bias_model *m, const bias_data *data, int64_t n_groups, co
     }
     BIAS_TRY(validate_on_device(m, m->K));
     BIAS_TRY(rebuild_counts(m));
-    m->sweep_index = 0;
+    m->sweep_index += 1;        // never reused: a re-fed batch must not replay the uniforms of the batch before it
     m->stats_pending = false;
     m->timing_valid = false;
     // the uploads came from caller-owned memory: finish them before returning
@@ -744,6 +750,12 @@ static int mirror16_update(bias_model *m) {
     }
     m->mirror16_valid = true;
     return BIAS_OK;
+}
+
+extern "C++" {
+namespace bias {
+int model_mirror16(bias_model *m) { return mirror16_update(m); }
+}
 }
 
 static int stage16_ready(bias_model *m) {
@@ -795,7 +807,7 @@ int bias_model_reload_u16(bias_model *m, int64_t n_items, const uint16_t *word, 
     }
     BIAS_TRY(validate_on_device(m, m->K));
     BIAS_TRY(rebuild_counts(m));
-    m->sweep_index = 0;
+    m->sweep_index += 1;        // never reused: a re-fed batch must not replay the uniforms of the batch before it
     m->stats_pending = false;
     m->timing_valid = false;
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));     // the uploads came from caller-owned memory
@@ -837,23 +849,14 @@ int bias_model_get_zz(bias_model *m, int32_t *zz) {
 }
 
 static int one_sweep(bias_model *m) {
-    cudaStream_t st = m->ctx->stream;
-    if (m->model == BIAS_MODEL_HDP) return hdp_sweep(m);
-    if (m->model == BIAS_MODEL_RCRP) return rcrp_sweep(m);
-    if (m->model == BIAS_MODEL_CRF) return crf_sweep(m, nullptr);
-    if (m->model == BIAS_MODEL_RCRF) return rcrf_sweep(m, nullptr);
-    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st));
-    if (m->fast) {
-        BIAS_TRY(launch_lda_fast(m, nullptr, 0, nullptr));
-    } else {
-        int32_t *prior = (m->model == BIAS_MODEL_BMM) ? m->n_items : m->group_rows;
-        const int32_t *row_of = (m->model == BIAS_MODEL_BMM) ? nullptr : m->group_of;
-        BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, row_of, prior, nullptr, 0, 0, nullptr, nullptr, nullptr,
-                                kStreamItemDraw));
+    if (m->world > 1 && !m->grouped) {
+        // one process per GPU: the sweep call is collective over the ranks (comm.cu)
+        if (!m->narrow_valid) BIAS_TRY(comm_prepare_flags(m));
+        BIAS_TRY(model_local_sweep(m));
+        return comm_exchange_flags(m);
     }
-    m->sweep_index += 1;
-    m->stats_pending = true;
-    return BIAS_OK;
+    if (m->world > 1) return fail(BIAS_ESTATE, "this model is a shard of a bias_group: sweep the group");
+    return model_local_sweep(m);
 }
 
 int bias_model_sweep(bias_model *m, int32_t n_sweeps) {
@@ -909,6 +912,8 @@ int bias_model_get_components(bias_model *m, int64_t *mi, int64_t *mm, double *m
     if (!m) return fail(BIAS_EINVAL, "null model");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     cudaStream_t st = m->ctx->stream;
+    BIAS_TRY(comm_check(m));
+    BIAS_TRY(ensure_wide(m));
     const int K = is_dynamic_K(m) ? m->hdp.KK : m->K;
     std::vector<int32_t> h_nk(m->Kpad), h_ni(m->Kpad);
     BIAS_CUDA_TRY(cudaMemcpyAsync(h_nk.data(), m->n_k, (size_t)m->Kpad * 4, cudaMemcpyDeviceToHost, st));
@@ -1048,6 +1053,72 @@ int bias_model_frozen_draws(bias_model *m, const double *uniforms, int32_t *draw
     return rc;
 }
 
+int bias_model_frozen_draws_dev(bias_model *m, const double *uniforms_dev, int32_t *draws_dev) {
+    if (!m || !uniforms_dev || !draws_dev) return fail(BIAS_EINVAL, "null argument");
+    if (is_dynamic_K(m)) return fail(BIAS_EINVAL, "frozen draws are defined for LDA and BMM");
+    if (m->N == 0) return BIAS_OK;
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch + 2, 0, sizeof(unsigned long long), m->ctx->stream));
+    if (m->fast) {
+        BIAS_TRY(launch_lda_fast(m, uniforms_dev, 1, draws_dev));
+    } else {
+        int32_t *prior = (m->model == BIAS_MODEL_BMM) ? m->n_items : m->group_rows;
+        const int32_t *row_of = (m->model == BIAS_MODEL_BMM) ? nullptr : m->group_of;
+        BIAS_TRY(launch_generic(m, m->N, nullptr, nullptr, row_of, prior, uniforms_dev, 1, 0, nullptr, nullptr, draws_dev, kStreamItemDraw));
+    }
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    return BIAS_OK;
+}
+
+int bias_model_sweep_with_uniforms(bias_model *m, const double *uniforms) {
+    if (!m || !uniforms) return fail(BIAS_EINVAL, "null argument");
+    if (is_dynamic_K(m)) return fail(BIAS_EINVAL, "sweeps with supplied uniforms are defined for LDA and BMM");
+    if (m->world > 1) return fail(BIAS_ESTATE, "sweeps with supplied uniforms are a single-GPU verification entry point");
+    if (m->N == 0) return BIAS_OK;
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    cudaStream_t st = m->ctx->stream;
+    double *d_u = nullptr;
+    BIAS_TRY(dev_alloc(&d_u, (size_t)m->N));
+    cudaError_t e = cudaMemcpyAsync(d_u, uniforms, (size_t)m->N * 8, cudaMemcpyHostToDevice, st);
+    int rc = BIAS_OK;
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->scratch, 0, 4 * sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        if (m->fast) {
+            rc = launch_lda_fast(m, d_u, 0, nullptr);
+        } else {
+            int32_t *prior = (m->model == BIAS_MODEL_BMM) ? m->n_items : m->group_rows;
+            const int32_t *row_of = (m->model == BIAS_MODEL_BMM) ? nullptr : m->group_of;
+            rc = launch_generic(m, m->N, nullptr, nullptr, row_of, prior, d_u, 0, 0, nullptr, nullptr, nullptr, kStreamItemDraw);
+        }
+    }
+    cudaStreamSynchronize(st);
+    cudaFree(d_u);
+    if (e != cudaSuccess) return fail(BIAS_ECUDA, "sweep with uniforms: %s", cudaGetErrorString(e));
+    if (rc != BIAS_OK) return rc;
+    m->sweep_index += 1;
+    m->stats_pending = true;
+    m->mirror16_valid = false;
+    return BIAS_OK;
+}
+
+int bias_model_narrow_info(bias_model *m, int32_t *narrow_current, int32_t *n_hot, int32_t *hot_cap) {
+    if (!m) return fail(BIAS_EINVAL, "null model");
+    if (narrow_current) *narrow_current = (m->n_wk16 && m->narrow_valid) ? 1 : 0;
+    if (hot_cap) *hot_cap = m->hot_cap;
+    if (n_hot) {
+        *n_hot = 0;
+        if (m->n_wk16 && m->class_valid) {
+            BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+            int32_t h[2] = {0, 0};
+            BIAS_CUDA_TRY(cudaMemcpyAsync(h, m->hot_info, sizeof h, cudaMemcpyDeviceToHost, m->ctx->stream));
+            BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+            if (h[1]) return fail(BIAS_ESTATE, "%d words need 32-bit rows but the table has room for %d", h[0], m->hot_cap);
+            *n_hot = h[0];
+        }
+    }
+    return BIAS_OK;
+}
+
 int bias_model_log_likelihood(bias_model *m, double *sum_log_p, int64_t *n_items) {
     if (!m || !sum_log_p) return fail(BIAS_EINVAL, "null argument");
     if (!m->fast) return fail(BIAS_EINVAL, "the log-likelihood evaluator covers LDA x MultinomialDirichlet x word ids");
@@ -1124,6 +1195,7 @@ int bias_model_delta_begin(bias_model *m) {
     if (!m) return fail(BIAS_EINVAL, "null model");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
     BIAS_TRY(ensure_exchange(m));
+    BIAS_TRY(ensure_wide(m));
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->base_i32, m->i32_block, (size_t)m->n_i32 * 4, cudaMemcpyDeviceToDevice, m->ctx->stream));
     if (m->n_f64)
         BIAS_CUDA_TRY(cudaMemcpyAsync(m->base_f64, m->f64_block, (size_t)m->n_f64 * 8, cudaMemcpyDeviceToDevice, m->ctx->stream));
@@ -1143,6 +1215,7 @@ int bias_model_delta_pack(bias_model *m, void **delta_i32_dev, int64_t *n_i32, v
     if (!m || !delta_i32_dev || !n_i32) return fail(BIAS_EINVAL, "null argument");
     if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(ensure_wide(m));
     cudaStream_t st = m->ctx->stream;
     const int64_t n4 = m->n_i32 / 4;
     delta_pack_i32_kernel<<<grid_for(m->ctx, n4, 256), 256, 0, st>>>(m->i32_block, m->base_i32, m->delta_i32, n4);
@@ -1167,6 +1240,7 @@ int bias_model_delta_pack16(bias_model *m, int32_t world, void **d16_dev, int64_
     if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
     if (m->conj.kind != BIAS_MD || m->n_f64 != 0 || world < 1) return fail(BIAS_EINVAL, "the 16-bit exchange covers MultinomialDirichlet count tables");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(ensure_wide(m));
     cudaStream_t st = m->ctx->stream;
     const int64_t n_wk_elems = m->V * (int64_t)m->Kpad, n_small_i = m->n_i32 - n_wk_elems;
     int32_t *small = m->delta_i32 + n_wk_elems, *flag = m->delta_i32 + m->n_i32;
@@ -1174,6 +1248,7 @@ int bias_model_delta_pack16(bias_model *m, int32_t world, void **d16_dev, int64_
     if (n_wk_elems > 0) {
         delta_pack16_kernel<<<grid_for(m->ctx, n_wk_elems / 8, 256), 256, 0, st>>>(m->i32_block, m->base_i32,
             reinterpret_cast<int16_t *>(m->delta_i32), n_wk_elems / 8, 32767 / world, flag);
+        BIAS_CUDA_TRY(cudaGetLastError());
         m->ctx->launches += 1;
     }
     delta_pack_i32_kernel<<<grid_for(m->ctx, n_small_i / 4, 256), 256, 0, st>>>(m->i32_block + n_wk_elems, m->base_i32 + n_wk_elems,
@@ -1191,6 +1266,8 @@ int bias_model_delta_apply16(bias_model *m) {
     if (!m) return fail(BIAS_EINVAL, "null model");
     if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(ensure_wide(m));
+    m->narrow_valid = false;        // the int32 table is written below
     cudaStream_t st = m->ctx->stream;
     const int64_t n_wk_elems = m->V * (int64_t)m->Kpad, n_small_i = m->n_i32 - n_wk_elems;
     if (n_wk_elems > 0) {
@@ -1210,6 +1287,8 @@ int bias_model_delta_apply(bias_model *m) {
     if (!m) return fail(BIAS_EINVAL, "null model");
     if (!m->base_i32) return fail(BIAS_ESTATE, "bias_model_delta_begin has not been called");
     BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_TRY(ensure_wide(m));
+    m->narrow_valid = false;        // the int32 table is written below
     cudaStream_t st = m->ctx->stream;
     const int64_t n4 = m->n_i32 / 4;
     delta_apply_i32_kernel<<<grid_for(m->ctx, n4, 256), 256, 0, st>>>(m->i32_block, m->base_i32, m->delta_i32, n4);

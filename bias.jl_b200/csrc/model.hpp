@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 constexpr int kMaxDevices = 64;     // size of the per-device caches of launch configurations
+constexpr int kMaxPeers = 8;        // ranks of a sharded run (the GPUs of one NVSwitch domain)
 
 struct bias_ctx {
     int device = 0;
@@ -49,10 +50,31 @@ struct bias_model {
     int64_t n_f64 = 0;
     double *sumx = nullptr;
     int32_t *group_rows = nullptr;  // [G][Kpad] n_jk for the generic LDA/HDP path
-    uint16_t *n_wk16 = nullptr;     // fast LDA path: 16-bit shadow of n_wk, rebuilt at the start of every sweep
+    // fast LDA path (K <= 1024): the narrow tables (lda_half16.cuh) hold the word-topic counts while sweeps run and the
+    // int32 table n_wk above is a view refreshed on demand.  Exactly one of the two may be stale at any time.
+    uint16_t *n_wk16 = nullptr;     // [V + 2 * hot_cap][Kpad]: 16-bit rows of all words, then the int32 rows of the hot words
+    int32_t hot_cap = 0;            // hot rows allocated: no corpus of the model's capacity can have more words above 65,535
+    int32_t *word_hot = nullptr;    // [V] index of the word's hot row, or -1
+    int32_t *hot_word = nullptr;    // [hot_cap] the reverse map
+    int32_t *hot_info = nullptr;    // [0] number of hot words, [1] set when they did not fit (cannot happen by construction)
     int32_t *word_freq = nullptr;   // [V] occurrences of each word in the local shard
+    int32_t *word_freq_g = nullptr; // [V] ... in the whole corpus (all ranks of a sharded run); == word_freq on one GPU
     int32_t *nk_rep = nullptr;      // [kNkRep][Kpad] replicas collecting a sweep's changes of n_k (half-warp kernels)
-    int32_t *wide_flag = nullptr;   // [1] set by shadow_build_kernel when a count may leave 16 bits this sweep
+    bool wide_valid = true;         // n_wk holds the current counts
+    bool narrow_valid = false;      // the narrow tables hold the current counts
+    bool class_valid = false;       // word_hot matches the loaded corpus
+
+    // sharded run (comm.cu): the narrow tables sit at the start of one allocation that the other ranks map
+    unsigned char *share_base = nullptr;
+    size_t share_bytes = 0, off_nk_pub = 0, off_freq_pub = 0, off_flags = 0;
+    int32_t rank = 0, world = 1, world_pending = 0;
+    bool grouped = false;                                 // the ranks are models of this process (bias_group): events order them
+    unsigned char *peer_base[kMaxPeers] = {};             // every rank's block as addressed from this device
+    bool peer_ipc[kMaxPeers] = {};                        // mapped with cudaIpcOpenMemHandle
+    uint16_t *base16 = nullptr;                           // [V / world + 1][Kpad] agreed counts of the rows this rank owns
+    int32_t *base_hot = nullptr, *nk_base = nullptr, *comm_err = nullptr;
+    uint32_t barrier_epoch = 0;
+    uint64_t seed_mix = 0;                                // folded into the Philox key: the ranks of a sharded run draw different uniforms
     uint16_t *stage16 = nullptr;    // [3][N_cap rounded up to 8]: uint16 word ids and assignments as uploaded by reload_u16, and the
                                     // uint16 mirror of z that every sweep call leaves behind for get_zz_u16; allocated on first use
     bool mirror16_valid = false;    // the mirror holds the current z
@@ -115,4 +137,19 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
                    int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,
                    int row_by_work = 0);
 int rebuild_counts(bias_model *m);
+int ensure_wide(bias_model *m);       // n_wk (int32) is current on return
+int ensure_narrow(bias_model *m);     // the narrow tables are current on return
+int model_local_sweep(bias_model *m); // one sweep over this model's items, no exchange
+int model_mirror16(bias_model *m);
+// comm.cu
+int32_t narrow_hot_cap(int64_t V, int64_t n_items_cap);
+int narrow_alloc(bias_model *m, int32_t hot_cap);
+void narrow_free(bias_model *m);
+int narrow_classify(bias_model *m);
+int narrow_build(bias_model *m);
+int narrow_fold(bias_model *m);
+int comm_global_word_freq(bias_model *m);
+int comm_prepare_flags(bias_model *m);
+int comm_exchange_flags(bias_model *m);
+int comm_check(bias_model *m);
 }  // namespace bias

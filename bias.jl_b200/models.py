@@ -380,6 +380,41 @@ class ResidentSampler:
         check(lib().bias_model_frozen_draws(self.h, ptr(u), ptr(out)))
         return out
 
+    def frozen_draws_dev(self, uniforms_dev_ptr: int, draws_dev_ptr: int):
+        """frozen_draws with both arrays in device memory (raw pointers: float64[n_items], int32[n_items])."""
+        check(lib().bias_model_frozen_draws_dev(self.h, C.c_void_p(uniforms_dev_ptr), C.c_void_p(draws_dev_ptr)))
+
+    def sweep_with_uniforms(self, uniforms):
+        """One production sweep that draws with the caller's uniforms (verification; a one-document corpus is swept
+        serially exactly as src/LDA.jl:116-131)."""
+        u = _lib.as_f64(uniforms)
+        assert u.size == self.data.n_items
+        check(lib().bias_model_sweep_with_uniforms(self.h, ptr(u)))
+
+    # -- sharded runs inside the library (csrc/comm.cu)
+    def share_prepare(self, rank: int, world: int, n_items_cap_global: int):
+        check(lib().bias_model_share_prepare(self.h, rank, world, n_items_cap_global))
+
+    def share_export(self) -> bytes:
+        h = _lib.ShareHandle()
+        check(lib().bias_model_share_export(self.h, C.byref(h)))
+        return bytes(h)
+
+    def share_attach(self, handles: list[bytes]):
+        arr = (_lib.ShareHandle * len(handles))(*[_lib.ShareHandle.from_buffer_copy(b) for b in handles])
+        check(lib().bias_model_share_attach(self.h, arr, len(handles)))
+
+    def narrow_info(self):
+        """-> (sweeps run on the narrow tables, number of hot words, hot rows allocated)"""
+        cur, n_hot, cap = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().bias_model_narrow_info(self.h, C.byref(cur), C.byref(n_hot), C.byref(cap)))
+        return bool(cur.value), n_hot.value, cap.value
+
+    def replica_digest(self) -> int:
+        d = C.c_uint64()
+        check(lib().bias_model_replica_digest(self.h, C.byref(d)))
+        return d.value
+
     def log_likelihood(self):
         """(sum_i log p(x_i | point estimates), n_items); perplexity = exp(-sum / n)."""
         s, n = C.c_double(), C.c_int64()
@@ -475,6 +510,47 @@ class ResidentSampler:
 
 
 # ------------------------------------------------------------------ the reference entry points
+class Group:
+    """bias_group: resident LDA shards of THIS process (one per GPU, or several on one GPU) swept together, with the
+    library's own count exchange after every sweep.  The shards stay owned by the caller."""
+
+    def __init__(self, samplers):
+        self.samplers = list(samplers)
+        self.h = C.c_void_p()
+        arr = (C.c_void_p * len(self.samplers))(*[s.h for s in self.samplers])
+        check(lib().bias_group_create(arr, len(self.samplers), C.byref(self.h)))
+
+    def sweep(self, n: int = 1):
+        check(lib().bias_group_sweep(self.h, n))
+
+    def close(self):
+        if self.h:
+            lib().bias_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def lda_run_multi(devices, lda: LDA, xx, zz, n_sweeps: int, seed: int = 0):
+    """bias_lda_run_multi: collapsed_gibbs_sampler!(lda, xx, zz, ...) over several GPUs of this process; zz is mutated in
+    place like the reference's.  Returns the per-sweep stats."""
+    data = FlatData(lda.component, xx, True)
+    if data.datum != _lib.INT:
+        raise TypeError("lda_run_multi covers word-id observations")
+    flat = _lib.as_i32(_flat_zz(zz, True))
+    dev = _lib.as_i32(devices)
+    stats = (_lib.SweepStats * max(1, n_sweeps))()
+    spec = lda.component.spec(data.datum)
+    check(lib().bias_lda_run_multi(ptr(dev), len(dev), C.c_uint64(seed), C.byref(spec), C.byref(data.c), data.n_groups,
+                                   ptr(data.group_ptr), ptr(flat), lda.KK, lda.aa, n_sweeps, stats))
+    _scatter_zz(flat, zz, True, data.group_ptr)
+    return list(stats)[:n_sweeps]
+
+
 def _store(filename: str, i: int, **arrays):
     """storesample (src/LDA.jl:45-64): the reference writes JLD (HDF5); no HDF5 tooling exists in
     this image, so samples are stored as .npz with the same keys."""

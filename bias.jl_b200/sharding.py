@@ -67,6 +67,7 @@ class ShardedSampler:
 
     def merge_local_counts(self):
         """After (re)building the counts from the local shard only: sum them into the global replica."""
+        self._flag_host, self._flag_event = None, None      # a flag raised before the reload says nothing about the new counts
         if self.world > 1:
             self.shard.delta_begin_zero()
             self._exchange(force32=True)        # whole counts, not deltas: they do not fit 16 bits in general
@@ -83,11 +84,14 @@ class ShardedSampler:
             self._flag_event.synchronize()      # recorded one sweep ago: returns at once
             use16 = int(self._flag_host[0]) == 0
             self._flag_event = None
+        fence = getattr(self.shard, "fence", lambda before: None)
         ts = pack16(self.world) if use16 else None
         if ts is not None:
             import torch
+            fence(True)
             for t in ts:
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            fence(False)
             self.shard.delta_apply16()
             if ts[1].is_cuda:
                 if self._flag_host is None:
@@ -99,8 +103,11 @@ class ShardedSampler:
                 self._flag_host = ts[1][-4:-3].clone()
                 self._flag_event = _Done()
             return
-        for t in self.shard.delta_tensors():
+        ts = self.shard.delta_tensors()
+        fence(True)
+        for t in ts:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        fence(False)
         self.shard.delta_apply()
 
     def sweep(self, n_sweeps: int = 1):
@@ -116,6 +123,19 @@ class GpuShard:
 
     def __init__(self, resident, device):
         self.rs, self.device = resident, device
+
+    def fence(self, before: bool):
+        """The library launches on its context's stream, torch.distributed on torch's current stream.  When the two
+        differ (a Context created without a stream owns a private one) the pack kernels must finish before the
+        collective reads the buffers, and the collective before the apply kernels read them."""
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        if self.rs.ctx.stream_handle == cur.cuda_stream and cur.cuda_stream != 0:
+            return                              # same stream: already ordered
+        if before:
+            self.rs.ctx.sync()
+        else:
+            cur.synchronize()
 
     def delta_begin(self):
         self.rs.delta_begin()
@@ -140,6 +160,22 @@ class GpuShard:
 
     def delta_apply16(self):
         self.rs.delta_apply16()
+
+
+def attach_ranks(rs, n_items_cap: int, group=None):
+    """One process per GPU: make the resident LDA model `rs` of every rank a shard of one run whose count exchange
+    happens inside the library (csrc/comm.cu, peer memory over NVLink).  torch.distributed only carries the few bytes
+    of host-side plumbing: the capacities and the IPC handles of the ranks' shared blocks.  Afterwards rs.sweep(n) is
+    collective."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    caps = [None] * world
+    dist.all_gather_object(caps, int(n_items_cap), group=group)
+    rs.share_prepare(rank, world, int(sum(caps)))
+    handles = [None] * world
+    dist.all_gather_object(handles, rs.share_export(), group=group)
+    rs.share_attach(handles)
+    dist.barrier(group)
 
 
 # ------------------------------------------------------------------ sharded HDP

@@ -191,6 +191,12 @@ BIAS_API int bias_model_conditionals(bias_model *m, int64_t n_query, const int64
 /* One pass of the PRODUCTION sweep kernel with counts frozen and uniforms supplied
  * (uniforms[n_items]); draws[n_items] out.  State is not modified. */
 BIAS_API int bias_model_frozen_draws(bias_model *m, const double *uniforms, int32_t *draws);
+/* The same with uniforms and draws in DEVICE memory ([n_items] each; synchronises before returning). */
+BIAS_API int bias_model_frozen_draws_dev(bias_model *m, const double *uniforms_dev, int32_t *draws_dev);
+/* One PRODUCTION sweep (counts updated, zz rewritten) that draws with the caller's uniforms[n_items] instead of the
+ * Philox stream: a one-document corpus is then swept serially, token by token, exactly as src/LDA.jl:116-131 does,
+ * and can be followed by the oracle (tests/test_gpu_headline.py).  LDA and BMM, single GPU. */
+BIAS_API int bias_model_sweep_with_uniforms(bias_model *m, const double *uniforms);
 /* HDP table-count conditional (src/HDP.jl:353-358) for n_query (n, a = aa*beta_k) pairs:
  * prob[q*n_max + m-1] for m = 1..n, draws[q] in 1..n. */
 BIAS_API int bias_hdp_table_conditionals(bias_ctx *ctx, int64_t n_query, const int32_t *n, const double *a,
@@ -281,6 +287,48 @@ BIAS_API int bias_model_delta_apply(bias_model *m);
  * one (bias_model_delta_pack / apply) once it has seen the flag; no host synchronisation is needed in between. */
 BIAS_API int bias_model_delta_pack16(bias_model *m, int32_t world, void **d16_dev, int64_t *n16, void **small_dev, int64_t *n_small);
 BIAS_API int bias_model_delta_apply16(bias_model *m);
+
+/* ---- sharded LDA inside the library (csrc/comm.cu): no external collective ------------------------------------
+ * The reference is single-process; these replace nothing in it and are what lets its entry point
+ * collapsed_gibbs_sampler!(lda, xx, zz, ...) (src/LDA.jl:67-72) use every GPU of a box.  Documents are split over the
+ * ranks, every rank keeps a replica of the word-topic counts and once per sweep the replicas are reconciled by the
+ * library's own reduce-scatter / all-gather kernel over NVLink peer memory.  LDA x MultinomialDirichlet x word ids,
+ * KK <= 1024, documents shorter than 65,536 tokens, at most 8 ranks (one NVSwitch domain). */
+
+/* (1) One process, several GPUs — what the Julia shim calls.  Splits the documents contiguously over `devices`, runs
+ * n_sweeps sweeps, returns the assignments in zz (caller-owned, mutated in place like the reference's zz). */
+BIAS_API int bias_lda_run_multi(const int32_t *devices, int32_t n_dev, uint64_t seed, const bias_conjugate *conj,
+                       const bias_data *data, int64_t n_groups, const int64_t *group_ptr, int32_t *zz /* in/out */,
+                       int32_t K, double alpha, int32_t n_sweeps, bias_sweep_stats *stats /* [n_sweeps] or NULL */);
+/* The same with resident shards: models created by the caller (one per device, or several on one device) become the
+ * ranks of a group; bias_group_sweep = sweep of every shard + the exchange, ordered by CUDA events.  After a reload
+ * of the shards (all of them) the next bias_group_sweep first merges their local counts.  The group does not own
+ * the models. */
+typedef struct bias_group bias_group;
+BIAS_API int bias_group_create(bias_model **models, int32_t n, bias_group **out);
+BIAS_API int bias_group_sweep(bias_group *g, int32_t n_sweeps);
+BIAS_API int bias_group_destroy(bias_group *g);
+
+/* (2) One process per GPU (torchrun / MPI / one Julia worker per GPU).  Every rank: create its model on its shard,
+ * bias_model_share_prepare(rank, world, sum over ranks of the item capacities), bias_model_share_export, exchange
+ * the handles by any host-side means (they are plain bytes), bias_model_share_attach.  From then on
+ * bias_model_sweep is COLLECTIVE: every rank must call it with the same n_sweeps; it runs the local sweep and the
+ * exchange (ranks are ordered by arrival counters in peer memory; a rank that waits more than 60 s for a peer
+ * gives up and the next bias_model_get_components / bias_model_replica_digest reports BIAS_ESTATE). */
+typedef struct {
+    unsigned char ipc[64];      /* cudaIpcMemHandle_t of the rank's shared block */
+    int64_t bytes, dd;
+    int32_t Kpad, hot_cap, rank, device;
+} bias_share_handle;
+BIAS_API int bias_model_share_prepare(bias_model *m, int32_t rank, int32_t world, int64_t n_items_cap_global);
+BIAS_API int bias_model_share_export(bias_model *m, bias_share_handle *out);
+BIAS_API int bias_model_share_attach(bias_model *m, const bias_share_handle *all /* [world] */, int32_t world);
+/* 64-bit digest of the replica's counts (word-topic table and n_k): equal on all ranks after an exchange. */
+BIAS_API int bias_model_replica_digest(bias_model *m, uint64_t *digest);
+
+/* Which representation of the word-topic counts is current on the fast LDA path: *narrow_current = 1 when the sweeps run
+ * on the 16-bit rows (+ int32 rows for the *n_hot words whose corpus frequency exceeds 65,535; room for *hot_cap). */
+BIAS_API int bias_model_narrow_info(bias_model *m, int32_t *narrow_current, int32_t *n_hot, int32_t *hot_cap);
 
 /* ---- instrumentation ------------------------------------------------------------------ */
 /* Device time of the most recent bias_model_sweep call's sweep kernels, measured with CUDA

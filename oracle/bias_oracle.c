@@ -328,6 +328,48 @@ double orc_lda_sweep(orc_comps *c, const orc_data *d, int64_t D, const int64_t *
     return ll;
 }
 
+/* Test support: the serial sweep of src/LDA.jl:113-133 (identity order) FOLLOWING another sampler's result.  At every
+ * token the oracle computes its own conditional on its own state and its own draw for uniforms[i]; where that differs
+ * from other_z[i] it records how far uniforms[i] is from the nearest edge of its CDF (the only legitimate reason for
+ * two samplers fed the same uniform to disagree) and then ADOPTS other_z[i], so that the states stay comparable for
+ * the rest of the sweep.  Returns the number of disagreements; *max_edge_dist <- the largest recorded distance,
+ * *max_rel_logp <- largest |log p_or(k) - log p_or(k')| is not computed here (draws only). */
+int64_t orc_lda_sweep_follow(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
+                             int64_t *z, int64_t *nn, double alpha, const double *uniforms,
+                             const int64_t *other_z, double *max_edge_dist)
+{
+    int64_t K = c->K, n_diff = 0;
+    double *pp = (double *)malloc((size_t)K * sizeof(double));
+    double worst = 0.0;
+    for (int64_t j = 0; j < D; ++j) {
+        for (int64_t i = ptr[j]; i < ptr[j + 1]; ++i) {
+            int64_t k = z[i];
+            orc_delitem(c, k, d, i);
+            nn[j * K + k] -= 1;
+            lda_scores(c, d, i, nn + j * K, alpha, pp);
+            orc_lognormalize(pp, K);
+            k = orc_sample(pp, K, uniforms[i]);
+            if (k != other_z[i]) {
+                double cw = 0.0, best = 1.0;
+                for (int64_t q = 0; q < K; ++q) {
+                    cw += pp[q];
+                    double dist = fabs(cw - uniforms[i]);
+                    if (dist < best) best = dist;
+                }
+                if (best > worst) worst = best;
+                n_diff += 1;
+                k = other_z[i];
+            }
+            z[i] = k;
+            orc_additem(c, k, d, i);
+            nn[j * K + k] += 1;
+        }
+    }
+    free(pp);
+    if (max_edge_dist) *max_edge_dist = worst;
+    return n_diff;
+}
+
 int64_t orc_lda_conditional(orc_comps *c, const orc_data *d, int64_t j, int64_t i,
                             int64_t zi, int64_t *nn, double alpha, double r,
                             double *raw, double *prob)

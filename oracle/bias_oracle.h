@@ -82,6 +82,10 @@ double orc_lda_sweep(orc_comps *c, const orc_data *d, int64_t D, const int64_t *
                      int64_t *z, int64_t *nn, double alpha,
                      const int64_t *doc_order, const int64_t *tok_order,
                      const double *uniforms, int faithful_diag);
+/* Test support: the same serial sweep following another sampler's assignments other_z[N] (see bias_oracle.c). */
+int64_t orc_lda_sweep_follow(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
+                             int64_t *z, int64_t *nn, double alpha, const double *uniforms,
+                             const int64_t *other_z, double *max_edge_dist);
 /* Conditional of one item on the current state with the item removed (LDA_sample_zz, src/LDA.jl:26-42).
  * raw[K] <- unnormalised log scores, prob[K] <- after lognormalize!. Returns the 0-based draw for r.
  * State is restored on return. */

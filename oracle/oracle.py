@@ -110,6 +110,8 @@ def lib():
         L.orc_lda_sweep.argtypes = [cp, dpp, i64, vp, vp, vp, f64, vp, vp, vp, i32]
         L.orc_lda_conditional.restype = i64
         L.orc_lda_conditional.argtypes = [cp, dpp, i64, i64, i64, vp, f64, f64, vp, vp]
+        L.orc_lda_sweep_follow.restype = i64
+        L.orc_lda_sweep_follow.argtypes = [cp, dpp, i64, vp, vp, vp, f64, vp, vp, C.POINTER(f64)]
         L.orc_bmm_init.restype = f64
         L.orc_bmm_init.argtypes = [cp, dpp, i64, vp, vp]
         L.orc_bmm_sweep.restype = f64
@@ -304,6 +306,15 @@ class LDAState:
         self.loglik = lib().orc_lda_sweep(self.c.ref(), self.d.ref(), self.D, _p(self.ptr), _p(self.z),
                                           _p(self.nn), self.alpha, _p(do), _p(to), _p(u), diag_mode)
         return self.loglik
+
+    def sweep_follow(self, uniforms, other_z):
+        """Serial sweep that adopts other_z wherever its own draw differs -> (number of disagreements, largest distance
+        of a disagreeing uniform from the nearest edge of the oracle's CDF)."""
+        u, oz = _f64(uniforms), _i64(other_z)
+        worst = C.c_double(0.0)
+        n = lib().orc_lda_sweep_follow(self.c.ref(), self.d.ref(), self.D, _p(self.ptr), _p(self.z), _p(self.nn),
+                                       self.alpha, _p(u), _p(oz), C.byref(worst))
+        return int(n), float(worst.value)
 
     def conditional(self, j, i, r):
         K = self.c.K

@@ -96,23 +96,6 @@ def test_two_bmm_gaussian_shards_on_one_gpu(ctx):
         rs.close()
 
 
-def test_sharded_lda_over_nccl_two_processes():
-    """The real N>1 path: two processes, two GPUs, NCCL all-reduce of the count deltas (tools/lda_sharded_check.py)."""
-    import json
-    import os
-    import subprocess
-    import sys
-    if b.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(root, "tools", "lda_sharded_check.py")],
-                         capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["replicas_equal_recount"] and line["loglik_improved"]
-
-
 def test_16_bit_exchange_of_word_topic_deltas(ctx):
     """bias_model_delta_pack16 / apply16: int16 deltas for n_wk, int32 for n_k / n_items, overflow flag raised when a
     delta times the number of ranks would not fit; both shards end up with the recount from the gathered zz."""

@@ -191,3 +191,44 @@ def test_lda_gaussian_groups(ctx):
         st.sweep(r.random(len(allx)), diag_mode=0)
     want = sum(any(abs(st.c.mu[k] - a) < 0.05 and st.c.nn[k] > 50 for k in range(5)) for a in atoms)
     assert got >= min(want, 4) - 1 and got >= 2, (got, want)
+
+
+def test_bmm_sent_conditionals_at_the_config2_shape(ctx):
+    """BASELINE config 2 shape (BMM x MultinomialDirichlet x Sent, K = 64 — two lane strides of the warp-per-item kernel —
+    V = 1024, 64 tokens per sentence, src/BMM.jl:92-115 with the predictive of src/conjugates.jl:181-198): conditionals
+    and draws against the oracle on a non-trivial state (after sweeps), then exact conservation."""
+    K, V, L, n = 64, 1024, 64, 1500
+    sp, sw, sc, _, _ = b.data.bars_bmm_sentences_csr(n, L, K, V, seed=321)
+    bmm = b.BMM(b.MultinomialDirichlet(V, 1.0), K, 0.1)
+    data = b.FlatData.from_csr(b._lib.SENT, n, sent_ptr=sp, sent_word=sw, sent_count=sc)
+    rng = np.random.default_rng(11)
+    z0 = rng.integers(0, K, n).astype(np.int32)
+    rs = b.ResidentSampler(ctx, bmm, data, z0)
+    rs.sweep(3)
+    z = rs.get_zz()
+    odata = orc.Data.sents(sp.astype(np.int64), sw.astype(np.int64), sc.astype(np.int64))
+    st = orc.BMMState(orc.Comps.md(K, V, 1.0), odata, z, 0.1)
+    idx = rng.choice(n, 400, replace=False)
+    u = rng.random(len(idx))
+    raw, prob, draw = rs.conditionals(idx, u)
+    oraw, oprob, odraw = np.zeros((len(idx), K)), np.zeros((len(idx), K)), np.zeros(len(idx), dtype=np.int64)
+    for q, i in enumerate(idx):
+        odraw[q], oraw[q], oprob[q] = st.conditional(int(i), float(u[q]))
+    assert_conditionals_close(raw, oraw, "BMM x Sent, K=64, V=1024")
+    assert np.allclose(raw, oraw, rtol=1e-9, atol=1e-7), np.abs(raw - oraw).max()
+    assert_draws_match(draw, odraw, oprob, u, 1e-9, "verification draws")
+    uu = rng.random(n)
+    fd = rs.frozen_draws(uu)
+    fo = np.zeros(n, dtype=np.int64)
+    fp = np.zeros((n, K))
+    for i in range(n):
+        fo[i], _, fp[i] = st.conditional(i, float(uu[i]))
+    assert_draws_match(fd, fo, fp, uu, 1e-9, "production draws")
+    rs.sweep(2)
+    z = rs.get_zz()
+    comp = rs.components()
+    item = np.repeat(np.arange(n), np.diff(sp))
+    mi = np.zeros((K, V), dtype=np.int64)
+    np.add.at(mi, (z[item], sw), sc)
+    assert np.array_equal(comp["mi"], mi) and np.array_equal(comp["nn"], np.bincount(z, minlength=K))
+    rs.close()
