@@ -47,14 +47,14 @@ def emit(line: dict):
         os.write(fd, (json.dumps(line) + "\n").encode())
 
 
-def sweep_kernel_name():
+def sweep_kernel_name(n_hot=0):
     """The kernel bias_model_sweep launches for this workload (csrc/model.cu: use_half16_kernel / use_half_kernel)."""
     force = os.environ.get("BIAS_LDA_KERNEL", "")
     if force.startswith("r"):
         return "lda_md_int_sweep_kernel<8>"
     if force.startswith("h"):
         return "lda_md_int_sweep_half_kernel<16, 8>"
-    return "lda_md_int_sweep_half16_kernel<8, 6, 3, true>"
+    return f"lda_md_int_sweep_half16_kernel<8, 6, 3, true, {'true' if n_hot > 0 else 'false'}>"
 
 
 def peaks():
@@ -571,7 +571,7 @@ def ours(args):
                                 "ncu sector hit rate in roofline.l2)" if table_mb < 126 else "larger than L2"),
                        "corpus_gen_s": round(gen_s, 2)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": sweep_kernel_name(),
+                         "traffic": traffic, "peak_source": peak_src, "kernel": sweep_kernel_name(n_hot),
                          "kernel_ms": kern_ms, "alg_bytes_per_token": B_ALG, "tokens_per_launch": tokens_per_launch,
                          "note": "achieved uses SURVEY 8(d)'s 4 K + 12 bytes (int32 row from HBM) for continuity; the kernel reads "
                                  "2 K-byte 16-bit rows that mostly hit in L2, so frac > 1 says the metric's HBM bound no longer binds "

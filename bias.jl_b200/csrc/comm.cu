@@ -319,6 +319,12 @@ int narrow_classify(bias_model *m) {
     BIAS_CUDA_TRY(cudaGetLastError());
     m->ctx->launches += 1;
     m->class_valid = true;
+    // the host picks the kernel instantiation by whether hot words exist: one small read-back per (re)load
+    int32_t h[2] = {0, 0};
+    BIAS_CUDA_TRY(cudaMemcpyAsync(h, m->hot_info, sizeof h, cudaMemcpyDeviceToHost, m->ctx->stream));
+    BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
+    if (h[1]) return fail(BIAS_ESTATE, "%d words need 32-bit rows but the table has room for %d", h[0], m->hot_cap);
+    m->n_hot_host = h[0];
     return BIAS_OK;
 }
 

@@ -108,7 +108,10 @@ __device__ __forceinline__ float dot8i(const uint4 a, const uint4 b, const float
     return s + t;
 }
 
-template <int NC8, int WARPS = kH16Warps, int CTAS = kH16Ctas, bool CNT8 = false>
+// HOT = false: the corpus has no word above 65,535 occurrences (decided on the host after every (re)load) and the
+// hot-row route is compiled out.  It is a separate instantiation because the route's mere presence in the token loop
+// slows the 16-bit route by 20 % (37.6 -> 45.9 ms per 100 M tokens, profiles/r02_hot_route_variants.md).
+template <int NC8, int WARPS = kH16Warps, int CTAS = kH16Ctas, bool CNT8 = false, bool HOT = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
 lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
     using cnt_t = typename std::conditional<CNT8, uint8_t, uint16_t>::type;
@@ -218,8 +221,10 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
         float my_u = 0.5f;
         if (l16 < nb) {
             my_w = p.word[t_cur + l16];
-            const int h = __ldg(p.word_hot + my_w);
-            if (h >= 0) my_w = p.V + 2 * h;
+            if constexpr (HOT) {
+                const int h = __ldg(p.word_hot + my_w);
+                if (h >= 0) my_w = p.V + 2 * h;
+            }
             my_z = p.z[t_cur + l16];
             const uint64_t tid = (uint64_t)(t_cur + l16);
             if (p.ext_uniforms) {
@@ -242,12 +247,12 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
 #pragma unroll
             for (int j = 0; j < NC8; ++j) c[j] = __ldcg(row + j * 16 + l16);
         }
-        int c_own = (w >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(p.n_wk16 + (size_t)w * KPAD) + r_pos(kold))
+        int c_own = (HOT && w >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(p.n_wk16 + (size_t)w * KPAD) + r_pos(kold))
                                : (int)__ldcg(p.n_wk16 + (size_t)w * KPAD + kold);
 
         for (int i = 0; i < nb_both; ++i) {
             const bool on = i < nb;
-            const bool hot = w >= p.V;         // uniform over the half; the two halves of the warp may differ
+            const bool hot = HOT && w >= p.V;  // uniform over the half; the two halves of the warp may differ
             const uint4 *row_cur = reinterpret_cast<const uint4 *>(p.n_wk16 + (size_t)w * KPAD);
 
             // ---- delitem!, arithmetically: r[kold] with n_dk and n_k one lower; nothing is stored ----
@@ -311,7 +316,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             const int jsel = src_lane >> GSHIFT;
             const float base = __shfl_sync(kFull, P - T, src_lane, 16);
             uint4 cs = pick_chunk16<NC8>(c, jsel), cs2 = make_uint4(0, 0, 0, 0);
-            if (hot) {                   // the selected chunk of a hot row is read again (two pieces per lane)
+            if (hot) {  // the selected chunk of a hot row is read again (two pieces per lane)
                 cs = __ldcg(row_cur + (2 * jsel) * 16 + l16);
                 cs2 = __ldcg(row_cur + (2 * jsel + 1) * 16 + l16);
             }
@@ -326,7 +331,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
 #pragma unroll
                 for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
-                c_own_n = (w_n >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(rown) + r_pos(kold_n)) : (int)__ldcg(rown + kold_n);
+                c_own_n = (HOT && w_n >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(rown) + r_pos(kold_n)) : (int)__ldcg(rown + kold_n);
             }
 
             // ---- pass 2: CDF inside the selected chunk (8 topics per lane) ----

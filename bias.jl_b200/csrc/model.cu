@@ -99,23 +99,23 @@ static int launch_lda_half_t(bias_model *m, const LdaFastParams &p) {
     return BIAS_OK;
 }
 
-template <int NC8, int WARPS, int CTAS, bool CNT8>
+template <int NC8, int WARPS, int CTAS, bool CNT8, bool HOT>
 static int launch_lda_half16_t(bias_model *m, const LdaFastParams &p) {
     static int ctas_cache[kMaxDevices] = {};          // function attributes are per device
     int &ctas_per_sm = ctas_cache[m->ctx->device % kMaxDevices];
     const size_t smem = lda_half16_smem_bytes(NC8, WARPS, CNT8);
     const int threads = WARPS * 32;
     if (ctas_per_sm == 0) {
-        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS, CNT8>,
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS, CNT8, HOT>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS, CNT8>, threads, smem));
+        BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS, CNT8, HOT>, threads, smem));
         if (occ < 1) return fail(BIAS_ECUDA, "LDA 16-bit sweep kernel does not fit on an SM (K padded to %d)", NC8 * 128);
         ctas_per_sm = std::min(occ, CTAS);
     }
     const int64_t want = (p.D + WARPS * 2 - 1) / (WARPS * 2);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)m->ctx->num_sms * ctas_per_sm));
-    lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS, CNT8><<<grid, threads, smem, m->ctx->stream>>>(p);
+    lda_md_int_sweep_half16_kernel<NC8, WARPS, CTAS, CNT8, HOT><<<grid, threads, smem, m->ctx->stream>>>(p);
     BIAS_CUDA_TRY(cudaGetLastError());
     m->ctx->launches += 1;
     return BIAS_OK;
@@ -127,8 +127,12 @@ template <int NC8>
 static int launch_lda_half16(bias_model *m, const LdaFastParams &p) {
     const char *force = getenv("BIAS_LDA_CNT8");
     const bool cnt8 = force ? atoi(force) != 0 && m->max_group_len <= 255 : m->max_group_len <= 255;
-    if (cnt8) return launch_lda_half16_t<NC8, kH16Warps8, kH16Ctas, true>(m, p);
-    return launch_lda_half16_t<NC8, kH16Warps, kH16Ctas, false>(m, p);
+    if (m->n_hot_host > 0) {            // some words need int32 rows: the instantiation with the hot-row route
+        if (cnt8) return launch_lda_half16_t<NC8, kH16Warps8, kH16Ctas, true, true>(m, p);
+        return launch_lda_half16_t<NC8, kH16Warps, kH16Ctas, false, true>(m, p);
+    }
+    if (cnt8) return launch_lda_half16_t<NC8, kH16Warps8, kH16Ctas, true, false>(m, p);
+    return launch_lda_half16_t<NC8, kH16Warps, kH16Ctas, false, false>(m, p);
 }
 
 // the narrow tables (lda_half16.cuh): the default whenever they were allocated (K <= 1024) and every document is shorter
@@ -1105,17 +1109,7 @@ int bias_model_narrow_info(bias_model *m, int32_t *narrow_current, int32_t *n_ho
     if (!m) return fail(BIAS_EINVAL, "null model");
     if (narrow_current) *narrow_current = (m->n_wk16 && m->narrow_valid) ? 1 : 0;
     if (hot_cap) *hot_cap = m->hot_cap;
-    if (n_hot) {
-        *n_hot = 0;
-        if (m->n_wk16 && m->class_valid) {
-            BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
-            int32_t h[2] = {0, 0};
-            BIAS_CUDA_TRY(cudaMemcpyAsync(h, m->hot_info, sizeof h, cudaMemcpyDeviceToHost, m->ctx->stream));
-            BIAS_CUDA_TRY(cudaStreamSynchronize(m->ctx->stream));
-            if (h[1]) return fail(BIAS_ESTATE, "%d words need 32-bit rows but the table has room for %d", h[0], m->hot_cap);
-            *n_hot = h[0];
-        }
-    }
+    if (n_hot) *n_hot = (m->n_wk16 && m->class_valid) ? m->n_hot_host : 0;
     return BIAS_OK;
 }
 

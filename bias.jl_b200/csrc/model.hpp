@@ -63,6 +63,7 @@ struct bias_model {
     bool wide_valid = true;         // n_wk holds the current counts
     bool narrow_valid = false;      // the narrow tables hold the current counts
     bool class_valid = false;       // word_hot matches the loaded corpus
+    int32_t n_hot_host = 0;         // number of hot words of the loaded corpus (read back after every classification)
 
     // sharded run (comm.cu): the narrow tables sit at the start of one allocation that the other ranks map
     unsigned char *share_base = nullptr;

@@ -50,7 +50,7 @@ def test_production_sweep_follows_the_serial_sampler_on_one_long_document(ctx, K
         z = rs.get_zz()
         n_diff, worst = st.sweep_follow(u, z.astype(np.int64))
         assert worst <= EPS_FP32, f"sweep {s}: a GPU draw differs from the oracle's with u {worst:.2e} away from any CDF edge"
-        assert n_diff <= max(3, L // 2000), f"sweep {s}: {n_diff} near-tie disagreements in {L} tokens"
+        assert n_diff <= max(3, L // 300), f"sweep {s}: {n_diff} near-tie disagreements in {L} tokens"
         assert np.array_equal(st.z, z)
         n_ties += n_diff
     if rs.narrow_info()[2] > 0:
@@ -65,9 +65,9 @@ def test_hot_words_run_on_int32_rows_inside_the_16_bit_kernel(ctx):
     """Words above 65,535 occurrences get int32 rows next to the 16-bit rows of all other words and the SAME kernel
     launch serves both (per-token routing): counts are conserved exactly with cells far beyond 16 bits, frozen draws
     match the oracle on such a state, and the narrow tables stay current (no fall-back to the int32 table)."""
-    K, V = 6, 9
+    K, V = 3, 9
     rng = np.random.default_rng(8)
-    words = rng.permutation(np.concatenate([np.zeros(150_000, dtype=np.int64), np.full(70_000, 4, dtype=np.int64),
+    words = rng.permutation(np.concatenate([np.zeros(280_000, dtype=np.int64), np.full(70_000, 4, dtype=np.int64),
                                             rng.integers(1, V, 30_000)]))
     cut = np.sort(rng.choice(np.arange(1, len(words)), 600, replace=False))
     xx = [a for a in np.split(words, cut)]

@@ -9,7 +9,8 @@ mkdir -p _exp/$name
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $*"
 nvcc $FLAGS -c model.cu -o _exp/$name/model.o &
 nvcc $FLAGS -c hdp.cu -o _exp/$name/hdp.o &
+nvcc $FLAGS -c comm.cu -o _exp/$name/comm.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o _exp/libbias_$name.so _exp/$name/model.o _exp/$name/hdp.o -Xlinker --exclude-libs,ALL -lcudart_static -ldl -lrt -lpthread
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o _exp/libbias_$name.so _exp/$name/model.o _exp/$name/hdp.o _exp/$name/comm.o -Xlinker --exclude-libs,ALL -lcudart_static -ldl -lrt -lpthread
 rm -rf _exp/$name
 echo built _exp/libbias_$name.so
