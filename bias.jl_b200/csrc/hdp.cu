@@ -229,7 +229,7 @@ __global__ void hdp_table_conditionals_kernel(const int32_t *n_arr, const double
 // alpha0 auxiliaries (src/HDP.jl:133-147): w_j ~ Beta(aa+1, n_j), s_j ~ Bernoulli(n_j / (n_j + aa)).
 // out[0] += sum_j log w_j, out[1] += sum_j s_j
 __global__ void hdp_hyper_kernel(const int64_t *group_ptr, int64_t G, double aa, uint64_t seed, uint32_t sweep,
-                                 uint32_t internal, double *out) {
+                                 uint32_t internal, double *out, const double *ext_uniforms = nullptr) {
     double lw = 0.0, ss = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G; j += (int64_t)gridDim.x * blockDim.x) {
         const double nj = (double)(group_ptr[j + 1] - group_ptr[j]);
@@ -237,7 +237,8 @@ __global__ void hdp_hyper_kernel(const int64_t *group_ptr, int64_t G, double aa,
         if (nj > 0.0) {
             const double ga = rs.gamma(aa + 1.0), gb = rs.gamma(nj);
             lw += log(ga / (ga + gb));
-            ss += (rs.u01() < nj / (nj + aa)) ? 1.0 : 0.0;
+            const double u = rs.u01();
+            ss += ((ext_uniforms ? ext_uniforms[j] : u) < nj / (nj + aa)) ? 1.0 : 0.0;
         }
     }
     lw = warp_sum(lw);
@@ -563,30 +564,52 @@ static int hdp_phase_tables(bias_model *m, int hh) {
     return BIAS_OK;
 }
 
-// alpha0 (Teh et al. eq. 50 with the device-side auxiliaries sum log w_j, sum s_j) and gamma (Escobar-West), src/HDP.jl:124-159
-static void hdp_host_hyper_on(bias_model *m, double mt, double sum_logw, double sum_s, int KK, double &aa_io, double &gg_io);
-static void hdp_host_hyper(bias_model *m, double mt, double sum_logw, double sum_s) {
-    hdp_host_hyper_on(m, mt, sum_logw, sum_s, m->hdp.KK, m->hdp.aa, m->hdp.gg);
-}
-// the same update on any (aa, gg) pair: the HDP's, or one epoch's of the RCRF (src/RCRF.jl:80-118 with KK = dishes of the epoch)
-static void hdp_host_hyper_on(bias_model *m, double mt, double sum_logw, double sum_s, int KK, double &aa_io, double &gg_io) {
-    const double aa_shape = m->hdp.a1 + mt - sum_s;
-    const double aa_rate = m->hdp.a2 - sum_logw;
-    if (aa_shape > 0.0 && aa_rate > 0.0) {
-        std::gamma_distribution<double> ga(aa_shape, 1.0);
-        aa_io = ga(m->host_rng) / aa_rate;
-    }
-    std::gamma_distribution<double> g1(gg_io + 1.0, 1.0), g2(std::max(mt, 1e-300), 1.0);
-    const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
-    const double eta = x1 / (x1 + x2);                      // Beta(gg + 1, m), :151
+// alpha0 (Teh et al. eq. 50 with the device-side auxiliaries sum log w_j, sum s_j) and gamma (Escobar-West), src/HDP.jl:124-159,
+// as a function of the host RNG and the priors (the model's, or one epoch's of the RCRF: src/RCRF.jl:80-118 with KK = dishes
+// of the epoch).  A non-positive Gamma shape or rate is an error, as Distributions.Gamma's argument check is in the reference.
+static int host_hyper_draw(std::mt19937_64 &rng, double a1, double a2, double g1, double g2, double mt, double sum_logw,
+                           double sum_s, int KK, double &aa_io, double &gg_io) {
+    const double aa_shape = a1 + mt - sum_s;            // :146
+    const double aa_rate = a2 - sum_logw;               // :147
+    if (!(aa_shape > 0.0) || !(aa_rate > 0.0))
+        return fail(BIAS_EINVAL, "HDP: Gamma(%g) / %g for alpha0 is not a distribution (a1 = %g, a2 = %g, tables = %g, sum s = %g)",
+                    aa_shape, aa_rate, a1, a2, mt, sum_s);
+    std::gamma_distribution<double> ga(aa_shape, 1.0);
+    aa_io = ga(rng) / aa_rate;                          // :148
+    std::gamma_distribution<double> x1d(gg_io + 1.0, 1.0), x2d(std::max(mt, 1e-300), 1.0);
+    const double x1 = x1d(rng), x2 = x2d(rng);
+    const double eta = x1 / (x1 + x2);                  // Beta(gg + 1, m), :151
     const double le = std::log(eta);
-    const double pi_eta = 1.0 / (1.0 + (mt * (m->hdp.g2 - le)) / (m->hdp.g1 + KK - 1.0));   // :152
+    const double pi_eta = 1.0 / (1.0 + (mt * (g2 - le)) / (g1 + KK - 1.0));   // :152
     std::uniform_real_distribution<double> ud(0.0, 1.0);
-    const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.g1 + KK : m->hdp.g1 + KK - 1.0;   // :154-158
-    if (shape > 0.0) {
-        std::gamma_distribution<double> gg(shape, 1.0);
-        gg_io = gg(m->host_rng) / (m->hdp.g2 - le);
+    const double shape = (ud(rng) < pi_eta) ? g1 + KK : g1 + KK - 1.0;         // :154-158
+    if (!(shape > 0.0) || !(g2 - le > 0.0))
+        return fail(BIAS_EINVAL, "HDP: Gamma(%g) / %g for gamma is not a distribution (g1 = %g, g2 = %g, KK = %d)", shape, g2 - le, g1, g2, KK);
+    std::gamma_distribution<double> gd(shape, 1.0);
+    gg_io = gd(rng) / (g2 - le);
+    return BIAS_OK;
+}
+static int hdp_host_hyper_on(bias_model *m, double mt, double sum_logw, double sum_s, int KK, double &aa_io, double &gg_io) {
+    return host_hyper_draw(m->host_rng, m->hdp.a1, m->hdp.a2, m->hdp.g1, m->hdp.g2, mt, sum_logw, sum_s, KK, aa_io, gg_io);
+}
+static int hdp_host_hyper(bias_model *m, double mt, double sum_logw, double sum_s) {
+    return hdp_host_hyper_on(m, mt, sum_logw, sum_s, m->hdp.KK, m->hdp.aa, m->hdp.gg);
+}
+
+// beta ~ Dirichlet([sum_j M_j1, ..., sum_j M_jKK, gg]) (src/HDP.jl:362-364) as normalised Gamma draws
+static void host_beta_draw(std::mt19937_64 &rng, const unsigned long long *tables, int KK, double gg, double *beta) {
+    double tot = 0.0;
+    for (int k = 0; k <= KK; ++k) {
+        const double a = (k < KK) ? (double)tables[k] : gg;
+        double g = 0.0;
+        if (a > 0.0) {
+            std::gamma_distribution<double> gd(a, 1.0);
+            g = gd(rng);
+        }
+        beta[k] = g;
+        tot += g;
     }
+    for (int k = 0; k <= KK; ++k) beta[k] = tot > 0.0 ? beta[k] / tot : 1.0 / (KK + 1);
 }
 
 // beta ~ Dirichlet([sum_j M_jk ..., gg]) (src/HDP.jl:362-364), alpha0 and gamma (:124-159) from the (possibly
@@ -606,20 +629,9 @@ static int hdp_phase_draw(bias_model *m) {
     if (err == 1)
         return fail(BIAS_ERANGE, "HDP: some n_jk exceeds the %d-row Stirling table (the reference throws BoundsError, src/HDP.jl:355)",
                     ctx->stirling_rows);
-    double tot = 0.0;
-    for (int k = 0; k <= KK; ++k) {
-        const double a = (k < KK) ? (double)tables[k] : m->hdp.gg;
-        double g = 0.0;
-        if (a > 0.0) {
-            std::gamma_distribution<double> gd(a, 1.0);
-            g = gd(m->host_rng);
-        }
-        m->h_beta[k] = g;
-        tot += g;
-    }
-    for (int k = 0; k <= KK; ++k) m->h_beta[k] = tot > 0.0 ? m->h_beta[k] / tot : 1.0 / (KK + 1);
+    host_beta_draw(m->host_rng, tables.data(), KK, m->hdp.gg, m->h_beta.data());
     for (size_t k = (size_t)KK + 1; k < m->h_beta.size(); ++k) m->h_beta[k] = 0.0;
-    if (m->hdp.sample_hyperparam) hdp_host_hyper(m, (double)tables[Kpad], hyper[0], hyper[1]);
+    if (m->hdp.sample_hyperparam) BIAS_TRY(hdp_host_hyper(m, (double)tables[Kpad], hyper[0], hyper[1]));
     return BIAS_OK;
 }
 
@@ -851,7 +863,7 @@ int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
             ctx->launches += 1;
             BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
             BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-            hdp_host_hyper(m, (double)mt, hyper[0], hyper[1]);
+            BIAS_TRY(hdp_host_hyper(m, (double)mt, hyper[0], hyper[1]));
         }
     }
     BIAS_TRY(crf_launch_diag(m));
@@ -904,7 +916,7 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
                 ctx->launches += 1;
                 BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
                 BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-                hdp_host_hyper_on(m, (double)mt, hyper[0], hyper[1], KK_t, m->h_aa_t[t], m->h_gg_t[t]);
+                BIAS_TRY(hdp_host_hyper_on(m, (double)mt, hyper[0], hyper[1], KK_t, m->h_aa_t[t], m->h_gg_t[t]));
             }
         }
     }
@@ -1220,6 +1232,61 @@ int bias_hdp_table_conditionals(bias_ctx *ctx, int64_t n_query, const int32_t *n
     for (void *p : {(void *)d_n, (void *)d_draw, (void *)d_a, (void *)d_u, (void *)d_prob})
         if (p) cudaFree(p);
     if (e != cudaSuccess) return fail(BIAS_ECUDA, "table conditionals: %s", cudaGetErrorString(e));
+    return BIAS_OK;
+}
+
+// ---- verification of sample_hyperparam! (src/HDP.jl:124-159) and of the beta draw (:362-364) ----
+// The device part: out[0] = sum_j log w_j with w_j ~ Beta(aa + 1, n_j), out[1] = sum_j s_j with s_j ~ Bernoulli(n_j / (n_j + aa)),
+// for the Philox stream (seed of ctx, sweep, internal).  With uniforms[n_groups] supplied the Bernoulli draws use them
+// (s_j = uniforms[j] < n_j / (n_j + aa)), which makes out[1] comparable exactly.
+int bias_hdp_hyper_aux(bias_ctx *ctx, int64_t n_groups, const int64_t *group_ptr, double aa, uint32_t sweep, uint32_t internal,
+                       const double *uniforms, double *out) {
+    if (!ctx || !group_ptr || !out) return fail(BIAS_EINVAL, "null argument");
+    if (n_groups < 0 || !(aa > 0.0)) return fail(BIAS_EINVAL, "n_groups >= 0 and aa > 0 required");
+    BIAS_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int64_t *d_ptr = nullptr;
+    double *d_u = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_ptr, ((size_t)n_groups + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, 16);
+    if (e == cudaSuccess && uniforms) e = cudaMalloc((void **)&d_u, (size_t)std::max<int64_t>(1, n_groups) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ptr, group_ptr, ((size_t)n_groups + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && uniforms) e = cudaMemcpyAsync(d_u, uniforms, (size_t)n_groups * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, 16, st);
+    if (e == cudaSuccess && n_groups > 0) {
+        hdp_hyper_kernel<<<grid1d(ctx, n_groups, 128, 4), 128, 0, st>>>(d_ptr, n_groups, aa, ctx->seed, sweep, internal, d_out, d_u);
+        ctx->launches += 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 16, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    for (void *p : {(void *)d_ptr, (void *)d_u, (void *)d_out})
+        if (p) cudaFree(p);
+    if (e != cudaSuccess) return fail(BIAS_ECUDA, "hyper auxiliaries: %s", cudaGetErrorString(e));
+    return BIAS_OK;
+}
+
+// The host part: n successive draws of (alpha0, gamma) from the SAME conditioning values (the chain is not advanced:
+// every draw starts from aa, gg), with the library's host generator seeded by `seed`.  No device is needed.
+int bias_hdp_hyper_draws(uint64_t seed, double a1, double a2, double g1, double g2, double n_tables, double sum_logw, double sum_s,
+                         int32_t KK, double aa, double gg, int32_t n, double *aa_out, double *gg_out) {
+    if (!aa_out || !gg_out || n < 0) return fail(BIAS_EINVAL, "null argument");
+    std::mt19937_64 rng(seed);
+    for (int32_t i = 0; i < n; ++i) {
+        double a = aa, g = gg;
+        BIAS_TRY(host_hyper_draw(rng, a1, a2, g1, g2, n_tables, sum_logw, sum_s, KK, a, g));
+        aa_out[i] = a;
+        gg_out[i] = g;
+    }
+    return BIAS_OK;
+}
+
+// n draws of beta ~ Dirichlet([tables[0..KK-1], gg]) -> beta_out[n][KK + 1].  No device is needed.
+int bias_hdp_beta_draws(uint64_t seed, int32_t KK, const int64_t *tables, double gg, int32_t n, double *beta_out) {
+    if (!tables || !beta_out || KK < 1 || n < 0 || !(gg > 0.0)) return fail(BIAS_EINVAL, "bad argument");
+    std::mt19937_64 rng(seed);
+    std::vector<unsigned long long> t(tables, tables + KK);
+    for (int32_t i = 0; i < n; ++i) host_beta_draw(rng, t.data(), KK, gg, beta_out + (size_t)i * (KK + 1));
     return BIAS_OK;
 }
 

@@ -830,6 +830,30 @@ def posterior(model, xx, zz, KK: int | None = None, ctx: Context | None = None):
 
 
 # ------------------------------------------------------------------ HDP verification helpers
+def hdp_hyper_aux(ctx: Context, group_ptr, aa: float, sweep: int = 0, internal: int = 0, uniforms=None):
+    """Device part of sample_hyperparam! (src/HDP.jl:133-144) -> (sum_j log w_j, sum_j s_j)."""
+    gp = _lib.as_i64(group_ptr)
+    u = None if uniforms is None else _lib.as_f64(uniforms)
+    out = np.zeros(2)
+    check(lib().bias_hdp_hyper_aux(ctx.h, gp.size - 1, ptr(gp), aa, sweep, internal, ptr(u), ptr(out)))
+    return float(out[0]), float(out[1])
+
+
+def hdp_hyper_draws(seed, a1, a2, g1, g2, n_tables, sum_logw, sum_s, KK, aa, gg, n):
+    """Host part of sample_hyperparam! (src/HDP.jl:146-158): n draws of (alpha0, gamma) from the same conditioning values."""
+    a, g = np.zeros(n), np.zeros(n)
+    check(lib().bias_hdp_hyper_draws(C.c_uint64(seed), a1, a2, g1, g2, n_tables, sum_logw, sum_s, KK, aa, gg, n, ptr(a), ptr(g)))
+    return a, g
+
+
+def hdp_beta_draws(seed, tables, gg, n):
+    """n draws of my_beta ~ Dirichlet([sum_j M_jk ..., gg]) (src/HDP.jl:362-364) -> [n, KK + 1]."""
+    t = _lib.as_i64(tables)
+    out = np.zeros((n, t.size + 1))
+    check(lib().bias_hdp_beta_draws(C.c_uint64(seed), t.size, ptr(t), gg, n, ptr(out)))
+    return out
+
+
 def stirling_rows(ctx: Context, n_rows: int) -> np.ndarray:
     """Rows 1..n_rows of the device-resident normalised log-Stirling table (packed lower triangle)."""
     out = np.zeros(n_rows * (n_rows + 1) // 2)

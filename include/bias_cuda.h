@@ -204,6 +204,16 @@ BIAS_API int bias_hdp_table_conditionals(bias_ctx *ctx, int64_t n_query, const i
 /* Device-resident normalised log-Stirling table (regenerates StirlingNums_10K.mat, src/HDP.jl:207-209).
  * Copies rows 1..n_rows (packed lower triangle) to out; builds the table on first use. */
 BIAS_API int bias_stirling_rows(bias_ctx *ctx, int32_t n_rows, double *out);
+/* sample_hyperparam!(hdp, n_group_j, m), src/HDP.jl:124-159, in its two parts.  Device: out[0] = sum_j log w_j with
+ * w_j ~ Beta(aa + 1, n_j) and out[1] = sum_j s_j with s_j ~ Bernoulli(n_j / (n_j + aa)) (:133-144) for the context's
+ * Philox stream at (sweep, internal); with uniforms[n_groups] supplied, s_j = uniforms[j] < n_j / (n_j + aa). */
+BIAS_API int bias_hdp_hyper_aux(bias_ctx *ctx, int64_t n_groups, const int64_t *group_ptr, double aa, uint32_t sweep,
+                       uint32_t internal, const double *uniforms /* nullable */, double *out /* [2] */);
+/* Host: n independent draws of (alpha0, gamma) (:146-158) given the auxiliaries, each starting from (aa, gg). */
+BIAS_API int bias_hdp_hyper_draws(uint64_t seed, double a1, double a2, double g1, double g2, double n_tables, double sum_logw,
+                         double sum_s, int32_t KK, double aa, double gg, int32_t n, double *aa_out, double *gg_out);
+/* Host: n draws of my_beta ~ Dirichlet([sum_j M_jk ..., gg]), src/HDP.jl:362-364 -> beta_out[n][KK + 1]. */
+BIAS_API int bias_hdp_beta_draws(uint64_t seed, int32_t KK, const int64_t *tables, double gg, int32_t n, double *beta_out);
 
 /* Sum over items of log p(x_i | theta_group, phi) under the point estimates of the current state,
  * theta_jk = (n_jk + aa)/(n_j + K aa), phi = posterior mean of each component (LDA x MD x Int).

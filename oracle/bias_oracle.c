@@ -328,6 +328,42 @@ double orc_lda_sweep(orc_comps *c, const orc_data *d, int64_t D, const int64_t *
     return ll;
 }
 
+/* Test support (convergence fixtures): the same serial sweep for word-id items with the conditional evaluated in the
+ * linear domain — exp(log(n_dk+a) + log((b+n_kw)/(bV+n_k)) - max) / sum of src/LDA.jl:35-41 + src/common.jl:42-52 IS the
+ * normalised weight (n_dk+a)(b+n_kw)/(bV+n_k) — in Float64, CDF walked in k order with the strict test of
+ * src/common.jl:74.  Ten times faster than orc_lda_sweep (no log / exp per topic), which makes chains of hundreds of
+ * sweeps at K = 1024 affordable; tests/test_oracle_golden.py checks that it makes the same draws as orc_lda_sweep. */
+void orc_lda_sweep_linear(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr, int64_t *z, int64_t *nn,
+                          double alpha, const int64_t *doc_order, const int64_t *tok_order, const double *uniforms)
+{
+    int64_t K = c->K, V = c->dd;
+    double *pp = (double *)malloc((size_t)K * sizeof(double));
+    double bV = c->aa * (double)V;
+    int64_t pos = 0;
+    for (int64_t jo = 0; jo < D; ++jo) {
+        int64_t j = doc_order ? doc_order[jo] : jo;
+        int64_t len = ptr[j + 1] - ptr[j];
+        int64_t *nj = nn + j * K;
+        for (int64_t io = 0; io < len; ++io) {
+            int64_t i = tok_order ? tok_order[pos + io] : ptr[j] + io;
+            int64_t w = d->w[i], k = z[i];
+            c->mi[k * V + w] -= 1; c->mm[k] -= 1; c->nn[k] -= 1; nj[k] -= 1;
+            double tot = 0.0;
+            for (int64_t q = 0; q < K; ++q) {
+                pp[q] = ((double)nj[q] + alpha) * ((c->aa + (double)c->mi[q * V + w]) / (bV + (double)c->mm[q]));
+                tot += pp[q];
+            }
+            double r = uniforms[i] * tot, cw = pp[0];
+            k = 0;
+            while (cw < r && k < K - 1) { k += 1; cw += pp[k]; }
+            z[i] = k;
+            c->mi[k * V + w] += 1; c->mm[k] += 1; c->nn[k] += 1; nj[k] += 1;
+        }
+        pos += len;
+    }
+    free(pp);
+}
+
 /* Test support: the serial sweep of src/LDA.jl:113-133 (identity order) FOLLOWING another sampler's result.  At every
  * token the oracle computes its own conditional on its own state and its own draw for uniforms[i]; where that differs
  * from other_z[i] it records how far uniforms[i] is from the nearest edge of its CDF (the only legitimate reason for

@@ -82,6 +82,9 @@ double orc_lda_sweep(orc_comps *c, const orc_data *d, int64_t D, const int64_t *
                      int64_t *z, int64_t *nn, double alpha,
                      const int64_t *doc_order, const int64_t *tok_order,
                      const double *uniforms, int faithful_diag);
+/* Test support: the serial sweep with the conditional in the linear domain (word-id items; see bias_oracle.c). */
+void orc_lda_sweep_linear(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr, int64_t *z, int64_t *nn,
+                          double alpha, const int64_t *doc_order, const int64_t *tok_order, const double *uniforms);
 /* Test support: the same serial sweep following another sampler's assignments other_z[N] (see bias_oracle.c). */
 int64_t orc_lda_sweep_follow(orc_comps *c, const orc_data *d, int64_t D, const int64_t *ptr,
                              int64_t *z, int64_t *nn, double alpha, const double *uniforms,

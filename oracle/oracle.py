@@ -110,6 +110,8 @@ def lib():
         L.orc_lda_sweep.argtypes = [cp, dpp, i64, vp, vp, vp, f64, vp, vp, vp, i32]
         L.orc_lda_conditional.restype = i64
         L.orc_lda_conditional.argtypes = [cp, dpp, i64, i64, i64, vp, f64, f64, vp, vp]
+        L.orc_lda_sweep_linear.restype = None
+        L.orc_lda_sweep_linear.argtypes = [cp, dpp, i64, vp, vp, vp, f64, vp, vp, vp]
         L.orc_lda_sweep_follow.restype = i64
         L.orc_lda_sweep_follow.argtypes = [cp, dpp, i64, vp, vp, vp, f64, vp, vp, C.POINTER(f64)]
         L.orc_bmm_init.restype = f64
@@ -307,6 +309,14 @@ class LDAState:
                                           _p(self.nn), self.alpha, _p(do), _p(to), _p(u), diag_mode)
         return self.loglik
 
+    def sweep_linear(self, uniforms, doc_order=None, tok_order=None):
+        """The serial sweep with linear-domain Float64 weights (word ids; convergence fixtures)."""
+        u = _f64(uniforms)
+        do = None if doc_order is None else _i64(doc_order)
+        to = None if tok_order is None else _i64(tok_order)
+        lib().orc_lda_sweep_linear(self.c.ref(), self.d.ref(), self.D, _p(self.ptr), _p(self.z), _p(self.nn),
+                                   self.alpha, _p(do), _p(to), _p(u))
+
     def sweep_follow(self, uniforms, other_z):
         """Serial sweep that adopts other_z wherever its own draw differs -> (number of disagreements, largest distance
         of a disagreeing uniform from the nearest edge of the oracle's CDF)."""
@@ -420,6 +430,15 @@ class HDPState:
         if rc != 0:
             raise IndexError("n_jk exceeds the Stirling table (the reference throws BoundsError)")
         return M
+
+
+def hdp_sample_hyperparam(KK, gg, g1, g2, aa, a1, a2, ptr, m, rng: "Rng"):
+    """One call of sample_hyperparam!(hdp, n_group_j, m) (src/HDP.jl:124-159) on a bare parameter set -> (aa, gg)."""
+    beta = np.zeros(2)
+    h = _Hdp(int(KK), int(KK) + 1, gg, g1, g2, aa, a1, a2, _p(beta))
+    p = _i64(ptr)
+    lib().orc_hdp_sample_hyperparam(C.byref(h), p.size - 1, _p(p), int(m), rng.ref())
+    return float(h.aa), float(h.gg)
 
 
 # ------------------------------------------------------------------ RCRP.jl
