@@ -3,8 +3,10 @@ tables reconciled once per sweep by the library's own reduce-scatter / all-gathe
 
 * several shards in ONE process (bias_group; here all on one GPU, ordered by CUDA events);
 * bias_lda_run_multi, the one-call entry point the Julia shim uses;
-* one PROCESS per rank with CUDA IPC and the arrival-counter barriers (tools/lda_sharded_check.py under torchrun) —
-  on a one-GPU box the ranks share the GPU, on the round-end multi-GPU box they get one each.
+* one PROCESS per rank with CUDA IPC and the arrival-counter barriers (tools/lda_sharded_check.py under torchrun): needs
+  one GPU per rank — kernels of different processes that wait on one another must not share a GPU (nothing guarantees
+  that they run at the same time), so on a one-GPU box this test is skipped and the path is covered by bench.py at
+  N >= 2, which ends with the same recount of every replica ("replica_check": "ok").
 """
 import json
 import os
@@ -112,6 +114,8 @@ def test_one_process_per_rank_over_cuda_ipc(zipf):
     """Two processes; each maps the other's tables with CUDA IPC, every exchange is ordered by the arrival counters in
     peer memory.  The check script recounts every replica from the gathered assignments."""
     n_gpu = b.device_count()
+    if n_gpu < 2:
+        pytest.skip("needs one GPU per rank (two)")
     env = dict(os.environ, LDA_DOCS="6000", LDA_K="256", LDA_V="3000", LDA_SWEEPS="4")
     if zipf:
         env["LDA_ZIPF"] = "1"

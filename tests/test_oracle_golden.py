@@ -175,3 +175,31 @@ def test_table_conditional_matches_antoniak():
         dist = new
     assert np.allclose(prob, dist[1:], rtol=1e-10, atol=1e-300)
     assert 1 <= m <= n and prob[:m].sum() >= 0.5 > prob[:m - 1].sum()
+
+
+def test_linear_domain_sweep_makes_the_same_draws_as_the_log_domain_restatement():
+    """orc_lda_sweep_linear (convergence fixtures, tools/make_convergence_fixture.py) against orc_lda_sweep, the
+    operation-by-operation restatement of src/LDA.jl:113-133: same uniforms, same randperm orders -> the same chain
+    (a draw could only differ at a CDF tie of Float64 width)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(0)
+    for K, V, D, L in [(64, 300, 40, 100), (1024, 500, 12, 90), (10, 25, 30, 50)]:
+        w = rng.integers(0, V, D * L)
+        ptr = np.arange(0, D * L + 1, L)
+        z0 = rng.integers(0, K, D * L)
+        a = orc.LDAState(orc.Comps.md(K, V, 0.1 * V), orc.Data.words(w), ptr, z0, 0.1, with_diag=False)
+        b_ = orc.LDAState(orc.Comps.md(K, V, 0.1 * V), orc.Data.words(w), ptr, z0, 0.1, with_diag=False)
+        n_diff = 0
+        for _ in range(4):
+            u = rng.random(D * L)
+            do = rng.permutation(D)
+            to = np.concatenate([ptr[j] + rng.permutation(L) for j in do])
+            a.sweep(u, doc_order=do, tok_order=to, diag_mode=0)
+            b_.sweep_linear(u, doc_order=do, tok_order=to)
+            n_diff += int((a.z != b_.z).sum())
+            b_.z[:] = a.z                      # keep the states aligned should a tie have split them
+            b_.c.mi[:] = a.c.mi
+            b_.c.mm[:] = a.c.mm
+            b_.c.nn[:] = a.c.nn
+            b_.nn[:] = a.nn
+        assert n_diff <= 1, (K, n_diff)

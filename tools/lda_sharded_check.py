@@ -5,8 +5,8 @@
 
 The ranks map each other's count tables with CUDA IPC (bias_model_share_*; csrc/comm.cu) and bias_model_sweep is
 collective.  torch.distributed carries only host-side plumbing (handles, and the gather of the assignments for the
-check).  With fewer GPUs than ranks several ranks share a GPU (slower, but the same protocol: used by the tests on a
-one-GPU box).  After the sweeps every rank's replica of n_wk / n_k must equal the counts recomputed from the gathered
+check).  Every rank needs its own GPU: the ranks' barrier kernels wait on one another and must not share a device.
+After the sweeps every rank's replica of n_wk / n_k must equal the counts recomputed from the gathered
 assignments (exact integers), the replicas' digests must agree, and the training log-likelihood must have improved.
 One JSON line on rank 0.  LDA_ZIPF=1 makes the word frequencies heavy-tailed enough for hot words (int32 rows)."""
 import json
@@ -27,11 +27,12 @@ def main():
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     n_gpu = torch.cuda.device_count()
-    local = local % n_gpu
+    if world > n_gpu:
+        raise SystemExit(f"{world} ranks on {n_gpu} GPU(s): every rank needs its own GPU (use bias_group for several shards on one)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # gloo: the collectives here are host plumbing and checks only (and several ranks may share one GPU)
+        # gloo: the collectives here are host plumbing and checks only
         dist.init_process_group("gloo")
     K, V, D, L = int(os.environ.get("LDA_K", 1024)), int(os.environ.get("LDA_V", 20000)), int(os.environ.get("LDA_DOCS", 40000)), 100
     n_sweeps = int(os.environ.get("LDA_SWEEPS", 6))
