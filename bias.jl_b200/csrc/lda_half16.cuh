@@ -237,10 +237,26 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
         }
         int my_new = my_z;
 
+        // Visiting order inside the batch.  Without hot words: index order.  With them: the tokens on 16-bit rows first,
+        // then the hot ones (each group in index order), so that the two documents of the warp are mostly on the same
+        // route at the same time — a step whose halves differ pays for both routes.  (The reference visits the tokens
+        // of a document in randperm order, src/LDA.jl:114; any fixed order is one of its orders.)
+        int pos = l16;
+        int src = 0;
+        if constexpr (HOT) {
+            const bool my_hot = l16 < nb && my_w >= p.V;
+            const unsigned hm = (__ballot_sync(kFull, my_hot) >> (half * 16)) & 0xffffu;
+            const unsigned cm = ((nb >= 16) ? 0xffffu : ((1u << nb) - 1u)) & ~hm;
+            const unsigned lt = (1u << l16) - 1u;
+            if (l16 < nb) pos = my_hot ? __popc(cm) + __popc(hm & lt) : __popc(cm & lt);
+            const unsigned b0 = (__ballot_sync(kFull, pos == 0) >> (half * 16)) & 0xffffu;
+            src = __ffs(b0) - 1;
+        }
+
         // operands and row of the first token
-        int w = __shfl_sync(kFull, my_w, 0, 16);
-        int kold = __shfl_sync(kFull, my_z, 0, 16);
-        float u = __shfl_sync(kFull, my_u, 0, 16);
+        int w = __shfl_sync(kFull, my_w, src, 16);
+        int kold = __shfl_sync(kFull, my_z, src, 16);
+        float u = __shfl_sync(kFull, my_u, src, 16);
         uint4 c[NC8];
         {
             const uint4 *row = reinterpret_cast<const uint4 *>(p.n_wk16 + (size_t)w * KPAD);
@@ -322,7 +338,11 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             }
 
             // ---- the next token's operands and row: in flight during pass 2 and the update ----
-            const int inext = (i + 1) & 15;
+            int inext = (i + 1) & 15;       // lane that holds the token visited next
+            if constexpr (HOT) {
+                const unsigned bn = (__ballot_sync(kFull, pos == inext) >> (half * 16)) & 0xffffu;
+                inext = __ffs(bn) - 1;
+            }
             const int w_n = __shfl_sync(kFull, my_w, inext, 16);
             const int kold_n = __shfl_sync(kFull, my_z, inext, 16);
             const float u_n = __shfl_sync(kFull, my_u, inext, 16);
@@ -373,7 +393,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 knew = p.K - 1;
                 nsel = -1.f;             // diagnostic recomputed below from memory
             }
-            if (on && l16 == i) my_new = knew;
+            if (on && l16 == (HOT ? src : i)) my_new = knew;
 
             const bool moved = on && !p.frozen && knew != kold;
             if (!p.frozen) {
@@ -433,6 +453,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 }
                 __syncwarp();
             }
+            src = inext;
             w = w_n;
             kold = kold_n;
             u = u_n;
