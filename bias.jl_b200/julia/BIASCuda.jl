@@ -145,6 +145,18 @@ function scatter!(zz::Vector{Vector{Int}}, flat::Vector{Int32})
 end
 
 # ---- collapsed_gibbs_sampler!(lda::LDA, xx, zz, n_burnins, n_lags, n_samples, ...)  src/LDA.jl:67-148
+# With word-id observations, K <= 1024 and more than one GPU in BIAS_CUDA_DEVICES ("0,1,2,3,4,5,6,7"; default: every
+# device the library sees) the documents are split over the GPUs inside the library (bias_lda_run_multi: one count
+# exchange per sweep over NVLink peer memory); nothing else in the Julia program changes and no second process is needed.
+function devices()
+    if haskey(ENV, "BIAS_CUDA_DEVICES")
+        return Int32[parse(Int32, t) for t in split(ENV["BIAS_CUDA_DEVICES"], ",")]
+    end
+    n = Cint[0]
+    check(ccall((:bias_device_count, LIB), Cint, (Ptr{Cint},), n))
+    Int32[i for i in 0:min(n[1], 8) - 1]
+end
+
 function lda!(lda, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int; seed=0)
     n_sweeps = n_burnins + n_samples * (n_lags + 1)                     # src/LDA.jl:82
     items = vcat(xx...)
@@ -153,9 +165,16 @@ function lda!(lda, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int; seed=0)
     ptr = flat_ptr(zz)
     z = flat_zz(zz)
     stats = Array(SweepStats, n_sweeps)
-    check(ccall((:bias_lda_run, LIB), Cint,
-                (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Int32, Float64, Int32, Ptr{SweepStats}),
-                context(seed), [c], [d], length(zz), ptr, z, lda.KK, lda.aa, n_sweeps, stats))
+    devs = devices()
+    if datum == BIAS_INT && lda.KK <= 1024 && length(devs) > 1
+        check(ccall((:bias_lda_run_multi, LIB), Cint,
+                    (Ptr{Int32}, Int32, UInt64, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Int32, Float64, Int32, Ptr{SweepStats}),
+                    devs, length(devs), seed, [c], [d], length(zz), ptr, z, lda.KK, lda.aa, n_sweeps, stats))
+    else
+        check(ccall((:bias_lda_run, LIB), Cint,
+                    (Ptr{Void}, Ptr{Conjugate}, Ptr{Data}, Int64, Ptr{Int64}, Ptr{Int32}, Int32, Float64, Int32, Ptr{SweepStats}),
+                    context(seed), [c], [d], length(zz), ptr, z, lda.KK, lda.aa, n_sweeps, stats))
+    end
     scatter!(zz, z)
     stats
 end
