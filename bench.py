@@ -542,6 +542,18 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_hbm_regime and V == 50_000 and CORPUS == "dirichlet":
         hbm_regime = hbm_regime_line(b, ctx, dev, 3, 3)
 
+    others = None
+    if rank == 0 and world == 1 and not args.no_other_configs and V == 50_000 and CORPUS == "dirichlet" and n_docs_total == D_TOTAL:
+        others = {}
+        for name in OTHER:
+            try:
+                o = other_config(name)
+                others[name] = {"workload": o["config"]["workload"], "ms_per_sweep": o["ms_per_step"], "items_per_s": o["value"],
+                                "e2e_items_per_s": o["e2e"]["value"], "cpu_items_per_s_1core": o["cpu_baseline"]["value"],
+                                "cpu_sample": o["cpu_baseline"]["sample"], **o["extra"]}
+            except Exception as e:       # a secondary figure must not take the headline line down
+                others[name] = {"error": repr(e)[:300]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_tok, times = cpu_baseline_run(args.ref_docs, 1, 0)
@@ -596,6 +608,7 @@ def ours(args):
             "gpu_launches": int(launches),
             "clocks": clock_rec,
             "replica_check": replica_check,
+            "other_configs": others,
             "narrow_tables": {"current": bool(narrow_current), "hot_words": int(n_hot), "hot_rows_allocated": int(hot_cap)},
             "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood,
                             "train_loglik_per_token_rank0": ll_sum / max(1, ll_n), "sweeps_done": args.warmup + args.steps},
@@ -606,6 +619,38 @@ def ours(args):
         dist.destroy_process_group()
     if replica_check != "ok":
         raise SystemExit("replica check failed: a rank's count tables differ from the recount of all ranks' assignments")
+
+
+# ------------------------------------------------------------------ the other BASELINE configs
+OTHER = {"c1": "C1 LDA bars K=10 V=25, 1000 docs x 100 tokens", "c2": "C2 BMM x MultinomialDirichlet x Sent, K=64, V=1024, 1M sentences x 64 tokens",
+         "c4": "C4 HDP x Gaussian, 100,000 groups x 100 points, Stirling table counts, n_internals=10",
+         "c5": "C5 RCRP x Gaussian, 100 epochs x 500 points"}
+
+
+def other_config(name: str):
+    """One of BASELINE.json's other configurations (tools/bench_configs.py builds the workload, sweeps it on cuda:0 and
+    times the serial oracle on a bounded sample) as a dict in the shape of the headline line."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "tools", "bench_configs.py"))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    import bias_jl_b200 as b
+    ctx = b.Context(0, seed=SEED)
+    try:
+        r = {"c1": lambda: bc.c1(ctx), "c2": lambda: bc.c2(ctx, 1_000_000), "c4": lambda: bc.c4(ctx, 100_000),
+             "c5": lambda: bc.c5(ctx, 100, 500)}[name]()
+    finally:
+        ctx.close()
+    peak, peak_src = peaks()
+    ach = r["alg_bytes_per_item"] * r["gpu_items_per_s"] / 1e9
+    return {"metric": f"{name}_gibbs_item_samples_per_sec", "value": r["gpu_items_per_s"], "unit": "items/s", "ms_per_step": r["gpu_ms_per_sweep"],
+            "config": {"workload": OTHER[name], "detail": r["config"]}, "dtype": "f64" if name != "c1" else "f32",
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": peak_src, "alg_bytes_per_item": r["alg_bytes_per_item"],
+                         "note": "count tables of this configuration are KB to MB and live in L2 / shared memory: lgamma / fp64-issue / "
+                                 "atomic / launch-latency bound by construction (SURVEY 8d), the HBM fraction is stated for completeness"},
+            "cpu_baseline": {"value": r["cpu_items_per_s"], "unit": "items/s", "cores": 1, "kind": "port", "sample": r["cpu_sample"]},
+            "e2e": r["e2e"], "extra": {k: v for k, v in r.items() if k in ("KK", "KK_true", "KK_serial", "homogeneity", "n_moved_last", "gpu_tokens_per_s")}}
 
 
 def main():
@@ -622,6 +667,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-regime", action="store_true", help="skip the V = 200,000 measurement of roofline.hbm_regime")
     ap.add_argument("--corpus", default="dirichlet", choices=["dirichlet", "zipf"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c1", "c2", "c4", "c5"],
+                    help="c3 (default): the headline LDA workload; the others print one line for that BASELINE configuration (1 GPU)")
+    ap.add_argument("--no-other-configs", action="store_true", help="do not append the other configurations' figures to the headline line")
     ap.add_argument("--vocab", type=int, default=V, help="vocabulary size (default: BASELINE config 3's 50,000)")
     args = ap.parse_args()
     V, CORPUS = args.vocab, args.corpus
@@ -634,6 +682,11 @@ def main():
     emit.fd = saved_stdout
     if args.impl == "reference":
         reference_arm(args)
+    elif args.config != "c3":
+        line = other_config(args.config)
+        line.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "data": "synthetic"})
+        emit(line)
     else:
         ours(args)
 

@@ -10,9 +10,8 @@
 //
 // A 16-bit row is 2*Kpad bytes — half the L2->SM bytes and half the LSU wavefronts of an int32 row, 32 instead of
 // 64 registers per lane, and a 102 MB table at K = 1024, V = 50k that the 126 MB L2 can hold.  A hot row is 4*Kpad
-// bytes; its first half is fetched one token ahead exactly like a 16-bit row (same address pattern), the second half
-// streams through 16 registers during the chunk pass and the selected chunk is read again for the in-chunk pass (hot
-// rows are few and stay in L2).  The two halves of a warp may take different routes through the loads and the
+// bytes, fetched one token ahead like a 16-bit row (same address pattern for its first half, 32 more registers for the
+// second: the instantiation with the route runs 2 CTAs x 8 warps per SM at up to 128 registers).  The two halves of a warp may take different routes through the loads and the
 // int->float conversions; every shuffle, ballot and shared-memory update is common code.
 //
 // Chunks are 128 topics wide (16 lanes x 8 uint16 = one LDG.128 per lane); r is stored in shared memory with
@@ -106,6 +105,33 @@ __device__ __forceinline__ float dot8i(const uint4 a, const uint4 b, const float
     t = fmaf((float)(int)b.z, rb.z, t);
     t = fmaf((float)(int)b.w, rb.w, t);
     return s + t;
+}
+
+// A hot row held in registers: c = pieces 0 .. N-1, d = pieces N .. 2N-1 (piece jj of lane l: topics
+// (jj >> 1) * 128 + l * 8 + (jj & 1) * 4 .. + 3).
+template <int N, int I>
+__device__ __forceinline__ uint4 row_piece(const uint4 (&c)[N], const uint4 (&d)[N]) {
+    if constexpr (I < N) return c[I]; else return d[I - N];
+}
+// chunk sums of the whole row
+template <int N, int J = 0>
+__device__ __forceinline__ void hot_chunk_sums(const uint4 (&c)[N], const uint4 (&d)[N], const float4 *r4, int l16, float (&acc)[N]) {
+    if constexpr (J < N) {
+        acc[J] = dot8i(row_piece<N, 2 * J>(c, d), row_piece<N, 2 * J + 1>(c, d), r4[J * 32 + l16], r4[J * 32 + 16 + l16]);
+        hot_chunk_sums<N, J + 1>(c, d, r4, l16, acc);
+    }
+}
+// the two pieces of chunk j; j is uniform over the half
+template <int N, int J = 0>
+__device__ __forceinline__ void pick_pair(const uint4 (&c)[N], const uint4 (&d)[N], int j, uint4 &a, uint4 &b) {
+    if constexpr (J < N) {
+        if (j == J || J == N - 1) {
+            a = row_piece<N, 2 * J>(c, d);
+            b = row_piece<N, 2 * J + 1>(c, d);
+        } else {
+            pick_pair<N, J + 1>(c, d, j, a, b);
+        }
+    }
 }
 
 // HOT = false: the corpus has no word above 65,535 occurrences (decided on the host after every (re)load) and the
@@ -258,10 +284,17 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
         int kold = __shfl_sync(kFull, my_z, src, 16);
         float u = __shfl_sync(kFull, my_u, src, 16);
         uint4 c[NC8];
+        uint4 d[HOT ? NC8 : 1];            // HOT: the second half of a hot token's row (pieces NC8 .. 2 NC8 - 1)
         {
             const uint4 *row = reinterpret_cast<const uint4 *>(p.n_wk16 + (size_t)w * KPAD);
 #pragma unroll
             for (int j = 0; j < NC8; ++j) c[j] = __ldcg(row + j * 16 + l16);
+            if constexpr (HOT) {
+                if (w >= p.V) {
+#pragma unroll
+                    for (int j = 0; j < NC8; ++j) d[j] = __ldcg(row + (NC8 + j) * 16 + l16);
+                }
+            }
         }
         int c_own = (HOT && w >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(p.n_wk16 + (size_t)w * KPAD) + r_pos(kold))
                                : (int)__ldcg(p.n_wk16 + (size_t)w * KPAD + kold);
@@ -269,7 +302,6 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
         for (int i = 0; i < nb_both; ++i) {
             const bool on = i < nb;
             const bool hot = HOT && w >= p.V;  // uniform over the half; the two halves of the warp may differ
-            const uint4 *row_cur = reinterpret_cast<const uint4 *>(p.n_wk16 + (size_t)w * KPAD);
 
             // ---- delitem!, arithmetically: r[kold] with n_dk and n_k one lower; nothing is stored ----
             const int jo = kold >> 7;
@@ -285,31 +317,9 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
 #pragma unroll
                 for (int j = 0; j < NC8; ++j) acc[j] = dot8(c[j], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
             } else {
-                // c[] holds the first NC8 of the row's 2 * NC8 16-byte pieces (piece jj of lane l: topics
-                // (jj >> 1) * 128 + l * 8 + (jj & 1) * 4 .. + 3); the rest streams through d[]
-                constexpr int ND = NC8 < 4 ? NC8 : 4;
-                uint4 d[ND];
-#pragma unroll
-                for (int e = 0; e < ND; ++e) d[e] = __ldcg(row_cur + (NC8 + e) * 16 + l16);
-                if constexpr (NC8 == 1) {
-                    acc[0] = dot8i(c[0], d[0], r4[l16], r4[16 + l16]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NC8 / 2; ++j) acc[j] = dot8i(c[2 * j], c[2 * j + 1], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
-                    if constexpr (NC8 == 8) {
-                        // chunks 6, 7 go through c[0..3], which the first half no longer needs
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) c[e] = __ldcg(row_cur + (12 + e) * 16 + l16);
-                        acc[4] = dot8i(d[0], d[1], r4[4 * 32 + l16], r4[4 * 32 + 16 + l16]);
-                        acc[5] = dot8i(d[2], d[3], r4[5 * 32 + l16], r4[5 * 32 + 16 + l16]);
-                        acc[6] = dot8i(c[0], c[1], r4[6 * 32 + l16], r4[6 * 32 + 16 + l16]);
-                        acc[7] = dot8i(c[2], c[3], r4[7 * 32 + l16], r4[7 * 32 + 16 + l16]);
-                    } else {
-#pragma unroll
-                        for (int j = NC8 / 2; j < NC8; ++j)
-                            acc[j] = dot8i(d[2 * j - NC8], d[2 * j - NC8 + 1], r4[j * 32 + l16], r4[j * 32 + 16 + l16]);
-                    }
-                }
+                // the whole row is in registers: piece jj of lane l holds topics (jj >> 1) * 128 + l * 8 + (jj & 1) * 4 .. + 3;
+                // c[] = pieces 0 .. NC8 - 1, d[] = pieces NC8 .. 2 NC8 - 1 (only instantiated with HOT)
+                if constexpr (HOT) hot_chunk_sums<NC8>(c, d, r4, l16, acc);
             }
             float T = transpose_reduce_half<NC8>(acc, l16);                    // lane l: chunk (l >> GSHIFT)
             const int myj = l16 >> GSHIFT;
@@ -332,9 +342,8 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             const int jsel = src_lane >> GSHIFT;
             const float base = __shfl_sync(kFull, P - T, src_lane, 16);
             uint4 cs = pick_chunk16<NC8>(c, jsel), cs2 = make_uint4(0, 0, 0, 0);
-            if (hot) {  // the selected chunk of a hot row is read again (two pieces per lane)
-                cs = __ldcg(row_cur + (2 * jsel) * 16 + l16);
-                cs2 = __ldcg(row_cur + (2 * jsel + 1) * 16 + l16);
+            if constexpr (HOT) {
+                if (hot) pick_pair<NC8>(c, d, jsel, cs, cs2);
             }
 
             // ---- the next token's operands and row: in flight during pass 2 and the update ----
@@ -351,6 +360,12 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
 #pragma unroll
                 for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
+                if constexpr (HOT) {
+                    if (w_n >= p.V) {
+#pragma unroll
+                        for (int j = 0; j < NC8; ++j) d[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + (NC8 + j) * 16 + l16);
+                    }
+                }
                 c_own_n = (HOT && w_n >= p.V) ? __ldcg(reinterpret_cast<const int32_t *>(rown) + r_pos(kold_n)) : (int)__ldcg(rown + kold_n);
             }
 
@@ -448,6 +463,12 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                         const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;
 #pragma unroll
                         for (int j = 0; j < NC8; ++j) c[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + j * 16 + l16);
+                        if constexpr (HOT) {
+                            if (hot) {
+#pragma unroll
+                                for (int j = 0; j < NC8; ++j) d[j] = __ldcg(reinterpret_cast<const uint4 *>(rown) + (NC8 + j) * 16 + l16);
+                            }
+                        }
                         c_own_n = hot ? __ldcg(reinterpret_cast<const int32_t *>(rown) + r_pos(kold_n)) : (int)__ldcg(rown + kold_n);
                     }
                 }

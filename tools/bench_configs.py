@@ -19,7 +19,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bias_jl_b200 as b          # noqa: E402
-from oracle import oracle as orc  # noqa: E402
+from oracle import oracle as orc  # noqa: E402  (the CPU sample next to each measurement: bench.py's cpu_baseline leg)
 
 
 def timed_sweeps(rs, n, warm=2):
@@ -31,6 +31,22 @@ def timed_sweeps(rs, n, warm=2):
     return (time.perf_counter() - t0) / n
 
 
+def e2e(make_rs, n_items, n_sweeps=4):
+    """End to end through the public API with host buffers: upload (model creation = the initialisation pass of the
+    reference's sampler entry point), n_sweeps sweeps, assignments back on the host -> (items x sweeps / s, H2D, D2H bytes)."""
+    rs = make_rs()          # warm: allocator, first-touch
+    rs.sweep(1)
+    rs.get_zz()
+    rs.close()
+    t0 = time.perf_counter()
+    rs = make_rs()
+    rs.sweep(n_sweeps)
+    z = rs.get_zz()
+    dt = time.perf_counter() - t0
+    rs.close()
+    return {"value": n_items * n_sweeps / dt, "unit": "items/s", "sweeps_per_call": n_sweeps, "d2h_bytes_per_step": int(z.nbytes)}
+
+
 def c1(ctx):
     xx, _, _ = b.data.bars_lda_corpus(1000, 100, 10, 25, seed=123)
     lda = b.LDA(b.MultinomialDirichlet(25, 2.5), 10, 0.1)
@@ -39,13 +55,16 @@ def c1(ctx):
     rs = b.ResidentSampler(ctx, lda, data, z0)
     t = timed_sweeps(rs, 50)
     rs.close()
+    ee = e2e(lambda: b.ResidentSampler(ctx, lda, data, z0), data.n_items, 50)
+    ee["h2d_bytes_per_step"] = int(data.n_items * 8 + data.group_ptr.nbytes)
     st = orc.LDAState(orc.Comps.md(10, 25, 2.5), orc.Data.words(np.concatenate(xx)), data.group_ptr, z0, 0.1, with_diag=False)
     u = np.random.default_rng(1).random(data.n_items)
     t0 = time.perf_counter()
     st.sweep(u, diag_mode=0)
     tc = time.perf_counter() - t0
     return {"config": "C1 LDA bars K=10 V=25 1000x100", "items": data.n_items, "gpu_ms_per_sweep": 1e3 * t,
-            "gpu_items_per_s": data.n_items / t, "cpu_items_per_s": data.n_items / tc, "cpu_sample": "full corpus, 1 sweep"}
+            "gpu_items_per_s": data.n_items / t, "cpu_items_per_s": data.n_items / tc, "cpu_sample": "full corpus, 1 sweep", "e2e": ee,
+            "alg_bytes_per_item": 4 * 128 + 12}
 
 
 def c2(ctx, n_sent):
@@ -58,6 +77,9 @@ def c2(ctx, n_sent):
     t = timed_sweeps(rs, 5, warm=2)
     moved = rs.stats().n_moved
     rs.close()
+    ee = e2e(lambda: b.ResidentSampler(ctx, bmm, data, z0), n_sent, 4)
+    ee["h2d_bytes_per_step"] = int(sp.nbytes + sw.nbytes + sc.nbytes + z0.nbytes)
+    nnz = float(len(sw)) / n_sent
     ns = 300
     od = orc.Data.sents(sp[:ns + 1], sw[:sp[ns]], sc[:sp[ns]])
     st = orc.BMMState(orc.Comps.md(K, V, 1.0), od, z0[:ns], 0.1)
@@ -68,7 +90,8 @@ def c2(ctx, n_sent):
     return {"config": f"C2 BMM x Sent K=64 V=1024 {n_sent} sentences x 64 tokens", "items": n_sent, "tokens": n_sent * L,
             "gpu_ms_per_sweep": 1e3 * t, "gpu_items_per_s": n_sent / t, "gpu_tokens_per_s": n_sent * L / t,
             "n_moved_last": int(moved), "cpu_items_per_s": ns / tc,
-            "cpu_sample": f"first {ns} sentences, 1 sweep of the serial sampler (dense O(V K) predictive as in the reference)"}
+            "cpu_sample": f"first {ns} sentences, 1 sweep of the serial sampler (dense O(V K) predictive as in the reference)", "e2e": ee,
+            "alg_bytes_per_item": nnz * (8 + 4 * K) + 16}
 
 
 def c4(ctx, n_groups):
@@ -93,6 +116,9 @@ def c4(ctx, n_groups):
     t = timed_sweeps(rs, 5, warm=2)
     s = rs.stats()
     rs.close()
+    z00 = np.zeros(len(allx), dtype=np.int32)
+    ee = e2e(lambda: b.ResidentSampler(ctx, hdp, data, z00, sample_hyperparam=True, n_internals=10), len(allx), 4)
+    ee["h2d_bytes_per_step"] = int(allx.nbytes + z00.nbytes + ptr.nbytes)
     ng = min(n_groups, 40)
     st = orc.HDPState(orc.Comps.g1g1(256, float(allx.mean()), 10.0, 0.001), orc.Data.reals(allx[:ng * 100]), ptr[:ng + 1],
                       np.zeros(ng * 100, dtype=np.int64), 1, 1.0, 0.1, 0.1, 1.0, 0.1, 0.1)
@@ -107,7 +133,8 @@ def c4(ctx, n_groups):
     tc = time.perf_counter() - t0
     return {"config": f"C4 HDP x Gaussian {n_groups} groups x 100 points, n_internals=10", "items": len(allx),
             "gpu_ms_per_sweep": 1e3 * t, "gpu_ms_per_sweep_first3": 1e3 * t_first, "gpu_items_per_s": len(allx) / t,
-            "KK": int(s.KK), "cpu_items_per_s": ng * 100 / tc, "cpu_sample": f"first {ng} groups, 4th sweep of the serial sampler"}
+            "KK": int(s.KK), "cpu_items_per_s": ng * 100 / tc, "cpu_sample": f"first {ng} groups, 4th sweep of the serial sampler", "e2e": ee,
+            "alg_bytes_per_item": 16}
 
 
 def c4_crf(ctx, n_groups):
@@ -160,6 +187,9 @@ def c5(ctx, n_epochs, n_per):
     KK = rs.stats().KK
     z = rs.get_zz()
     rs.close()
+    z00 = np.zeros(len(allx), dtype=np.int32)
+    ee = e2e(lambda: b.ResidentSampler(ctx, rcrp, data, z00, sample_hyperparam=True, n_internals=10), len(allx), 4)
+    ee["h2d_bytes_per_step"] = int(allx.nbytes + z00.nbytes)
     zt = np.concatenate(zz_true)
     homog = sum(np.bincount(zt[z == c]).max() for c in np.unique(z)) / len(z)
     ptr = np.arange(n_epochs + 1, dtype=np.int64) * n_per
@@ -174,7 +204,8 @@ def c5(ctx, n_epochs, n_per):
     return {"config": f"C5 RCRP x Gaussian {n_epochs} epochs x {n_per} points", "items": len(allx),
             "gpu_ms_per_sweep": 1e3 * t, "gpu_items_per_s": len(allx) / t, "KK": int(KK), "KK_true": int(len(np.unique(zt))),
             "KK_serial": st.KK, "homogeneity": homog, "cpu_items_per_s": len(allx) / tc,
-            "cpu_sample": "full data, 4th sweep of the serial sampler (O(n_{t+1,k}) look-ahead loops as in the reference)"}
+            "cpu_sample": "full data, 4th sweep of the serial sampler (O(n_{t+1,k}) look-ahead loops as in the reference)", "e2e": ee,
+            "alg_bytes_per_item": 16}
 
 
 def c5_rcrf(ctx, n_epochs, n_rest, n_per):
