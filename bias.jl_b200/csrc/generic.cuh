@@ -148,6 +148,92 @@ __device__ __forceinline__ Datum load_datum(const GenericParams &p, int64_t i, i
     return d;
 }
 
+// log of a running product that is folded into `acc` before it can overflow (factors are below 2^32: 16 of them
+// multiply a value below 1e100 to less than 1e255)
+__device__ __forceinline__ void fold_product(double &prod, double &acc) {
+    if (prod > 1e100) {
+        acc += log(prod);
+        prod = 1.0;
+    }
+}
+
+// Production scoring of a Sent item (src/conjugates.jl:181-198 without the k-independent multinomial coefficient):
+//   sc[k] <- sum_w [lgamma(b + n_kw + c_w) - lgamma(b + n_kw)] + lgamma(bV + n_k) - lgamma(bV + n_k + m)
+// for every topic of the lane (k = lane, lane + 32, ...).  Counts are integers, so every lgamma difference is the log of
+// a rising factorial: the factors are multiplied in Float64 and one log is taken per ~1e100 of accumulated magnitude.
+// The item's (word, count) pairs are read once by the lanes and broadcast with shuffles; two topics of a lane advance
+// together (two independent product chains); 6,200 -> 1,100 warp-instructions per 64-token sentence at K = 64.
+template <int DUMMY = 0>
+__device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const Datum &d, int zold, int K, int n_out,
+                                                 double *sc, int lane) {
+    const int Kpad = p.Kpad;
+    const double beta = p.beta, bv = p.beta * (double)p.V, m_tot = d.m_tot;
+    const int32_t *const n_wk = p.n_wk, *const n_k = p.n_k;
+    const int32_t *const sent_word = p.sent_word, *const sent_count = p.sent_count;
+    const int64_t s0 = d.s0, s1 = d.s1;
+    const int m_int = (int)m_tot;
+    for (int kbase = 0; kbase < n_out; kbase += 64) {          // warp-uniform trip count: the loop body shuffles
+        const int ka = kbase + lane, kb = ka + 32;
+        const bool has_a = ka < n_out, has_b = kb < n_out;
+        const bool fresh_a = ka >= K, fresh_b = kb >= K;          // HDP: the empty prototype (or no topic at all)
+        const bool own_a = has_a && ka == zold, own_b = has_b && kb == zold;
+        const int ia = fresh_a ? 0 : ka, ib = fresh_b ? 0 : kb;  // columns to load (column 0 when unused)
+        double pa = 1.0, pb = 1.0, acc_a = 0.0, acc_b = 0.0;
+        for (int64_t t0 = s0; t0 < s1; t0 += 32) {
+            const int n_here = (int)min((int64_t)32, s1 - t0);
+            int w_l = 0, c_l = 0;
+            if (lane < n_here) {
+                w_l = sent_word[t0 + lane];
+                c_l = sent_count[t0 + lane];
+            }
+            for (int t = 0; t < n_here; ++t) {
+                const int wt = __shfl_sync(kFull, w_l, t), ct = __shfl_sync(kFull, c_l, t);
+                const int32_t *row = n_wk + (size_t)wt * Kpad;
+                int na = __ldcg(row + ia), nb = __ldcg(row + ib);
+                if (fresh_a) na = 0; else if (own_a) na -= ct;
+                if (fresh_b) nb = 0; else if (own_b) nb -= ct;
+                double fa = beta + (double)na, fb = beta + (double)nb;
+                // counts are small: the first four factors without a loop, the rest (rare) in one
+                if (ct > 0) { pa *= fa; pb *= fb; }
+                if (ct > 1) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+                if (ct > 2) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+                if (ct > 3) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+                for (int i = 4; i < ct; ++i) {
+                    fa += 1.0; fb += 1.0; pa *= fa; pb *= fb;
+                    if ((i & 7) == 7) { fold_product(pa, acc_a); fold_product(pb, acc_b); }
+                }
+                if ((t & 3) == 3 || ct > 4) { fold_product(pa, acc_a); fold_product(pb, acc_b); }    // <= 16 factors since the last fold
+            }
+            fold_product(pa, acc_a);
+            fold_product(pb, acc_b);
+        }
+        acc_a += log(pa);
+        acc_b += log(pb);
+        // lgamma(bV + n_k) - lgamma(bV + n_k + m) = -log prod_{i<m} (bV + n_k + i)
+        double nka = 0.0, nkb = 0.0;
+        if (!fresh_a) nka = (double)__ldcg(n_k + ia) - (own_a ? m_tot : 0.0);
+        if (!fresh_b) nkb = (double)__ldcg(n_k + ib) - (own_b ? m_tot : 0.0);
+        if (m_int <= 4096) {
+            double qa = 1.0, qb = 1.0, da = 0.0, db = 0.0, fa = bv + nka, fb = bv + nkb;
+            int i = 0;
+            for (; i + 8 <= m_int; i += 8) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { qa *= fa; qb *= fb; fa += 1.0; fb += 1.0; }
+                fold_product(qa, da);
+                fold_product(qb, db);
+            }
+            for (; i < m_int; ++i) { qa *= fa; qb *= fb; fa += 1.0; fb += 1.0; }
+            acc_a -= da + log(qa);
+            acc_b -= db + log(qb);
+        } else {
+            acc_a += lgamma(bv + nka) - lgamma(bv + nka + m_tot);
+            acc_b += lgamma(bv + nkb) - lgamma(bv + nkb + m_tot);
+        }
+        if (has_a) sc[ka] = acc_a;
+        if (has_b) sc[kb] = acc_b;
+    }
+}
+
 // K (+1) unnormalised log scores into sc[]; returns the warp-wide maximum.
 // zold < 0: the item is currently unassigned (nothing to remove).
 template <int KIND, int DATUM>
@@ -175,6 +261,7 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
             rc_a = alpha / (double)(alive + 1);
         }
     }
+    if (KIND == BIAS_MD && DATUM == BIAS_SENT && !p.faithful) sent_scores_fast(p, d, zold, K, n_out, sc, lane);
     for (int k = lane; k < n_out; k += 32) {
         const bool own = (k == zold);
         const bool fresh = (k >= K);                  // HDP new-component slot: the empty prototype
@@ -231,25 +318,10 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
                     if (!fresh) nw = (double)__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0.0);
                     acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
                 }
-            } else {
-                // lgamma(b+n+c) - lgamma(b+n) = sum_{i<c} log(b+n+i): rising-factorial products, one log per
-                // ~1e250 of accumulated magnitude instead of two lgamma calls per non-zero
-                double prod = 1.0;
-                for (int64_t t = d.s0; t < d.s1; ++t) {
-                    const int wt = p.sent_word[t];
-                    const int ct = p.sent_count[t];
-                    double base = p.beta;
-                    if (!fresh) base += (double)(__ldcg(p.n_wk + (size_t)wt * Kpad + k) - (own ? ct : 0));
-                    for (int i = 0; i < ct; ++i) prod *= base + (double)i;
-                    if (prod > 1e250) {
-                        acc += log(prod);
-                        prod = 1.0;
-                    }
-                }
-                acc += log(prod);
             }
             const double bv = p.beta * (double)p.V;
-            lp = d.coef + lgamma(bv + nk) - lgamma(bv + nk + d.m_tot) + acc; // src/conjugates.jl:193-195
+            if (p.faithful) lp = d.coef + lgamma(bv + nk) - lgamma(bv + nk + d.m_tot) + acc; // src/conjugates.jl:193-195
+            else lp = sc[k];                                                                   // sent_scores_fast
         }
         const double s = prior + lp;
         sc[k] = s;
