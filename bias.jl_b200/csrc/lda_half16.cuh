@@ -34,7 +34,10 @@ constexpr int kH16Ctas = BIAS_H16_CTAS;
 #ifndef BIAS_H16_WARPS8
 #define BIAS_H16_WARPS8 6
 #endif
-constexpr int kH16Warps8 = BIAS_H16_WARPS8;      // warps per CTA when the document counts are bytes (CNT8): the same
+constexpr int kH16Warps8 = BIAS_H16_WARPS8;
+// the instantiation with the hot-row route keeps a whole 4 KB row in registers: 2 CTAs of 8 warps at up to 128 registers
+// (6 x 3 at 112 registers spills in the hot route: 81.6 ms per Zipf sweep against 55.7)
+constexpr int kH16HotWarps = 8, kH16HotCtas = 2;      // warps per CTA when the document counts are bytes (CNT8): the same
                                                  // 36 documents per SM in 186 KB, which leaves 32 KB of L1 (7 x 3 spills)
 
 // per document: r (fp32) + the document's topic counts (uint16, or uint8 when no document has more than 255 tokens)
@@ -381,7 +384,11 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 n[4] = (float)(int)cs2.x; n[5] = (float)(int)cs2.y; n[6] = (float)(int)cs2.z; n[7] = (float)(int)cs2.w;
             }
             float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-            const int eo = kold - kb;           // own token excluded (the clamp only matters for a count caught mid-update)
+            // own token excluded (the clamp only matters for a count caught mid-update).  The lane-dependent jump this
+            // compiles to costs 8 % of the kernel's stall samples, but the branch-free form (r[kold] rewritten in shared
+            // memory before this pass, one taken off the packed cell) runs the whole sweep 20 % slower (45.4 against 37.6 ms):
+            // the schedule ptxas finds for this loop is fragile (see also profiles/r02_hot_route_variants.md).
+            const int eo = kold - kb;
 #pragma unroll
             for (int e = 0; e < 8; ++e)
                 if (eo == e) { n[e] = fmaxf(n[e] - 1.f, 0.f); q[e] = r_rm; }

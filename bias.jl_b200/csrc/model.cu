@@ -130,8 +130,8 @@ static int launch_lda_half16(bias_model *m, const LdaFastParams &p) {
     if (m->n_hot_host > 0 || getenv("BIAS_LDA_FORCE_HOT")) {       // (the switch: the same kernel on a corpus without hot words, for profiling)
         // some words need int32 rows: the instantiation with the hot-row route keeps a whole 4 KB row in registers
         // (up to 128 per thread: 2 CTAs of 8 warps per SM)
-        if (cnt8) return launch_lda_half16_t<NC8, 8, 2, true, true>(m, p);
-        return launch_lda_half16_t<NC8, 8, 2, false, true>(m, p);
+        if (cnt8) return launch_lda_half16_t<NC8, kH16HotWarps, kH16HotCtas, true, true>(m, p);
+        return launch_lda_half16_t<NC8, kH16HotWarps, kH16HotCtas, false, true>(m, p);
     }
     if (cnt8) return launch_lda_half16_t<NC8, kH16Warps8, kH16Ctas, true, false>(m, p);
     return launch_lda_half16_t<NC8, kH16Warps, kH16Ctas, false, false>(m, p);
