@@ -186,23 +186,44 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
                 w_l = sent_word[t0 + lane];
                 c_l = sent_count[t0 + lane];
             }
-            for (int t = 0; t < n_here; ++t) {
-                const int wt = __shfl_sync(kFull, w_l, t), ct = __shfl_sync(kFull, c_l, t);
-                const int32_t *row = n_wk + (size_t)wt * Kpad;
-                int na = __ldcg(row + ia), nb = __ldcg(row + ib);
-                if (fresh_a) na = 0; else if (own_a) na -= ct;
-                if (fresh_b) nb = 0; else if (own_b) nb -= ct;
-                double fa = beta + (double)na, fb = beta + (double)nb;
-                // counts are small: the first four factors without a loop, the rest (rare) in one
-                if (ct > 0) { pa *= fa; pb *= fb; }
-                if (ct > 1) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
-                if (ct > 2) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
-                if (ct > 3) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
-                for (int i = 4; i < ct; ++i) {
-                    fa += 1.0; fb += 1.0; pa *= fa; pb *= fb;
-                    if ((i & 7) == 7) { fold_product(pa, acc_a); fold_product(pb, acc_b); }
+            // four (word, count) pairs per step: their eight count loads are issued together (lanes past the end hold
+            // count 0 and word 0: no factors, a harmless load)
+            for (int t = 0; t < n_here; t += 4) {
+                int wt[4], ct[4], na[4], nb[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    wt[q] = __shfl_sync(kFull, w_l, (t + q) & 31);
+                    ct[q] = (t + q < 32) ? __shfl_sync(kFull, c_l, (t + q) & 31) : 0;
                 }
-                if ((t & 3) == 3 || ct > 4) { fold_product(pa, acc_a); fold_product(pb, acc_b); }    // <= 16 factors since the last fold
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int32_t *row = n_wk + (size_t)wt[q] * Kpad;
+                    na[q] = __ldcg(row + ia);
+                    nb[q] = __ldcg(row + ib);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = ct[q];
+                    int xa = na[q], xb = nb[q];
+                    if (fresh_a) xa = 0; else if (own_a) xa -= c;
+                    if (fresh_b) xb = 0; else if (own_b) xb -= c;
+                    double fa = beta + (double)xa, fb = beta + (double)xb;
+                    // counts are small: the first four factors without a loop, the rest (rare) in one
+                    if (c > 0) { pa *= fa; pb *= fb; }
+                    if (c > 1) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+                    if (c > 2) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+                    if (c > 3) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+                    if (c > 4) {
+                        for (int i = 4; i < c; ++i) {
+                            fa += 1.0; fb += 1.0; pa *= fa; pb *= fb;
+                            if ((i & 7) == 7) { fold_product(pa, acc_a); fold_product(pb, acc_b); }
+                        }
+                        fold_product(pa, acc_a);
+                        fold_product(pb, acc_b);
+                    }
+                }
+                fold_product(pa, acc_a);       // at most 16 factors since the last fold
+                fold_product(pb, acc_b);
             }
             fold_product(pa, acc_a);
             fold_product(pb, acc_b);
