@@ -159,3 +159,23 @@ def test_16_bit_exchange_of_word_topic_deltas(ctx):
     for rs in samplers:
         assert np.array_equal(rs.components()["mi"], mi)
         rs.close()
+
+
+def test_sharded_bmm_over_nccl_two_processes():
+    """BMM x MultinomialDirichlet x Sent at the config-2 shape on two GPUs through ShardedSampler (count deltas + NCCL
+    all-reduce, 16-bit packed with the 32-bit fall-back): 1 M sentences move some cells by more than 16,383 in one
+    sweep, so the overflow flag comes up, the refused exchange is completed in 32 bits (ShardedSampler.flush) and every
+    replica equals the recount from the gathered assignments (tools/bmm_sharded_check.py)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if b.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(root, "tools", "bmm_sharded_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["replicas_equal_recount"] and line["world"] == 2
