@@ -425,7 +425,8 @@ static int flag_barrier(bias_model *m) {
 
 static int comm_buffers(bias_model *m) {
     if (m->base16) return BIAS_OK;
-    const size_t rows = (size_t)(m->V / m->world + 1);
+    // the rows a rank owns: at most V / world + 1; sized for the worst case (2 ranks) so that it does not depend on the order of set-up
+    const size_t rows = (size_t)(m->V / 2 + 1);
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->base16, rows * m->Kpad * sizeof(uint16_t)));
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->base_hot, (size_t)std::max(1, m->hot_cap) * m->Kpad * sizeof(int32_t)));
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->nk_base, (size_t)m->Kpad * sizeof(int32_t)));
@@ -514,6 +515,44 @@ static int group_prepare(bias_group *g) {
 
 extern "C" {
 
+static int group_setup(bias_group *g, int32_t hot_cap) {
+    const int n = (int)g->ms.size();
+    for (int i = 0; i < n; ++i) {
+        bias_model *m = g->ms[i];
+        BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+        BIAS_TRY(ensure_wide(m));
+        BIAS_TRY(narrow_alloc(m, hot_cap));
+        BIAS_CUDA_TRY(cudaEventCreateWithFlags(&g->ev[i], cudaEventDisableTiming));
+        for (int j = 0; j < n; ++j)
+            if (g->ms[j]->ctx->device != m->ctx->device) {
+                int can = 0;
+                BIAS_CUDA_TRY(cudaDeviceCanAccessPeer(&can, m->ctx->device, g->ms[j]->ctx->device));
+                if (!can) return fail(BIAS_ENODEV, "device %d cannot address the memory of device %d", m->ctx->device, g->ms[j]->ctx->device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(g->ms[j]->ctx->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(BIAS_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+    }
+    for (int i = 0; i < n; ++i) {
+        bias_model *m = g->ms[i];
+        BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+        BIAS_TRY(comm_buffers(m));
+    }
+    // nothing can fail from here on: only now do the models become shards
+    for (int i = 0; i < n; ++i) {
+        bias_model *m = g->ms[i];
+        m->rank = i;
+        m->world = n;
+        m->grouped = true;
+        m->seed_mix = 0x9E3779B97F4A7C15ull * (uint64_t)i;
+        for (int j = 0; j < n; ++j) m->peer_base[j] = g->ms[j]->share_base;
+        m->narrow_valid = false;        // the tables hold this shard's counts only: the first sweep merges them
+        m->class_valid = false;
+    }
+    return BIAS_OK;
+}
+
 int bias_group_create(bias_model **models, int32_t n, bias_group **out) {
     if (!models || !out || n < 1) return fail(BIAS_EINVAL, "null argument");
     *out = nullptr;
@@ -525,41 +564,20 @@ int bias_group_create(bias_model **models, int32_t n, bias_group **out) {
         if (models[i]->world != 1) return fail(BIAS_ESTATE, "shard %d already belongs to a sharded run", i);
         if (models[i]->V != models[0]->V || models[i]->Kpad != models[0]->Kpad || models[i]->K != models[0]->K)
             return fail(BIAS_EINVAL, "the shards of a group must be the same model (KK, dd)");
+        for (int j = 0; j < i; ++j)
+            if (models[j] == models[i]) return fail(BIAS_EINVAL, "shard %d is listed twice", i);
         cap += models[i]->N_cap;
     }
     bias_group *g = new (std::nothrow) bias_group();
     if (!g) return fail(BIAS_ENOMEM, "out of host memory");
     g->ms.assign(models, models + n);
-    g->ev.resize(n);
-    const int32_t hot_cap = narrow_hot_cap(models[0]->V, cap);
-    for (int i = 0; i < n; ++i) {
-        bias_model *m = models[i];
-        BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
-        BIAS_TRY(ensure_wide(m));
-        BIAS_TRY(narrow_alloc(m, hot_cap));
-        BIAS_CUDA_TRY(cudaEventCreateWithFlags(&g->ev[i], cudaEventDisableTiming));
-        for (int j = 0; j < n; ++j)
-            if (models[j]->ctx->device != m->ctx->device) {
-                int can = 0;
-                BIAS_CUDA_TRY(cudaDeviceCanAccessPeer(&can, m->ctx->device, models[j]->ctx->device));
-                if (!can) return fail(BIAS_ENODEV, "device %d cannot address the memory of device %d", m->ctx->device, models[j]->ctx->device);
-                cudaError_t e = cudaDeviceEnablePeerAccess(models[j]->ctx->device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-                    return fail(BIAS_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
-                cudaGetLastError();
-            }
-    }
-    for (int i = 0; i < n; ++i) {
-        bias_model *m = models[i];
-        BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
-        m->rank = i;
-        m->world = n;
-        m->grouped = true;
-        m->seed_mix = 0x9E3779B97F4A7C15ull * (uint64_t)i;
-        for (int j = 0; j < n; ++j) m->peer_base[j] = models[j]->share_base;
-        BIAS_TRY(comm_buffers(m));
-        m->narrow_valid = false;        // the tables hold this shard's counts only: the first sweep merges them
-        m->class_valid = false;
+    g->ev.assign(n, nullptr);
+    const int rc = group_setup(g, narrow_hot_cap(models[0]->V, cap));
+    if (rc != BIAS_OK) {
+        for (cudaEvent_t e : g->ev)
+            if (e) cudaEventDestroy(e);
+        delete g;
+        return rc;
     }
     *out = g;
     return BIAS_OK;
