@@ -423,10 +423,9 @@ static int flag_barrier(bias_model *m) {
     return BIAS_OK;
 }
 
-static int comm_buffers(bias_model *m) {
+static int comm_buffers(bias_model *m, int world) {
     if (m->base16) return BIAS_OK;
-    // the rows a rank owns: at most V / world + 1; sized for the worst case (2 ranks) so that it does not depend on the order of set-up
-    const size_t rows = (size_t)(m->V / 2 + 1);
+    const size_t rows = (size_t)(m->V / world + 1);        // the rows a rank owns
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->base16, rows * m->Kpad * sizeof(uint16_t)));
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->base_hot, (size_t)std::max(1, m->hot_cap) * m->Kpad * sizeof(int32_t)));
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->nk_base, (size_t)m->Kpad * sizeof(int32_t)));
@@ -537,7 +536,7 @@ static int group_setup(bias_group *g, int32_t hot_cap) {
     for (int i = 0; i < n; ++i) {
         bias_model *m = g->ms[i];
         BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
-        BIAS_TRY(comm_buffers(m));
+        BIAS_TRY(comm_buffers(m, n));
     }
     // nothing can fail from here on: only now do the models become shards
     for (int i = 0; i < n; ++i) {
@@ -735,7 +734,7 @@ int bias_model_share_attach(bias_model *m, const bias_share_handle *all, int32_t
     }
     m->world = world;
     m->seed_mix = 0x9E3779B97F4A7C15ull * (uint64_t)m->rank;
-    BIAS_TRY(comm_buffers(m));
+    BIAS_TRY(comm_buffers(m, world));
     m->narrow_valid = false;
     m->class_valid = false;
     return BIAS_OK;
