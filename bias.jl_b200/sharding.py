@@ -1,9 +1,16 @@
 """Multi-GPU data parallelism for the assignment sweep (AD-LDA): groups (documents) are split
 into contiguous shards, one per rank; every rank keeps a full replica of the shared component
-statistics (n_wk, n_k / sum x, n) and samples its shard against it.  Once per sweep the ranks
-all-reduce the count DELTAS (NCCL over NVLink on GPUs; any torch.distributed backend works,
-the CPU tests use gloo) and rebase.  The reference is single-process; this
-is the one exchange step the path needs, there is no other collective.
+statistics (n_wk, n_k / sum x, n) and samples its shard against it, and once per sweep the
+replicas are reconciled.  The reference is single-process; this is the one
+exchange step the path needs, there is no other collective.
+
+* LDA x word ids (the headline): the exchange lives INSIDE the library (csrc/comm.cu: the library's
+  own reduce-scatter / all-gather kernel over NVLink peer memory).  `attach_ranks` below makes the
+  resident model of every torchrun rank a shard of one run — torch.distributed only carries the IPC
+  handles — and `models.Group` / `models.lda_run_multi` do the same for shards of one process.
+* BMM and the other fixed-K models: `ShardedSampler` all-reduces the count DELTAS with
+  torch.distributed (NCCL on GPUs; the CPU tests use gloo) between bias_model_delta_pack / apply.
+* HDP: `ShardedHDP` (group shards, turn-taking births).
 """
 from __future__ import annotations
 
