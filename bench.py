@@ -431,6 +431,16 @@ def ours(args):
         rs.sweep(1)
         k_ms.append(rs.last_sweep_ms()[0])
     kern_ms = max_over_ranks(float(np.mean(k_ms)))
+    exchange = None
+    if world > 1:
+        x_ms, x_bytes = rs.last_exchange()
+        x_ms = max_over_ranks(x_ms)
+        nvlink_peak = 770.0          # GB/s per direction per GPU, measured peer copy on this pool (B200_PROFILING.md)
+        exchange = {"kernel": "narrow_exchange_kernel", "ms": x_ms, "bytes_in_per_rank": x_bytes, "bytes_out_per_rank": x_bytes,
+                    "nvlink_gbs_per_direction": x_bytes / (x_ms * 1e-3) / 1e9, "peak": nvlink_peak,
+                    "frac": x_bytes / (x_ms * 1e-3) / 1e9 / nvlink_peak,
+                    "note": "device time between the exchange's two barriers (all ranks present), max over ranks; every rank reads "
+                            "(n-1)/n of the 16-bit table from its peers and writes as much back, both directions at once"}
 
     # ---- every replica against the recount from ALL ranks' assignments (not timed) ----
     z_now = torch.from_numpy(rs.get_zz()).to(dev)
@@ -608,6 +618,7 @@ def ours(args):
             "gpu_launches": int(launches),
             "clocks": clock_rec,
             "replica_check": replica_check,
+            "exchange": exchange,
             "other_configs": others,
             "narrow_tables": {"current": bool(narrow_current), "hot_words": int(n_hot), "hot_rows_allocated": int(hot_cap)},
             "sweep_stats": {"n_moved_last": int(stats.n_moved), "diag_last": stats.log_likelihood,

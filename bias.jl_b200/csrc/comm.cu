@@ -154,14 +154,11 @@ struct BarrierParams {
     int32_t *err;
 };
 
-__device__ __forceinline__ uint4 ld_sys(const uint4 *p) {
-    uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_sys(uint4 *p, const uint4 v) {
-    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+// Loads and stores on the mapped peer pointers.  Every address is read once and written once between the two barriers of
+// an exchange (release / acquire at system scope on the arrival counters), so plain L2-only accesses are enough; the
+// system-scope relaxed forms measured 296 GB/s per direction on two GPUs.
+__device__ __forceinline__ uint4 ld_sys(const uint4 *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_sys(uint4 *p, const uint4 v) { __stcg(p, v); }
 
 // new = base + sum over ranks of (x_r - base), independently in the two 16-bit halves of a word (mod 2^16: exact, since
 // the true count of a cell of a 16-bit row never exceeds the word's corpus frequency <= 65,535)
@@ -183,39 +180,64 @@ __device__ __forceinline__ unsigned merge32(const unsigned (&x)[kMaxPeers], int 
     return s + b - (unsigned)world * b;
 }
 
-template <bool HOT>
-__device__ __forceinline__ void exchange_piece(const XchgParams &p, int64_t q, uint4 *base_q) {
-    uint4 x[kMaxPeers];
+// U pieces at once for a run of W ranks (W = capacity of the unrolled loops; p.world <= W): all loads first, W * U of
+// them in flight per thread
+template <bool HOT, int W, int U>
+__device__ __forceinline__ void exchange_pieces(const XchgParams &p, const int64_t (&q)[U], int n, uint4 *base_minus_q0) {
+    uint4 x[U][W], b[U];
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r)
-        if (r < p.world) x[r] = ld_sys(reinterpret_cast<const uint4 *>(p.tab[r]) + q);
-    const uint4 b = p.merge ? make_uint4(0, 0, 0, 0) : *base_q;
-    unsigned xs[kMaxPeers];
-    uint4 acc;
-#define BIAS_LANE(f)                                                                      \
-    {                                                                                     \
-        _Pragma("unroll") for (int r = 0; r < kMaxPeers; ++r) xs[r] = r < p.world ? x[r].f : 0u; \
-        acc.f = HOT ? merge32(xs, p.world, b.f) : merge16(xs, p.world, b.f);              \
+    for (int u = 0; u < U; ++u)
+        if (u < n) {
+#pragma unroll
+            for (int r = 0; r < W; ++r)
+                if (r < p.world) x[u][r] = ld_sys(reinterpret_cast<const uint4 *>(p.tab[r]) + q[u]);
+            b[u] = p.merge ? make_uint4(0, 0, 0, 0) : base_minus_q0[q[u]];
+        }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (u < n) {
+            unsigned xs[kMaxPeers];
+            uint4 y;
+#define BIAS_LANE(f)                                                                                  \
+    {                                                                                                 \
+        _Pragma("unroll") for (int r = 0; r < kMaxPeers; ++r) xs[r] = (r < W && r < p.world) ? x[u][r < W ? r : 0].f : 0u; \
+        y.f = HOT ? merge32(xs, p.world, b[u].f) : merge16(xs, p.world, b[u].f);                      \
     }
-    BIAS_LANE(x) BIAS_LANE(y) BIAS_LANE(z) BIAS_LANE(w)
+            BIAS_LANE(x) BIAS_LANE(y) BIAS_LANE(z) BIAS_LANE(w)
 #undef BIAS_LANE
-    *base_q = acc;
+            base_minus_q0[q[u]] = y;
 #pragma unroll
-    for (int r = 0; r < kMaxPeers; ++r)
-        if (r < p.world) st_sys(reinterpret_cast<uint4 *>(p.tab[r]) + q, acc);
+            for (int r = 0; r < W; ++r)
+                if (r < p.world) st_sys(reinterpret_cast<uint4 *>(p.tab[r]) + q[u], y);
+        }
 }
 
+template <bool HOT, int W, int U>
+__device__ __forceinline__ void exchange_range(const XchgParams &p, int64_t q0, int64_t q1, int64_t off, uint4 *base, int64_t t0, int64_t stride) {
+    // pieces off + [q0, q1) of the tables, base[0 .. q1 - q0)
+    for (int64_t s = q0 + t0; s < q1; s += (int64_t)U * stride) {
+        int64_t q[U];
+        int n = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            q[u] = off + s + (int64_t)u * stride;
+            if (s + (int64_t)u * stride < q1) n = u + 1;
+        }
+        exchange_pieces<HOT, W, U>(p, q, n, base - (off + q0));
+    }
+}
+
+template <int W, int U>
 __global__ void __launch_bounds__(256) narrow_exchange_kernel(const XchgParams p) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // the 16-bit rows this rank owns, in 16-byte pieces
     const int64_t row0 = p.V * p.rank / p.world, row1 = p.V * (p.rank + 1) / p.world;
-    const int64_t q0 = row0 * (p.Kpad / 8), q1 = row1 * (p.Kpad / 8);
-    for (int64_t q = q0 + t0; q < q1; q += stride) exchange_piece<false>(p, q, reinterpret_cast<uint4 *>(p.base16) + (q - q0));
+    exchange_range<false, W, U>(p, row0 * (p.Kpad / 8), row1 * (p.Kpad / 8), 0, reinterpret_cast<uint4 *>(p.base16), t0, stride);
     // its share of the hot rows (int32 cells; row h starts V*Kpad/8 + h*Kpad/4 pieces into the table)
     const int64_t n_hot = p.hot_info[0];
     const int64_t h0 = n_hot * p.rank / p.world, h1 = n_hot * (p.rank + 1) / p.world;
-    const int64_t hq = p.V * (p.Kpad / 8), g0 = h0 * (p.Kpad / 4), g1 = h1 * (p.Kpad / 4);
-    for (int64_t g = g0 + t0; g < g1; g += stride) exchange_piece<true>(p, hq + g, reinterpret_cast<uint4 *>(p.base_hot) + g);
+    exchange_range<true, W, U>(p, h0 * (p.Kpad / 4), h1 * (p.Kpad / 4), p.V * (p.Kpad / 8),
+                               reinterpret_cast<uint4 *>(p.base_hot) + h0 * (p.Kpad / 4), t0, stride);
     // n_k: every rank sums the published deltas of all ranks
     if (blockIdx.x == 0)
         for (int k = threadIdx.x; k < p.Kpad; k += blockDim.x) {
@@ -303,6 +325,8 @@ int narrow_alloc(bias_model *m, int32_t hot_cap) {
 void narrow_free(bias_model *m) {
     for (int r = 0; r < kMaxPeers; ++r)
         if (m->peer_ipc[r] && m->peer_base[r]) cudaIpcCloseMemHandle(m->peer_base[r]);
+    if (m->ev_x0) cudaEventDestroy(m->ev_x0);
+    if (m->ev_x1) cudaEventDestroy(m->ev_x1);
     void *ptrs[] = {m->share_base, m->hot_word, m->base16, m->base_hot, m->nk_base, m->comm_err};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -394,7 +418,10 @@ static int step_exchange(bias_model *m, int merge) {
     p.base_hot = m->base_hot;
     p.n_k = m->n_k;
     p.nk_base = m->nk_base;
-    narrow_exchange_kernel<<<m->ctx->num_sms * 8, 256, 0, m->ctx->stream>>>(p);
+    const int grid = m->ctx->num_sms * 8;
+    if (m->world <= 2) narrow_exchange_kernel<2, 4><<<grid, 256, 0, m->ctx->stream>>>(p);
+    else if (m->world <= 4) narrow_exchange_kernel<4, 2><<<grid, 256, 0, m->ctx->stream>>>(p);
+    else narrow_exchange_kernel<8, 1><<<grid, 256, 0, m->ctx->stream>>>(p);
     BIAS_CUDA_TRY(cudaGetLastError());
     m->ctx->launches += 1;
     m->wide_valid = false;
@@ -457,7 +484,13 @@ int comm_prepare_flags(bias_model *m) {
 int comm_exchange_flags(bias_model *m) {
     BIAS_TRY(step_publish_nk(m));
     BIAS_TRY(flag_barrier(m));
+    if (!m->ev_x0) {
+        BIAS_CUDA_TRY(cudaEventCreate(&m->ev_x0));
+        BIAS_CUDA_TRY(cudaEventCreate(&m->ev_x1));
+    }
+    BIAS_CUDA_TRY(cudaEventRecord(m->ev_x0, m->ctx->stream));      // all ranks have arrived: what follows is transfer time
     BIAS_TRY(step_exchange(m, 0));
+    BIAS_CUDA_TRY(cudaEventRecord(m->ev_x1, m->ctx->stream));
     BIAS_TRY(flag_barrier(m));
     return BIAS_OK;
 }
@@ -737,6 +770,22 @@ int bias_model_share_attach(bias_model *m, const bias_share_handle *all, int32_t
     BIAS_TRY(comm_buffers(m, world));
     m->narrow_valid = false;
     m->class_valid = false;
+    return BIAS_OK;
+}
+
+int bias_model_last_exchange(bias_model *m, float *ms_out, int64_t *bytes_in_out) {
+    // device time of the most recent exchange kernel of a one-process-per-GPU run (between its two barriers) and the
+    // bytes this rank pulled from its peers in it (the same number goes out): the NVLink figure of bench.py
+    if (!m || !ms_out) return fail(BIAS_EINVAL, "null argument");
+    if (m->world <= 1 || !m->ev_x1) return fail(BIAS_ESTATE, "no exchange has been timed");
+    BIAS_CUDA_TRY(cudaSetDevice(m->ctx->device));
+    BIAS_CUDA_TRY(cudaEventSynchronize(m->ev_x1));
+    BIAS_CUDA_TRY(cudaEventElapsedTime(ms_out, m->ev_x0, m->ev_x1));
+    if (bytes_in_out) {
+        const int64_t rows = m->V * (m->rank + 1) / m->world - m->V * m->rank / m->world;
+        const int64_t hot = (int64_t)m->n_hot_host * (m->rank + 1) / m->world - (int64_t)m->n_hot_host * m->rank / m->world;
+        *bytes_in_out = (rows * m->Kpad * 2 + hot * m->Kpad * 4) * (m->world - 1);
+    }
     return BIAS_OK;
 }
 

@@ -75,6 +75,7 @@ struct bias_model {
     uint16_t *base16 = nullptr;                           // [V / world + 1][Kpad] agreed counts of the rows this rank owns
     int32_t *base_hot = nullptr, *nk_base = nullptr, *comm_err = nullptr;
     uint32_t barrier_epoch = 0;
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;         // around the most recent exchange kernel
     uint64_t seed_mix = 0;                                // folded into the Philox key: the ranks of a sharded run draw different uniforms
     uint16_t *stage16 = nullptr;    // [3][N_cap rounded up to 8]: uint16 word ids and assignments as uploaded by reload_u16, and the
                                     // uint16 mirror of z that every sweep call leaves behind for get_zz_u16; allocated on first use

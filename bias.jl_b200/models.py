@@ -410,6 +410,12 @@ class ResidentSampler:
         check(lib().bias_model_narrow_info(self.h, C.byref(cur), C.byref(n_hot), C.byref(cap)))
         return bool(cur.value), n_hot.value, cap.value
 
+    def last_exchange(self):
+        """-> (ms of the most recent exchange kernel, bytes pulled from the peers in it)"""
+        ms, nb = C.c_float(), C.c_int64()
+        check(lib().bias_model_last_exchange(self.h, C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
+
     def replica_digest(self) -> int:
         d = C.c_uint64()
         check(lib().bias_model_replica_digest(self.h, C.byref(d)))

@@ -333,6 +333,9 @@ typedef struct {
 BIAS_API int bias_model_share_prepare(bias_model *m, int32_t rank, int32_t world, int64_t n_items_cap_global);
 BIAS_API int bias_model_share_export(bias_model *m, bias_share_handle *out);
 BIAS_API int bias_model_share_attach(bias_model *m, const bias_share_handle *all /* [world] */, int32_t world);
+/* Device time of the most recent exchange kernel of this rank (one process per GPU; measured between the two barriers,
+ * i.e. with all ranks present) and the bytes it pulled from its peers (as many go out). */
+BIAS_API int bias_model_last_exchange(bias_model *m, float *ms_out, int64_t *bytes_in_out);
 /* 64-bit digest of the replica's counts (word-topic table and n_k): equal on all ranks after an exchange. */
 BIAS_API int bias_model_replica_digest(bias_model *m, uint64_t *digest);
 
