@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <cooperative_groups.h>
 #include "model.hpp"
 #include "generic.cuh"
 
@@ -252,22 +253,18 @@ __global__ void hdp_hyper_kernel(const int64_t *group_ptr, int64_t G, double aa,
 // ---------------------------------------------------------------------------------------
 // serial birth pass (src/HDP.jl:312-338 with the reference's sequential semantics): one warp
 // ---------------------------------------------------------------------------------------
+// the serial walk over list[0 .. n_list) by ONE warp; sc = (Kmax + 1) doubles of the warp.  Returns the new KK.
 template <int KIND, int DATUM>
-__global__ void __launch_bounds__(32)
-hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK, double *beta, double gg,
-                 int Kmax, int *err) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sc = reinterpret_cast<double *>(smem_raw);
-    const int lane = threadIdx.x & 31;
-    int KK = *d_KK;
+__device__ __forceinline__ int birth_serial(const GenericParams &p, const int32_t *list, int n_list, int KK, double *beta, double gg,
+                                            int Kmax, int *err, double *sc, int lane) {
     double diag_acc = 0.0;
     unsigned long long moved = 0;
     for (int q = 0; q < n_list; ++q) {
-        const int64_t i = list[q];
+        const int64_t i = __ldcg(list + q);
         int32_t *prow = p.prior_rows + (size_t)p.row_of[i] * p.Kpad;
         const Datum d = load_datum<KIND, DATUM>(p, i, lane);
         const int epoch = (p.model == BIAS_MODEL_RCRP) ? p.row_of[i] : 0;
-        const double alpha_i = (p.model == BIAS_MODEL_RCRP) ? p.rcrp_aa[epoch] : p.alpha;
+        const double alpha_i = (p.model == BIAS_MODEL_RCRP) ? __ldcg(p.rcrp_aa + epoch) : p.alpha;
         const double lmax = score_all<KIND, DATUM>(p, d, -1, KK, KK + 1, prow, beta, alpha_i, sc, lane, epoch);
         PhiloxStream rs(p.seed, (uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep * 8u + kStreamBirth);
         const double u = rs.u01();
@@ -296,10 +293,21 @@ hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK
         moved += 1;
     }
     if (lane == 0) {
-        *d_KK = KK;
         atomicAdd(p.diag_sum, diag_acc);
         atomicAdd(p.moved, moved);
     }
+    return KK;
+}
+
+template <int KIND, int DATUM>
+__global__ void __launch_bounds__(32)
+hdp_birth_kernel(GenericParams p, const int32_t *list, int n_list, int32_t *d_KK, double *beta, double gg,
+                 int Kmax, int *err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sc = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int KK = birth_serial<KIND, DATUM>(p, list, n_list, *d_KK, beta, gg, Kmax, err, sc, lane);
+    if (lane == 0) *d_KK = KK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -940,20 +948,6 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
 // ---------------------------------------------------------------------------------------
 // RCRP (reference src/RCRP.jl:77-416): epochs are visited serially, the items of an epoch in parallel
 // ---------------------------------------------------------------------------------------
-template <int KIND, int DATUM>
-__global__ void rcrp_split_kernel(GenericParams p, int64_t i0, int64_t i1, int k_from, int k_to) {
-    // src/RCRP.jl:309-331: everything chain k_from holds from epoch t+1 on moves to the new component k_to
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = i0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < i1; i += nw) {
-        if (p.z[i] != k_from) continue;
-        int32_t *prow = p.prior_rows + (size_t)p.row_of[i] * p.Kpad;
-        const Datum d = load_datum<KIND, DATUM>(p, i, lane);
-        apply_move<KIND, DATUM>(p, d, k_from, k_to, prow, lane);
-        if (lane == 0) p.z[i] = k_to;
-    }
-}
-
 int rcrp_create(bias_model *m, const bias_rcrp_params *rp, const double *aa) {
     m->h_aa_t.assign(aa, aa + m->G);
     BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_aa_t, (size_t)m->G * 8));
@@ -963,99 +957,265 @@ int rcrp_create(bias_model *m, const bias_rcrp_params *rp, const double *aa) {
     return BIAS_OK;
 }
 
-static void rcrp_host_hyper(bias_model *m, int64_t t, int KK_t) {
-    // src/RCRP.jl:60-74.  The reference's loop variable `for n = 1:iters` (:62) shadows the epoch size it
-    // was handed, so the "n" of the Escobar-West update is the iteration number; kept as is.
-    std::uniform_real_distribution<double> ud(0.0, 1.0);
-    for (int it = 1; it <= m->hdp.n_internals; ++it) {
-        const double n = (double)it;
-        std::gamma_distribution<double> g1(m->h_aa_t[t] + 1.0, 1.0), g2(n, 1.0);
-        const double x1 = g1(m->host_rng), x2 = g2(m->host_rng);
-        const double eta = x1 / (x1 + x2);                                   // Beta(aa + 1, n)
-        const double le = std::log(eta);
-        const double rr = (m->hdp.a1 + KK_t - 1.0) / (n * (m->hdp.a2 - le));
-        const double pi_eta = rr / (1.0 + rr);
-        const double shape = (ud(m->host_rng) < pi_eta) ? m->hdp.a1 + KK_t : m->hdp.a1 + KK_t - 1.0;
-        if (shape > 0.0) {
-            std::gamma_distribution<double> gs(shape, 1.0);
-            m->h_aa_t[t] = gs(m->host_rng) / (m->hdp.a2 - le);
+// ---- the whole sweep as ONE cooperative kernel: epochs serial, grid-wide barriers between the phases of an epoch ----
+//
+// Round 1 launched one pass per epoch from the host and read the birth queue (and the whole T x Kpad table, for the
+// chain-split rule) back after each: >= 100 host round trips for 50,000 points, 6 ms per sweep.  Here the loop over the
+// epochs runs on the device:
+//   A  the items of epoch t in parallel, one warp per item (score_all / draw_parallel / apply_move of generic.cuh);
+//      a draw of the new-component slot is queued                                     (src/RCRP.jl:191-306, 263-287, 366-377)
+//   -- grid barrier --
+//   B  while the queue is not empty: warp 0 of block 0 walks up to 256 queued items with the reference's sequential
+//      semantics (birth_serial), barrier, the rest of the queue is re-sampled in parallel against the enlarged
+//      component set into the other queue, barrier
+//   C  chain splits (src/RCRP.jl:309-331), middle epochs only: EVERY block derives the same list of split chains from the
+//      table (no barrier needed to agree on it), then the blocks move those chains' later items to the new components
+//   -- grid barrier --
+// and at the end the per-epoch concentrations are resampled, one thread per epoch (src/RCRP.jl:60-74: the update of
+// aa[t] needs only the number of components epoch t uses, which no later epoch changes).
+struct RcrpLoop {
+    const int64_t *group_ptr;      // [T + 1] first item of every epoch
+    int64_t N;
+    int32_t *d_KK;                 // in: KK at the start of the sweep; out: at its end
+    double *aa_t;                  // [T] per-epoch concentration (GenericParams::rcrp_aa points at the same array)
+    int32_t *list_a, *list_b;      // the two birth queues (N entries each)
+    unsigned int *cnt;             // [2] their lengths
+    int *err;                      // 2: Kmax exhausted by a birth, 3: by a chain split
+    int32_t Kmax, sample_hyper, n_internals;
+    double a1, a2;
+    uint64_t hyper_seed;
+};
+
+constexpr int kRcrpSerial = 256;   // queue entries walked serially before the rest is re-sampled in parallel
+
+// one item against K components + the new-component slot
+template <int KIND, int DATUM>
+__device__ __forceinline__ void rcrp_sample_item(const GenericParams &p, const Philox &philox, int64_t i, int K, uint32_t stream,
+                                                 double *sc, int lane, int32_t *queue, unsigned int *queue_len, double &diag_acc,
+                                                 unsigned long long &moved_acc) {
+    const int zold = __ldcg(p.z + i);                 // -1: queued by an earlier round
+    const int epoch = p.row_of[i];
+    int32_t *prow = p.prior_rows + (size_t)epoch * p.Kpad;
+    const Datum d = load_datum<KIND, DATUM>(p, i, lane);
+    const double lmax = score_all<KIND, DATUM>(p, d, zold, K, K + 1, prow, nullptr, __ldcg(p.rcrp_aa + epoch), sc, lane, epoch);
+    uint32_t o[4];
+    philox((uint32_t)i, (uint32_t)((uint64_t)i >> 32), p.sweep, stream, o);
+    const int knew = draw_parallel(sc, K + 1, lmax, u01_double(o[0], o[1]), lane);
+    __syncwarp();
+    if (knew >= K) {
+        if (zold >= 0) apply_move<KIND, DATUM>(p, d, zold, -1, prow, lane);
+        if (lane == 0) {
+            p.z[i] = -1;
+            queue[atomicAdd(queue_len, 1u)] = (int32_t)i;
+        }
+        return;
+    }
+    if (knew != zold) {
+        apply_move<KIND, DATUM>(p, d, zold, knew, prow, lane);
+        if (lane == 0) {
+            p.z[i] = knew;
+            moved_acc += 1;
         }
     }
+    const double dv = diag_after<KIND, DATUM>(p, d, knew, lane);
+    if (lane == 0) diag_acc += dv;
+}
+
+template <int KIND, int DATUM>
+__global__ void __launch_bounds__(256) rcrp_loop_kernel(const GenericParams p, const RcrpLoop q) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int sc_len = (q.Kmax + 4) & ~3;
+    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * sc_len;
+    int32_t *split_to = reinterpret_cast<int32_t *>(smem_raw);       // [Kmax], phase C only (overlays warp 0's scores)
+    __shared__ int s_nsplit;
+    const int64_t gw = (int64_t)blockIdx.x * warps + warp, n_warps = (int64_t)gridDim.x * warps;
+    const bool lead = blockIdx.x == 0 && warp == 0;
+    const Philox philox(p.seed);
+    const int T = p.rcrp_T, Kpad = p.Kpad;
+    double diag_acc = 0.0;
+    unsigned long long moved_acc = 0;
+    int K = __ldcg(q.d_KK);
+    int32_t *lcur = q.list_a, *lnext = q.list_b;
+    int c = 0;                                          // q.cnt[c] is the length of lcur
+
+    for (int t = 0; t < T; ++t) {
+        const int64_t i0 = q.group_ptr[t], i1 = q.group_ptr[t + 1];
+        // ---- A ----
+        for (int64_t i = i0 + gw; i < i1; i += n_warps)
+            rcrp_sample_item<KIND, DATUM>(p, philox, i, K, kStreamItemDraw, sc, lane, lcur, q.cnt + c, diag_acc, moved_acc);
+        grid.sync();
+        // ---- B ----
+        for (uint32_t round = 1;; ++round) {
+            const unsigned int n_pending = __ldcg(q.cnt + c);
+            if (n_pending == 0) break;
+            const int n_serial = (int)min(n_pending, (unsigned int)kRcrpSerial);
+            if (lead) {
+                K = birth_serial<KIND, DATUM>(p, lcur, n_serial, K, nullptr, 1.0, q.Kmax, q.err, sc, lane);
+                if (lane == 0) {
+                    *q.d_KK = K;
+                    q.cnt[c ^ 1] = 0;
+                }
+            }
+            grid.sync();
+            K = __ldcg(q.d_KK);
+            const int64_t rest = (int64_t)n_pending - n_serial;
+            if (rest > 0) {
+                for (int64_t w = gw; w < rest; w += n_warps)
+                    rcrp_sample_item<KIND, DATUM>(p, philox, (int64_t)__ldcg(lcur + n_serial + w), K, kStreamBirth + 8u * round, sc, lane,
+                                                  lnext, q.cnt + (c ^ 1), diag_acc, moved_acc);
+                grid.sync();
+            }
+            int32_t *tmp = lcur;
+            lcur = lnext;
+            lnext = tmp;
+            c ^= 1;
+        }
+        // ---- C ----
+        if (t > 0 && t < T - 1) {
+            __syncthreads();                             // the block's warps are done with their score buffers
+            if (warp == 0) {
+                const int32_t *row_t = p.prior_rows + (size_t)t * Kpad;
+                int n_split = 0;
+                for (int kb = 0; kb < K; kb += 32) {
+                    const int k = kb + lane;
+                    // a chain with a gap at t: empty here, alive at t + 1 and somewhere before t
+                    bool gap = k < K && __ldcg(row_t + k) == 0 && __ldcg(row_t + Kpad + k) != 0;
+                    if (gap) {
+                        int64_t before = 0;
+                        for (int tt = 0; tt < t; ++tt) before += __ldcg(p.prior_rows + (size_t)tt * Kpad + k);
+                        gap = before != 0;
+                    }
+                    const unsigned bal = __ballot_sync(kFull, gap);
+                    if (k < K) split_to[k] = gap ? K + n_split + __popc(bal & ((1u << lane) - 1u)) : -1;
+                    n_split += __popc(bal);
+                }
+                if (n_split > 0 && K + n_split + 1 > q.Kmax) {
+                    if (lead && lane == 0) *q.err = 3;
+                    n_split = 0;
+                }
+                if (lane == 0) s_nsplit = n_split;
+            }
+            __syncthreads();
+            const int n_split = s_nsplit;
+            if (n_split > 0) {
+                // everything a split chain holds from epoch t + 1 on moves to its new component
+                for (int64_t base = i1 + gw * 32; base < q.N; base += n_warps * 32) {
+                    const int64_t i = base + lane;
+                    const int zf = i < q.N ? __ldcg(p.z + i) : -1;
+                    const int kto = (zf >= 0 && zf < K) ? split_to[zf] : -1;
+                    unsigned bal = __ballot_sync(kFull, kto >= 0);
+                    while (bal) {
+                        const int src = __ffs(bal) - 1;
+                        bal &= bal - 1;
+                        const int64_t ii = base + src;
+                        const int kf = __shfl_sync(kFull, zf, src), kt = __shfl_sync(kFull, kto, src);
+                        const Datum d = load_datum<KIND, DATUM>(p, ii, lane);
+                        apply_move<KIND, DATUM>(p, d, kf, kt, p.prior_rows + (size_t)p.row_of[ii] * Kpad, lane);
+                        if (lane == 0) p.z[ii] = kt;
+                    }
+                }
+                K += n_split;
+            }
+            __syncthreads();                             // split_to is warp 0's score buffer again
+            grid.sync();
+        }
+    }
+    if (lead && lane == 0) *q.d_KK = K;
+    if (lane == 0) {
+        atomicAdd(p.diag_sum, diag_acc);
+        if (moved_acc) atomicAdd(p.moved, moved_acc);
+    }
+    // ---- per-epoch concentration (src/RCRP.jl:60-74), one thread per epoch.  The reference's loop variable
+    //      `for n = 1:iters` (:62) shadows the epoch size it was handed, so the "n" of the Escobar-West update is the
+    //      iteration number; kept as is. ----
+    if (q.sample_hyper && blockIdx.x == 0) {
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            int KK_t = 0;
+            for (int k = 0; k < K; ++k) KK_t += __ldcg(p.prior_rows + (size_t)t * Kpad + k) != 0;
+            PhiloxStream rs(q.hyper_seed, (uint32_t)t, 0u, p.sweep * 8u + kStreamHyper);
+            double aa = q.aa_t[t];
+            for (int it = 1; it <= q.n_internals; ++it) {
+                const double n = (double)it;
+                const double x1 = rs.gamma(aa + 1.0), x2 = rs.gamma(n);
+                const double le = log(x1 / (x1 + x2));                       // log of Beta(aa + 1, n)
+                const double rr = (q.a1 + KK_t - 1.0) / (n * (q.a2 - le));
+                const double shape = (rs.u01() < rr / (1.0 + rr)) ? q.a1 + KK_t : q.a1 + KK_t - 1.0;
+                if (shape > 0.0) aa = rs.gamma(shape) / (q.a2 - le);
+            }
+            q.aa_t[t] = aa;
+        }
+    }
+}
+
+template <int KIND, int DATUM>
+static int launch_rcrp_loop(bias_model *m, GenericParams &p, RcrpLoop &q) {
+    bias_ctx *ctx = m->ctx;
+    // warps per block: as many score buffers of Kmax + 1 doubles as fit 200 KB, at most 8
+    const size_t per_warp = (size_t)((m->hdp.Kmax + 4) & ~3) * sizeof(double);
+    const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
+    const size_t smem = per_warp * warps;
+    if (smem > 227 * 1024) return fail(BIAS_ERANGE, "RCRP: Kmax = %d does not fit the score buffers", m->hdp.Kmax);
+    if (smem > 48 * 1024)
+        BIAS_CUDA_TRY(cudaFuncSetAttribute(rcrp_loop_kernel<KIND, DATUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    BIAS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rcrp_loop_kernel<KIND, DATUM>, warps * 32, smem));
+    if (occ < 1) return fail(BIAS_ECUDA, "RCRP: the sweep kernel cannot be resident");
+    // no more blocks than the longest epoch has work for: barriers cost by the block
+    const int64_t want = (m->max_group_len + warps - 1) / warps;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * std::min(occ, 2)));
+    void *args[] = {(void *)&p, (void *)&q};
+    BIAS_CUDA_TRY(cudaLaunchCooperativeKernel((const void *)rcrp_loop_kernel<KIND, DATUM>, dim3(grid), dim3(warps * 32), args, smem, ctx->stream));
+    ctx->launches += 1;
+    return BIAS_OK;
 }
 
 int rcrp_sweep(bias_model *m) {
     bias_ctx *ctx = m->ctx;
     cudaStream_t st = ctx->stream;
-    const int Kpad = m->Kpad, Kmax = m->hdp.Kmax;
     const int64_t TT = m->G;
     BIAS_TRY(hdp_prune(m));                       // src/RCRP.jl:116-128 (and the in-loop deletions, once per sweep)
+    BIAS_TRY(ensure_wide(m));
+    m->narrow_valid = false;
     BIAS_CUDA_TRY(cudaMemsetAsync(m->scratch, 0, 6 * sizeof(unsigned long long), st));
-    int32_t *list_cur = m->pending, *list_next = m->pending + std::max<int64_t>(1, m->N);
-    int32_t *const list_base = m->pending;
-    std::vector<int32_t> rows((size_t)TT * Kpad);
-    for (int64_t t = 0; t < TT; ++t) {
-        const int64_t i0 = m->h_group_ptr[t], i1 = m->h_group_ptr[t + 1];
-        // aa changes between epochs only while the hyper-parameters are resampled
-        if (t == 0 || m->hdp.sample_hyperparam)
-            BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)TT * 8, cudaMemcpyHostToDevice, st));
-        const bool middle = (t > 0 && t < TT - 1);
-        const bool need_rows = middle || m->hdp.sample_hyperparam;
-        bool have_rows = false;
-        if (i1 > i0) {
-            m->pending = list_cur;
-            m->work_base = i0;
-            int rc = launch_generic(m, i1 - i0, nullptr, nullptr, m->group_of, m->group_rows, nullptr, 0, 0, nullptr,
-                                    nullptr, nullptr, kStreamItemDraw);
-            m->work_base = 0;
-            BIAS_TRY(rc);
-            // one round trip for the common case of an epoch without births: the queue length and the table together
-            unsigned int n_pending = 0;
-            BIAS_CUDA_TRY(cudaMemcpyAsync(&n_pending, reinterpret_cast<unsigned int *>(m->scratch + 3), 4, cudaMemcpyDeviceToHost, st));
-            if (need_rows) BIAS_CUDA_TRY(cudaMemcpyAsync(rows.data(), m->group_rows, rows.size() * 4, cudaMemcpyDeviceToHost, st));
-            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-            if (n_pending > 0) BIAS_TRY(resolve_births(m, list_cur, list_next));
-            else have_rows = need_rows;
-        }
-        if (need_rows && !have_rows) {
-            BIAS_CUDA_TRY(cudaMemcpyAsync(rows.data(), m->group_rows, rows.size() * 4, cudaMemcpyDeviceToHost, st));
-            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-        }
-        if (middle) {
-            const int KK0 = m->hdp.KK;
-            for (int k = 0; k < KK0; ++k) {
-                if (rows[(size_t)t * Kpad + k] != 0 || rows[(size_t)(t + 1) * Kpad + k] == 0) continue;
-                int64_t before = 0;
-                for (int64_t tt = 0; tt <= t; ++tt) before += rows[(size_t)tt * Kpad + k];
-                if (before == 0) continue;
-                if (m->hdp.KK + 2 > Kmax)
-                    return fail(BIAS_ERANGE, "RCRP: Kmax = %d component slots exhausted while splitting a chain", Kmax);
-                const int kn = m->hdp.KK;
-                GenericParams bp = birth_params(m);
-                const int64_t j0 = m->h_group_ptr[t + 1], j1 = m->N;
-                const int grid = grid1d(ctx, (j1 - j0) * 32, 128, 8);
-                if (bp.kind == BIAS_G1G1) rcrp_split_kernel<BIAS_G1G1, BIAS_F64><<<grid, 128, 0, st>>>(bp, j0, j1, k, kn);
-                else if (bp.datum == BIAS_INT) rcrp_split_kernel<BIAS_MD, BIAS_INT><<<grid, 128, 0, st>>>(bp, j0, j1, k, kn);
-                else rcrp_split_kernel<BIAS_MD, BIAS_SENT><<<grid, 128, 0, st>>>(bp, j0, j1, k, kn);
-                BIAS_CUDA_TRY(cudaGetLastError());
-                ctx->launches += 1;
-                m->hdp.KK += 1;
-                // keep the host copy of the table in step for the remaining checks of this epoch
-                for (int64_t tt = t + 1; tt < TT; ++tt) {
-                    rows[(size_t)tt * Kpad + kn] = rows[(size_t)tt * Kpad + k];
-                    rows[(size_t)tt * Kpad + k] = 0;
-                }
-            }
-        }
-        if (m->hdp.sample_hyperparam) {
-            int KK_t = 0;
-            for (int k = 0; k < m->hdp.KK; ++k) KK_t += rows[(size_t)t * Kpad + k] != 0;
-            rcrp_host_hyper(m, t, KK_t);
-        }
-    }
-    m->pending = list_base;
-    BIAS_TRY(hdp_prune(m));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)TT * 8, cudaMemcpyHostToDevice, st));
+    if (m->N > 0 && TT > 0) {
+        GenericParams p = birth_params(m);
+        p.seed = ctx->seed ^ m->seed_mix;
+        RcrpLoop q{};
+        q.group_ptr = m->group_ptr;
+        q.N = m->N;
+        q.d_KK = m->d_KK;
+        q.aa_t = m->d_aa_t;
+        q.list_a = m->pending;
+        q.list_b = m->pending + std::max<int64_t>(1, m->N);
+        q.cnt = reinterpret_cast<unsigned int *>(m->scratch + 3);
+        q.err = reinterpret_cast<int *>(m->scratch + 4);
+        q.Kmax = m->hdp.Kmax;
+        q.sample_hyper = m->hdp.sample_hyperparam;
+        q.n_internals = m->hdp.n_internals;
+        q.a1 = m->hdp.a1;
+        q.a2 = m->hdp.a2;
+        q.hyper_seed = m->host_rng();             // the host stream (bias_model_set_host_seed) keys the device draws
+        if (p.kind == BIAS_G1G1) BIAS_TRY((launch_rcrp_loop<BIAS_G1G1, BIAS_F64>(m, p, q)));
+        else if (p.datum == BIAS_INT) BIAS_TRY((launch_rcrp_loop<BIAS_MD, BIAS_INT>(m, p, q)));
+        else BIAS_TRY((launch_rcrp_loop<BIAS_MD, BIAS_SENT>(m, p, q)));
+    }
+    int32_t kk = 0;
+    int err = 0;
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&kk, m->d_KK, 4, cudaMemcpyDeviceToHost, st));
+    BIAS_CUDA_TRY(cudaMemcpyAsync(&err, reinterpret_cast<int *>(m->scratch + 4), 4, cudaMemcpyDeviceToHost, st));
+    if (m->hdp.sample_hyperparam)
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->h_aa_t.data(), m->d_aa_t, (size_t)TT * 8, cudaMemcpyDeviceToHost, st));
     BIAS_CUDA_TRY(cudaStreamSynchronize(st));
+    m->hdp.KK = kk;
+    if (err == 2)
+        return fail(BIAS_ERANGE, "RCRP: Kmax = %d component slots exhausted (KK = %d); construct the model with a larger Kmax", m->hdp.Kmax, kk);
+    if (err == 3) return fail(BIAS_ERANGE, "RCRP: Kmax = %d component slots exhausted while splitting a chain", m->hdp.Kmax);
+    BIAS_TRY(hdp_prune(m));
     m->hdp.aa = m->h_aa_t[0];
     m->sweep_index += 1;
     m->stats_pending = true;
