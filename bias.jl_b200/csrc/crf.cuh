@@ -51,10 +51,14 @@ struct CrfParams {
 };
 
 constexpr int kCrfWarps = 4;
-__host__ __device__ inline size_t crf_smem_bytes(int max_len, int Kmax) {
-    // per warp: scores double[max(max_len, Kmax) + 2] + staged values double[max_len]
+__host__ __device__ inline size_t crf_warp_doubles(int max_len, int Kmax) {
     const size_t n = (size_t)(max_len > Kmax ? max_len : Kmax) + 2;
-    return (size_t)kCrfWarps * (n + (size_t)max_len) * sizeof(double);
+    return n + (size_t)max_len + (3 * (size_t)max_len + 1) / 2;
+}
+__host__ __device__ inline size_t crf_smem_bytes(int max_len, int Kmax) {
+    // per warp: scores double[max(max_len, Kmax) + 2] + staged values double[max_len] + the restaurant's tji / njt / kjt
+    // (3 x int32[max_len], pass 1)
+    return (size_t)kCrfWarps * crf_warp_doubles(max_len, Kmax) * sizeof(double);
 }
 
 // first-appearance tables from z (src/HDP.jl:441-470): kjt[jj] = unique(zz[jj])
@@ -96,26 +100,30 @@ __device__ __forceinline__ int crf_draw(double *sc, int n_out, double u, int lan
 }
 
 // ---- the conjugate, by item kind -------------------------------------------------------------------------
-// logpredictive(components[k], item) (src/conjugates.jl:92-103, :180, :181-198); k < 0: the empty prototype
+// logpredictive(components[k], item) (src/conjugates.jl:92-103, :180, :181-198); k < 0: the empty prototype.
+// own: the item itself is still counted in dish k's statistics and is taken out arithmetically (delitem!).
 template <int DATUM>
-__device__ __forceinline__ double crf_logpred(const CrfParams &p, int k, int64_t idx, double x) {
+__device__ __forceinline__ double crf_logpred(const CrfParams &p, int k, int64_t idx, double x, bool own = false) {
     if (DATUM == BIAS_F64) {         // x = p.x[idx], loaded once by the caller (a re-load after every fence goes to L2)
-        const double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
+        double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
+        if (own) { cn -= 1.0; sx -= x; }
         return g1g1_logpred(cn, sx, x, p.m0, p.v0, p.vv);
     } else if (DATUM == BIAS_INT) {
-        const double nw = k < 0 ? 0.0 : (double)__ldcg(p.n_wk + (size_t)p.word[idx] * p.Kpad + k);
-        const double nk = k < 0 ? 0.0 : (double)__ldcg(p.n_k + k);
+        const double nw = k < 0 ? 0.0 : (double)(__ldcg(p.n_wk + (size_t)p.word[idx] * p.Kpad + k) - (own ? 1 : 0));
+        const double nk = k < 0 ? 0.0 : (double)(__ldcg(p.n_k + k) - (own ? 1 : 0));
         return log((p.beta + nw) / (p.beta * (double)p.V + nk));
     } else {
-        const double nk = k < 0 ? 0.0 : (double)__ldcg(p.n_k + k), bv = p.beta * (double)p.V;
+        const double bv = p.beta * (double)p.V;
+        double nk = k < 0 ? 0.0 : (double)__ldcg(p.n_k + k);
         double m = 0.0, acc = 0.0, coef = 0.0;
         for (int64_t t = p.sent_ptr[idx]; t < p.sent_ptr[idx + 1]; ++t) {
             const double ct = (double)p.sent_count[t];
-            const double nw = k < 0 ? 0.0 : (double)__ldcg(p.n_wk + (size_t)p.sent_word[t] * p.Kpad + k);
+            const double nw = k < 0 ? 0.0 : (double)__ldcg(p.n_wk + (size_t)p.sent_word[t] * p.Kpad + k) - (own ? ct : 0.0);
             acc += lgamma(p.beta + nw + ct) - lgamma(p.beta + nw);
             coef -= lgamma(ct + 1.0);
             m += ct;
         }
+        if (own) nk -= m;
         return (lgamma(m + 1.0) + coef) + lgamma(bv + nk) - lgamma(bv + nk + m) + acc;       // src/conjugates.jl:193-195
     }
 }
@@ -222,36 +230,53 @@ __device__ __forceinline__ int crf_new_dish(const CrfParams &p, int lane) {
 }
 
 // ---- pass 1: a table for every customer (src/HDP.jl:506-587) ----
+// The restaurant's table arrays (tji, njt, kjt) and, for Float64 items, its values are staged in shared memory for the
+// whole visit: a step's only dependent trips to L2 are the dish statistics it scores against and the atomics that move
+// the customer.  (The first version kept the arrays in global memory and fenced twice per customer: 9 + 8 of 20 stalled
+// warps per issue were membar and long-scoreboard stalls, profiles/r02_crf_ncu_summary.md.)  z is not read: a customer's
+// dish is its table's, z[i] == kjt[tji[i]].
 template <int DATUM>
-__global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p) {
+__global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t n_sc = (size_t)(p.max_len > p.Kmax ? p.max_len : p.Kmax) + 2;
-    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n_sc + p.max_len);
+    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * crf_warp_doubles(p.max_len, p.Kmax);
+    double *xs = sc + n_sc;
+    int32_t *tji = reinterpret_cast<int32_t *>(xs + p.max_len), *njt = tji + p.max_len, *kjt = njt + p.max_len;
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
     unsigned long long moved = 0;
     int32_t *const mm_t = p.mm + (size_t)p.t * p.Kpad;
+    const double log_aa = log(p.aa), log_gg = log(p.gg);
     for (int64_t j = p.g0 + (int64_t)blockIdx.x * kCrfWarps + warp; j < p.g1; j += n_warps) {
         const int64_t p0 = p.group_ptr[j];
         const int n = (int)(p.group_ptr[j + 1] - p0);
-        int32_t *njt = p.njt + p0, *kjt = p.kjt + p0, *tji = p.tji + p0;
         int nt = p.n_tbls[j];
+        __syncwarp();
+        for (int q = lane; q < n; q += 32) {
+            tji[q] = p.tji[p0 + q];
+            if (q < nt) {
+                njt[q] = p.njt[p0 + q];
+                kjt[q] = p.kjt[p0 + q];
+            }
+            if (DATUM == BIAS_F64) xs[q] = p.x[p0 + q];
+        }
+        __syncwarp();
         for (int ii = 0; ii < n; ++ii) {
             const int64_t i = p0 + ii;
-            int kk = p.z[i], tbl = tji[ii];
-            const double x = (DATUM == BIAS_F64) ? p.x[i] : 0.0;
-            // remove the customer (:511-515)
-            int left = 0;
-            if (lane == 0) {
-                crf_item_move<DATUM>(p, kk, i, -1, x);
-                left = njt[tbl] - 1;
-                njt[tbl] = left;
-            }
-            left = __shfl_sync(kFull, left, 0);
+            int tbl = tji[ii];
+            const int kk = kjt[tbl];
+            const double x = (DATUM == BIAS_F64) ? xs[ii] : 0.0;
+            // remove the customer (:511-515) — from its table here, from its dish ARITHMETICALLY: the statistics of dish kk
+            // keep counting it until it is known to leave (every score of kk below takes it out again), so a customer
+            // that stays with its dish — nearly all of them once the chain has settled — costs no atomics on the
+            // handful of addresses every restaurant shares
+            const int left = njt[tbl] - 1;
+            __syncwarp();
+            if (lane == 0) njt[tbl] = left;
             if (left == 0) {
                 // the table empties: it is removed and the tables after it move down (:517-529); the dish keeps its
                 // slot even if this was its last table
-                if (lane == 0) atomicAdd(mm_t + kjt[tbl], -1);
+                if (lane == 0) atomicAdd(mm_t + kk, -1);
                 __syncwarp();
                 for (int b = tbl; b < nt - 1; b += 32) {
                     const int q = b + lane;
@@ -265,11 +290,12 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                 for (int q = lane; q < n; q += 32)
                     if (tji[q] > tbl) tji[q] -= 1;
             }
-            __threadfence();
+            // the table count taken off mm must have reached what the lanes are about to read
+            __threadfence_block();
             __syncwarp();
             // scores of the tables and of a new one (:549-555)
-            for (int t = lane; t < nt; t += 32) sc[t] = log((double)njt[t]) + crf_logpred<DATUM>(p, kjt[t], i, x);
-            if (lane == 0) sc[nt] = log(p.aa) + crf_logpred<DATUM>(p, -1, i, x);
+            for (int t = lane; t < nt; t += 32) sc[t] = log((double)njt[t]) + crf_logpred<DATUM>(p, kjt[t], i, x, kjt[t] == kk);
+            if (lane == (nt & 31)) sc[nt] = log_aa + crf_logpred<DATUM>(p, -1, i, x);
             __syncwarp();
             tbl = crf_draw(sc, nt + 1, crf_draw_uniform(p, i, 0), lane);
             if (tbl == nt) {
@@ -278,9 +304,9 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                 const CrfLook L = crf_look(p, KK, lane);
                 for (int k = lane; k < KK; k += 32) {
                     const double pr = crf_dish_prior(p, L, k);
-                    sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i, x);
+                    sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i, x, k == kk);
                 }
-                if (lane == 0) sc[KK] = log(p.gg) + crf_logpred<DATUM>(p, -1, i, x);
+                if (lane == (KK & 31)) sc[KK] = log_gg + crf_logpred<DATUM>(p, -1, i, x);
                 __syncwarp();
                 const double u_dish = crf_draw_uniform(p, i, 1);
                 int knew = crf_draw(sc, KK + 1, u_dish, lane);
@@ -293,9 +319,9 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                         const CrfLook L2 = crf_look(p, KK2, lane);
                         for (int k = lane; k < KK2; k += 32) {
                             const double pr = crf_dish_prior(p, L2, k);
-                            sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i, x);
+                            sc[k] = (pr == -INFINITY) ? pr : pr + crf_logpred<DATUM>(p, k, i, x, k == kk);
                         }
-                        if (lane == 0) sc[KK2] = log(p.gg) + crf_logpred<DATUM>(p, -1, i, x);
+                        if (lane == 0) sc[KK2] = log_gg + crf_logpred<DATUM>(p, -1, i, x);
                         __syncwarp();
                         knew = crf_draw(sc, KK2 + 1, u_dish, lane);
                         __syncwarp();
@@ -317,22 +343,37 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_tables_kernel(CrfParams p)
                     if (lane == 0) {
                         tji[ii] = tbl;
                         njt[tbl] = 1;
-                        crf_item_move<DATUM>(p, knew, i, 1, x);
-                        if (knew != kk) { p.z[i] = knew; moved += 1; }
+                        if (knew != kk) {
+                            crf_item_move<DATUM>(p, knew, i, 1, x);
+                            crf_item_move<DATUM>(p, kk, i, -1, x);
+                            p.z[i] = knew;
+                            moved += 1;
+                        }
                     }
                     crf_unlock(p, lane);
                     continue;
                 }
             }
             const int kn = kjt[tbl];
+            __syncwarp();
             if (lane == 0) {
                 tji[ii] = tbl;
                 njt[tbl] += 1;
-                crf_item_move<DATUM>(p, kn, i, 1, x);
-                if (kn != kk) { p.z[i] = kn; moved += 1; }
+                if (kn != kk) {
+                    crf_item_move<DATUM>(p, kn, i, 1, x);
+                    crf_item_move<DATUM>(p, kk, i, -1, x);
+                    p.z[i] = kn;
+                    moved += 1;
+                }
             }
-            __threadfence();
             __syncwarp();
+        }
+        for (int q = lane; q < n; q += 32) {
+            p.tji[p0 + q] = tji[q];
+            if (q < nt) {
+                p.njt[p0 + q] = njt[q];
+                p.kjt[p0 + q] = kjt[q];
+            }
         }
         if (lane == 0) p.n_tbls[j] = nt;
     }
@@ -358,7 +399,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32) crf_dishes_kernel(CrfParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t n_sc = (size_t)(p.max_len > p.Kmax ? p.max_len : p.Kmax) + 2;
-    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (n_sc + p.max_len);
+    double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * crf_warp_doubles(p.max_len, p.Kmax);
     double *xs = sc + n_sc;                                   // Float64 items: the values of the table's customers
     int32_t *ids = reinterpret_cast<int32_t *>(xs);           // other items: their positions in the restaurant
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
