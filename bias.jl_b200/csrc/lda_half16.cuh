@@ -85,7 +85,51 @@ __device__ __forceinline__ uint4 pick_chunk16(const uint4 (&c)[N], int j) {
 __device__ __forceinline__ float cvt_lo(unsigned x) { return (float)(x & 0xffffu); }
 __device__ __forceinline__ float cvt_hi(unsigned x) { return (float)(x >> 16); }
 
+#ifndef BIAS_H16_F32X2
+#define BIAS_H16_F32X2 1
+#endif
+// Two fp32 values in one 64-bit register: sm_100's packed fp32 instructions (FFMA2 / FADD2 / FMUL2) do two topics per
+// issue slot.  cvt2: both 16-bit counts of a word to floats WITHOUT the conversion unit — a byte permute puts each count
+// under the exponent of 2^23 (0x4B00xxxx = 2^23 + x exactly) and one packed add takes the 2^23 off again.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 cvt2(unsigned x) {
+    const unsigned lo = __byte_perm(x, 0x4B000000u, 0x7410), hi = __byte_perm(x, 0x4B000000u, 0x7432);
+    f32x2 f;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(f) : "r"(lo), "r"(hi));
+    return fadd2(f, pack2(-8388608.f, -8388608.f));
+}
+
 __device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float4 b) {
+#if BIAS_H16_F32X2
+    f32x2 s = fmul2(cvt2(x.x), pack2(a.x, a.y));
+    s = ffma2(cvt2(x.y), pack2(a.z, a.w), s);
+    s = ffma2(cvt2(x.z), pack2(b.x, b.y), s);
+    s = ffma2(cvt2(x.w), pack2(b.z, b.w), s);
+    float lo, hi;
+    unpack2(s, lo, hi);
+    return lo + hi;
+#else
     float s = cvt_lo(x.x) * a.x;
     s = fmaf(cvt_hi(x.x), a.y, s);
     s = fmaf(cvt_lo(x.y), a.z, s);
@@ -95,6 +139,7 @@ __device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float
     t = fmaf(cvt_lo(x.w), b.z, t);
     t = fmaf(cvt_hi(x.w), b.w, t);
     return s + t;
+#endif
 }
 
 // the same eight products for a hot row: a = cells of topics +0..3, b = +4..7 (int32, stored in r_pos order)
@@ -377,8 +422,13 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             const int kb = jsel * 128 + l16 * 8;
             float n[8];
             if (!hot) {
+#if BIAS_H16_F32X2 >= 2
+                unpack2(cvt2(cs.x), n[0], n[1]); unpack2(cvt2(cs.y), n[2], n[3]);
+                unpack2(cvt2(cs.z), n[4], n[5]); unpack2(cvt2(cs.w), n[6], n[7]);
+#else
                 n[0] = (float)(cs.x & 0xffffu); n[1] = (float)(cs.x >> 16); n[2] = (float)(cs.y & 0xffffu); n[3] = (float)(cs.y >> 16);
                 n[4] = (float)(cs.z & 0xffffu); n[5] = (float)(cs.z >> 16); n[6] = (float)(cs.w & 0xffffu); n[7] = (float)(cs.w >> 16);
+#endif
             } else {
                 n[0] = (float)(int)cs.x; n[1] = (float)(int)cs.y; n[2] = (float)(int)cs.z; n[3] = (float)(int)cs.w;
                 n[4] = (float)(int)cs2.x; n[5] = (float)(int)cs2.y; n[6] = (float)(int)cs2.z; n[7] = (float)(int)cs2.w;

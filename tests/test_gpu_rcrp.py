@@ -161,6 +161,34 @@ def test_rcrp_gaussian_recovers_clusters_like_the_serial_sampler(ctx):
     assert set(centres) == set(int(k) + 1 for k in np.unique(zt))
 
 
+def test_rcrp_long_birth_queue(ctx):
+    """Epochs of 700 points starting from ONE component: the first sweep queues more new-component draws per epoch than
+    the serial birth walk takes at once (256), so the parallel re-sampling rounds of the device loop run too."""
+    TT, n = 6, 700
+    rng = np.random.default_rng(3)
+    zt = [rng.integers(t // 2, t // 2 + 4, n) for t in range(TT)]
+    xx = [10.0 * (z + 1) + 0.1 * rng.standard_normal(n) for z in zt]
+    allx = np.concatenate(xx)
+    rcrp = b.RCRP(b.Gaussian1DGaussian1D(float(allx.mean()), 4.0, 0.01), 1, 1.0, TT, 1.0, 1.0, Kmax=64)
+    data = b.FlatData(rcrp.component, xx, True)
+    rs = b.ResidentSampler(ctx, rcrp, data, np.zeros(TT * n, dtype=np.int32), sample_hyperparam=True, n_internals=5)
+    ptr = np.arange(TT + 1) * n
+    for s in range(6):
+        rs.sweep(1)
+        z, KK = rs.get_zz(), rs.stats().KK
+        assert ((z >= 0) & (z < KK)).all() and set(np.unique(z)) == set(range(KK))
+        comp, nn = rs.components(), rs.group_counts()
+        assert np.array_equal(comp["nn"], np.bincount(z, minlength=KK))
+        for t in range(TT):
+            assert np.array_equal(nn[t], np.bincount(z[ptr[t]:ptr[t + 1]], minlength=KK))
+        for k in range(KK):
+            assert abs(comp["mu"][k] - allx[z == k].mean()) < 1e-9
+    truth = np.concatenate(zt)
+    homog = sum(np.bincount(truth[z == c]).max() for c in np.unique(z)) / len(z)
+    assert homog > 0.98 and len(np.unique(truth)) <= KK <= len(np.unique(truth)) + 6, (homog, KK)
+    rs.close()
+
+
 def test_rcrp_argument_errors(ctx):
     x = [np.array([1.0, 2.0])]
     with pytest.raises(ValueError):
