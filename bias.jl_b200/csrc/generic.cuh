@@ -148,21 +148,24 @@ __device__ __forceinline__ Datum load_datum(const GenericParams &p, int64_t i, i
     return d;
 }
 
-// log of a running product that is folded into `acc` before it can overflow (factors are below 2^32: 16 of them
-// multiply a value below 1e100 to less than 1e255)
-__device__ __forceinline__ void fold_product(double &prod, double &acc) {
-    if (prod > 1e100) {
-        acc += log(prod);
-        prod = 1.0;
-    }
+// A running product of positive factors kept as mantissa x 2^e: renorm() moves the exponent bits of `m` into `e` and leaves
+// m in [1, 2).  Branch-free and exact (no rounding), so products of any length never overflow and ONE log is taken at the
+// end.  (The first version folded log(prod) into an accumulator whenever a lane's product passed 1e100: a quarter of the
+// kernel's instructions at config 2 were those logs, profiles/r02_other_configs_ncu_summary.md.)
+__device__ __forceinline__ void renorm(double &m, int &e) {
+    const int hi = __double2hiint(m);
+    e += (hi >> 20) - 1023;
+    m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
 }
 
 // Production scoring of a Sent item (src/conjugates.jl:181-198 without the k-independent multinomial coefficient):
-//   sc[k] <- sum_w [lgamma(b + n_kw + c_w) - lgamma(b + n_kw)] + lgamma(bV + n_k) - lgamma(bV + n_k + m)
-// for every topic of the lane (k = lane, lane + 32, ...).  Counts are integers, so every lgamma difference is the log of
-// a rising factorial: the factors are multiplied in Float64 and one log is taken per ~1e100 of accumulated magnitude.
-// The item's (word, count) pairs are read once by the lanes and broadcast with shuffles; two topics of a lane advance
-// together (two independent product chains); 6,200 -> 1,100 warp-instructions per 64-token sentence at K = 64.
+//   sc[k] <- log prior_k + sum_w [lgamma(b + n_kw + c_w) - lgamma(b + n_kw)] + lgamma(bV + n_k) - lgamma(bV + n_k + m)
+// for every topic of the lane (k = lane, lane + 32, ...).  On entry sc[k] holds the PRIOR FACTOR of topic k in the linear
+// domain (0 = the topic cannot be chosen).  Counts are integers, so every lgamma difference is the log of a rising
+// factorial: score_k = log( prior_k * prod_w prod_{i<c_w} (b + n_kw + i) / prod_{i<m} (bV + n_k + i) ) — two products in
+// Float64 with the exponents kept apart (renorm), one division and one log per topic.  The item's (word, count) pairs
+// are read once by the lanes and broadcast with shuffles; two topics of a lane advance together (independent chains);
+// in the denominator consecutive factors are taken in pairs, f (f + 1) = fma(f, f, f).
 template <int DUMMY = 0>
 __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const Datum &d, int zold, int K, int n_out,
                                                  double *sc, int lane) {
@@ -178,7 +181,13 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
         const bool fresh_a = ka >= K, fresh_b = kb >= K;          // HDP: the empty prototype (or no topic at all)
         const bool own_a = has_a && ka == zold, own_b = has_b && kb == zold;
         const int ia = fresh_a ? 0 : ka, ib = fresh_b ? 0 : kb;  // columns to load (column 0 when unused)
-        double pa = 1.0, pb = 1.0, acc_a = 0.0, acc_b = 0.0;
+        double pa = has_a ? sc[ka] : 1.0, pb = has_b ? sc[kb] : 1.0;
+        const bool dead_a = !(pa > 0.0), dead_b = !(pb > 0.0);
+        if (dead_a) pa = 1.0;
+        if (dead_b) pb = 1.0;
+        int ea = 0, eb = 0;
+        renorm(pa, ea);
+        renorm(pb, eb);
         for (int64_t t0 = s0; t0 < s1; t0 += 32) {
             const int n_here = (int)min((int64_t)32, s1 - t0);
             int w_l = 0, c_l = 0;
@@ -203,7 +212,7 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int c = ct[q];
+                    const int c = ct[q];                       // the same for every lane
                     int xa = na[q], xb = nb[q];
                     if (fresh_a) xa = 0; else if (own_a) xa -= c;
                     if (fresh_b) xb = 0; else if (own_b) xb -= c;
@@ -214,44 +223,50 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
                     if (c > 2) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
                     if (c > 3) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
                     if (c > 4) {
+                        renorm(pa, ea);
+                        renorm(pb, eb);
                         for (int i = 4; i < c; ++i) {
                             fa += 1.0; fb += 1.0; pa *= fa; pb *= fb;
-                            if ((i & 7) == 7) { fold_product(pa, acc_a); fold_product(pb, acc_b); }
+                            if ((i & 7) == 7) { renorm(pa, ea); renorm(pb, eb); }
                         }
-                        fold_product(pa, acc_a);
-                        fold_product(pb, acc_b);
+                        renorm(pa, ea);
+                        renorm(pb, eb);
                     }
                 }
-                fold_product(pa, acc_a);       // at most 16 factors since the last fold
-                fold_product(pb, acc_b);
+                renorm(pa, ea);                // at most 16 factors below 2^32 since the last one
+                renorm(pb, eb);
             }
-            fold_product(pa, acc_a);
-            fold_product(pb, acc_b);
         }
-        acc_a += log(pa);
-        acc_b += log(pb);
         // lgamma(bV + n_k) - lgamma(bV + n_k + m) = -log prod_{i<m} (bV + n_k + i)
         double nka = 0.0, nkb = 0.0;
         if (!fresh_a) nka = (double)__ldcg(n_k + ia) - (own_a ? m_tot : 0.0);
         if (!fresh_b) nkb = (double)__ldcg(n_k + ib) - (own_b ? m_tot : 0.0);
-        if (m_int <= 4096) {
-            double qa = 1.0, qb = 1.0, da = 0.0, db = 0.0, fa = bv + nka, fb = bv + nkb;
-            int i = 0;
+        double acc_a, acc_b;
+        if (m_int <= (1 << 16)) {
+            double qa = 1.0, qb = 1.0, fa = bv + nka, fb = bv + nkb;
+            int ga = 0, gb = 0, i = 0;
             for (; i + 8 <= m_int; i += 8) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { qa *= fa; qb *= fb; fa += 1.0; fb += 1.0; }
-                fold_product(qa, da);
-                fold_product(qb, db);
+                for (int e = 0; e < 4; ++e) {                  // four pairs of factors: below 2^(4 * 70)
+                    qa *= fma(fa, fa, fa);
+                    qb *= fma(fb, fb, fb);
+                    fa += 2.0;
+                    fb += 2.0;
+                }
+                renorm(qa, ga);
+                renorm(qb, gb);
             }
-            for (; i < m_int; ++i) { qa *= fa; qb *= fb; fa += 1.0; fb += 1.0; }
-            acc_a -= da + log(qa);
-            acc_b -= db + log(qb);
+            for (; i < m_int; ++i) { qa *= fa; qb *= fb; fa += 1.0; fb += 1.0; }    // at most seven more
+            renorm(qa, ga);
+            renorm(qb, gb);
+            acc_a = (double)(ea - ga) * 0.6931471805599453 + log(pa / qa);
+            acc_b = (double)(eb - gb) * 0.6931471805599453 + log(pb / qb);
         } else {
-            acc_a += lgamma(bv + nka) - lgamma(bv + nka + m_tot);
-            acc_b += lgamma(bv + nkb) - lgamma(bv + nkb + m_tot);
+            acc_a = (double)ea * 0.6931471805599453 + log(pa) + (lgamma(bv + nka) - lgamma(bv + nka + m_tot));
+            acc_b = (double)eb * 0.6931471805599453 + log(pb) + (lgamma(bv + nkb) - lgamma(bv + nkb + m_tot));
         }
-        if (has_a) sc[ka] = acc_a;
-        if (has_b) sc[kb] = acc_b;
+        if (has_a) sc[ka] = dead_a ? -INFINITY : acc_a;
+        if (has_b) sc[kb] = dead_b ? -INFINITY : acc_b;
     }
 }
 
@@ -282,7 +297,34 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
             rc_a = alpha / (double)(alive + 1);
         }
     }
-    if (KIND == BIAS_MD && DATUM == BIAS_SENT && !p.faithful) sent_scores_fast(p, d, zold, K, n_out, sc, lane);
+    if (KIND == BIAS_MD && DATUM == BIAS_SENT && !p.faithful) {
+        // the prior FACTOR of every outcome (the log of the code below, in the linear domain; 0 = cannot be chosen) goes
+        // into the item's one product: no log of its own
+        for (int k = lane; k < n_out; k += 32) {
+            const bool own = (k == zold), fresh = (k >= K);
+            double pf;
+            if (is_hdp) {
+                pf = fresh ? alpha * hdp_beta[K] : (double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha * hdp_beta[k];
+            } else if (is_rcrp) {
+                if (fresh) {
+                    pf = alpha;
+                } else {
+                    const int cur = __ldcg(prow + k) - (own ? 1 : 0);
+                    const int cnt = cur + (rprev ? __ldcg(rprev + k) : 0);
+                    pf = cnt <= 0 ? 0.0 : (double)cnt;
+                    if (cnt > 0 && rnext) pf *= ((double)cur + (double)__ldcg(rnext + k) + rc_a) / ((double)cur + rc_a);
+                }
+            } else {
+                pf = (double)(__ldcg(prow + k) - (own ? 1 : 0)) + alpha;
+            }
+            sc[k] = pf;
+        }
+        sent_scores_fast(p, d, zold, K, n_out, sc, lane);       // a lane reads and writes its own entries only
+        for (int k = lane; k < n_out; k += 32) lmax = fmax(lmax, sc[k]);
+        lmax = warp_max(lmax);
+        __syncwarp();
+        return lmax;
+    }
     for (int k = lane; k < n_out; k += 32) {
         const bool own = (k == zold);
         const bool fresh = (k >= K);                  // HDP new-component slot: the empty prototype
@@ -341,8 +383,7 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
                 }
             }
             const double bv = p.beta * (double)p.V;
-            if (p.faithful) lp = d.coef + lgamma(bv + nk) - lgamma(bv + nk + d.m_tot) + acc; // src/conjugates.jl:193-195
-            else lp = sc[k];                                                                   // sent_scores_fast
+            lp = d.coef + lgamma(bv + nk) - lgamma(bv + nk + d.m_tot) + acc;                   // src/conjugates.jl:193-195
         }
         const double s = prior + lp;
         sc[k] = s;
