@@ -160,7 +160,7 @@ __device__ __forceinline__ void renorm(double &m, int &e) {
 
 // Production scoring of a Sent item (src/conjugates.jl:181-198 without the k-independent multinomial coefficient):
 //   sc[k] <- log prior_k + sum_w [lgamma(b + n_kw + c_w) - lgamma(b + n_kw)] + lgamma(bV + n_k) - lgamma(bV + n_k + m)
-// for every topic of the lane (k = lane, lane + 32, ...).  On entry sc[k] holds the PRIOR FACTOR of topic k in the linear
+// for the topics of the lane (2 lane, 2 lane + 1 of every block of 64).  On entry sc[k] holds the PRIOR FACTOR of topic k in the linear
 // domain (0 = the topic cannot be chosen).  Counts are integers, so every lgamma difference is the log of a rising
 // factorial: score_k = log( prior_k * prod_w prod_{i<c_w} (b + n_kw + i) / prod_{i<m} (bV + n_k + i) ) — two products in
 // Float64 with the exponents kept apart (renorm), one division and one log per topic.  The item's (word, count) pairs
@@ -176,11 +176,12 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
     const int64_t s0 = d.s0, s1 = d.s1;
     const int m_int = (int)m_tot;
     for (int kbase = 0; kbase < n_out; kbase += 64) {          // warp-uniform trip count: the loop body shuffles
-        const int ka = kbase + lane, kb = ka + 32;
+        // a lane owns two ADJACENT topics: their counts of a word are one 8-byte load
+        const int ka = kbase + 2 * lane, kb = ka + 1;
         const bool has_a = ka < n_out, has_b = kb < n_out;
         const bool fresh_a = ka >= K, fresh_b = kb >= K;          // HDP: the empty prototype (or no topic at all)
         const bool own_a = has_a && ka == zold, own_b = has_b && kb == zold;
-        const int ia = fresh_a ? 0 : ka, ib = fresh_b ? 0 : kb;  // columns to load (column 0 when unused)
+        const int ia = fresh_a ? 0 : ka;                          // column pair to load (pair 0 when unused; padded columns are 0)
         double pa = has_a ? sc[ka] : 1.0, pb = has_b ? sc[kb] : 1.0;
         const bool dead_a = !(pa > 0.0), dead_b = !(pb > 0.0);
         if (dead_a) pa = 1.0;
@@ -188,6 +189,28 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
         int ea = 0, eb = 0;
         renorm(pa, ea);
         renorm(pb, eb);
+        // one (word, count) pair: c >= 1 factors per topic
+        auto one_word = [&](const int2 n2, const int c) {
+            int xa = n2.x, xb = n2.y;
+            if (fresh_a) xa = 0; else if (own_a) xa -= c;
+            if (fresh_b) xb = 0; else if (own_b) xb -= c;
+            double fa = beta + (double)xa, fb = beta + (double)xb;
+            // counts are small: the first four factors without a loop, the rest (rare) in one
+            pa *= fa; pb *= fb;
+            if (c > 1) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+            if (c > 2) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+            if (c > 3) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
+            if (c > 4) {
+                renorm(pa, ea);
+                renorm(pb, eb);
+                for (int i = 4; i < c; ++i) {
+                    fa += 1.0; fb += 1.0; pa *= fa; pb *= fb;
+                    if ((i & 7) == 7) { renorm(pa, ea); renorm(pb, eb); }
+                }
+                renorm(pa, ea);
+                renorm(pb, eb);
+            }
+        };
         for (int64_t t0 = s0; t0 < s1; t0 += 32) {
             const int n_here = (int)min((int64_t)32, s1 - t0);
             int w_l = 0, c_l = 0;
@@ -195,52 +218,36 @@ __device__ __forceinline__ void sent_scores_fast(const GenericParams &p, const D
                 w_l = sent_word[t0 + lane];
                 c_l = sent_count[t0 + lane];
             }
-            // four (word, count) pairs per step: their eight count loads are issued together (lanes past the end hold
-            // count 0 and word 0: no factors, a harmless load)
-            for (int t = 0; t < n_here; t += 4) {
-                int wt[4], ct[4], na[4], nb[4];
+            // four (word, count) pairs per step: their count loads are issued together
+            int t = 0;
+            for (; t + 4 <= n_here; t += 4) {
+                int ct[4];
+                int2 n2[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    wt[q] = __shfl_sync(kFull, w_l, (t + q) & 31);
-                    ct[q] = (t + q < 32) ? __shfl_sync(kFull, c_l, (t + q) & 31) : 0;
+                    const int wq = __shfl_sync(kFull, w_l, t + q);
+                    ct[q] = __shfl_sync(kFull, c_l, t + q);
+                    n2[q] = __ldcg(reinterpret_cast<const int2 *>(n_wk + (size_t)wq * Kpad + ia));
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int32_t *row = n_wk + (size_t)wt[q] * Kpad;
-                    na[q] = __ldcg(row + ia);
-                    nb[q] = __ldcg(row + ib);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = ct[q];                       // the same for every lane
-                    int xa = na[q], xb = nb[q];
-                    if (fresh_a) xa = 0; else if (own_a) xa -= c;
-                    if (fresh_b) xb = 0; else if (own_b) xb -= c;
-                    double fa = beta + (double)xa, fb = beta + (double)xb;
-                    // counts are small: the first four factors without a loop, the rest (rare) in one
-                    if (c > 0) { pa *= fa; pb *= fb; }
-                    if (c > 1) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
-                    if (c > 2) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
-                    if (c > 3) { fa += 1.0; fb += 1.0; pa *= fa; pb *= fb; }
-                    if (c > 4) {
-                        renorm(pa, ea);
-                        renorm(pb, eb);
-                        for (int i = 4; i < c; ++i) {
-                            fa += 1.0; fb += 1.0; pa *= fa; pb *= fb;
-                            if ((i & 7) == 7) { renorm(pa, ea); renorm(pb, eb); }
-                        }
-                        renorm(pa, ea);
-                        renorm(pb, eb);
-                    }
-                }
+                for (int q = 0; q < 4; ++q)
+                    if (ct[q] > 0) one_word(n2[q], ct[q]);       // a pair with count 0 has no factors (uniform branch)
                 renorm(pa, ea);                // at most 16 factors below 2^32 since the last one
                 renorm(pb, eb);
             }
+            for (; t < n_here; ++t) {
+                const int wq = __shfl_sync(kFull, w_l, t), cq = __shfl_sync(kFull, c_l, t);
+                const int2 n2 = __ldcg(reinterpret_cast<const int2 *>(n_wk + (size_t)wq * Kpad + ia));
+                if (cq > 0) one_word(n2, cq);
+            }
+            renorm(pa, ea);
+            renorm(pb, eb);
         }
         // lgamma(bV + n_k) - lgamma(bV + n_k + m) = -log prod_{i<m} (bV + n_k + i)
         double nka = 0.0, nkb = 0.0;
-        if (!fresh_a) nka = (double)__ldcg(n_k + ia) - (own_a ? m_tot : 0.0);
-        if (!fresh_b) nkb = (double)__ldcg(n_k + ib) - (own_b ? m_tot : 0.0);
+        const int2 nk2 = __ldcg(reinterpret_cast<const int2 *>(n_k + ia));
+        if (!fresh_a) nka = (double)nk2.x - (own_a ? m_tot : 0.0);
+        if (!fresh_b) nkb = (double)nk2.y - (own_b ? m_tot : 0.0);
         double acc_a, acc_b;
         if (m_int <= (1 << 16)) {
             double qa = 1.0, qb = 1.0, fa = bv + nka, fb = bv + nkb;
@@ -319,7 +326,9 @@ __device__ __forceinline__ double score_all(const GenericParams &p, const Datum 
             }
             sc[k] = pf;
         }
-        sent_scores_fast(p, d, zold, K, n_out, sc, lane);       // a lane reads and writes its own entries only
+        __syncwarp();
+        sent_scores_fast(p, d, zold, K, n_out, sc, lane);
+        __syncwarp();
         for (int k = lane; k < n_out; k += 32) lmax = fmax(lmax, sc[k]);
         lmax = warp_max(lmax);
         __syncwarp();
