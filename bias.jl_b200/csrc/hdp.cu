@@ -186,32 +186,118 @@ __device__ __forceinline__ int table_draw(const double *row, int n, double la, d
     return res;
 }
 
+// Cells (j, k) with n_jk > kTablesThreadMax: one warp per cell, the cells taken from a list (see hdp_tables_kernel).
 __global__ void __launch_bounds__(128)
-hdp_tables_kernel(const int32_t *rows, int64_t G, int Kpad, int KK, const double *beta, double aa,
-                  const double *stirling, int stirling_rows, uint64_t seed, uint32_t sweep, uint32_t internal,
-                  unsigned long long *tables, int *err) {
+hdp_tables_big_kernel(const int32_t *rows, int Kpad, int KK, const double *beta, double aa, const double *stirling, int stirling_rows,
+                      uint64_t seed, uint32_t sweep, uint32_t internal, unsigned long long *tables, int *err,
+                      const long long *cells, const unsigned int *n_cells) {
     const int lane = threadIdx.x & 31;
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const Philox philox(seed);
-    for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < G; j += nw) {
-        for (int k = 0; k < KK; ++k) {
-            const int n = rows[(size_t)j * Kpad + k];
-            if (n <= 0) continue;
-            if (n > stirling_rows) {            // the reference indexes past its 10k table: BoundsError
-                if (lane == 0) *err = 1;
-                continue;
-            }
-            uint32_t o[4];
-            philox((uint32_t)j, (uint32_t)((uint64_t)j >> 32) ^ ((uint32_t)k << 8), sweep * 64u + internal, kStreamTable, o);
-            const double u = u01_double(o[0], o[1]);
-            const double *row = stirling + (size_t)n * (n - 1) / 2;
-            const int mjk = table_draw(row, n, log(aa * beta[k]), u, lane, false, nullptr);
-            if (lane == 0) {
-                atomicAdd(tables + k, (unsigned long long)mjk);
-                atomicAdd(tables + Kpad, (unsigned long long)mjk);
-            }
+    const int64_t n_list = *n_cells;
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_list; q += nw) {
+        const int64_t c = cells[q], j = c / KK;
+        const int k = (int)(c - j * KK);
+        const int n = rows[(size_t)j * Kpad + k];
+        if (n > stirling_rows) {            // the reference indexes past its 10k table: BoundsError
+            if (lane == 0) *err = 1;
+            continue;
+        }
+        uint32_t o[4];
+        philox((uint32_t)j, (uint32_t)((uint64_t)j >> 32) ^ ((uint32_t)k << 8), sweep * 64u + internal, kStreamTable, o);
+        const double u = u01_double(o[0], o[1]);
+        const double *row = stirling + (size_t)n * (n - 1) / 2;
+        const int mjk = table_draw(row, n, log(aa * beta[k]), u, lane, false, nullptr);
+        if (lane == 0) {
+            atomicAdd(tables + k, (unsigned long long)mjk);
+            atomicAdd(tables + Kpad, (unsigned long long)mjk);
         }
     }
+}
+
+// All cells (j, k) with 0 < n_jk <= kTablesThreadMax: ONE THREAD per cell.  A group uses a handful of the KK components
+// and its counts are tens, so a warp per cell left three quarters of the issue slots to idle lanes and to the shuffles
+// of 32-wide sums over ~25 terms (0.23 ms per pass over 100,000 groups, ten passes per sweep).  Here a warp scans 32
+// cells at a time, queues the non-empty ones in shared memory and hands each lane a cell of its own: the lane walks its
+// Stirling row (the rows up to n = 128 are 66 KB: L1-resident) three times — maximum, sum of exp, CDF walk in m order —
+// which is the reference's lognormalize! + sample (src/common.jl:42-52, 69-79) with its left-to-right sums.  Same uniforms
+// as the warp-per-cell kernel (Philox keyed by group, component, sweep, pass).  The per-component totals are collected
+// in shared memory and flushed once per CTA (every cell used to do two atomics on the same ~20 addresses).
+constexpr int kTablesThreadMax = 128;
+constexpr int kTablesWarps = 4;
+__global__ void __launch_bounds__(kTablesWarps * 32)
+hdp_tables_kernel(const int32_t *rows, int64_t G, int Kpad, int KK, const double *beta, double aa,
+                  const double *stirling, int stirling_rows, uint64_t seed, uint32_t sweep, uint32_t internal,
+                  unsigned long long *tables, int *err, long long *big_cells, unsigned int *n_big) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *la_s = reinterpret_cast<double *>(smem_raw);                                   // [KK] log(aa beta_k)
+    unsigned long long *tot_s = reinterpret_cast<unsigned long long *>(la_s + KK);         // [KK]
+    long long *queue = reinterpret_cast<long long *>(tot_s + KK) + (threadIdx.x >> 5) * 64; // [64] cells of this warp
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < KK; k += blockDim.x) {
+        la_s[k] = log(aa * beta[k]);
+        tot_s[k] = 0ull;
+    }
+    __syncthreads();
+    const Philox philox(seed);
+    const int64_t n_cells = G * (int64_t)KK, n_chunks = (n_cells + 31) / 32;
+    const int64_t nw = (int64_t)gridDim.x * kTablesWarps;
+    int queued = 0;
+    for (int64_t ch = (int64_t)blockIdx.x * kTablesWarps + (threadIdx.x >> 5);; ch += nw) {
+        const bool more = ch < n_chunks;                       // warp-uniform
+        if (more) {
+            const int64_t c = ch * 32 + lane;
+            int n = 0;
+            if (c < n_cells) {
+                const int64_t j = c / KK;
+                n = rows[(size_t)j * Kpad + (c - j * KK)];
+            }
+            if (n > kTablesThreadMax) big_cells[atomicAdd(n_big, 1u)] = c;
+            const bool mine = n > 0 && n <= kTablesThreadMax;
+            const unsigned bal = __ballot_sync(kFull, mine);
+            if (mine) queue[queued + __popc(bal & ((1u << lane) - 1u))] = c;
+            queued += __popc(bal);
+            __syncwarp();
+        }
+        // a full warp of cells — or whatever is left at the end
+        if (queued >= 32 || (!more && queued > 0)) {
+            const int take = min(queued, 32);
+            if (lane < take) {
+                const int64_t c = queue[queued - take + lane], j = c / KK;
+                const int k = (int)(c - j * KK);
+                const int n = rows[(size_t)j * Kpad + k];
+                uint32_t o[4];
+                philox((uint32_t)j, (uint32_t)((uint64_t)j >> 32) ^ ((uint32_t)k << 8), sweep * 64u + internal, kStreamTable, o);
+                const double u = u01_double(o[0], o[1]);
+                const double *row = stirling + (size_t)n * (n - 1) / 2;
+                const double la = la_s[k];
+                double lmax = -INFINITY;
+                for (int m = 1; m <= n; ++m) lmax = fmax(lmax, row[m - 1] + (double)m * la);
+                double total = 0.0;
+                for (int m = 1; m <= n; ++m) total += exp(row[m - 1] + (double)m * la - lmax);
+                const double target = u * total;
+                double cw = 0.0;
+                int mjk = n;
+                for (int m = 1; m <= n; ++m) {
+                    cw += exp(row[m - 1] + (double)m * la - lmax);
+                    if (cw >= target) { mjk = m; break; }
+                }
+                atomicAdd(tot_s + k, (unsigned long long)mjk);
+            }
+            queued -= take;
+            __syncwarp();
+        }
+        if (!more) break;
+    }
+    __syncthreads();
+    unsigned long long all = 0;
+    for (int k = threadIdx.x; k < KK; k += blockDim.x) {
+        const unsigned long long v = tot_s[k];
+        if (v) atomicAdd(tables + k, v);
+        all += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) all += __shfl_xor_sync(kFull, all, o);
+    if (lane == 0 && all) atomicAdd(tables + Kpad, all);
 }
 
 __global__ void hdp_table_conditionals_kernel(const int32_t *n_arr, const double *a_arr, const double *u_arr,
@@ -558,10 +644,28 @@ static int hdp_phase_tables(bias_model *m, int hh) {
     BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_beta, m->h_beta.data(), ((size_t)Kpad + 1) * 8, cudaMemcpyHostToDevice, st));
     if (m->G > 0) {
-        hdp_tables_kernel<<<grid1d(ctx, m->G * 32, 128, 16), 128, 0, st>>>(
-            m->group_rows, m->G, Kpad, KK, m->d_beta, m->hdp.aa, ctx->stirling, ctx->stirling_rows, ctx->seed,
-            m->sweep_index, (uint32_t)hh, reinterpret_cast<unsigned long long *>(m->d_tables), d_err);
+        // cells up to kTablesThreadMax items by one thread each; the others are listed (in the birth queue's buffer, idle in
+        // this phase: 2 N int32 = N cells, and at most N / 129 cells can be that large) for the warp-per-cell kernel
+        unsigned int *n_big = reinterpret_cast<unsigned int *>(m->scratch + 5);
+        long long *big = reinterpret_cast<long long *>(m->pending_base ? m->pending_base : m->pending);
+        BIAS_CUDA_TRY(cudaMemsetAsync(n_big, 0, 4, st));
+        const size_t tsm = (size_t)KK * 16 + (size_t)kTablesWarps * 64 * 8;
+        static size_t tsm_cache[kMaxDevices] = {};
+        if (tsm > 48 * 1024 && tsm > tsm_cache[ctx->device % kMaxDevices]) {
+            BIAS_CUDA_TRY(cudaFuncSetAttribute(hdp_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+            tsm_cache[ctx->device % kMaxDevices] = tsm;
+        }
+        const int64_t chunks = (m->G * (int64_t)KK + 31) / 32;
+        hdp_tables_kernel<<<grid1d(ctx, chunks * 32, kTablesWarps * 32, 8), kTablesWarps * 32, tsm, st>>>(
+            m->group_rows, m->G, Kpad, KK, m->d_beta, m->hdp.aa, ctx->stirling, ctx->stirling_rows, ctx->seed ^ m->seed_mix,
+            m->sweep_index, (uint32_t)hh, reinterpret_cast<unsigned long long *>(m->d_tables), d_err, big, n_big);
         ctx->launches += 1;
+        if (m->max_group_len > kTablesThreadMax) {
+            hdp_tables_big_kernel<<<ctx->num_sms * 4, 128, 0, st>>>(
+                m->group_rows, Kpad, KK, m->d_beta, m->hdp.aa, ctx->stirling, ctx->stirling_rows, ctx->seed ^ m->seed_mix,
+                m->sweep_index, (uint32_t)hh, reinterpret_cast<unsigned long long *>(m->d_tables), d_err, big, n_big);
+            ctx->launches += 1;
+        }
         if (m->hdp.sample_hyperparam) {
             hdp_hyper_kernel<<<grid1d(ctx, m->G, 128, 4), 128, 0, st>>>(m->group_ptr, m->G, m->hdp.aa, ctx->seed,
                                                                        m->sweep_index, (uint32_t)hh, m->d_hyper);

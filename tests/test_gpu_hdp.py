@@ -51,6 +51,52 @@ def test_table_count_conditionals_match_oracle(ctx):
     assert e.value.code == 5
 
 
+def test_production_table_pass_matches_the_conditionals_in_distribution(ctx):
+    """hdp_tables_kernel (one thread per (group, component) cell up to 128 items, one warp per larger cell) against the
+    exact expectation of M_jk under the oracle's conditional (src/HDP.jl:348-361): sums over all groups, 120 passes."""
+    from bias_jl_b200.sharding import device_tensor
+    rng = np.random.default_rng(5)
+    KK, G = 5, 600
+    lens = rng.integers(1, 90, G)
+    lens[:6] = [400, 300, 260, 1, 2, 129]                     # cells beyond the per-thread limit go to the warp kernel
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    N = int(ptr[-1])
+    z0 = rng.integers(0, KK, N).astype(np.int32)
+    z0[:400] = 2                                              # one cell of 400 items
+    x = 2.0 * (z0 + 1) + 0.05 * rng.standard_normal(N)
+    hdp = b.HDP(b.Gaussian1DGaussian1D(float(x.mean()), 10.0, 0.01), KK, 1.0, 0.1, 0.1, 1.5, 0.1, 0.1, Kmax=16)
+    xx = [x[ptr[j]:ptr[j + 1]] for j in range(G)]
+    rs = b.ResidentSampler(ctx, hdp, b.FlatData(hdp.component, xx, True), z0, sample_hyperparam=False, n_internals=1)
+    hp, beta = rs.hdp_state()
+    nn = rs.group_counts()
+    tab = orc.stirling_table(int(nn.max()))
+    expect, var = np.zeros(KK), np.zeros(KK)
+    cache = {}
+    for j in range(G):
+        for k in range(KK):
+            n = int(nn[j, k])
+            if n == 0:
+                continue
+            if (n, k) not in cache:
+                _, p = orc.hdp_table_conditional(tab, n, float(hp.aa * beta[k]), 0.5)
+                m = np.arange(1, n + 1)
+                mu = float((m * p).sum())
+                cache[(n, k)] = (mu, float((m * m * p).sum()) - mu * mu)
+            expect[k] += cache[(n, k)][0]
+            var[k] += cache[(n, k)][1]
+    reps = 120
+    tot = np.zeros(KK)
+    for hh in range(reps):
+        (pt, n_t, _), _ = rs.hdp_shard_tables(hh)
+        ctx.sync()
+        t = device_tensor(pt, n_t, "int64", "cuda:0").cpu().numpy()
+        assert t[-1] == t[:KK].sum() and (t[KK:-1] == 0).all()
+        tot += t[:KK]
+    mean = tot / reps
+    assert (np.abs(mean - expect) < 5.0 * np.sqrt(var / reps) + 1e-9).all(), (mean, expect, np.sqrt(var / reps))
+    rs.close()
+
+
 def _hdp_case(kind, seed):
     rng = np.random.default_rng(seed)
     KK, Kmax = 4, 16
