@@ -315,7 +315,7 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
         // few Gaussian components: one thread per item (generic.cuh: gauss_item_sweep_kernel)
         const int64_t blocks = (p.n_work + kItemThreads - 1) / kItemThreads;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)m->ctx->num_sms * 8));
-        gauss_item_sweep_kernel<<<grid, kItemThreads, 0, m->ctx->stream>>>(p);
+        gauss_item_sweep_kernel<<<grid, kItemThreads, gauss_item_smem_bytes(p.n_out), m->ctx->stream>>>(p);
         BIAS_CUDA_TRY(cudaGetLastError());
         m->ctx->launches += 1;
         return BIAS_OK;
