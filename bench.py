@@ -436,11 +436,16 @@ def ours(args):
         x_ms, x_bytes = rs.last_exchange()
         x_ms = max_over_ranks(x_ms)
         nvlink_peak = 770.0          # GB/s per direction per GPU, measured peer copy on this pool (B200_PROFILING.md)
-        exchange = {"kernel": "narrow_exchange_kernel", "ms": x_ms, "bytes_in_per_rank": x_bytes, "bytes_out_per_rank": x_bytes,
-                    "nvlink_gbs_per_direction": x_bytes / (x_ms * 1e-3) / 1e9, "peak": nvlink_peak,
-                    "frac": x_bytes / (x_ms * 1e-3) / 1e9 / nvlink_peak,
-                    "note": "device time between the exchange's two barriers (all ranks present), max over ranks; every rank reads "
-                            "(n-1)/n of the 16-bit table from its peers and writes as much back, both directions at once"}
+        # NVLink traffic of one rank per direction: INCOMING = the rows it owns read from the n - 1 peers (x_bytes) + the n - 1
+        # peers' merged rows written into its replica (as many bytes); OUTGOING = the mirror image
+        per_dir = 2 * x_bytes
+        exchange = {"kernel": "narrow_exchange_kernel", "ms": x_ms, "bytes_read_from_peers_per_rank": x_bytes,
+                    "bytes_written_to_peers_per_rank": x_bytes, "nvlink_bytes_per_direction_per_rank": per_dir,
+                    "nvlink_gbs_per_direction": per_dir / (x_ms * 1e-3) / 1e9, "peak": nvlink_peak,
+                    "frac": per_dir / (x_ms * 1e-3) / 1e9 / nvlink_peak,
+                    "note": "device time between the exchange's two barriers (all ranks present), max over ranks; a rank reads the "
+                            "rows it owns from every peer and writes the merged rows into every peer's replica, while its peers do "
+                            "the same to it: (n-1)/n of the 16-bit table read + as much written arrive at every GPU, and leave it"}
 
     # ---- every replica against the recount from ALL ranks' assignments (not timed) ----
     z_now = torch.from_numpy(rs.get_zz()).to(dev)

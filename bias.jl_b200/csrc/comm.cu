@@ -155,8 +155,9 @@ struct BarrierParams {
 };
 
 // Loads and stores on the mapped peer pointers.  Every address is read once and written once between the two barriers of
-// an exchange (release / acquire at system scope on the arrival counters), so plain L2-only accesses are enough; the
-// system-scope relaxed forms measured 296 GB/s per direction on two GPUs.
+// an exchange (release / acquire at system scope on the arrival counters), so plain L2-only accesses are enough.  Measured:
+// 600 - 640 GB/s per direction and GPU on 2 to 8 GPUs (a rank's own reads and its peers' writes arrive together; bench.py
+// `exchange`), about 0.8 of the 770 GB/s a peer copy reaches on this pool.
 __device__ __forceinline__ uint4 ld_sys(const uint4 *p) { return __ldcg(p); }
 __device__ __forceinline__ void st_sys(uint4 *p, const uint4 v) { __stcg(p, v); }
 
