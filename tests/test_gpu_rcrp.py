@@ -189,6 +189,29 @@ def test_rcrp_long_birth_queue(ctx):
     rs.close()
 
 
+def test_rcrp_concentration_draws_match_the_serial_sampler_in_distribution(ctx):
+    """The per-epoch concentration update of the device loop (src/RCRP.jl:60-74, drawn at the end of rcrp_loop_kernel) against
+    the oracle's: 3000 epochs that all use exactly one component, so every aa[t] is an independent draw of the same update."""
+    from scipy.stats import ks_2samp
+    TT, n = 3000, 2
+    x = np.zeros(TT * n)
+    xx = [x[t * n:(t + 1) * n] for t in range(TT)]
+    comp = b.Gaussian1DGaussian1D(0.0, 1e12, 0.01)        # the prior predictive is ~1e-7 of the component's: no births
+    rcrp = b.RCRP(comp, 1, 1.0, TT, 1.0, 1.0, Kmax=8)
+    rs = b.ResidentSampler(ctx, rcrp, b.FlatData(comp, xx, True), np.zeros(TT * n, dtype=np.int32), sample_hyperparam=True, n_internals=6)
+    rs.sweep(1)
+    rp, aa_gpu = rs.rcrp_state()
+    assert rp.KK == 1
+    rs.close()
+    ptr = np.arange(TT + 1, dtype=np.int64) * n
+    st = orc.RCRPState(orc.Comps.g1g1(8, 0.0, 1e12, 0.01), orc.Data.reals(x), ptr, np.zeros(TT * n, dtype=np.int64), 1, 1.0, 1.0, 1.0)
+    st.sweep(orc.Rng(5), shuffle=True, sample_hyper=True, n_internals=6)
+    assert st.KK == 1
+    assert (aa_gpu > 0).all() and not np.allclose(aa_gpu, 1.0)
+    assert ks_2samp(aa_gpu, st.aa).pvalue > 1e-3, (aa_gpu.mean(), st.aa.mean())
+    assert abs(aa_gpu.mean() - st.aa.mean()) < 5 * st.aa.std() / np.sqrt(TT) * np.sqrt(2)
+
+
 def test_rcrp_argument_errors(ctx):
     x = [np.array([1.0, 2.0])]
     with pytest.raises(ValueError):
