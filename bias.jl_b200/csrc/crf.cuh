@@ -58,7 +58,8 @@ __host__ __device__ inline size_t crf_warp_doubles(int max_len, int Kmax) {
 __host__ __device__ inline size_t crf_smem_bytes(int max_len, int Kmax) {
     // per warp: scores double[max(max_len, Kmax) + 2] + staged values double[max_len] + the restaurant's tji / njt / kjt
     // (3 x int32[max_len], pass 1)
-    return (size_t)kCrfWarps * crf_warp_doubles(max_len, Kmax) * sizeof(double);
+    // + log(n) for n = 0 .. max_len, shared by the CTA (pass 1: the weight of a table with n customers)
+    return ((size_t)kCrfWarps * crf_warp_doubles(max_len, Kmax) + (size_t)max_len + 1) * sizeof(double);
 }
 
 // first-appearance tables from z (src/HDP.jl:441-470): kjt[jj] = unique(zz[jj])
@@ -243,6 +244,9 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
     double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * crf_warp_doubles(p.max_len, p.Kmax);
     double *xs = sc + n_sc;
     int32_t *tji = reinterpret_cast<int32_t *>(xs + p.max_len), *njt = tji + p.max_len, *kjt = njt + p.max_len;
+    double *logn = reinterpret_cast<double *>(smem_raw) + (size_t)kCrfWarps * crf_warp_doubles(p.max_len, p.Kmax);
+    for (int q = threadIdx.x; q <= p.max_len; q += blockDim.x) logn[q] = log((double)q);
+    __syncthreads();
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
     unsigned long long moved = 0;
     int32_t *const mm_t = p.mm + (size_t)p.t * p.Kpad;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
             __threadfence_block();
             __syncwarp();
             // scores of the tables and of a new one (:549-555)
-            for (int t = lane; t < nt; t += 32) sc[t] = log((double)njt[t]) + crf_logpred<DATUM>(p, kjt[t], i, x, kjt[t] == kk);
+            for (int t = lane; t < nt; t += 32) sc[t] = logn[njt[t]] + crf_logpred<DATUM>(p, kjt[t], i, x, kjt[t] == kk);
             if (lane == (nt & 31)) sc[nt] = log_aa + crf_logpred<DATUM>(p, -1, i, x);
             __syncwarp();
             tbl = crf_draw(sc, nt + 1, crf_draw_uniform(p, i, 0), lane);
