@@ -34,7 +34,7 @@ SYMBOLS = [
     "bias_hdp_shard_tables", "bias_hdp_shard_draw", "bias_hdp_shard_end",
     "bias_crf_sweep_with_uniforms", "bias_crf_get_tables", "bias_model_delta_pack16", "bias_model_delta_apply16",
     "bias_rcrf_create", "bias_model_get_rcrf",
-    "bias_model_frozen_draws_dev", "bias_model_sweep_with_uniforms", "bias_lda_run_multi", "bias_group_create", "bias_group_sweep",
+    "bias_model_frozen_draws_dev", "bias_model_sweep_with_uniforms", "bias_lda_run_multi", "bias_lda_run_multi_timing", "bias_group_create", "bias_group_sweep",
     "bias_group_destroy", "bias_model_share_prepare", "bias_model_share_export", "bias_model_share_attach", "bias_model_replica_digest", "bias_model_last_exchange", "bias_model_narrow_info", "bias_hdp_hyper_aux", "bias_hdp_hyper_draws", "bias_hdp_beta_draws",
 ]
 
@@ -160,6 +160,7 @@ def lib():
     L.bias_model_share_export.argtypes = [vp, C.POINTER(ShareHandle)]
     L.bias_model_share_attach.argtypes = [vp, C.POINTER(ShareHandle), i32]
     L.bias_model_replica_digest.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.bias_lda_run_multi_timing.argtypes = [vp]
     L.bias_model_last_exchange.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i64)]
     L.bias_hdp_hyper_aux.argtypes = [vp, i64, vp, f64, C.c_uint32, C.c_uint32, vp, vp]
     L.bias_hdp_hyper_draws.argtypes = [C.c_uint64, f64, f64, f64, f64, f64, f64, f64, i32, f64, f64, i32, vp, vp]

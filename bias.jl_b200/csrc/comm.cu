@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <vector>
 #include "model.hpp"
 #include "narrow.cuh"
@@ -658,6 +659,11 @@ int bias_group_sweep(bias_group *g, int32_t n_sweeps) {
 // collapsed_gibbs_sampler!(lda, xx, zz, ...) on several GPUs of this process: documents split contiguously over
 // `devices`, one context and resident model per device, sweeps through bias_group_sweep, assignments gathered back
 // into zz.  stats[s] is filled after every sweep only when stats != NULL (n_moved and the diagnostic summed over shards).
+// where the most recent bias_lda_run_multi of this thread spent its time: set-up (contexts, shard upload, initialisation pass, peer
+// mappings), the sweeps (with their exchanges), the rest (download, teardown); milliseconds of host wall clock with the devices idle at
+// both ends of each span
+static thread_local double g_run_ms[3] = {0.0, 0.0, 0.0};
+
 int bias_lda_run_multi(const int32_t *devices, int32_t n_dev, uint64_t seed, const bias_conjugate *conj, const bias_data *data,
                        int64_t n_groups, const int64_t *group_ptr, int32_t *zz, int32_t K, double alpha, int32_t n_sweeps,
                        bias_sweep_stats *stats) {
@@ -667,6 +673,8 @@ int bias_lda_run_multi(const int32_t *devices, int32_t n_dev, uint64_t seed, con
     if (conj->kind != BIAS_MD || conj->datum != BIAS_INT || !data->word)
         return fail(BIAS_EINVAL, "bias_lda_run_multi covers LDA x MultinomialDirichlet x word ids");
     if (n_groups < 0 || group_ptr[0] != 0 || group_ptr[n_groups] != data->n_items) return fail(BIAS_EINVAL, "group_ptr must start at 0 and end at n_items");
+    const auto t_start = std::chrono::steady_clock::now();
+    g_run_ms[0] = g_run_ms[1] = g_run_ms[2] = 0.0;
     std::vector<bias_ctx *> ctxs(n_dev, nullptr);
     std::vector<bias_model *> ms(n_dev, nullptr);
     std::vector<std::vector<int64_t>> ptrs(n_dev);
@@ -687,6 +695,9 @@ int bias_lda_run_multi(const int32_t *devices, int32_t n_dev, uint64_t seed, con
             rc = bias_model_create(ctxs[i], BIAS_MODEL_LDA, conj, &d, g1 - g0, ptrs[i].data(), zz + item0[i], K, alpha, nullptr, &ms[i]);
     }
     if (rc == BIAS_OK && n_dev > 1) rc = bias_group_create(ms.data(), n_dev, &g);
+    for (int i = 0; i < n_dev && rc == BIAS_OK; ++i) rc = bias_ctx_sync(ctxs[i]);
+    const auto t_sweeps = std::chrono::steady_clock::now();
+    g_run_ms[0] = std::chrono::duration<double, std::milli>(t_sweeps - t_start).count();
     for (int32_t s = 0; s < n_sweeps && rc == BIAS_OK; ++s) {
         rc = n_dev > 1 ? bias_group_sweep(g, 1) : bias_model_sweep(ms[0], 1);
         if (rc == BIAS_OK && stats) {
@@ -703,13 +714,23 @@ int bias_lda_run_multi(const int32_t *devices, int32_t n_dev, uint64_t seed, con
             stats[s] = acc;
         }
     }
+    for (int i = 0; i < n_dev && rc == BIAS_OK; ++i) rc = bias_ctx_sync(ctxs[i]);
+    const auto t_done = std::chrono::steady_clock::now();
+    g_run_ms[1] = std::chrono::duration<double, std::milli>(t_done - t_sweeps).count();
     for (int i = 0; i < n_dev && rc == BIAS_OK; ++i) rc = bias_model_get_zz(ms[i], zz + item0[i]);
     if (g) bias_group_destroy(g);
     for (int i = 0; i < n_dev; ++i) {
         if (ms[i]) bias_model_destroy(ms[i]);
         if (ctxs[i]) bias_ctx_destroy(ctxs[i]);
     }
+    g_run_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_done).count();
     return rc;
+}
+
+int bias_lda_run_multi_timing(double *ms) {
+    if (!ms) return fail(BIAS_EINVAL, "null argument");
+    for (int i = 0; i < 3; ++i) ms[i] = g_run_ms[i];
+    return BIAS_OK;
 }
 
 // ---- one process per GPU ----

@@ -310,6 +310,10 @@ BIAS_API int bias_model_delta_apply16(bias_model *m);
 BIAS_API int bias_lda_run_multi(const int32_t *devices, int32_t n_dev, uint64_t seed, const bias_conjugate *conj,
                        const bias_data *data, int64_t n_groups, const int64_t *group_ptr, int32_t *zz /* in/out */,
                        int32_t K, double alpha, int32_t n_sweeps, bias_sweep_stats *stats /* [n_sweeps] or NULL */);
+/* Where the most recent bias_lda_run_multi of the calling thread spent its time, in milliseconds of host wall clock:
+ * ms[0] set-up (contexts, shard upload, initialisation pass, peer mappings), ms[1] the sweeps with their exchanges,
+ * ms[2] download and teardown.  (The reference prints the elapsed time of every iteration, src/LDA.jl:110.) */
+BIAS_API int bias_lda_run_multi_timing(double *ms /* [3] */);
 /* The same with resident shards: models created by the caller (one per device, or several on one device) become the
  * ranks of a group; bias_group_sweep = sweep of every shard + the exchange, ordered by CUDA events.  After a reload
  * of the shards (all of them) the next bias_group_sweep first merges their local counts.  The group does not own
