@@ -54,7 +54,8 @@ def sweep_kernel_name(n_hot=0):
         return "lda_md_int_sweep_kernel<8>"
     if force.startswith("h"):
         return "lda_md_int_sweep_half_kernel<16, 8>"
-    return f"lda_md_int_sweep_half16_kernel<8, 6, 3, true, {'true' if n_hot > 0 else 'false'}>"
+    # corpora with hot words run the instantiation with the int32-row route: 2 CTAs of 8 warps (csrc/lda_half16.cuh, kH16HotWarps)
+    return "lda_md_int_sweep_half16_kernel<8, 8, 2, true, true>" if n_hot > 0 else "lda_md_int_sweep_half16_kernel<8, 6, 3, true, false>"
 
 
 def peaks():
