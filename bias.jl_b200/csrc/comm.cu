@@ -309,7 +309,10 @@ int narrow_alloc(bias_model *m, int32_t hot_cap) {
         m->hot_word = nullptr;
         m->base_hot = nullptr;
     }
-    const size_t tab = round_up(((size_t)m->V + 2 * (size_t)hot_cap) * m->Kpad * sizeof(uint16_t), 256);
+    // the hot rows exist kHotRep times (lda_fast.cuh) unless that would be hundreds of MB; the first copy is the canonical one
+    m->hot_rep = hot_cap <= 16384 ? kHotRep : 1;
+    m->hot_rep_valid = false;
+    const size_t tab = round_up(((size_t)m->V + 2 * (size_t)hot_cap * m->hot_rep) * m->Kpad * sizeof(uint16_t), 256);
     const size_t nk = round_up((size_t)m->Kpad * 4, 256), fr = round_up((size_t)std::max<int64_t>(1, m->V) * 4, 256);
     m->off_nk_pub = tab;
     m->off_freq_pub = tab + nk;
@@ -342,6 +345,30 @@ static int narrow_grid(bias_model *m) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((m->V * 32 + 255) / 256, (int64_t)m->ctx->num_sms * 8));
 }
 
+// copies 1 .. rep-1 of the hot rows <- the canonical copy (after a conversion or an exchange wrote it)
+__global__ void narrow_replicate_kernel(uint16_t *tab, int64_t V, int Kpad, int hot_cap, int rep, const int32_t *hot_info) {
+    const int n_hot = min(hot_info[0], hot_cap);
+    const int64_t per_row = Kpad / 4, total = (int64_t)n_hot * per_row;          // 16-byte pieces of the canonical hot rows
+    const uint4 *src = reinterpret_cast<const uint4 *>(tab + (size_t)V * Kpad);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcg(src + q);
+        for (int c = 1; c < rep; ++c) reinterpret_cast<uint4 *>(tab + ((size_t)V + 2 * (size_t)c * hot_cap) * Kpad)[q] = v;
+    }
+}
+
+int narrow_replicate(bias_model *m) {
+    if (m->hot_rep_valid) return BIAS_OK;
+    if (m->hot_rep > 1 && m->n_hot_host > 0) {
+        const int64_t total = (int64_t)m->n_hot_host * (m->Kpad / 4);
+        narrow_replicate_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, (int64_t)m->ctx->num_sms * 8)), 256, 0,
+                                  m->ctx->stream>>>(m->n_wk16, m->V, m->Kpad, m->hot_cap, m->hot_rep, m->hot_info);
+        BIAS_CUDA_TRY(cudaGetLastError());
+        m->ctx->launches += 1;
+    }
+    m->hot_rep_valid = true;
+    return BIAS_OK;
+}
+
 int narrow_classify(bias_model *m) {
     classify_words_kernel<<<1, 1024, 0, m->ctx->stream>>>(m->word_freq_g, m->V, m->hot_cap, m->word_hot, m->hot_word, m->hot_info);
     BIAS_CUDA_TRY(cudaGetLastError());
@@ -361,6 +388,7 @@ int narrow_build(bias_model *m) {
     BIAS_CUDA_TRY(cudaGetLastError());
     m->ctx->launches += 1;
     m->narrow_valid = true;
+    m->hot_rep_valid = false;
     return BIAS_OK;
 }
 
@@ -429,6 +457,7 @@ static int step_exchange(bias_model *m, int merge) {
     BIAS_CUDA_TRY(cudaGetLastError());
     m->ctx->launches += 1;
     m->wide_valid = false;
+    m->hot_rep_valid = false;       // this rank and its peers write the canonical copy of the hot rows
     return BIAS_OK;
 }
 

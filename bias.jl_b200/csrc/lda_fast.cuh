@@ -54,6 +54,7 @@ struct LdaFastParams {
     const int32_t *eval_word;   //   their word ids; theta_d still comes from the document's training tokens (z)
     uint16_t *n_wk16;           // lda_half16.cuh: the narrow tables, [V + 2 * hot_cap][Kpad]
     const int32_t *word_hot;    // lda_half16.cuh: [V] hot-row index of each word or -1
+    int32_t hot_cap, hot_rep;   // lda_half16.cuh: copy c of hot row h is row V + 2 (h + c * hot_cap); hot_rep copies (narrow.cuh: kHotRep)
     int32_t *nk_rep;            // half-warp kernels: [kNkRep][Kpad] replicas collecting this sweep's changes of n_k
     int32_t pf_dist;            // lda_half.cuh: rows are pulled into L2 this many tokens ahead (0: off; at most 16)
 };
@@ -63,6 +64,7 @@ struct LdaFastParams {
 // therefore send their n_k updates to one of kNkRep zero-initialised replicas (chosen by CTA index), read
 // n_k + sum of the replicas when a document starts, and a small kernel folds the replicas into n_k after the sweep.
 constexpr int kNkRep = 8;
+
 
 // warps per CTA: 8 up to K = 1024, 4 above (the per-warp rows are 8*Kpad bytes of shared memory)
 __host__ __device__ constexpr int lda_fast_warps(int nch) { return nch <= 8 ? 8 : 4; }

@@ -297,7 +297,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
             my_w = p.word[t_cur + l16];
             if constexpr (HOT) {
                 const int h = __ldg(p.word_hot + my_w);
-                if (h >= 0) my_w = p.V + 2 * h;
+                if (h >= 0) my_w = p.V + 2 * (h + (int)(blockIdx.x % (unsigned)p.hot_rep) * p.hot_cap);     // this CTA's copy of the row
             }
             my_z = p.z[t_cur + l16];
             const uint64_t tid = (uint64_t)(t_cur + l16);
@@ -488,16 +488,31 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                         r_s[r_pos(knew)] = r_new;
                         R_s[knew >> 7] += r_new - r2;
                     }
-                    if (l16 >= 8 && l16 < 12) {
-                        // lanes 8..11: row[kold]--, row[knew]++, n_k[kold]--, n_k[knew]++ (a 16-bit cell is half of a 32-bit
-                        // word, a hot cell a whole one)
+                    if constexpr (HOT) {
+                        // lanes 6..15: row[kold]--, row[knew]++ on every copy of a hot row (a 16-bit row has one), n_k[kold]--, n_k[knew]++
+                        const int which = l16 - 6, kk = (which & 1) ? knew : kold, copy = which >> 1;
+                        if (which >= 8 || (which >= 0 && (copy == 0 || (hot && copy < p.hot_rep)))) {
+                            unsigned *ptr;
+                            unsigned val = 1u;
+                            if (which < 8) {
+                                const int w_c = hot ? w + 2 * (copy - (int)(blockIdx.x % (unsigned)p.hot_rep)) * p.hot_cap : w;
+                                unsigned *rowu = reinterpret_cast<unsigned *>(p.n_wk16 + (size_t)w_c * KPAD);
+                                ptr = hot ? rowu + r_pos(kk) : rowu + (kk >> 1);
+                                if (!hot) val = 1u << ((kk & 1) * 16);
+                            } else {
+                                ptr = reinterpret_cast<unsigned *>(my_nk) + kk;
+                            }
+                            red_add(ptr, (which & 1) ? val : 0u - val);
+                        }
+                    } else if (l16 >= 8 && l16 < 12) {
+                        // lanes 8..11: row[kold]--, row[knew]++, n_k[kold]--, n_k[knew]++ (a 16-bit cell is half of a 32-bit word)
                         const int which = l16 - 8, kk = (which & 1) ? knew : kold;
                         unsigned *ptr;
                         unsigned val;
                         if (which < 2) {
                             unsigned *rowu = reinterpret_cast<unsigned *>(p.n_wk16 + (size_t)w * KPAD);
-                            ptr = hot ? rowu + r_pos(kk) : rowu + (kk >> 1);
-                            val = hot ? 1u : 1u << ((kk & 1) * 16);
+                            ptr = rowu + (kk >> 1);
+                            val = 1u << ((kk & 1) * 16);
                         } else {
                             ptr = reinterpret_cast<unsigned *>(my_nk) + kk;
                             val = 1u;
@@ -514,7 +529,7 @@ lda_md_int_sweep_half16_kernel(const LdaFastParams p) {
                 }
                 // the next token's row was read before this update: when it is the same word, read it again
                 if (__any_sync(kFull, moved && w_n == w && i + 1 < nb)) {
-                    if (l16 >= 8 && l16 < 12) __threadfence();
+                    if (l16 >= (HOT ? 6 : 8) && l16 < (HOT ? 16 : 12)) __threadfence();
                     __syncwarp();
                     if (moved && w_n == w && i + 1 < nb) {
                         const uint16_t *rown = p.n_wk16 + (size_t)w_n * KPAD;

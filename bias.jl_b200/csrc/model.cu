@@ -185,8 +185,11 @@ static int launch_lda_fast(bias_model *m, const double *ext_uniforms, int frozen
     const bool half_path = use_half_kernel(m) && !eval && m->nk_rep;
     if (use_half16_kernel(m) && !eval && m->V > 0 && m->nk_rep) {
         BIAS_TRY(ensure_narrow(m));
+        BIAS_TRY(narrow_replicate(m));
         p.n_wk16 = m->n_wk16;
         p.word_hot = m->word_hot;
+        p.hot_cap = m->hot_cap;
+        p.hot_rep = m->hot_rep;
         switch (m->Kpad / 128) {
             case 1: BIAS_TRY(launch_lda_half16<1>(m, p)); break;
             case 2: BIAS_TRY(launch_lda_half16<2>(m, p)); break;

@@ -64,6 +64,8 @@ struct bias_model {
     bool narrow_valid = false;      // the narrow tables hold the current counts
     bool class_valid = false;       // word_hot matches the loaded corpus
     int32_t n_hot_host = 0;         // number of hot words of the loaded corpus (read back after every classification)
+    int32_t hot_rep = 1;            // copies of the hot rows in the narrow tables (kHotRep, or 1 when hot_cap is huge)
+    bool hot_rep_valid = false;     // the copies equal the first one
 
     // sharded run (comm.cu): the narrow tables sit at the start of one allocation that the other ranks map
     unsigned char *share_base = nullptr;
@@ -139,6 +141,7 @@ int launch_generic(bias_model *m, int64_t n_work, const int64_t *item_idx, const
                    int faithful, double *raw_out, double *prob_out, int32_t *draw_out, uint32_t rng_stream,
                    int row_by_work = 0);
 int rebuild_counts(bias_model *m);
+int narrow_replicate(bias_model *m);  // the copies of the hot rows equal the canonical one on return
 int ensure_wide(bias_model *m);       // n_wk (int32) is current on return
 int ensure_narrow(bias_model *m);     // the narrow tables are current on return
 int model_local_sweep(bias_model *m); // one sweep over this model's items, no exchange
