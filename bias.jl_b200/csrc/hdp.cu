@@ -984,6 +984,74 @@ int crf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     return BIAS_OK;
 }
 
+// The hyper-parameters of ONE epoch of the RCRF (src/RCRF.jl:80-118 = sample_hyperparam! of src/HDP.jl:124-159 with the epoch's
+// restaurants, tables and dishes): n_internals rounds of { w_j ~ Beta(aa + 1, n_j), s_j ~ Bernoulli(n_j / (n_j + aa)) over the epoch's
+// restaurants; aa ~ Gamma(a1 + m - sum s) / (a2 - sum log w); gg by Escobar-West } in one block, no host round trip (the first version
+// read two sums back per round: 1,100 synchronisations per sweep of 100 epochs).  err = 4: a Gamma parameter is not positive
+// (Distributions.Gamma's argument check in the reference).
+__global__ void __launch_bounds__(256)
+rcrf_hyper_kernel(const int64_t *group_ptr, const int32_t *n_tbls, int64_t g0, int64_t g1, const int32_t *mm_row, int Kpad,
+                  double *aa_t, double *gg_t, int t, double a1, double a2, double g1p, double g2p, int n_internals,
+                  uint64_t seed, uint32_t sweep, int *err) {
+    __shared__ double s_a[8], s_b[8], s_out[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto block_sum2 = [&](double a, double b, double &ra, double &rb) {
+        a = warp_sum(a);
+        b = warp_sum(b);
+        __syncthreads();
+        if (lane == 0) { s_a[warp] = a; s_b[warp] = b; }
+        __syncthreads();
+        if (tid == 0) {
+            double x = 0.0, y = 0.0;
+            for (int w = 0; w < 8; ++w) { x += s_a[w]; y += s_b[w]; }
+            s_out[0] = x;
+            s_out[1] = y;
+        }
+        __syncthreads();
+        ra = s_out[0];
+        rb = s_out[1];
+    };
+    double m_loc = 0.0, kk_loc = 0.0;
+    for (int64_t j = g0 + tid; j < g1; j += 256) m_loc += (double)n_tbls[j];
+    for (int k = tid; k < Kpad; k += 256) kk_loc += mm_row[k] != 0 ? 1.0 : 0.0;
+    double mt, KK;
+    block_sum2(m_loc, kk_loc, mt, KK);
+    double aa = aa_t[t], gg = gg_t[t];
+    for (int hh = 0; hh < n_internals; ++hh) {
+        double lw = 0.0, ss = 0.0;
+        for (int64_t j = g0 + tid; j < g1; j += 256) {
+            const double nj = (double)(group_ptr[j + 1] - group_ptr[j]);
+            if (nj > 0.0) {
+                PhiloxStream rs(seed, (uint32_t)j, (uint32_t)((uint64_t)j >> 32), ((sweep * 1024u + (uint32_t)t) * 64u + (uint32_t)hh) * 8u + kStreamHyper);
+                const double ga = rs.gamma(aa + 1.0), gb = rs.gamma(nj);
+                lw += log(ga / (ga + gb));
+                ss += (rs.u01() < nj / (nj + aa)) ? 1.0 : 0.0;
+            }
+        }
+        double sum_logw, sum_s;
+        block_sum2(lw, ss, sum_logw, sum_s);
+        if (tid == 0) {
+            PhiloxStream rs(seed ^ 0x5851F42D4C957F2Dull, (uint32_t)t, 0x52435246u, (sweep * 64u + (uint32_t)hh) * 8u + kStreamHyper);
+            const double aa_shape = a1 + mt - sum_s, aa_rate = a2 - sum_logw;              // :146-147
+            if (!(aa_shape > 0.0) || !(aa_rate > 0.0)) *err = 4;
+            else aa = rs.gamma(aa_shape) / aa_rate;                                          // :148
+            const double x1 = rs.gamma(gg + 1.0), x2 = rs.gamma(fmax(mt, 1e-300));
+            const double le = log(x1 / (x1 + x2));                                          // log of Beta(gg + 1, m), :151
+            const double pi_eta = 1.0 / (1.0 + (mt * (g2p - le)) / (g1p + KK - 1.0));       // :152
+            const double shape = (rs.u01() < pi_eta) ? g1p + KK : g1p + KK - 1.0;           // :154-158
+            if (!(shape > 0.0) || !(g2p - le > 0.0)) *err = 4;
+            else gg = rs.gamma(shape) / (g2p - le);
+            s_out[0] = aa;
+        }
+        __syncthreads();
+        aa = s_out[0];
+    }
+    if (tid == 0) {
+        aa_t[t] = aa;
+        gg_t[t] = gg;
+    }
+}
+
 // RCRF (reference src/RCRF.jl:122-938): per epoch the CRF's two passes over that epoch's restaurants with the dish
 // prior coupled to the neighbouring epochs' menus, same-dish tables joined in between, the epoch's hyper-parameters after
 int rcrf_create(bias_model *m, int64_t n_epochs, const int64_t *epoch_ptr, const double *gg, const double *aa, int join_tables) {
@@ -991,6 +1059,8 @@ int rcrf_create(bias_model *m, int64_t n_epochs, const int64_t *epoch_ptr, const
     m->h_gg_t.assign(gg, gg + n_epochs);
     m->h_aa_t.assign(aa, aa + n_epochs);
     m->crf_join = join_tables ? 1 : 0;
+    if (!m->d_aa_t) BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_aa_t, (size_t)std::max<int64_t>(1, n_epochs) * 8));
+    if (!m->d_gg_t) BIAS_CUDA_TRY(cudaMalloc((void **)&m->d_gg_t, (size_t)std::max<int64_t>(1, n_epochs) * 8));
     return crf_create(m);
 }
 
@@ -1002,35 +1072,28 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_KK, &m->hdp.KK, 4, cudaMemcpyHostToDevice, st));
     const size_t smem = crf_smem_bytes((int)m->max_group_len, m->hdp.Kmax);
     BIAS_TRY(crf_set_smem(m, smem));
-    std::vector<int32_t> mm_row(Kpad);
+    const uint64_t hyper_seed = m->host_rng();          // the host stream (bias_model_set_host_seed) keys the device draws
+    if (m->hdp.sample_hyperparam) {
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_aa_t, m->h_aa_t.data(), (size_t)T * 8, cudaMemcpyHostToDevice, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->d_gg_t, m->h_gg_t.data(), (size_t)T * 8, cudaMemcpyHostToDevice, st));
+    }
     for (int t = 0; t < T; ++t) {
         const CrfParams p = rcrf_params(m, t, ext_uniforms_dev);
         const int64_t Gt = p.g1 - p.g0;
         if (Gt <= 0) continue;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((Gt + kCrfWarps - 1) / kCrfWarps, (int64_t)ctx->num_sms * 8));
         BIAS_TRY(crf_launch_passes(m, p, grid, smem, m->crf_join != 0));
-        if (m->hdp.sample_hyperparam) {             // src/RCRF.jl:464-468 -> :80-118
-            unsigned long long *d_m = m->scratch + 5;
-            unsigned long long mt = 0;
-            BIAS_CUDA_TRY(cudaMemsetAsync(d_m, 0, 8, st));
-            crf_sum_tables_kernel<<<grid1d(ctx, Gt, 256, 4), 256, 0, st>>>(m->crf_n_tbls + p.g0, Gt, d_m);
+        if (m->hdp.sample_hyperparam) {             // src/RCRF.jl:464-468 -> :80-118, on the device
+            rcrf_hyper_kernel<<<1, 256, 0, st>>>(m->group_ptr, m->crf_n_tbls, p.g0, p.g1, m->crf_mm + (size_t)t * Kpad, Kpad, m->d_aa_t,
+                                                 m->d_gg_t, t, m->hdp.a1, m->hdp.a2, m->hdp.g1, m->hdp.g2, m->hdp.n_internals,
+                                                 hyper_seed, m->sweep_index, reinterpret_cast<int *>(m->scratch + 4));
+            BIAS_CUDA_TRY(cudaGetLastError());
             ctx->launches += 1;
-            BIAS_CUDA_TRY(cudaMemcpyAsync(&mt, d_m, 8, cudaMemcpyDeviceToHost, st));
-            BIAS_CUDA_TRY(cudaMemcpyAsync(mm_row.data(), m->crf_mm + (size_t)t * Kpad, (size_t)Kpad * 4, cudaMemcpyDeviceToHost, st));
-            BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-            int KK_t = 0;
-            for (int k = 0; k < Kpad; ++k) KK_t += mm_row[k] != 0;
-            for (int hh = 0; hh < m->hdp.n_internals; ++hh) {
-                double hyper[2] = {0.0, 0.0};
-                BIAS_CUDA_TRY(cudaMemsetAsync(m->d_hyper, 0, 16, st));
-                hdp_hyper_kernel<<<grid1d(ctx, Gt, 128, 4), 128, 0, st>>>(m->group_ptr + p.g0, Gt, m->h_aa_t[t], ctx->seed,
-                                                                          m->sweep_index * 1024u + (uint32_t)t, (uint32_t)hh, m->d_hyper);
-                ctx->launches += 1;
-                BIAS_CUDA_TRY(cudaMemcpyAsync(hyper, m->d_hyper, 16, cudaMemcpyDeviceToHost, st));
-                BIAS_CUDA_TRY(cudaStreamSynchronize(st));
-                BIAS_TRY(hdp_host_hyper_on(m, (double)mt, hyper[0], hyper[1], KK_t, m->h_aa_t[t], m->h_gg_t[t]));
-            }
         }
+    }
+    if (m->hdp.sample_hyperparam) {
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->h_aa_t.data(), m->d_aa_t, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+        BIAS_CUDA_TRY(cudaMemcpyAsync(m->h_gg_t.data(), m->d_gg_t, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
     }
     int32_t kk = 0;
     int err = 0;
@@ -1040,6 +1103,9 @@ int rcrf_sweep(bias_model *m, const double *ext_uniforms_dev) {
     m->hdp.KK = kk;
     if (err == 2)
         return fail(BIAS_ERANGE, "RCRF: Kmax = %d dish slots exhausted (KK = %d); construct the model with a larger Kmax", m->hdp.Kmax, kk);
+    if (err == 4)
+        return fail(BIAS_EINVAL, "RCRF: a Gamma parameter of the hyper-parameter update is not positive (a1 = %g, a2 = %g, g1 = %g, g2 = %g)",
+                    m->hdp.a1, m->hdp.a2, m->hdp.g1, m->hdp.g2);
     BIAS_TRY(crf_prune(m));
     BIAS_TRY(crf_launch_diag(m));
     m->hdp.aa = m->h_aa_t[0];

@@ -568,7 +568,7 @@ int bias_model_destroy(bias_model *m) {
     crf_destroy(m);
     void *ptrs[] = {m->word, m->x, m->sent_ptr, m->sent_word, m->sent_count, m->group_ptr, m->group_of, m->z,
                     m->i32_block, m->f64_block, m->group_rows, m->base_i32, m->delta_i32, m->base_f64,
-                    m->delta_f64, m->scratch, m->d_aa_t, m->word_freq, m->word_freq_g, m->word_hot, m->hot_info, m->nk_rep, m->stage16};
+                    m->delta_f64, m->scratch, m->d_aa_t, m->d_gg_t, m->word_freq, m->word_freq_g, m->word_hot, m->hot_info, m->nk_rep, m->stage16};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     narrow_free(m);

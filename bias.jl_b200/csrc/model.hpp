@@ -114,6 +114,7 @@ struct bias_model {
     // RCRF: restaurants of all epochs are the groups; first restaurant of each epoch, per-epoch gg (aa in h_aa_t)
     std::vector<int64_t> h_epoch_gptr;
     std::vector<double> h_gg_t;
+    double *d_gg_t = nullptr;       // [T] device copy (the per-epoch hyper-parameter draws run on the device)
     int32_t crf_join = 1;
 
     // RCRP (epochs are the groups)

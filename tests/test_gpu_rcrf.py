@@ -142,6 +142,34 @@ def test_rcrf_gibbs_sampler_entry_point(ctx):
     assert abs(rcrf.KK - st.KK) <= 3, (rcrf.KK, st.KK)
 
 
+def test_rcrf_hyper_parameter_draws_match_the_serial_sampler_in_distribution(ctx):
+    """The per-epoch aa / gg update (src/RCRF.jl:80-118) runs on the device (rcrf_hyper_kernel).  800 epochs of one restaurant with
+    identical customers and a single dish are independent replicas of the same small chain (seating by CRP(aa_t), then the update of
+    aa_t and gg_t from the epoch's tables): after four iterations the GPU's aa_t and gg_t must be distributed like the serial sampler's."""
+    from scipy.stats import ks_2samp
+    TT, n = 800, 12
+    N = TT * n
+    x = np.zeros(N)
+    eptr = np.arange(TT + 1, dtype=np.int64)
+    ptr = np.arange(TT + 1, dtype=np.int64) * n
+    z0 = np.zeros(N, dtype=np.int32)
+    comp = b.Gaussian1DGaussian1D(0.0, 1e12, 0.01)          # the prior predictive is ~1e-7 of the dish's: no second dish
+    rcrf = b.RCRF(comp, 1, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, TT, Kmax=8)
+    data = b.FlatData.from_csr(b._lib.F64, N, group_ptr=ptr, x=x)
+    rs = b.ResidentSampler(ctx, rcrf, data, z0, sample_hyperparam=True, n_internals=5, epoch_ptr=eptr)
+    rs.sweep(4)
+    KK, gg_gpu, aa_gpu = rs.rcrf_state()
+    rs.close()
+    st = orc.RCRFState(orc.Comps.g1g1(8, 0.0, 1e12, 0.01), orc.Data.reals(x), eptr, ptr, z0.astype(np.int64), 1, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
+    r = orc.Rng(3)
+    for _ in range(4):
+        st.sweep(r, defer_deaths=True, sample_hyper=True, n_internals=5)
+    assert KK == 1 and st.KK == 1
+    assert (aa_gpu > 0).all() and (gg_gpu > 0).all()
+    assert ks_2samp(aa_gpu, st.aa).pvalue > 1e-3, (aa_gpu.mean(), st.aa.mean())
+    assert ks_2samp(gg_gpu, st.gg).pvalue > 1e-3, (gg_gpu.mean(), st.gg.mean())
+
+
 def test_rcrf_argument_errors(ctx):
     x = np.arange(6, dtype=np.float64)
     with pytest.raises(ValueError):        # a single epoch
