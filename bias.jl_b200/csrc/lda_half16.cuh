@@ -144,6 +144,15 @@ __device__ __forceinline__ float dot8(const uint4 x, const float4 a, const float
 
 // the same eight products for a hot row: a = cells of topics +0..3, b = +4..7 (int32, stored in r_pos order)
 __device__ __forceinline__ float dot8i(const uint4 a, const uint4 b, const float4 ra, const float4 rb) {
+#if BIAS_H16_F32X2
+    f32x2 s = fmul2(pack2((float)(int)a.x, (float)(int)a.y), pack2(ra.x, ra.y));
+    s = ffma2(pack2((float)(int)a.z, (float)(int)a.w), pack2(ra.z, ra.w), s);
+    s = ffma2(pack2((float)(int)b.x, (float)(int)b.y), pack2(rb.x, rb.y), s);
+    s = ffma2(pack2((float)(int)b.z, (float)(int)b.w), pack2(rb.z, rb.w), s);
+    float lo, hi;
+    unpack2(s, lo, hi);
+    return lo + hi;
+#else
     float s = (float)(int)a.x * ra.x;
     s = fmaf((float)(int)a.y, ra.y, s);
     s = fmaf((float)(int)a.z, ra.z, s);
@@ -153,6 +162,7 @@ __device__ __forceinline__ float dot8i(const uint4 a, const uint4 b, const float
     t = fmaf((float)(int)b.z, rb.z, t);
     t = fmaf((float)(int)b.w, rb.w, t);
     return s + t;
+#endif
 }
 
 // A hot row held in registers: c = pieces 0 .. N-1, d = pieces N .. 2N-1 (piece jj of lane l: topics
