@@ -179,6 +179,14 @@ function lda!(lda, xx, zz, n_burnins::Int, n_lags::Int, n_samples::Int; seed=0)
     stats
 end
 
+# Where the most recent multi-GPU lda! spent its time: (set-up, sweeps, download and teardown) in milliseconds — the elapsed
+# time the reference prints per iteration (src/LDA.jl:108-110), for the whole call.
+function lda_timing()
+    ms = zeros(Float64, 3)
+    check(ccall((:bias_lda_run_multi_timing, LIB), Cint, (Ptr{Float64},), ms))
+    (ms[1], ms[2], ms[3])
+end
+
 # ---- collapsed_gibbs_sampler!(bmm::BMM, xx, zz, ...)  src/BMM.jl:46-130
 function bmm!(bmm, xx, zz::Vector{Int}, n_burnins::Int, n_lags::Int, n_samples::Int; seed=0)
     n_sweeps = n_burnins + n_samples * (n_lags + 1)
