@@ -51,9 +51,10 @@ struct CrfParams {
 };
 
 constexpr int kCrfWarps = 4;
+constexpr int kCrfSnapT = 32;          // tables of a restaurant whose dishes' predictive constants are cached (pass 1, Float64 items)
 __host__ __device__ inline size_t crf_warp_doubles(int max_len, int Kmax) {
     const size_t n = (size_t)(max_len > Kmax ? max_len : Kmax) + 2;
-    return n + (size_t)max_len + (3 * (size_t)max_len + 1) / 2;
+    return n + (size_t)max_len + (3 * (size_t)max_len + 1) / 2 + 7 * (size_t)kCrfSnapT;
 }
 __host__ __device__ inline size_t crf_smem_bytes(int max_len, int Kmax) {
     // per warp: scores double[max(max_len, Kmax) + 2] + staged values double[max_len] + the restaurant's tji / njt / kjt
@@ -244,9 +245,16 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
     double *sc = reinterpret_cast<double *>(smem_raw) + (size_t)warp * crf_warp_doubles(p.max_len, p.Kmax);
     double *xs = sc + n_sc;
     int32_t *tji = reinterpret_cast<int32_t *>(xs + p.max_len), *njt = tji + p.max_len, *kjt = njt + p.max_len;
+    // Float64 items: per table, the constants of its dish's predictive (src/conjugates.jl:92-103) — without the customer being
+    // scored (mu, 1 / (2 (v_post + vv)), log-normaliser) and with it taken out of the dish (mean = oA - oB x).  They are rebuilt
+    // from the live statistics only when this restaurant changed something (a table opened or closed, a customer changed dish);
+    // a customer that stays costs three multiply-adds per table instead of two divisions and a log.
+    double *c_mu = sc + crf_warp_doubles(p.max_len, p.Kmax) - 7 * kCrfSnapT, *c_i2d = c_mu + kCrfSnapT, *c_lc = c_i2d + kCrfSnapT,
+           *c_oA = c_lc + kCrfSnapT, *c_oB = c_oA + kCrfSnapT, *c_oi2d = c_oB + kCrfSnapT, *c_olc = c_oi2d + kCrfSnapT;
     double *logn = reinterpret_cast<double *>(smem_raw) + (size_t)kCrfWarps * crf_warp_doubles(p.max_len, p.Kmax);
     for (int q = threadIdx.x; q <= p.max_len; q += blockDim.x) logn[q] = log((double)q);
     __syncthreads();
+    const double i2d0 = 1.0 / (2.0 * (p.v0 + p.vv)), lc0 = 0.5 * log(2.0 * 3.141592653589793 * (p.v0 + p.vv));   // the empty prototype
     const int64_t n_warps = (int64_t)gridDim.x * kCrfWarps;
     unsigned long long moved = 0;
     int32_t *const mm_t = p.mm + (size_t)p.t * p.Kpad;
@@ -255,6 +263,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
         const int64_t p0 = p.group_ptr[j];
         const int n = (int)(p.group_ptr[j + 1] - p0);
         int nt = p.n_tbls[j];
+        bool dirty = true;                   // the cached constants do not describe the current tables / statistics
         __syncwarp();
         for (int q = lane; q < n; q += 32) {
             tji[q] = p.tji[p0 + q];
@@ -291,6 +300,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
                     __syncwarp();
                 }
                 nt -= 1;
+                dirty = true;
                 for (int q = lane; q < n; q += 32)
                     if (tji[q] > tbl) tji[q] -= 1;
             }
@@ -298,11 +308,49 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
             __threadfence_block();
             __syncwarp();
             // scores of the tables and of a new one (:549-555)
-            for (int t = lane; t < nt; t += 32) sc[t] = logn[njt[t]] + crf_logpred<DATUM>(p, kjt[t], i, x, kjt[t] == kk);
-            if (lane == (nt & 31)) sc[nt] = log_aa + crf_logpred<DATUM>(p, -1, i, x);
+            if (DATUM == BIAS_F64 && nt <= kCrfSnapT) {
+                if (dirty) {
+                    if (lane < nt) {
+                        const int k = kjt[lane];
+                        const double cn = (double)__ldcg(p.n_items + k), sx = __ldcg(p.sumx + k);
+                        double mu = p.m0, vp = p.v0;
+                        if (cn > 0.0) {
+                            const double denom = p.vv + cn * p.v0;
+                            mu = (p.v0 * sx + p.vv * p.m0) / denom;
+                            vp = p.v0 * p.vv / denom;
+                        }
+                        c_mu[lane] = mu;
+                        c_i2d[lane] = 1.0 / (2.0 * (vp + p.vv));
+                        c_lc[lane] = 0.5 * log(2.0 * 3.141592653589793 * (vp + p.vv));
+                        double oA = p.m0, oB = 0.0, vp1 = p.v0;          // the dish without one of its customers
+                        if (cn - 1.0 > 0.0) {
+                            const double d1 = p.vv + (cn - 1.0) * p.v0;
+                            oA = (p.v0 * sx + p.vv * p.m0) / d1;
+                            oB = p.v0 / d1;
+                            vp1 = p.v0 * p.vv / d1;
+                        }
+                        c_oA[lane] = oA;
+                        c_oB[lane] = oB;
+                        c_oi2d[lane] = 1.0 / (2.0 * (vp1 + p.vv));
+                        c_olc[lane] = 0.5 * log(2.0 * 3.141592653589793 * (vp1 + p.vv));
+                    }
+                    dirty = false;
+                    __syncwarp();
+                }
+                if (lane < nt) {
+                    const bool own = kjt[lane] == kk;
+                    const double dx = x - (own ? c_oA[lane] - c_oB[lane] * x : c_mu[lane]);
+                    sc[lane] = logn[njt[lane]] + (-(dx * dx) * (own ? c_oi2d[lane] : c_i2d[lane]) - (own ? c_olc[lane] : c_lc[lane]));
+                }
+                if (lane == (nt & 31)) sc[nt] = log_aa + (-((x - p.m0) * (x - p.m0)) * i2d0 - lc0);
+            } else {
+                for (int t = lane; t < nt; t += 32) sc[t] = logn[njt[t]] + crf_logpred<DATUM>(p, kjt[t], i, x, kjt[t] == kk);
+                if (lane == (nt & 31)) sc[nt] = log_aa + crf_logpred<DATUM>(p, -1, i, x);
+            }
             __syncwarp();
             tbl = crf_draw(sc, nt + 1, crf_draw_uniform(p, i, 0), lane);
             if (tbl == nt) {
+                dirty = true;
                 // a new table draws its dish from the menu (:559-581)
                 const int KK = crf_read_KK(p, lane);
                 const CrfLook L = crf_look(p, KK, lane);
@@ -359,6 +407,7 @@ __global__ void __launch_bounds__(kCrfWarps * 32, 5) crf_tables_kernel(CrfParams
                 }
             }
             const int kn = kjt[tbl];
+            if (kn != kk) dirty = true;
             __syncwarp();
             if (lane == 0) {
                 tji[ii] = tbl;
