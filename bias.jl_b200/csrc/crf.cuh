@@ -439,8 +439,20 @@ template <int DATUM>
 __device__ __forceinline__ double crf_table_score(const CrfParams &p, int k, const double *xs, const int32_t *ids, int64_t p0, int nti) {
     double s = 0.0;
     if (DATUM == BIAS_F64) {
+        // the dish's posterior predictive (src/conjugates.jl:92-103) is the same Gaussian for every customer of the table: its mean,
+        // 1 / (2 (v_post + vv)) and log-normaliser once, then one multiply-add per customer
         const double cn = k < 0 ? 0.0 : (double)__ldcg(p.n_items + k), sx = k < 0 ? 0.0 : __ldcg(p.sumx + k);
-        for (int q = 0; q < nti; ++q) s += g1g1_logpred(cn, sx, xs[q], p.m0, p.v0, p.vv);
+        double mu = p.m0, vp = p.v0;
+        if (cn > 0.0) {
+            const double denom = p.vv + cn * p.v0;
+            mu = (p.v0 * sx + p.vv * p.m0) / denom;
+            vp = p.v0 * p.vv / denom;
+        }
+        const double dummy = vp + p.vv, i2d = 1.0 / (2.0 * dummy), lc = 0.5 * log(2.0 * 3.141592653589793 * dummy);
+        for (int q = 0; q < nti; ++q) {
+            const double dx = xs[q] - mu;
+            s += -(dx * dx) * i2d - lc;
+        }
     } else {
         for (int q = 0; q < nti; ++q) s += crf_logpred<DATUM>(p, k, p0 + ids[q], 0.0);
     }
